@@ -1,0 +1,174 @@
+"""The DDSP DSP core with the reference's function signatures (ddsp/core.py), running on the
+hand-written sm_100a kernels.
+
+Every hot function of the reference module is here under the same name and argument list, so
+``ddsp.<name>`` call sites (modules.py:33,53-56,74-78,113,117,125; train.py:92-103) keep working:
+
+    safe_log  multiscale_fft  upsample  remove_above_nyquist  scale_function
+    harmonic_synth  amp_to_impulse_response  fft_convolve
+
+plus the non-hot helpers that must stay importable (mean_std_loudness, resample, extract_loudness,
+extract_pitch, mlp, gru).  Tensors must be CUDA float32: there is no CPU implementation of the
+kernels and a CPU tensor raises from the dispatcher.  Additions that have no counterpart in the
+reference are marked "extension".
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import functions as _F
+
+__all__ = [
+    "safe_log", "mean_std_loudness", "multiscale_fft", "resample", "upsample", "remove_above_nyquist",
+    "scale_function", "extract_loudness", "extract_pitch", "mlp", "gru", "harmonic_synth",
+    "amp_to_impulse_response", "fft_convolve",
+    "harmonic_synth_frames", "filtered_noise", "multiscale_spectral_loss",
+]
+
+
+def safe_log(x):
+    """ddsp/core.py:10-11."""
+    return torch.log(x + 1e-7)
+
+
+@torch.no_grad()
+def mean_std_loudness(dataset):
+    """ddsp/core.py:14-24: running mean of the per-batch loudness mean / std (host side)."""
+    mean, std = 0.0, 0.0
+    for count, batch in enumerate(dataset, start=1):
+        loud = batch["loudness"]
+        mean += (loud.mean().item() - mean) / count
+        std += (loud.std().item() - std) / count
+    return mean, std
+
+
+def multiscale_fft(signal, scales: Sequence[int], overlap: float) -> List[torch.Tensor]:
+    """ddsp/core.py:27-41: |STFT| of ``signal`` (B,N) at every scale, hop = int(s*(1-overlap)).
+    Returns a list of (B, s/2+1, 1+N//hop) tensors, differentiable w.r.t. ``signal``."""
+    squeeze = signal.dim() == 1
+    sig = signal.unsqueeze(0) if squeeze else signal
+    out = []
+    for s in scales:
+        mag = _F.StftMag.apply(sig, int(s), int(s * (1 - overlap)))
+        out.append(mag[0] if squeeze else mag)
+    return out
+
+
+def resample(x, factor: int):
+    """ddsp/core.py:44-61 (unused by the reference itself): zero-stuff by ``factor`` and smooth with
+    a Hann kernel of 2*factor taps.  Kept for import compatibility; stock torch ops."""
+    b, t, c = x.shape
+    rows = x.permute(0, 2, 1).reshape(b * c, 1, t)
+    stuffed = rows.new_zeros(b * c, 1, t * factor)
+    stuffed[..., ::factor] = rows
+    stuffed[..., -1:] = rows[..., -1:]
+    kernel = torch.hann_window(2 * factor, dtype=x.dtype, device=x.device).view(1, 1, -1)
+    smooth = nn.functional.conv1d(nn.functional.pad(stuffed, [factor, factor]), kernel)[..., :-1]
+    return smooth.reshape(b, c, t * factor).permute(0, 2, 1)
+
+
+def upsample(signal, factor):
+    """ddsp/core.py:64-67: nearest-neighbour hold, (B,T,C) -> (B,T*factor,C).  F.interpolate's default
+    mode is 'nearest', i.e. exactly repeat_interleave.  Inside the model this tensor
+    is never materialised: HarmonicSynth.forward calls the fused frame-rate kernel instead."""
+    return signal.repeat_interleave(int(factor), dim=1)
+
+
+def remove_above_nyquist(amplitudes, f0, sample_rate):
+    """ddsp/core.py:70-74."""
+    return _F.RemoveAboveNyquist.apply(amplitudes, f0, float(sample_rate))
+
+
+def scale_function(x):
+    """ddsp/core.py:77-78."""
+    return _F.ScaleFunction.apply(x)
+
+
+def extract_loudness(signal, sample_rate, block_size, n_fft=2048):
+    """ddsp/core.py:81-97 (offline preprocessing, numpy + librosa; out of the hot path)."""
+    import numpy as np
+    import librosa as li
+    spec = li.stft(signal, n_fft=n_fft, hop_length=block_size, win_length=n_fft, center=True)
+    spec = np.log(abs(spec) + 1e-7)
+    weight = li.A_weighting(li.fft_frequencies(sr=sample_rate, n_fft=n_fft))
+    return np.mean(spec + weight.reshape(-1, 1), 0)[..., :-1]
+
+
+def extract_pitch(signal, sample_rate, block_size):
+    """ddsp/core.py:100-119 (offline preprocessing with CREPE; out of the hot path)."""
+    import numpy as np
+    import crepe
+    length = signal.shape[-1] // block_size
+    f0 = crepe.predict(signal, sample_rate, step_size=int(1000 * block_size / sample_rate),
+                       verbose=1, center=True, viterbi=True)[1].reshape(-1)[:-1]
+    if f0.shape[-1] != length:
+        f0 = np.interp(np.linspace(0, 1, length, endpoint=False),
+                       np.linspace(0, 1, f0.shape[-1], endpoint=False), f0)
+    return f0
+
+
+def mlp(in_size, hidden_size, n_layers):
+    """ddsp/core.py:122-129: n_layers x (Linear, LayerNorm, LeakyReLU); same Sequential indices so
+    state_dict keys match the reference's checkpoints."""
+    sizes = [in_size] + [hidden_size] * n_layers
+    layers = []
+    for a, b in zip(sizes[:-1], sizes[1:]):
+        layers += [nn.Linear(a, b), nn.LayerNorm(b), nn.LeakyReLU()]
+    return nn.Sequential(*layers)
+
+
+def gru(n_input, hidden_size):
+    """ddsp/core.py:132-133."""
+    return nn.GRU(n_input * hidden_size, hidden_size, batch_first=True)
+
+
+def harmonic_synth(f0, amplitudes, sample_rate):
+    """ddsp/core.py:136-141, generic audio-rate signature: f0 (B,N,1), amplitudes (B,N,H) -> (B,N,1)."""
+    return _F.HarmonicAudioRate.apply(f0, amplitudes, float(sample_rate))
+
+
+def amp_to_impulse_response(amp, target_size):
+    """ddsp/core.py:144-166."""
+    return _F.AmpToImpulseResponse.apply(amp, int(target_size))
+
+
+def fft_convolve(signal, kernel):
+    """ddsp/core.py:169-176: causal convolution truncated to the signal length, last dim; leading
+    dims broadcast like the reference's rfft product."""
+    n = signal.shape[-1]
+    lead = torch.broadcast_shapes(signal.shape[:-1], kernel.shape[:-1])
+    rows = 1
+    for d in lead:
+        rows *= d
+    sig2 = signal.expand(*lead, n).reshape(rows, n)
+    k_rows = 1
+    for d in kernel.shape[:-1]:
+        k_rows *= d
+    if k_rows == 1:
+        ker2 = kernel.reshape(1, kernel.shape[-1])
+    else:
+        ker2 = kernel.expand(*lead, kernel.shape[-1]).reshape(rows, kernel.shape[-1])
+    return _F.FFTConvolve.apply(sig2, ker2).reshape(*lead, n)
+
+
+# ------------------------------------------------------------------------------------ extensions
+def harmonic_synth_frames(f0, weights, block_size: int, sample_rate, phase0: Optional[torch.Tensor] = None):
+    """Extension: the fused form of ``harmonic_synth(upsample(f0), upsample(weights))`` that
+    HarmonicSynth.forward uses.  f0 (B,T,1), weights (B,T,H) -> (audio (B,T*block,1), phase_end (B)).
+    ``phase0`` / ``phase_end`` carry the oscillator phase (turns, float64) across streaming calls."""
+    return _F.HarmonicFrames.apply(f0, weights, int(block_size), float(sample_rate), phase0)
+
+
+def filtered_noise(magnitudes, noise):
+    """Extension: FilteredNoise.forward with the uniform(-1,1) draw passed in (B,T,block)."""
+    return _F.FilteredNoise.apply(magnitudes, noise)
+
+
+def multiscale_spectral_loss(target, rec, scales: Sequence[int], overlap: float):
+    """Extension: train.py:70-76 applied to multiscale_fft(target), multiscale_fft(rec), as one fused
+    op (the magnitude lists are never written to HBM).  Differentiable w.r.t. ``rec`` only."""
+    return _F.MultiScaleSpectralLoss.apply(target, rec, [int(s) for s in scales], float(overlap))

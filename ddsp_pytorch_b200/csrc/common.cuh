@@ -1,0 +1,81 @@
+// Shared device/host helpers for libddsp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ddsp_b200.h"
+
+#define DDSP_SM_COUNT 148  // B200: 2 dies x 74 SMs; grids of persistent kernels are sized off this
+
+// Launch-status helper: argument errors are negative, CUDA errors positive (header contract).
+// Every successful kernel launch is also counted (ddsp_b200_launch_count: bench.py's gpu_launches).
+void ddsp_note_launch();
+static inline int ddsp_launch_status() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    ddsp_note_launch();
+    return DDSP_B200_OK;
+}
+
+#define DDSP_REQUIRE(cond) \
+    do {                   \
+        if (!(cond)) return DDSP_B200_EINVAL; \
+    } while (0)
+
+static inline int64_t ddsp_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Phase arithmetic.  Phases are kept in TURNS as Q0.64 unsigned fixed point: wrap-around of the
+// 64-bit integer is exactly "mod 1 turn", so k*phase for harmonic k is exact however long the
+// signal (the reference's float32 k*omega loses ~4e-2 over 4 s).
+// ---------------------------------------------------------------------------------------------
+
+// Fold a Q0.64 phase to [-1/4, 1/4) turns plus a half-turn count parity:
+//   phase = psi + r/2 (mod 1),  sin(2*pi*k*phase) = (-1)^(k*r) * sin(2*pi*k*psi).
+// Returns psi as a float in turns; *flip = r & 1.
+__device__ __forceinline__ float ddsp_fold_quarter(uint64_t p, int *flip) {
+    uint32_t r = (uint32_t)(((p >> 62) + 1) >> 1);      // round(2*p) in {0,1,2}
+    uint64_t psi = p - ((uint64_t)r << 63);             // r == 2 wraps to -1 turn
+    *flip = (int)(r & 1u);
+    return (float)(int32_t)(psi >> 32) * 2.3283064365386963e-10f;   // * 2^-32
+}
+
+// Q0.64 (signed view) -> float turns in [-1/2, 1/2)
+__device__ __forceinline__ float ddsp_turns_signed(uint64_t p) {
+    return (float)(int32_t)(p >> 32) * 2.3283064365386963e-10f;
+}
+
+// sin / cos of x for |x| <= pi/4 (no range reduction; ~1 ulp).  Minimax coefficients as used by
+// the usual single-precision kernels (Cephes sinf/cosf).
+__device__ __forceinline__ float ddsp_sin_q(float x) {
+    float z = x * x;
+    float p = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    p = fmaf(z, p, -1.6666654611e-1f);
+    return fmaf(x * z, p, x);
+}
+__device__ __forceinline__ float ddsp_cos_q(float x) {
+    float z = x * x;
+    float p = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    p = fmaf(z, p, 4.166664568298827e-2f);
+    return fmaf(z * z, p, fmaf(z, -0.5f, 1.0f));
+}
+
+// Reinsch form of the sine recurrence, stable for |psi| <= pi/2 (cos(psi) >= 0):
+//   u = -4 sin^2(psi/2);   d_{k+1} = d_k + u*s_k;   s_{k+1} = s_k + d_{k+1}
+// Error grows ~1.2e-7 * steps (measured in oracle-side simulation), against ~k^2 for Chebyshev.
+struct ddsp_osc {
+    float s, d, u;
+    __device__ __forceinline__ void step() {
+        d = fmaf(u, s, d);
+        s += d;
+    }
+};
+
+#define DDSP_PI_F 3.14159265358979323846f
+#define DDSP_2PI_F 6.28318530717958647692f
+
+__device__ __forceinline__ float ddsp_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,160 @@
+// Frame-rate control maps (SURVEY 8a rows a1, a2, a3 and their backward).
+//
+// Reference path replaced:
+//   ddsp/core.py:77-78               scale_function          2*sigmoid(x)^ln10 + 1e-7
+//   ddsp/core.py:70-74               remove_above_nyquist    amp * ((f0*k < sr/2).float() + 1e-4)
+//   ddsp/models/modules.py:44-67     HarmonicSynth.get_controls  (both of the above + /= sum)
+// ~15 eager elementwise/reduction launches at frame rate become one launch; one warp owns one
+// (voice, frame) row so the normalising sum is a shuffle reduction.
+#include "common.cuh"
+
+namespace {
+
+constexpr float kLn10 = 2.302585092994046f;
+
+// softplus(-x) = log(1 + exp(-x)), stable for both signs
+__device__ __forceinline__ float softplus_neg(float x) {
+    return fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+// sigmoid(x)^ln10 * 2  ( = exp(-ln10 * softplus(-x)) * 2 )
+__device__ __forceinline__ float scale_core(float x) { return 2.f * expf(-kLn10 * softplus_neg(x)); }
+__device__ __forceinline__ float scale_fn(float x) { return scale_core(x) + 1e-7f; }
+// d/dx scale_fn = ln10 * 2 sigmoid^ln10 * (1 - sigmoid(x))
+__device__ __forceinline__ float scale_grad(float x) {
+    return kLn10 * scale_core(x) * (1.f / (1.f + expf(x)));
+}
+// (mask.float() + 1e-4) of core.py:73: both branches are float32 sums
+__device__ __forceinline__ float nyquist_mask(float f0, int k1, float nyq) {
+    return (__fmul_rn(f0, (float)k1) < nyq) ? (1.0f + 1e-4f) : 1e-4f;   // single rounded product
+}
+
+__global__ void scale_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = scale_fn(x[i]);
+}
+__global__ void scale_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                 float *__restrict__ dx, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dx[i] = dy[i] * scale_grad(x[i]);
+}
+__global__ void nyquist_kernel(const float *__restrict__ amp, const float *__restrict__ f0,
+                               float *__restrict__ out, int64_t rows, int H, float nyq) {
+    const int64_t n = rows * H;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / H;
+        const int k = (int)(i - r * H);
+        out[i] = amp[i] * nyquist_mask(f0[r], k + 1, nyq);
+    }
+}
+
+constexpr int kRowWarps = 8;
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+controls_fwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__ dist_raw,
+                    const float *__restrict__ f0, float *__restrict__ amps,
+                    float *__restrict__ dist, int64_t rows, int H, float nyq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float f = f0[row];
+    const float *dr = dist_raw + row * H;
+    float *dn = dist + row * H;
+    float sum = 0.f;
+    for (int k = lane; k < H; k += 32) {
+        const float v = scale_fn(dr[k]) * nyquist_mask(f, k + 1, nyq);
+        dn[k] = v;
+        sum += v;
+    }
+    sum = ddsp_warp_sum(sum);
+    for (int k = lane; k < H; k += 32) dn[k] = dn[k] / sum;     // same thread re-reads its own write
+    if (lane == 0) amps[row] = scale_fn(amp_raw[row]);
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+controls_bwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__ dist_raw,
+                    const float *__restrict__ f0, const float *__restrict__ d_amps,
+                    const float *__restrict__ d_dist, float *__restrict__ d_amp_raw,
+                    float *__restrict__ d_dist_raw, int64_t rows, int H, float nyq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float f = f0[row];
+    const float *dr = dist_raw + row * H;
+    const float *gd = d_dist + row * H;
+    float *out = d_dist_raw + row * H;
+    // n_k = v_k / S  ->  dv_k = (g_k - sum_j g_j n_j) / S
+    float sum = 0.f, dot = 0.f;
+    for (int k = lane; k < H; k += 32) {
+        const float v = scale_fn(dr[k]) * nyquist_mask(f, k + 1, nyq);
+        sum += v;
+        dot = fmaf(gd[k], v, dot);
+    }
+    sum = ddsp_warp_sum(sum);
+    dot = ddsp_warp_sum(dot) / sum;                   // sum_j g_j n_j
+    const float inv = 1.f / sum;
+    for (int k = lane; k < H; k += 32)
+        out[k] = (gd[k] - dot) * inv * nyquist_mask(f, k + 1, nyq) * scale_grad(dr[k]);
+    if (lane == 0) d_amp_raw[row] = d_amps[row] * scale_grad(amp_raw[row]);
+}
+
+inline int ew_blocks(int64_t n) {
+    int64_t b = ddsp_ceil_div(n, 256);
+    const int64_t cap = (int64_t)DDSP_SM_COUNT * 8;
+    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int ddsp_b200_scale_function_fwd(const float *x, float *y, int64_t n, void *stream) {
+    DDSP_REQUIRE(x && y && n >= 0);
+    if (n == 0) return DDSP_B200_OK;
+    scale_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_scale_function_bwd(const float *x, const float *dy, float *dx, int64_t n,
+                                            void *stream) {
+    DDSP_REQUIRE(x && dy && dx && n >= 0);
+    if (n == 0) return DDSP_B200_OK;
+    scale_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, n);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_remove_above_nyquist(const float *amp, const float *f0, float *out,
+                                              int64_t rows, int H, float sample_rate,
+                                              void *stream) {
+    DDSP_REQUIRE(amp && f0 && out && rows >= 0 && H > 0);
+    if (rows == 0) return DDSP_B200_OK;
+    nyquist_kernel<<<ew_blocks(rows * H), 256, 0, (cudaStream_t)stream>>>(amp, f0, out, rows, H,
+                                                                           sample_rate * 0.5f);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_harmonic_controls_fwd(const float *amp_raw, const float *dist_raw,
+                                               const float *f0, float *amps, float *dist,
+                                               int64_t rows, int H, float sample_rate,
+                                               void *stream) {
+    DDSP_REQUIRE(amp_raw && dist_raw && f0 && amps && dist && rows >= 0 && H > 0);
+    if (rows == 0) return DDSP_B200_OK;
+    controls_fwd_kernel<<<(unsigned)ddsp_ceil_div(rows, kRowWarps), kRowWarps * 32, 0,
+                          (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, amps, dist, rows, H,
+                                                  sample_rate * 0.5f);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_harmonic_controls_bwd(const float *amp_raw, const float *dist_raw,
+                                               const float *f0, const float *d_amps,
+                                               const float *d_dist, float *d_amp_raw,
+                                               float *d_dist_raw, int64_t rows, int H,
+                                               float sample_rate, void *stream) {
+    DDSP_REQUIRE(amp_raw && dist_raw && f0 && d_amps && d_dist && d_amp_raw && d_dist_raw);
+    DDSP_REQUIRE(rows >= 0 && H > 0);
+    if (rows == 0) return DDSP_B200_OK;
+    controls_bwd_kernel<<<(unsigned)ddsp_ceil_div(rows, kRowWarps), kRowWarps * 32, 0,
+                          (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, d_amps, d_dist, d_amp_raw,
+                                                  d_dist_raw, rows, H, sample_rate * 0.5f);
+    return ddsp_launch_status();
+}

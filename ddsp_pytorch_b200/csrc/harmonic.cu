@@ -1,0 +1,548 @@
+// K1: harmonic oscillator bank (SURVEY 8a rows a4, a5, a6 and their backward).
+//
+// Reference path replaced (all eager ATen, each streaming a (B,N,H) float32 tensor):
+//   ddsp/models/modules.py:69-80   HarmonicSynth.forward  (upsample x2, harmonic_synth)
+//   ddsp/core.py:64-67             upsample = nearest hold of a frame for block_size samples
+//   ddsp/core.py:136-141           harmonic_synth = cumsum phase, sin(k*phase) bank, weighted sum
+//
+// Design.  Only frame-rate controls are read and only audio is written.
+//  * phase: Q0.64 turns.  phi[t] = phase before the first sample of frame t, delta[t] = per-sample
+//    increment; sample j of frame t has phase phi[t] + (j+1)*delta[t]  (inclusive cumsum).
+//  * forward: one thread owns SPT consecutive samples and walks the harmonics with a Reinsch
+//    sine recurrence (2 FMA-pipe ops) + 1 FFMA for the weighted sum; the frame's H weights are
+//    broadcast from shared memory, one LDS.128 per 4 harmonics per SPT samples.  The phase is folded
+//    to |psi| <= pi/2 where the recurrence is stable; the fold's sign (-1)^k goes to two
+//    accumulators (odd / even harmonics).
+//  * backward (d weights): one thread owns (frame, harmonic, chunk of samples) and walks TIME with
+//    the same recurrence (the frame's phase increment is constant), so the reduction over the
+//    frame's samples is a private accumulation; g is broadcast from shared memory.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kReseed = 128;   // harmonics (fwd) between exact re-seeds of the recurrence
+constexpr int kChunk = 128;    // samples (bwd) per recurrence run
+
+// ------------------------------------------------------------------------------------------
+// Phase scan at frame rate: one CTA per voice.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t turns_to_q64(double turns) {
+    turns -= floor(turns);
+    return __double2ull_rz(turns * 18446744073709551616.0);
+}
+
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads)
+phase_scan_kernel(const float *__restrict__ f0, const double *__restrict__ phase0,
+                  uint64_t *__restrict__ phi, uint64_t *__restrict__ delta,
+                  double *__restrict__ phase_end, int T, int block_size, double inv_sr) {
+    __shared__ uint64_t tot[kScanThreads];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int per = (T + kScanThreads - 1) / kScanThreads;
+    const int lo = min(tid * per, T), hi = min(lo + per, T);
+    const float *f = f0 + (size_t)b * T;
+    uint64_t sum = 0;
+    for (int t = lo; t < hi; ++t) {
+        uint64_t d = turns_to_q64((double)f[t] * inv_sr);
+        delta[(size_t)b * T + t] = d;
+        sum += d * (uint64_t)block_size;
+    }
+    tot[tid] = sum;
+    __syncthreads();
+    uint64_t run = phase0 ? turns_to_q64(phase0[b]) : 0ull;
+    for (int i = 0; i < tid; ++i) run += tot[i];
+    for (int t = lo; t < hi; ++t) {
+        phi[(size_t)b * T + t] = run;
+        run += delta[(size_t)b * T + t] * (uint64_t)block_size;
+    }
+    if (phase_end && tid == kScanThreads - 1) {
+        // last thread's `run` is the total only if it owns the tail; recompute from totals
+        uint64_t total = phase0 ? turns_to_q64(phase0[b]) : 0ull;
+        for (int i = 0; i < kScanThreads; ++i) total += tot[i];
+        phase_end[b] = (double)total * 5.421010862427522e-20;   // * 2^-64
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Forward.  CTA = FR consecutive frames of one voice; thread = SPT consecutive samples.
+// ------------------------------------------------------------------------------------------
+constexpr int kFwdThreads = 128;
+
+template <int SPT>
+__global__ void __launch_bounds__(kFwdThreads)
+harmonic_frames_fwd_kernel(const float *__restrict__ weights, const uint64_t *__restrict__ phi,
+                           const uint64_t *__restrict__ delta, float *__restrict__ audio, int T,
+                           int H, int Hp, int bs, int FR) {
+    extern __shared__ __align__(16) float smem[];
+    float *w = smem;                                          // [FR][Hp], zero padded to Hp
+    uint64_t *sphi = reinterpret_cast<uint64_t *>(w + (size_t)FR * Hp);   // [FR]
+    uint64_t *sdel = sphi + FR;                               // [FR]
+
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FR;
+    const int nfr = min(FR, T - t0);
+    const int tid = threadIdx.x;
+
+    const float *wg = weights + ((size_t)b * T + t0) * H;
+    for (int i = tid; i < nfr * Hp; i += kFwdThreads) {
+        int f = i / Hp, k = i - f * Hp;
+        w[i] = k < H ? __ldg(wg + (size_t)f * H + k) : 0.f;
+    }
+    if (tid < nfr) {
+        sphi[tid] = phi[(size_t)b * T + t0 + tid];
+        sdel[tid] = delta[(size_t)b * T + t0 + tid];
+    }
+    __syncthreads();
+
+    const int S = nfr * bs;
+    float *out = audio + ((size_t)b * T + t0) * bs;
+    for (int i0 = tid * SPT; i0 < S; i0 += kFwdThreads * SPT) {
+        const int f = i0 / bs;
+        const int j0 = i0 - f * bs;                // SPT | bs, so the SPT samples share frame f
+        const uint64_t ph = sphi[f], dl = sdel[f];
+        const float4 *wr = reinterpret_cast<const float4 *>(w + (size_t)f * Hp);
+
+        ddsp_osc o[SPT];
+        float q[SPT], ch[SPT], ae[SPT], ao[SPT];
+        int flip[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            uint64_t p = ph + (uint64_t)(j0 + s + 1) * dl;
+            float x = ddsp_fold_quarter(p, &flip[s]) * DDSP_PI_F;   // psi/2 in radians
+            float sh = ddsp_sin_q(x);
+            ch[s] = ddsp_cos_q(x);
+            q[s] = 2.f * sh;
+            o[s].u = -q[s] * q[s];
+            o[s].s = q[s] * ch[s];                 // sin(psi)
+            o[s].d = o[s].s;                       // s_1 - s_0
+            ae[s] = 0.f;
+            ao[s] = 0.f;
+        }
+        for (int k0 = 0; k0 < Hp; k0 += kReseed) {
+            if (k0 > 0) {
+                // exact re-seed at harmonic k = k0+1 from the fixed-point phase
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) {
+                    uint64_t p = ph + (uint64_t)(j0 + s + 1) * dl;
+                    uint32_t r = (uint32_t)(((p >> 62) + 1) >> 1);
+                    uint64_t psi = p - ((uint64_t)r << 63);
+                    float a = ddsp_turns_signed((uint64_t)(k0 + 1) * psi) * DDSP_2PI_F;
+                    float sk, ck;
+                    __sincosf(a, &sk, &ck);
+                    o[s].s = sk;
+                    // s_k - s_{k-1} = 2 sin(psi/2) cos((k-1/2) psi)
+                    o[s].d = q[s] * fmaf(ck, ch[s], sk * (0.5f * q[s]));
+                }
+            }
+            const int kend = min(k0 + kReseed, Hp);
+            for (int k = k0; k < kend; k += 4) {
+                const float4 a = wr[k >> 2];
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) {
+                    ao[s] = fmaf(a.x, o[s].s, ao[s]); o[s].step();
+                    ae[s] = fmaf(a.y, o[s].s, ae[s]); o[s].step();
+                    ao[s] = fmaf(a.z, o[s].s, ao[s]); o[s].step();
+                    ae[s] = fmaf(a.w, o[s].s, ae[s]); o[s].step();
+                }
+            }
+        }
+        float y[SPT];
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) y[s] = flip[s] ? ae[s] - ao[s] : ae[s] + ao[s];
+        if (SPT == 4) {
+            *reinterpret_cast<float4 *>(out + i0) = make_float4(y[0], y[1], y[2], y[3]);
+        } else if (SPT == 2) {
+            *reinterpret_cast<float2 *>(out + i0) = make_float2(y[0], y[1]);
+        } else {
+            out[i0] = y[0];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward w.r.t. weights.  CTA = FR frames of one voice; work item = (chunk, frame, harmonic).
+// ------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 256;
+
+__global__ void __launch_bounds__(kBwdThreads)
+harmonic_frames_bwd_w_kernel(const float *__restrict__ g_audio, const uint64_t *__restrict__ phi,
+                             const uint64_t *__restrict__ delta, float *__restrict__ d_weights,
+                             int T, int H, int bs, int FR, int nchunk, int clen) {
+    extern __shared__ __align__(16) float smem[];
+    float *g = smem;                                   // [FR*bs]
+    float *part = g + (((size_t)FR * bs + 3) & ~(size_t)3);   // [nchunk][FR][H]
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FR;
+    const int nfr = min(FR, T - t0);
+    const int tid = threadIdx.x;
+
+    const float *gg = g_audio + ((size_t)b * T + t0) * bs;
+    for (int i = tid; i < nfr * bs; i += kBwdThreads) g[i] = __ldg(gg + i);
+    __syncthreads();
+
+    const int items = nchunk * nfr * H;
+    for (int it = tid; it < items; it += kBwdThreads) {
+        const int k = it % H;                          // harmonic index k+1; fastest -> g broadcasts
+        const int fc = it / H;
+        const int f = fc % nfr;
+        const int c = fc / nfr;
+        const int jlo = c * clen, jhi = min(jlo + clen, bs);
+        const uint64_t ph = phi[(size_t)b * T + t0 + f], dl = delta[(size_t)b * T + t0 + f];
+        const uint64_t kk = (uint64_t)(k + 1);
+        // per-sample rotation of harmonic k: alpha = k*delta, folded to [-1/4,1/4) + parity
+        const uint64_t alpha = kk * dl;
+        const uint32_t r = (uint32_t)(((alpha >> 62) + 1) >> 1);
+        const uint64_t af = alpha - ((uint64_t)r << 63);
+        const float xa = ddsp_turns_signed(af) * DDSP_PI_F;          // alpha_f/2 in radians
+        const float q = 2.f * ddsp_sin_q(xa);
+        ddsp_osc o;
+        o.u = -q * q;
+        // phase of the chunk's first sample
+        const uint64_t th = kk * (ph + (uint64_t)(jlo + 1) * dl);
+        o.s = __sinf(ddsp_turns_signed(th) * DDSP_2PI_F);
+        // s_0 - s_{-1} = 2 sin(alpha_f/2) cos(theta - alpha_f/2)
+        o.d = q * __cosf(ddsp_turns_signed(th - (uint64_t)((int64_t)af >> 1)) * DDSP_2PI_F);
+        const float *gp = g + (size_t)f * bs;
+        float a0 = 0.f, a1 = 0.f;                      // even / odd offsets from jlo
+        int j = jlo;
+        for (; j + 1 < jhi; j += 2) {
+            a0 = fmaf(gp[j], o.s, a0);
+            o.step();
+            a1 = fmaf(gp[j + 1], o.s, a1);
+            o.step();
+        }
+        if (j < jhi) a0 = fmaf(gp[j], o.s, a0);
+        part[((size_t)c * nfr + f) * H + k] = (r & 1u) ? a0 - a1 : a0 + a1;
+    }
+    __syncthreads();
+    float *dw = d_weights + ((size_t)b * T + t0) * H;
+    for (int i = tid; i < nfr * H; i += kBwdThreads) {
+        float acc = 0.f;
+        for (int c = 0; c < nchunk; ++c) acc += part[(size_t)c * nfr * H + i];
+        dw[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward w.r.t. f0 (only when f0 requires grad): per frame S0 = sum dphi, S1 = sum (j+1) dphi,
+// dphi_n = g_n * sum_k k w_k cos(k phase_n); then d f0[t] = 2 pi/sr (S1[t] + bs * sum_{t'>t} S0[t']).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFwdThreads)
+harmonic_frames_dphi_kernel(const float *__restrict__ g_audio, const float *__restrict__ weights,
+                            const uint64_t *__restrict__ phi, const uint64_t *__restrict__ delta,
+                            float *__restrict__ s01, int T, int H, int bs) {
+    extern __shared__ __align__(16) float smem[];
+    float *w = smem;                                   // [H] pre-multiplied by k
+    __shared__ float red0[kFwdThreads / 32], red1[kFwdThreads / 32];
+    const int b = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+    for (int k = tid; k < H; k += kFwdThreads)
+        w[k] = weights[((size_t)b * T + t) * H + k] * (float)(k + 1);
+    __syncthreads();
+    const uint64_t ph = phi[(size_t)b * T + t], dl = delta[(size_t)b * T + t];
+    const float *g = g_audio + ((size_t)b * T + t) * bs;
+    float s0 = 0.f, s1 = 0.f;
+    for (int j = tid; j < bs; j += kFwdThreads) {
+        const uint64_t p = ph + (uint64_t)(j + 1) * dl;
+        int flip;
+        const float x = ddsp_fold_quarter(p, &flip) * DDSP_PI_F;
+        const float sh = ddsp_sin_q(x), chh = ddsp_cos_q(x);
+        const float q = 2.f * sh;
+        // cosine via the same recurrence: c_1 = cos(psi) = 1 - 2 sin^2(psi/2), e_1 = c_1 - c_0
+        ddsp_osc o;
+        o.u = -q * q;
+        o.d = 0.5f * o.u;
+        o.s = 1.f + o.d;
+        float ae = 0.f, ao = 0.f;
+        for (int k0 = 0; k0 < H; k0 += kReseed) {
+            if (k0 > 0) {
+                uint32_t r = (uint32_t)(((p >> 62) + 1) >> 1);
+                uint64_t psi = p - ((uint64_t)r << 63);
+                float a = ddsp_turns_signed((uint64_t)(k0 + 1) * psi) * DDSP_2PI_F;
+                float sk, ck;
+                __sincosf(a, &sk, &ck);
+                o.s = ck;
+                // c_k - c_{k-1} = -2 sin(psi/2) sin((k-1/2) psi)
+                o.d = -q * fmaf(sk, chh, -ck * (0.5f * q));
+            }
+            const int kend = min(k0 + kReseed, H);
+            for (int k = k0; k < kend; ++k) {
+                if (k & 1) ae = fmaf(w[k], o.s, ae); else ao = fmaf(w[k], o.s, ao);
+                o.step();
+            }
+        }
+        const float dphi = g[j] * (flip ? ae - ao : ae + ao);
+        s0 += dphi;
+        s1 = fmaf((float)(j + 1), dphi, s1);
+    }
+    s0 = ddsp_warp_sum(s0);
+    s1 = ddsp_warp_sum(s1);
+    if ((tid & 31) == 0) { red0[tid >> 5] = s0; red1[tid >> 5] = s1; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, c = 0.f;
+        for (int i = 0; i < kFwdThreads / 32; ++i) { a += red0[i]; c += red1[i]; }
+        s01[((size_t)b * T + t) * 2 + 0] = a;
+        s01[((size_t)b * T + t) * 2 + 1] = c;
+    }
+}
+
+// one thread per voice: suffix sum over frames (T is a few hundred; only runs if f0 needs grad)
+__global__ void harmonic_frames_df0_scan_kernel(const float *__restrict__ s01,
+                                                float *__restrict__ d_f0, int B, int T, int bs,
+                                                double scale) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double suffix = 0.0;
+    for (int t = T - 1; t >= 0; --t) {
+        const double s0 = s01[((size_t)b * T + t) * 2 + 0];
+        const double s1 = s01[((size_t)b * T + t) * 2 + 1];
+        d_f0[(size_t)b * T + t] = (float)(scale * (s1 + (double)bs * suffix));
+        suffix += s0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Audio-rate generic harmonic_synth (core.py:136-141): per-sample f0 and amplitudes.
+// ------------------------------------------------------------------------------------------
+constexpr int kArThreads = 256;
+
+__global__ void __launch_bounds__(kArThreads)
+phase_scan_audio_rate_kernel(const float *__restrict__ f0, uint64_t *__restrict__ phase, int64_t N,
+                             double inv_sr) {
+    __shared__ uint64_t tot[kArThreads];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int64_t per = (N + kArThreads - 1) / kArThreads;
+    const int64_t lo = min((int64_t)tid * per, N), hi = min(lo + per, N);
+    const float *f = f0 + (size_t)b * N;
+    uint64_t *p = phase + (size_t)b * N;
+    uint64_t sum = 0;
+    for (int64_t n = lo; n < hi; ++n) {
+        sum += turns_to_q64((double)f[n] * inv_sr);
+        p[n] = sum;                                   // inclusive within the chunk
+    }
+    tot[tid] = sum;
+    __syncthreads();
+    uint64_t base = 0;
+    for (int i = 0; i < tid; ++i) base += tot[i];
+    for (int64_t n = lo; n < hi; ++n) p[n] += base;
+}
+
+constexpr int kArTile = 128;   // samples per CTA (one per thread), harmonics staged 32 at a time
+
+template <bool BWD>
+__global__ void __launch_bounds__(kArTile)
+harmonic_audio_rate_kernel(const float *__restrict__ amps, const uint64_t *__restrict__ phase,
+                           const float *__restrict__ g_audio, float *__restrict__ audio,
+                           float *__restrict__ d_amps, float *__restrict__ dphi, int64_t N, int H) {
+    __shared__ float tile[kArTile][33];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * kArTile;
+    const int64_t n = n0 + tid;
+    const bool live = n < N;
+    const int rows = (int)min((int64_t)kArTile, N - n0);
+    const uint64_t p = live ? phase[(size_t)b * N + n] : 0ull;
+    int flip;
+    const float x = ddsp_fold_quarter(p, &flip) * DDSP_PI_F;
+    const float sh = ddsp_sin_q(x), chh = ddsp_cos_q(x);
+    const float q = 2.f * sh;
+    const uint32_t r = (uint32_t)(((p >> 62) + 1) >> 1);
+    const uint64_t psi = p - ((uint64_t)r << 63);
+    const float g = (BWD && live) ? g_audio[(size_t)b * N + n] : 0.f;
+    float acc = 0.f, dacc = 0.f;
+    const float *abase = amps + ((size_t)b * N + n0) * H;
+    float *dbase = BWD ? d_amps + ((size_t)b * N + n0) * H : nullptr;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k0 = 0; k0 < H; k0 += 32) {
+        const int kn = min(32, H - k0);
+        __syncthreads();
+        // coalesced staging: each warp loads whole 32-harmonic runs of successive samples
+        for (int rr = warp; rr < rows; rr += kArTile / 32)
+            tile[rr][lane] = lane < kn ? __ldg(abase + (size_t)rr * H + k0 + lane) : 0.f;
+        __syncthreads();
+        // exact seed at harmonic k0+1 (every 32 harmonics)
+        float a = ddsp_turns_signed((uint64_t)(k0 + 1) * psi) * DDSP_2PI_F;
+        float sk, ck;
+        if (k0 == 0) { sk = q * chh; ck = fmaf(-0.5f * q, q, 1.f); }
+        else __sincosf(a, &sk, &ck);
+        ddsp_osc os, oc;
+        os.u = oc.u = -q * q;
+        os.s = sk;
+        os.d = q * fmaf(ck, chh, sk * (0.5f * q));
+        oc.s = ck;
+        oc.d = -q * fmaf(sk, chh, -ck * (0.5f * q));
+        for (int k = 0; k < kn; ++k) {
+            const float sgn = (flip && !((k0 + k) & 1)) ? -1.f : 1.f;   // (-1)^(k+1) for harmonic k0+k+1
+            const float a_k = tile[tid][k];
+            const float sv = sgn * os.s;
+            if (!BWD) {
+                acc = fmaf(a_k, sv, acc);
+            } else {
+                tile[tid][k] = g * sv;                                  // d_amps, staged for a coalesced store
+                dacc = fmaf(a_k * (float)(k0 + k + 1), sgn * oc.s, dacc);
+                oc.step();
+            }
+            os.step();
+        }
+        if (BWD) {
+            __syncthreads();
+            for (int rr = warp; rr < rows; rr += kArTile / 32)
+                if (lane < kn) dbase[(size_t)rr * H + k0 + lane] = tile[rr][lane];
+        }
+    }
+    if (live) {
+        if (!BWD) audio[(size_t)b * N + n] = acc;
+        else if (dphi) dphi[(size_t)b * N + n] = g * dacc;
+    }
+}
+
+// d_f0[n] = 2 pi / sr * sum_{m >= n} dphi[m]  (reverse inclusive scan), one CTA per voice
+__global__ void __launch_bounds__(kArThreads)
+audio_rate_df0_kernel(const float *__restrict__ dphi, float *__restrict__ d_f0, int64_t N,
+                      double scale) {
+    __shared__ double tot[kArThreads];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int64_t per = (N + kArThreads - 1) / kArThreads;
+    const int64_t lo = min((int64_t)tid * per, N), hi = min(lo + per, N);
+    const float *d = dphi + (size_t)b * N;
+    double sum = 0.0;
+    for (int64_t n = lo; n < hi; ++n) sum += d[n];
+    tot[tid] = sum;
+    __syncthreads();
+    double suffix = 0.0;
+    for (int i = tid + 1; i < kArThreads; ++i) suffix += tot[i];
+    for (int64_t n = hi - 1; n >= lo; --n) {
+        suffix += d[n];
+        d_f0[(size_t)b * N + n] = (float)(scale * suffix);
+    }
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int ddsp_b200_phase_scan(const float *f0, const double *phase0, uint64_t *phi,
+                                    uint64_t *delta, double *phase_end, int B, int T,
+                                    int block_size, double sample_rate, void *stream) {
+    DDSP_REQUIRE(f0 && phi && delta && B > 0 && T > 0 && block_size > 0 && sample_rate > 0);
+    phase_scan_kernel<<<B, kScanThreads, 0, (cudaStream_t)stream>>>(
+        f0, phase0, phi, delta, phase_end, T, block_size, 1.0 / sample_rate);
+    return ddsp_launch_status();
+}
+
+// frames per CTA: the smallest count that makes the CTA's samples a whole number of
+// (threads x SPT) sweeps, so no thread idles in the last sweep (bs=160 -> 16 frames, 512 -> 1)
+static int frames_per_cta(int bs, int T, int sweep, int cap) {
+    int fr = 1;
+    while (fr < cap && (fr * bs) % sweep != 0) ++fr;
+    if ((fr * bs) % sweep != 0) fr = (sweep + bs - 1) / bs;
+    if (fr > T) fr = T;
+    return fr < 1 ? 1 : fr;
+}
+
+extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_t *phi,
+                                             const uint64_t *delta, float *audio, int B, int T,
+                                             int H, int block_size, void *stream) {
+    DDSP_REQUIRE(weights && phi && delta && audio && B > 0 && T > 0 && H > 0 && block_size > 0);
+    DDSP_REQUIRE(B <= 65535);
+    const int bs = block_size;
+    const int spt = (bs % 4 == 0) ? 4 : (bs % 2 == 0) ? 2 : 1;
+    const int Hp = (H + 3) & ~3;
+    const int fr = frames_per_cta(bs, T, kFwdThreads * spt, 32);
+    const size_t smem = (size_t)fr * Hp * sizeof(float) + 2 * (size_t)fr * sizeof(uint64_t);
+    if (smem > 200 * 1024) return DDSP_B200_EUNSUPPORTED;
+    dim3 grid((T + fr - 1) / fr, B);
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(SPT)                                                                              \
+    do {                                                                                         \
+        if (smem > 48 * 1024)                                                                    \
+            cudaFuncSetAttribute(harmonic_frames_fwd_kernel<SPT>,                                \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        harmonic_frames_fwd_kernel<SPT><<<grid, kFwdThreads, smem, st>>>(weights, phi, delta,    \
+                                                                         audio, T, H, Hp, bs, fr); \
+    } while (0)
+    if (spt == 4) LAUNCH(4); else if (spt == 2) LAUNCH(2); else LAUNCH(1);
+#undef LAUNCH
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_harmonic_frames_bwd_weights(const float *g_audio, const uint64_t *phi,
+                                                     const uint64_t *delta, float *d_weights, int B,
+                                                     int T, int H, int block_size, void *stream) {
+    DDSP_REQUIRE(g_audio && phi && delta && d_weights && B > 0 && T > 0 && H > 0 && block_size > 0);
+    DDSP_REQUIRE(B <= 65535);
+    const int bs = block_size;
+    const int nchunk = (bs + kChunk - 1) / kChunk;
+    const int clen = (((bs + nchunk - 1) / nchunk) + 1) & ~1;   // even, so chunk parity is uniform
+    // enough (chunk, frame, harmonic) items for >= 4 sweeps of the CTA
+    int fr = (4 * kBwdThreads + nchunk * H - 1) / (nchunk * H);
+    if (fr > T) fr = T;
+    if (fr < 1) fr = 1;
+    size_t smem = ((((size_t)fr * bs + 3) & ~(size_t)3) + (size_t)nchunk * fr * H) * sizeof(float);
+    while (smem > 200 * 1024 && fr > 1) {
+        fr = (fr + 1) / 2;
+        smem = ((((size_t)fr * bs + 3) & ~(size_t)3) + (size_t)nchunk * fr * H) * sizeof(float);
+    }
+    if (smem > 200 * 1024) return DDSP_B200_EUNSUPPORTED;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(harmonic_frames_bwd_w_kernel,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((T + fr - 1) / fr, B);
+    harmonic_frames_bwd_w_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(
+        g_audio, phi, delta, d_weights, T, H, bs, fr, nchunk, clen);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_harmonic_frames_bwd_f0(const float *g_audio, const float *weights,
+                                                const uint64_t *phi, const uint64_t *delta,
+                                                float *scratch, float *d_f0, int B, int T, int H,
+                                                int block_size, double sample_rate, void *stream) {
+    DDSP_REQUIRE(g_audio && weights && phi && delta && scratch && d_f0);
+    DDSP_REQUIRE(B > 0 && B <= 65535 && T > 0 && H > 0 && block_size > 0 && sample_rate > 0);
+    if ((size_t)H * sizeof(float) > 40 * 1024) return DDSP_B200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    harmonic_frames_dphi_kernel<<<dim3(T, B), kFwdThreads, (size_t)H * sizeof(float), st>>>(
+        g_audio, weights, phi, delta, scratch, T, H, block_size);
+    int s = ddsp_launch_status();
+    if (s) return s;
+    harmonic_frames_df0_scan_kernel<<<(B + 63) / 64, 64, 0, st>>>(
+        scratch, d_f0, B, T, block_size, 6.283185307179586476925 / sample_rate);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_phase_scan_audio_rate(const float *f0, uint64_t *phase, int B, int64_t N,
+                                               double sample_rate, void *stream) {
+    DDSP_REQUIRE(f0 && phase && B > 0 && N > 0 && sample_rate > 0);
+    phase_scan_audio_rate_kernel<<<B, kArThreads, 0, (cudaStream_t)stream>>>(f0, phase, N,
+                                                                              1.0 / sample_rate);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_harmonic_audio_rate_fwd(const float *amps, const uint64_t *phase,
+                                                 float *audio, int B, int64_t N, int H,
+                                                 void *stream) {
+    DDSP_REQUIRE(amps && phase && audio && B > 0 && B <= 65535 && N > 0 && H > 0);
+    dim3 grid((unsigned)ddsp_ceil_div(N, kArTile), B);
+    harmonic_audio_rate_kernel<false><<<grid, kArTile, 0, (cudaStream_t)stream>>>(
+        amps, phase, nullptr, audio, nullptr, nullptr, N, H);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_harmonic_audio_rate_bwd(const float *g_audio, const float *amps,
+                                                 const uint64_t *phase, float *d_amps, float *dphi,
+                                                 float *d_f0, int B, int64_t N, int H,
+                                                 double sample_rate, void *stream) {
+    DDSP_REQUIRE(g_audio && amps && phase && d_amps && B > 0 && B <= 65535 && N > 0 && H > 0);
+    DDSP_REQUIRE(!d_f0 || dphi);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)ddsp_ceil_div(N, kArTile), B);
+    harmonic_audio_rate_kernel<true><<<grid, kArTile, 0, st>>>(amps, phase, g_audio, nullptr,
+                                                               d_amps, d_f0 ? dphi : nullptr, N, H);
+    int s = ddsp_launch_status();
+    if (s || !d_f0) return s;
+    audio_rate_df0_kernel<<<B, kArThreads, 0, st>>>(dphi, d_f0, N,
+                                                    6.283185307179586476925 / sample_rate);
+    return ddsp_launch_status();
+}

@@ -1,0 +1,528 @@
+// K4 / K4L: STFT magnitudes and the fused multi-scale spectral loss (SURVEY 8a rows a11, a12 and
+// their backward).
+//
+// Reference path replaced:
+//   ddsp/core.py:27-41     multiscale_fft: per scale torch.stft(center=True reflect pad, periodic hann,
+//                          normalized) .abs()  -> reflection_pad1d + cuFFT R2C + abs per scale
+//   train.py:70-76,92-103  multiscale_spec_loss: ~40 elementwise/reduction launches over 12.4 M bins
+//   autograd backward of both (sgn, irfft, fold of the overlapping frames, reflection_pad backward)
+//
+// Design.  One CTA owns a tile of FT*hop consecutive positions of the PADDED signal
+// of one voice and computes every frame that overlaps the tile (ov = ceil(s/hop)-1 extra frames at
+// the left), so the overlap-add of the gradient is an exclusive, ordered gather in shared memory:
+// no atomics, bit-reproducible.  Two real sequences ride in one complex FFT:
+//   loss     : frame of rec (re) + frame of target (im)          -> one forward FFT per frame
+//   gradient : Hermitian-extended gradient spectra of two frames  -> one inverse FFT per frame pair
+//   mags     : two frames of the same signal                      -> one forward FFT per frame pair
+// Gradient of the samples in the reflect padding goes to a small per-voice edge buffer and is folded
+// back by ddsp_b200_stft_fold_edges (again a gather).
+#include "fft.cuh"
+
+namespace {
+
+constexpr int kStftThreads = 256;
+
+__device__ __forceinline__ int64_t reflect_index(int64_t m, int64_t N) {
+    if (m < 0) m = -m;
+    if (m >= N) m = 2 * (N - 1) - m;
+    return m;
+}
+
+struct TileGeom {
+    int s, lg, hop, frames, FT, ov, NF;       // NF = frame slots per batch (even)
+    int64_t N;
+};
+
+__device__ __forceinline__ float2 untangle_re(float2 zk, float2 zm) {   // (Z[k] + conj(Z[s-k]))/2
+    return make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+}
+__device__ __forceinline__ float2 untangle_im(float2 zk, float2 zm) {   // (Z[k] - conj(Z[s-k]))/(2i)
+    return make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+}
+
+// Ordered gather overlap-add of the frames of one batch into the tile's owned positions.
+//   frame slot q (frame fb+q) has its real gradient sequence in buf + (q>>1)*pair_pitch, component
+//   (q&1 ? .y : .x).
+__device__ __forceinline__ void gather_ola(float *ola, const float2 *buf, int pair_pitch,
+                                           const float *__restrict__ window, const TileGeom &g,
+                                           int64_t P0, int fb, int fe, int tid) {
+    const int owned = g.FT * g.hop;
+    for (int t = tid; t < owned; t += kStftThreads) {
+        const int64_t i = P0 + t;
+        int flo = (int)((i - g.s + g.hop) / g.hop);            // ceil((i-s+1)/hop) for i-s+1 >= 0
+        if (i - g.s + 1 <= 0) flo = 0;
+        int fhi = (int)(i / g.hop);
+        flo = max(flo, fb);
+        fhi = min(fhi, min(fb + g.NF, fe) - 1);
+        float acc = ola[t];
+        for (int f = flo; f <= fhi; ++f) {
+            const int q = f - fb;
+            const int n = (int)(i - (int64_t)f * g.hop);
+            const float2 v = buf[(q >> 1) * pair_pitch + fpad(n)];
+            acc = fmaf(__ldg(window + n), (q & 1) ? v.y : v.x, acc);
+        }
+        ola[t] = acc;
+    }
+}
+
+// Owned positions -> d_sig (interior) or edge buffer (reflect padding).
+__device__ __forceinline__ void store_owned(const float *ola, float *__restrict__ d_sig,
+                                            float *__restrict__ edge, const TileGeom &g, int64_t P0,
+                                            int accumulate, int tid) {
+    const int owned = g.FT * g.hop;
+    const int hs = g.s >> 1;
+    for (int t = tid; t < owned; t += kStftThreads) {
+        const int64_t i = P0 + t;
+        if (i >= g.N + g.s) break;
+        const float v = ola[t];
+        if (i < hs) edge[i] = v;
+        else if (i < g.N + hs) {
+            float *p = d_sig + (i - hs);
+            *p = accumulate ? *p + v : v;
+        } else edge[hs + (i - g.N - hs)] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused loss (+ gradient w.r.t. rec) for one scale.
+// ---------------------------------------------------------------------------------------------
+template <bool GRAD>
+__global__ void __launch_bounds__(kStftThreads)
+mss_scale_kernel(const float *__restrict__ target, const float *__restrict__ rec,
+                 const float *__restrict__ window, const float2 *__restrict__ tw, int tws,
+                 float *__restrict__ partial, float *__restrict__ d_rec, float *__restrict__ edge,
+                 TileGeom g, int accumulate, float inv_cnt) {
+    extern __shared__ __align__(16) float smem[];
+    const int pitch = fpad_size(g.s);
+    float2 *bufA = reinterpret_cast<float2 *>(smem);
+    float2 *bufB = bufA + (size_t)g.NF * pitch;
+    float *ola = reinterpret_cast<float *>(bufB + (size_t)g.NF * pitch);
+    __shared__ float red[2][kStftThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int f0 = blockIdx.x * g.FT;
+    const int64_t P0 = (int64_t)f0 * g.hop;
+    const int fs = GRAD ? max(0, f0 - g.ov) : min(f0, g.frames);
+    const int fe = min(f0 + g.FT, g.frames);
+    const float *xr = rec + (size_t)b * g.N;
+    const float *xt = target + (size_t)b * g.N;
+    const float rs = rsqrtf((float)g.s);
+    const int hs = g.s >> 1;
+
+    if (GRAD)
+        for (int t = tid; t < g.FT * g.hop; t += kStftThreads) ola[t] = 0.f;
+    float lin = 0.f, lg_ = 0.f;
+
+    for (int fb = fs; fb < fe; fb += g.NF) {
+        __syncthreads();
+        // 1. windowed frames: re = rec, im = target
+        for (int idx = tid; idx < g.NF * g.s; idx += kStftThreads) {
+            const int q = idx >> g.lg, n = idx & (g.s - 1);
+            const int f = fb + q;
+            float2 v = make_float2(0.f, 0.f);
+            if (f < fe) {
+                const int64_t m = reflect_index((int64_t)f * g.hop + n - hs, g.N);
+                const float w = __ldg(window + n);
+                v = make_float2(__ldg(xr + m) * w, __ldg(xt + m) * w);
+            }
+            bufA[q * pitch + fpad(n)] = v;
+        }
+        __syncthreads();
+        float2 *Z = cta_fft<false>(bufA, bufB, pitch, g.NF, g.s, g.lg, tw, tws, tid, kStftThreads);
+        float2 *other = (Z == bufA) ? bufB : bufA;
+        // 2. per bin: magnitudes, loss terms, gradient spectrum; pairs of frames share a buffer
+        const int bins = hs + 1;
+        for (int idx = tid; idx < (g.NF >> 1) * bins; idx += kStftThreads) {
+            const int pr = idx / bins, k = idx - pr * bins;
+            const int km = (g.s - k) & (g.s - 1);
+            float2 u[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int q = 2 * pr + e, f = fb + q;
+                u[e] = make_float2(0.f, 0.f);
+                if (f < fe) {
+                    const float2 zk = Z[q * pitch + fpad(k)], zm = Z[q * pitch + fpad(km)];
+                    const float2 Y = untangle_re(zk, zm);     // rec spectrum
+                    const float2 X = untangle_im(zk, zm);     // target spectrum
+                    const float ay = sqrtf(fmaf(Y.x, Y.x, Y.y * Y.y));
+                    const float ax = sqrtf(fmaf(X.x, X.x, X.y * X.y));
+                    const float sy = ay * rs, sx = ax * rs;
+                    const float dl = logf(sy + 1e-7f) - logf(sx + 1e-7f);
+                    if (f >= f0) {                              // loss counted by the owning tile only
+                        lin += fabsf(sx - sy);
+                        lg_ += fabsf(dl);
+                    }
+                    if (GRAD && ay > 0.f) {
+                        const float d = sy - sx;
+                        const float sg = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+                        const float sl = (dl > 0.f) ? 1.f : (dl < 0.f ? -1.f : 0.f);
+                        // dL/dSy * (1/sqrt(s)) / |Y|
+                        const float c = (sg + sl / (sy + 1e-7f)) * inv_cnt * rs / ay;
+                        u[e] = make_float2(c * Y.x, c * Y.y);
+                    }
+                }
+            }
+            if (GRAD) {
+                float2 *dst = Z + (2 * pr) * pitch;
+                if (k == 0 || k == hs) {
+                    dst[fpad(k)] = make_float2(u[0].x, u[1].x);
+                } else {
+                    // Zi[k] = (Ua + i Ub)/2 ; Zi[s-k] = (conj Ua + i conj Ub)/2
+                    dst[fpad(k)] = make_float2(0.5f * (u[0].x - u[1].y), 0.5f * (u[0].y + u[1].x));
+                    dst[fpad(km)] = make_float2(0.5f * (u[0].x + u[1].y), 0.5f * (-u[0].y + u[1].x));
+                }
+            }
+        }
+        if (GRAD) {
+            __syncthreads();
+            float2 *R = cta_fft<true>(Z, other, 2 * pitch, g.NF >> 1, g.s, g.lg, tw, tws, tid,
+                                      kStftThreads);
+            gather_ola(ola, R, 2 * pitch, window, g, P0, fb, fe, tid);
+        }
+    }
+    __syncthreads();
+    if (GRAD) store_owned(ola, d_rec + (size_t)b * g.N, edge + (size_t)b * g.s, g, P0, accumulate, tid);
+
+    lin = ddsp_warp_sum(lin);
+    lg_ = ddsp_warp_sum(lg_);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = lin; red[1][tid >> 5] = lg_; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, c = 0.f;
+        for (int i = 0; i < kStftThreads / 32; ++i) { a += red[0][i]; c += red[1][i]; }
+        float *p = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+        p[0] = a;
+        p[1] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// |STFT| forward (API path of multiscale_fft): two frames of the signal per complex FFT.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStftThreads)
+stft_mag_fwd_kernel(const float *__restrict__ signal, const float *__restrict__ window,
+                    const float2 *__restrict__ tw, int tws, float *__restrict__ mag, TileGeom g) {
+    extern __shared__ __align__(16) float smem[];
+    const int pitch = fpad_size(g.s);
+    const int NP = g.NF >> 1;                           // FFTs per batch
+    float2 *bufA = reinterpret_cast<float2 *>(smem);
+    float2 *bufB = bufA + (size_t)NP * pitch;
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const int f0 = blockIdx.x * g.FT;
+    const int fe = min(f0 + g.FT, g.frames);
+    const float *x = signal + (size_t)b * g.N;
+    const float rs = rsqrtf((float)g.s);
+    const int hs = g.s >> 1, bins = hs + 1;
+    float *mg = mag + (size_t)b * bins * g.frames;
+
+    for (int fb = f0; fb < fe; fb += g.NF) {
+        __syncthreads();
+        for (int idx = tid; idx < NP * g.s; idx += kStftThreads) {
+            const int p = idx >> g.lg, n = idx & (g.s - 1);
+            const int fa = fb + 2 * p;
+            float2 v = make_float2(0.f, 0.f);
+            const float w = __ldg(window + n);
+            if (fa < fe) v.x = __ldg(x + reflect_index((int64_t)fa * g.hop + n - hs, g.N)) * w;
+            if (fa + 1 < fe) v.y = __ldg(x + reflect_index((int64_t)(fa + 1) * g.hop + n - hs, g.N)) * w;
+            bufA[p * pitch + fpad(n)] = v;
+        }
+        __syncthreads();
+        const float2 *Z = cta_fft<false>(bufA, bufB, pitch, NP, g.s, g.lg, tw, tws, tid, kStftThreads);
+        for (int idx = tid; idx < NP * bins; idx += kStftThreads) {
+            const int p = idx / bins, k = idx - p * bins;
+            const int fa = fb + 2 * p;
+            if (fa >= fe) continue;
+            const float2 zk = Z[p * pitch + fpad(k)], zm = Z[p * pitch + fpad((g.s - k) & (g.s - 1))];
+            const float2 A = untangle_re(zk, zm), C = untangle_im(zk, zm);
+            mg[(size_t)k * g.frames + fa] = sqrtf(fmaf(A.x, A.x, A.y * A.y)) * rs;
+            if (fa + 1 < fe) mg[(size_t)k * g.frames + fa + 1] = sqrtf(fmaf(C.x, C.x, C.y * C.y)) * rs;
+        }
+    }
+}
+
+// |STFT| backward: d_signal from d_mag (recomputes the spectra).
+__global__ void __launch_bounds__(kStftThreads)
+stft_mag_bwd_kernel(const float *__restrict__ signal, const float *__restrict__ d_mag,
+                    const float *__restrict__ window, const float2 *__restrict__ tw, int tws,
+                    float *__restrict__ d_sig, float *__restrict__ edge, TileGeom g, int accumulate) {
+    extern __shared__ __align__(16) float smem[];
+    const int pitch = fpad_size(g.s);
+    const int NP = g.NF >> 1;
+    float2 *bufA = reinterpret_cast<float2 *>(smem);
+    float2 *bufB = bufA + (size_t)NP * pitch;
+    float *ola = reinterpret_cast<float *>(bufB + (size_t)NP * pitch);
+    const int tid = threadIdx.x, b = blockIdx.y;
+    const int f0 = blockIdx.x * g.FT;
+    const int64_t P0 = (int64_t)f0 * g.hop;
+    const int fs = max(0, f0 - g.ov);
+    const int fe = min(f0 + g.FT, g.frames);
+    const float *x = signal + (size_t)b * g.N;
+    const float rs = rsqrtf((float)g.s);
+    const int hs = g.s >> 1, bins = hs + 1;
+    const float *gm = d_mag + (size_t)b * bins * g.frames;
+
+    for (int t = tid; t < g.FT * g.hop; t += kStftThreads) ola[t] = 0.f;
+    for (int fb = fs; fb < fe; fb += g.NF) {
+        __syncthreads();
+        for (int idx = tid; idx < NP * g.s; idx += kStftThreads) {
+            const int p = idx >> g.lg, n = idx & (g.s - 1);
+            const int fa = fb + 2 * p;
+            float2 v = make_float2(0.f, 0.f);
+            const float w = __ldg(window + n);
+            if (fa < fe) v.x = __ldg(x + reflect_index((int64_t)fa * g.hop + n - hs, g.N)) * w;
+            if (fa + 1 < fe) v.y = __ldg(x + reflect_index((int64_t)(fa + 1) * g.hop + n - hs, g.N)) * w;
+            bufA[p * pitch + fpad(n)] = v;
+        }
+        __syncthreads();
+        float2 *Z = cta_fft<false>(bufA, bufB, pitch, NP, g.s, g.lg, tw, tws, tid, kStftThreads);
+        float2 *other = (Z == bufA) ? bufB : bufA;
+        for (int idx = tid; idx < NP * bins; idx += kStftThreads) {
+            const int p = idx / bins, k = idx - p * bins;
+            const int km = (g.s - k) & (g.s - 1);
+            const int fa = fb + 2 * p;
+            float2 *zb = Z + p * pitch;
+            const float2 zk = zb[fpad(k)], zm = zb[fpad(km)];
+            const float2 A = untangle_re(zk, zm), C = untangle_im(zk, zm);
+            float2 ua = make_float2(0.f, 0.f), ub = ua;
+            if (fa < fe) {
+                const float a = sqrtf(fmaf(A.x, A.x, A.y * A.y));
+                if (a > 0.f) {
+                    const float c = __ldg(gm + (size_t)k * g.frames + fa) * rs / a;
+                    ua = make_float2(c * A.x, c * A.y);
+                }
+            }
+            if (fa + 1 < fe) {
+                const float a = sqrtf(fmaf(C.x, C.x, C.y * C.y));
+                if (a > 0.f) {
+                    const float c = __ldg(gm + (size_t)k * g.frames + fa + 1) * rs / a;
+                    ub = make_float2(c * C.x, c * C.y);
+                }
+            }
+            if (k == 0 || k == hs) {
+                zb[fpad(k)] = make_float2(ua.x, ub.x);
+            } else {
+                zb[fpad(k)] = make_float2(0.5f * (ua.x - ub.y), 0.5f * (ua.y + ub.x));
+                zb[fpad(km)] = make_float2(0.5f * (ua.x + ub.y), 0.5f * (-ua.y + ub.x));
+            }
+        }
+        __syncthreads();
+        float2 *R = cta_fft<true>(Z, other, pitch, NP, g.s, g.lg, tw, tws, tid, kStftThreads);
+        gather_ola(ola, R, pitch, window, g, P0, fb, fe, tid);
+    }
+    __syncthreads();
+    store_owned(ola, d_sig + (size_t)b * g.N, edge + (size_t)b * g.s, g, P0, accumulate, tid);
+}
+
+// d_sig[b,m] += edge contributions of every scale, gathered per target sample (deterministic).
+struct FoldArgs {
+    int n_scales;
+    int s[8];
+    int64_t off[8];          // float offset of scale i's edge block: layout [scale][B][s]
+};
+
+__global__ void stft_fold_kernel(const float *__restrict__ edge, float *__restrict__ d_sig, int B,
+                                 int64_t N, FoldArgs fa) {
+    const int b = blockIdx.y;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N;
+         m += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < fa.n_scales; ++i) {
+            const int hs = fa.s[i] >> 1;
+            const float *e = edge + fa.off[i] + (size_t)b * fa.s[i];
+            if (m >= 1 && m <= hs) acc += e[hs - m];                         // left pad: i = hs - m
+            if (m <= N - 2 && m >= N - 1 - hs) acc += e[hs + (N - 2 - m)];   // right pad
+        }
+        if (acc != 0.f) d_sig[(size_t)b * N + m] += acc;
+    }
+}
+
+struct FinArgs {
+    int n_scales;
+    int64_t off[8];          // pair offset of scale i's partials
+    int64_t cnt[8];          // pairs for scale i
+    float inv[8];            // 1 / (B * bins * frames)
+};
+
+__global__ void mss_finalize_kernel(const float *__restrict__ partial, float *__restrict__ loss,
+                                    FinArgs fa) {
+    __shared__ double red[256];
+    double total = 0.0;
+    for (int i = 0; i < fa.n_scales; ++i) {
+        double acc = 0.0;
+        const float *p = partial + 2 * fa.off[i];
+        for (int64_t j = threadIdx.x; j < fa.cnt[i]; j += blockDim.x) acc += (double)p[2 * j] + (double)p[2 * j + 1];
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        total += red[0] * (double)fa.inv[i];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) loss[0] = (float)total;
+}
+
+// ---- host-side geometry ---------------------------------------------------------------------
+struct HostGeom {
+    TileGeom g;
+    int tiles;
+    size_t smem_loss, smem_mag_fwd, smem_mag_bwd;
+};
+
+int make_geom(int64_t N, int n_fft, int hop, bool with_overlap, HostGeom *out) {
+    if (n_fft < 8 || (n_fft & (n_fft - 1)) || n_fft > 8192) return DDSP_B200_EUNSUPPORTED;
+    if (hop < 1 || hop > n_fft) return DDSP_B200_EUNSUPPORTED;
+    if (N <= n_fft / 2) return DDSP_B200_EUNSUPPORTED;            // reflect padding needs pad < N
+    TileGeom g;
+    g.s = n_fft; g.lg = ddsp_ilog2(n_fft); g.hop = hop; g.N = N;
+    g.frames = 1 + (int)(N / hop);
+    g.ov = (n_fft + hop - 1) / hop - 1;
+    int nf = 2048 / n_fft;                                         // frame slots per batch
+    if (nf < 2) nf = 2;
+    if (nf > 16) nf = 16;
+    g.NF = nf;
+    // tile = a whole number of batches of frames, minus the overlap frames it recomputes
+    int ft = nf * ((16 + nf - 1) / nf);
+    if (with_overlap) {
+        ft -= g.ov;
+        while (ft < 1) ft += nf;
+    }
+    const size_t pitch = fpad_size(n_fft);
+    auto total = [&](int ft_) {
+        return 2 * (size_t)nf * pitch * sizeof(float2) + (size_t)ft_ * hop * sizeof(float);
+    };
+    while (total(ft) > 200 * 1024 && ft > nf) ft -= nf;
+    if (total(ft) > 220 * 1024) return DDSP_B200_EUNSUPPORTED;
+    g.FT = ft;
+    out->g = g;
+    out->smem_loss = total(ft);
+    out->smem_mag_fwd = 2 * (size_t)(nf / 2) * pitch * sizeof(float2);
+    out->smem_mag_bwd = out->smem_mag_fwd + (size_t)ft * hop * sizeof(float);
+    // gradient tiles must cover every padded position; magnitude tiles only the frames
+    const int64_t span = (int64_t)ft * hop;
+    out->tiles = with_overlap ? (int)ddsp_ceil_div(N + n_fft, span) : (int)ddsp_ceil_div(g.frames, ft);
+    return DDSP_B200_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop) {
+    HostGeom hg;
+    if (make_geom(N, n_fft, hop, true, &hg)) return -1;
+    return hg.tiles;
+}
+
+extern "C" int ddsp_b200_mss_scale(const float *target, const float *rec, const float *window,
+                                   const float *twiddle, int n_tab, float *partial, float *d_rec,
+                                   float *edge, int B, int64_t N, int n_fft, int hop, int accumulate,
+                                   void *stream) {
+    DDSP_REQUIRE(target && rec && window && twiddle && partial && B > 0 && B <= 65535);
+    DDSP_REQUIRE(!d_rec || edge);
+    DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
+    HostGeom hg;
+    int s = make_geom(N, n_fft, hop, true, &hg);
+    if (s) return s;
+    const float inv_cnt = 1.0f / ((float)B * (float)(n_fft / 2 + 1) * (float)hg.g.frames);
+    dim3 grid(hg.tiles, B);
+    const float2 *tw = reinterpret_cast<const float2 *>(twiddle);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_rec) {
+        if ((s = set_smem(mss_scale_kernel<true>, hg.smem_loss))) return s;
+        mss_scale_kernel<true><<<grid, kStftThreads, hg.smem_loss, st>>>(
+            target, rec, window, tw, n_tab / n_fft, partial, d_rec, edge, hg.g, accumulate, inv_cnt);
+    } else {
+        if ((s = set_smem(mss_scale_kernel<false>, hg.smem_loss))) return s;
+        mss_scale_kernel<false><<<grid, kStftThreads, hg.smem_loss, st>>>(
+            target, rec, window, tw, n_tab / n_fft, partial, nullptr, nullptr, hg.g, accumulate, inv_cnt);
+    }
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, float *d_rec, float *loss,
+                                    int B, int64_t N, const int *scales, const int *hops,
+                                    int n_scales, void *stream) {
+    DDSP_REQUIRE(partial && loss && scales && hops && n_scales > 0 && n_scales <= 8 && B > 0);
+    DDSP_REQUIRE(!d_rec || edge);
+    FinArgs fin;
+    FoldArgs fold;
+    fin.n_scales = fold.n_scales = n_scales;
+    int64_t poff = 0, eoff = 0;
+    for (int i = 0; i < n_scales; ++i) {
+        HostGeom hg;
+        int s = make_geom(N, scales[i], hops[i], true, &hg);
+        if (s) return s;
+        fin.off[i] = poff;
+        fin.cnt[i] = (int64_t)hg.tiles * B;
+        fin.inv[i] = 1.0f / ((float)B * (float)(scales[i] / 2 + 1) * (float)hg.g.frames);
+        poff += fin.cnt[i];
+        fold.s[i] = scales[i];
+        fold.off[i] = eoff;
+        eoff += (int64_t)B * scales[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    mss_finalize_kernel<<<1, 256, 0, st>>>(partial, loss, fin);
+    int s = ddsp_launch_status();
+    if (s || !d_rec) return s;
+    int gx = (int)ddsp_ceil_div(N, 256);
+    if (gx > 1024) gx = 1024;
+    stft_fold_kernel<<<dim3(gx, B), 256, 0, st>>>(edge, d_rec, B, N, fold);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_stft_mag_fwd(const float *signal, const float *window, const float *twiddle,
+                                      int n_tab, float *mag, int B, int64_t N, int n_fft, int hop,
+                                      void *stream) {
+    DDSP_REQUIRE(signal && window && twiddle && mag && B > 0 && B <= 65535);
+    DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
+    HostGeom hg;
+    int s = make_geom(N, n_fft, hop, false, &hg);
+    if (s) return s;
+    if ((s = set_smem(stft_mag_fwd_kernel, hg.smem_mag_fwd))) return s;
+    stft_mag_fwd_kernel<<<dim3(hg.tiles, B), kStftThreads, hg.smem_mag_fwd, (cudaStream_t)stream>>>(
+        signal, window, reinterpret_cast<const float2 *>(twiddle), n_tab / n_fft, mag, hg.g);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_stft_mag_bwd(const float *signal, const float *d_mag, const float *window,
+                                      const float *twiddle, int n_tab, float *d_signal, float *edge,
+                                      int B, int64_t N, int n_fft, int hop, int accumulate,
+                                      void *stream) {
+    DDSP_REQUIRE(signal && d_mag && window && twiddle && d_signal && edge && B > 0 && B <= 65535);
+    DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
+    HostGeom hg;
+    int s = make_geom(N, n_fft, hop, true, &hg);
+    if (s) return s;
+    if ((s = set_smem(stft_mag_bwd_kernel, hg.smem_mag_bwd))) return s;
+    stft_mag_bwd_kernel<<<dim3(hg.tiles, B), kStftThreads, hg.smem_mag_bwd, (cudaStream_t)stream>>>(
+        signal, d_mag, window, reinterpret_cast<const float2 *>(twiddle), n_tab / n_fft, d_signal, edge,
+        hg.g, accumulate);
+    return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int B, int64_t N,
+                                         const int *scales, int n_scales, void *stream) {
+    DDSP_REQUIRE(edge && d_signal && scales && n_scales > 0 && n_scales <= 8 && B > 0 && B <= 65535);
+    FoldArgs fold;
+    fold.n_scales = n_scales;
+    int64_t eoff = 0;
+    for (int i = 0; i < n_scales; ++i) {
+        fold.s[i] = scales[i];
+        fold.off[i] = eoff;
+        eoff += (int64_t)B * scales[i];
+    }
+    int gx = (int)ddsp_ceil_div(N, 256);
+    if (gx > 1024) gx = 1024;
+    stft_fold_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(edge, d_signal, B, N, fold);
+    return ddsp_launch_status();
+}

@@ -1,0 +1,509 @@
+// TORCH_LIBRARY shim over the C ABI of libddsp_b200.so (include/ddsp_b200.h).
+//
+// This file is plumbing only: it checks tensors (CUDA, float32, contiguous), allocates outputs
+// and workspaces with torch's caching allocator, takes the current CUDA stream and calls the
+// extern "C" entry points.  A non-zero status becomes a c10::Error (Python RuntimeError).  The
+// ops are registered for the CUDA dispatch key only: there is no CPU implementation and a CPU
+// tensor fails loudly in the dispatcher.  The schemas are visible to eager Python, to
+// torch.jit.script and to libtorch C++ (the realtime ddsp~ host dlopen()s this library before
+// torch::jit::load).
+#include <ATen/ATen.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/library.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include "ddsp_b200.h"
+
+namespace {
+
+using at::Tensor;
+
+void check(int status, const char *what) {
+    TORCH_CHECK(status == DDSP_B200_OK, "ddsp_b200::", what, " failed: ", ddsp_b200_strerror(status),
+                " (status ", status, ")");
+}
+
+Tensor prep(const Tensor &t, const char *name) {
+    TORCH_CHECK(t.is_cuda(), "ddsp_b200: ", name, " must be a CUDA tensor (no CPU fallback exists)");
+    TORCH_CHECK(t.scalar_type() == at::kFloat, "ddsp_b200: ", name, " must be float32, got ",
+                t.scalar_type());
+    return t.contiguous();
+}
+
+void *cur_stream() { return (void *)at::cuda::getCurrentCUDAStream().stream(); }
+const float *fp(const Tensor &t) { return t.data_ptr<float>(); }
+float *fpm(Tensor &t) { return t.data_ptr<float>(); }
+
+// Caller-owned constant tables, created lazily per (device, size); safe from any thread.
+Tensor twiddle_table(const at::Device &dev, int64_t n) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int64_t>, Tensor> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair((int)dev.index(), n);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    Tensor t = at::empty({n, 2}, at::TensorOptions().device(dev).dtype(at::kFloat));
+    check(ddsp_b200_twiddle_table(fpm(t), (int)n, cur_stream()), "twiddle_table");
+    cache[key] = t;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------- a1-a3
+Tensor scale_function_fwd(const Tensor &x_) {
+    Tensor x = prep(x_, "x");
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor y = at::empty_like(x);
+    check(ddsp_b200_scale_function_fwd(fp(x), fpm(y), x.numel(), cur_stream()), "scale_function_fwd");
+    return y;
+}
+
+Tensor scale_function_bwd(const Tensor &x_, const Tensor &dy_) {
+    Tensor x = prep(x_, "x"), dy = prep(dy_, "dy");
+    TORCH_CHECK(x.numel() == dy.numel(), "scale_function_bwd: size mismatch");
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor dx = at::empty_like(x);
+    check(ddsp_b200_scale_function_bwd(fp(x), fp(dy), fpm(dx), x.numel(), cur_stream()),
+          "scale_function_bwd");
+    return dx;
+}
+
+Tensor remove_above_nyquist(const Tensor &amp_, const Tensor &f0_, double sample_rate) {
+    Tensor amp = prep(amp_, "amplitudes"), f0 = prep(f0_, "f0");
+    TORCH_CHECK(amp.dim() >= 1 && f0.numel() * amp.size(-1) == amp.numel(),
+                "remove_above_nyquist: f0 must have one value per row of amplitudes");
+    c10::cuda::CUDAGuard guard(amp.device());
+    Tensor out = at::empty_like(amp);
+    check(ddsp_b200_remove_above_nyquist(fp(amp), fp(f0), fpm(out), f0.numel(), (int)amp.size(-1),
+                                         (float)sample_rate, cur_stream()),
+          "remove_above_nyquist");
+    return out;
+}
+
+std::tuple<Tensor, Tensor> harmonic_controls_fwd(const Tensor &amp_raw_, const Tensor &dist_raw_,
+                                                 const Tensor &f0_, double sample_rate) {
+    Tensor a = prep(amp_raw_, "amplitudes"), d = prep(dist_raw_, "harmonic_distribution"),
+           f = prep(f0_, "f0");
+    const int64_t H = d.size(-1), rows = d.numel() / H;
+    TORCH_CHECK(a.numel() == rows && f.numel() == rows, "harmonic_controls: shape mismatch");
+    c10::cuda::CUDAGuard guard(d.device());
+    Tensor amps = at::empty_like(a), dist = at::empty_like(d);
+    check(ddsp_b200_harmonic_controls_fwd(fp(a), fp(d), fp(f), fpm(amps), fpm(dist), rows, (int)H,
+                                          (float)sample_rate, cur_stream()),
+          "harmonic_controls_fwd");
+    return {amps, dist};
+}
+
+std::tuple<Tensor, Tensor> harmonic_controls_bwd(const Tensor &amp_raw_, const Tensor &dist_raw_,
+                                                 const Tensor &f0_, const Tensor &d_amps_,
+                                                 const Tensor &d_dist_, double sample_rate) {
+    Tensor a = prep(amp_raw_, "amplitudes"), d = prep(dist_raw_, "harmonic_distribution"),
+           f = prep(f0_, "f0"), ga = prep(d_amps_, "d_amps"), gd = prep(d_dist_, "d_dist");
+    const int64_t H = d.size(-1), rows = d.numel() / H;
+    TORCH_CHECK(a.numel() == rows && f.numel() == rows && ga.numel() == rows && gd.numel() == d.numel(),
+                "harmonic_controls_bwd: shape mismatch");
+    c10::cuda::CUDAGuard guard(d.device());
+    Tensor da = at::empty_like(a), dd = at::empty_like(d);
+    check(ddsp_b200_harmonic_controls_bwd(fp(a), fp(d), fp(f), fp(ga), fp(gd), fpm(da), fpm(dd), rows,
+                                          (int)H, (float)sample_rate, cur_stream()),
+          "harmonic_controls_bwd");
+    return {da, dd};
+}
+
+// ---------------------------------------------------------------------------------------- a4-a6
+// f0 (B,T,1), weights (B,T,H) -> audio (B,T*bs,1), phase_end (B) float64 turns,
+// phi/delta (B,T) int64 views of the Q0.64 phase workspace (kept for the backward).
+std::tuple<Tensor, Tensor, Tensor, Tensor> harmonic_fwd(const Tensor &f0_, const Tensor &weights_,
+                                                        int64_t block_size, double sample_rate,
+                                                        const c10::optional<Tensor> &phase0_) {
+    Tensor f0 = prep(f0_, "f0"), w = prep(weights_, "weights");
+    TORCH_CHECK(w.dim() == 3, "harmonic_fwd: weights must be (B,T,H)");
+    const int64_t B = w.size(0), T = w.size(1), H = w.size(2);
+    TORCH_CHECK(f0.numel() == B * T, "harmonic_fwd: f0 must be (B,T,1)");
+    c10::cuda::CUDAGuard guard(w.device());
+    auto opt64 = w.options().dtype(at::kLong);
+    Tensor phi = at::empty({B, T}, opt64), delta = at::empty({B, T}, opt64);
+    Tensor phase_end = at::empty({B}, w.options().dtype(at::kDouble));
+    Tensor audio = at::empty({B, T * block_size, 1}, w.options());
+    const double *p0 = nullptr;
+    Tensor phase0;
+    if (phase0_.has_value() && phase0_->defined()) {
+        phase0 = phase0_->contiguous();
+        TORCH_CHECK(phase0.is_cuda() && phase0.scalar_type() == at::kDouble && phase0.numel() == B,
+                    "harmonic_fwd: phase0 must be a CUDA float64 tensor of B turns");
+        p0 = phase0.data_ptr<double>();
+    }
+    check(ddsp_b200_phase_scan(fp(f0), p0, (uint64_t *)phi.data_ptr<int64_t>(),
+                               (uint64_t *)delta.data_ptr<int64_t>(), phase_end.data_ptr<double>(),
+                               (int)B, (int)T, (int)block_size, sample_rate, cur_stream()),
+          "phase_scan");
+    check(ddsp_b200_harmonic_frames_fwd(fp(w), (const uint64_t *)phi.data_ptr<int64_t>(),
+                                        (const uint64_t *)delta.data_ptr<int64_t>(), fpm(audio), (int)B,
+                                        (int)T, (int)H, (int)block_size, cur_stream()),
+          "harmonic_frames_fwd");
+    return {audio, phase_end, phi, delta};
+}
+
+std::tuple<Tensor, Tensor> harmonic_bwd(const Tensor &g_, const Tensor &weights_, const Tensor &phi,
+                                        const Tensor &delta, int64_t block_size, double sample_rate,
+                                        bool need_f0) {
+    Tensor g = prep(g_, "grad_audio"), w = prep(weights_, "weights");
+    const int64_t B = w.size(0), T = w.size(1), H = w.size(2);
+    TORCH_CHECK(g.numel() == B * T * block_size, "harmonic_bwd: grad shape mismatch");
+    TORCH_CHECK(phi.is_cuda() && phi.scalar_type() == at::kLong && phi.is_contiguous() &&
+                    delta.is_cuda() && delta.scalar_type() == at::kLong && delta.is_contiguous() &&
+                    phi.numel() == B * T && delta.numel() == B * T,
+                "harmonic_bwd: bad phase workspace");
+    c10::cuda::CUDAGuard guard(w.device());
+    Tensor dw = at::empty_like(w);
+    const uint64_t *ph = (const uint64_t *)phi.data_ptr<int64_t>();
+    const uint64_t *dl = (const uint64_t *)delta.data_ptr<int64_t>();
+    check(ddsp_b200_harmonic_frames_bwd_weights(fp(g), ph, dl, fpm(dw), (int)B, (int)T, (int)H,
+                                                (int)block_size, cur_stream()),
+          "harmonic_frames_bwd_weights");
+    Tensor df0;
+    if (need_f0) {
+        df0 = at::empty({B, T, 1}, w.options());
+        Tensor scratch = at::empty({B, T, 2}, w.options());
+        check(ddsp_b200_harmonic_frames_bwd_f0(fp(g), fp(w), ph, dl, fpm(scratch), fpm(df0), (int)B, (int)T,
+                                               (int)H, (int)block_size, sample_rate, cur_stream()),
+              "harmonic_frames_bwd_f0");
+    } else {
+        df0 = at::empty({0}, w.options());
+    }
+    return {dw, df0};
+}
+
+// ---------------------------------------------------------------------------------------- a5 generic
+std::tuple<Tensor, Tensor> harmonic_ar_fwd(const Tensor &f0_, const Tensor &amps_, double sample_rate) {
+    Tensor f0 = prep(f0_, "f0"), a = prep(amps_, "amplitudes");
+    TORCH_CHECK(a.dim() == 3, "harmonic_synth: amplitudes must be (B,N,H)");
+    const int64_t B = a.size(0), N = a.size(1), H = a.size(2);
+    TORCH_CHECK(f0.numel() == B * N, "harmonic_synth: f0 must be (B,N,1)");
+    c10::cuda::CUDAGuard guard(a.device());
+    Tensor phase = at::empty({B, N}, a.options().dtype(at::kLong));
+    Tensor audio = at::empty({B, N, 1}, a.options());
+    check(ddsp_b200_phase_scan_audio_rate(fp(f0), (uint64_t *)phase.data_ptr<int64_t>(), (int)B, N,
+                                          sample_rate, cur_stream()),
+          "phase_scan_audio_rate");
+    check(ddsp_b200_harmonic_audio_rate_fwd(fp(a), (const uint64_t *)phase.data_ptr<int64_t>(), fpm(audio),
+                                            (int)B, N, (int)H, cur_stream()),
+          "harmonic_audio_rate_fwd");
+    return {audio, phase};
+}
+
+std::tuple<Tensor, Tensor> harmonic_ar_bwd(const Tensor &g_, const Tensor &amps_, const Tensor &phase,
+                                           double sample_rate, bool need_f0) {
+    Tensor g = prep(g_, "grad_audio"), a = prep(amps_, "amplitudes");
+    const int64_t B = a.size(0), N = a.size(1), H = a.size(2);
+    TORCH_CHECK(g.numel() == B * N && phase.numel() == B * N && phase.scalar_type() == at::kLong &&
+                    phase.is_cuda() && phase.is_contiguous(),
+                "harmonic_synth backward: shape mismatch");
+    c10::cuda::CUDAGuard guard(a.device());
+    Tensor da = at::empty_like(a);
+    Tensor df0 = need_f0 ? at::empty({B, N, 1}, a.options()) : at::empty({0}, a.options());
+    Tensor dphi = need_f0 ? at::empty({B, N}, a.options()) : Tensor();
+    check(ddsp_b200_harmonic_audio_rate_bwd(fp(g), fp(a), (const uint64_t *)phase.data_ptr<int64_t>(),
+                                            fpm(da), need_f0 ? fpm(dphi) : nullptr,
+                                            need_f0 ? fpm(df0) : nullptr, (int)B, N, (int)H, sample_rate,
+                                            cur_stream()),
+          "harmonic_audio_rate_bwd");
+    return {da, df0};
+}
+
+// ---------------------------------------------------------------------------------------- a7, a8
+Tensor amp_to_ir_fwd(const Tensor &amp_, int64_t target) {
+    Tensor amp = prep(amp_, "amp");
+    const int64_t NB = amp.size(-1), rows = amp.numel() / NB;
+    c10::cuda::CUDAGuard guard(amp.device());
+    auto shape = amp.sizes().vec();
+    shape.back() = target;
+    Tensor ir = at::empty(shape, amp.options());
+    check(ddsp_b200_amp_to_ir_fwd(fp(amp), fpm(ir), rows, (int)NB, (int)target, cur_stream()),
+          "amp_to_ir_fwd");
+    return ir;
+}
+
+Tensor amp_to_ir_bwd(const Tensor &d_ir_, int64_t NB) {
+    Tensor d_ir = prep(d_ir_, "d_ir");
+    const int64_t target = d_ir.size(-1), rows = d_ir.numel() / target;
+    c10::cuda::CUDAGuard guard(d_ir.device());
+    auto shape = d_ir.sizes().vec();
+    shape.back() = NB;
+    Tensor d_amp = at::empty(shape, d_ir.options());
+    check(ddsp_b200_amp_to_ir_bwd(fp(d_ir), fpm(d_amp), rows, (int)NB, (int)target, cur_stream()),
+          "amp_to_ir_bwd");
+    return d_amp;
+}
+
+Tensor noise_fwd(const Tensor &mags_, const Tensor &noise_) {
+    Tensor mags = prep(mags_, "magnitudes"), noise = prep(noise_, "noise");
+    TORCH_CHECK(mags.dim() == 3 && noise.dim() == 3 && mags.size(0) == noise.size(0) &&
+                    mags.size(1) == noise.size(1),
+                "filtered noise: magnitudes (B,T,NB) and noise (B,T,block) expected");
+    const int64_t B = mags.size(0), T = mags.size(1), NB = mags.size(2), bs = noise.size(2);
+    c10::cuda::CUDAGuard guard(mags.device());
+    Tensor out = at::empty({B, T * bs, 1}, mags.options());
+    check(ddsp_b200_filtered_noise_fwd(fp(mags), fp(noise), fpm(out), B * T, (int)NB, (int)bs, cur_stream()),
+          "filtered_noise_fwd");
+    return out;
+}
+
+Tensor noise_bwd(const Tensor &g_, const Tensor &noise_, int64_t NB) {
+    Tensor g = prep(g_, "grad_out"), noise = prep(noise_, "noise");
+    const int64_t B = noise.size(0), T = noise.size(1), bs = noise.size(2);
+    TORCH_CHECK(g.numel() == B * T * bs, "filtered noise backward: shape mismatch");
+    c10::cuda::CUDAGuard guard(noise.device());
+    Tensor d_mags = at::empty({B, T, NB}, noise.options());
+    check(ddsp_b200_filtered_noise_bwd(fp(g), fp(noise), fpm(d_mags), B * T, (int)NB, (int)bs, cur_stream()),
+          "filtered_noise_bwd");
+    return d_mags;
+}
+
+// ---------------------------------------------------------------------------------------- a9, a10
+struct ConvPlan {
+    int n1, n2;
+    int64_t n;
+    Tensor tw;
+};
+
+ConvPlan conv_plan(const at::Device &dev, int64_t min_len) {
+    ConvPlan p;
+    check(ddsp_b200_conv_plan(min_len, &p.n1, &p.n2), "conv_plan");
+    p.n = (int64_t)p.n1 * p.n2;
+    p.tw = twiddle_table(dev, p.n);
+    return p;
+}
+
+// signal (R,n), kernel (Rk,Lk) with Rk in {1,R}: out[r,i] = sum_{j<=i} signal[r,j] kernel[rk,i-j]
+Tensor fftconv_fwd(const Tensor &signal_, const Tensor &kernel_) {
+    Tensor sig = prep(signal_, "signal"), ker = prep(kernel_, "kernel");
+    TORCH_CHECK(sig.dim() == 2 && ker.dim() == 2, "fftconv: 2-D (rows, length) tensors expected");
+    const int64_t R = sig.size(0), n = sig.size(1), Rk = ker.size(0), Lk = ker.size(1);
+    TORCH_CHECK(Rk == 1 || Rk == R, "fftconv: kernel rows must be 1 or match the signal rows");
+    c10::cuda::CUDAGuard guard(sig.device());
+    Tensor out = at::empty_like(sig);
+    if (R == 0 || n == 0) return out;
+    const int64_t Lc = std::min(Lk, n);                 // taps beyond the signal length never matter
+    Tensor kc = Lc == Lk ? ker : ker.narrow(1, 0, Lc).contiguous();
+    ConvPlan p = conv_plan(sig.device(), n + Lc - 1);
+    const int pair = Rk == 1;
+    const int64_t slots = pair ? (R + 1) / 2 : R;
+    void *st = cur_stream();
+    Tensor hspec = at::empty({Rk, p.n, 2}, sig.options());
+    check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+    check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), p.n1, p.n2, st), "fft4_rows_spectrum");
+    Tensor work = at::empty({slots, p.n, 2}, sig.options());
+    check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(x)");
+    check(ddsp_b200_fft4_rows_filter(fpm(work), slots, fp(hspec), pair ? 0 : p.n, 0, fp(p.tw), p.n1, p.n2, st),
+          "fft4_rows_filter");
+    check(ddsp_b200_fft4_cols_inv(fp(work), fpm(out), R, n, pair, fp(p.tw), p.n1, p.n2, st), "fft4_cols_inv");
+    return out;
+}
+
+std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, const Tensor &kernel_,
+                                       bool need_signal, bool need_kernel) {
+    Tensor g = prep(g_, "grad_out"), sig = prep(signal_, "signal"), ker = prep(kernel_, "kernel");
+    const int64_t R = sig.size(0), n = sig.size(1), Rk = ker.size(0), Lk = ker.size(1);
+    TORCH_CHECK(g.dim() == 2 && g.size(0) == R && g.size(1) == n, "fftconv backward: grad shape mismatch");
+    c10::cuda::CUDAGuard guard(sig.device());
+    Tensor d_sig = need_signal ? at::empty_like(sig) : at::empty({0}, sig.options());
+    Tensor d_ker = need_kernel ? at::zeros_like(ker) : at::empty({0}, sig.options());
+    if (R == 0 || n == 0 || (!need_signal && !need_kernel)) return {d_sig, d_ker};
+    const int64_t Lc = std::min(Lk, n);
+    Tensor kc = Lc == Lk ? ker : ker.narrow(1, 0, Lc).contiguous();
+    ConvPlan p = conv_plan(sig.device(), n + Lc - 1);
+    const int pair = Rk == 1;
+    const int64_t slots = pair ? (R + 1) / 2 : R;
+    void *st = cur_stream();
+    Tensor work_g = at::empty({slots, p.n, 2}, sig.options());
+    check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(g)");
+    if (need_kernel) {
+        Tensor work_x = at::empty({slots, p.n, 2}, sig.options());
+        check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), p.n1, p.n2, st),
+              "fft4_cols_fwd(x)");
+        Tensor corr = at::empty({Rk, p.n, 2}, sig.options());
+        check(ddsp_b200_fft4_rows_correlate(fp(work_g), fp(work_x), slots, pair, fpm(corr), fp(p.tw), p.n1, p.n2,
+                                            st),
+              "fft4_rows_correlate");
+        Tensor dk = Lc == Lk ? d_ker : at::empty({Rk, Lc}, sig.options());
+        check(ddsp_b200_fft4_cols_inv(fp(corr), fpm(dk), Rk, Lc, 0, fp(p.tw), p.n1, p.n2, st), "fft4_cols_inv(dh)");
+        if (Lc != Lk) d_ker.narrow(1, 0, Lc).copy_(dk);
+    }
+    if (need_signal) {
+        Tensor hspec = at::empty({Rk, p.n, 2}, sig.options());
+        check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+        check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), p.n1, p.n2, st), "fft4_rows_spectrum");
+        check(ddsp_b200_fft4_rows_filter(fpm(work_g), slots, fp(hspec), pair ? 0 : p.n, 1, fp(p.tw), p.n1, p.n2,
+                                         st),
+              "fft4_rows_filter(conj)");
+        check(ddsp_b200_fft4_cols_inv(fp(work_g), fpm(d_sig), R, n, pair, fp(p.tw), p.n1, p.n2, st),
+              "fft4_cols_inv(dx)");
+    }
+    return {d_sig, d_ker};
+}
+
+Tensor reverb_impulse_fwd(const Tensor &noise_, const Tensor &decay_, const Tensor &wet_, const Tensor &t_) {
+    Tensor noise = prep(noise_, "noise"), decay = prep(decay_, "decay"), wet = prep(wet_, "wet"),
+           t = prep(t_, "t");
+    const int64_t L = noise.numel();
+    TORCH_CHECK(t.numel() == L && decay.numel() == 1 && wet.numel() == 1, "reverb impulse: shape mismatch");
+    c10::cuda::CUDAGuard guard(noise.device());
+    Tensor imp = at::empty({1, L, 1}, noise.options());
+    check(ddsp_b200_reverb_impulse_fwd(fp(noise), fp(decay), fp(wet), fp(t), fpm(imp), (int)L, cur_stream()),
+          "reverb_impulse_fwd");
+    return imp;
+}
+
+std::tuple<Tensor, Tensor, Tensor> reverb_impulse_bwd(const Tensor &d_imp_, const Tensor &noise_,
+                                                      const Tensor &decay_, const Tensor &wet_,
+                                                      const Tensor &t_) {
+    Tensor d_imp = prep(d_imp_, "d_impulse"), noise = prep(noise_, "noise"), decay = prep(decay_, "decay"),
+           wet = prep(wet_, "wet"), t = prep(t_, "t");
+    const int64_t L = noise.numel();
+    TORCH_CHECK(d_imp.numel() <= L, "reverb impulse backward: d_impulse longer than the impulse");
+    c10::cuda::CUDAGuard guard(noise.device());
+    Tensor dn = at::empty_like(noise), dd = at::empty_like(decay), dw = at::empty_like(wet);
+    check(ddsp_b200_reverb_impulse_bwd(fp(d_imp), (int)d_imp.numel(), fp(noise), fp(decay), fp(wet), fp(t),
+                                       fpm(dn), fpm(dd), fpm(dw), (int)L, cur_stream()),
+          "reverb_impulse_bwd");
+    return {dn, dd, dw};
+}
+
+// ---------------------------------------------------------------------------------------- a11, a12
+int64_t pow2_ge(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+Tensor stft_mag_fwd(const Tensor &signal_, const Tensor &window_, int64_t n_fft, int64_t hop) {
+    Tensor sig = prep(signal_, "signal"), win = prep(window_, "window");
+    TORCH_CHECK(sig.dim() == 2 && win.numel() == n_fft, "stft_mag: signal (B,N) and window (n_fft) expected");
+    const int64_t B = sig.size(0), N = sig.size(1);
+    c10::cuda::CUDAGuard guard(sig.device());
+    Tensor tw = twiddle_table(sig.device(), std::max<int64_t>(4096, n_fft));
+    Tensor mag = at::empty({B, n_fft / 2 + 1, 1 + N / hop}, sig.options());
+    check(ddsp_b200_stft_mag_fwd(fp(sig), fp(win), fp(tw), (int)tw.size(0), fpm(mag), (int)B, N, (int)n_fft,
+                                 (int)hop, cur_stream()),
+          "stft_mag_fwd");
+    return mag;
+}
+
+Tensor stft_mag_bwd(const Tensor &signal_, const Tensor &d_mag_, const Tensor &window_, int64_t n_fft,
+                    int64_t hop) {
+    Tensor sig = prep(signal_, "signal"), gm = prep(d_mag_, "d_mag"), win = prep(window_, "window");
+    const int64_t B = sig.size(0), N = sig.size(1);
+    TORCH_CHECK(gm.numel() == B * (n_fft / 2 + 1) * (1 + N / hop), "stft_mag backward: shape mismatch");
+    c10::cuda::CUDAGuard guard(sig.device());
+    Tensor tw = twiddle_table(sig.device(), std::max<int64_t>(4096, n_fft));
+    Tensor d_sig = at::empty_like(sig);
+    Tensor edge = at::empty({B, n_fft}, sig.options());
+    void *st = cur_stream();
+    check(ddsp_b200_stft_mag_bwd(fp(sig), fp(gm), fp(win), fp(tw), (int)tw.size(0), fpm(d_sig), fpm(edge), (int)B,
+                                 N, (int)n_fft, (int)hop, 0, st),
+          "stft_mag_bwd");
+    const int sc = (int)n_fft;
+    check(ddsp_b200_stft_fold_edges(fp(edge), fpm(d_sig), (int)B, N, &sc, 1, st), "stft_fold_edges");
+    return d_sig;
+}
+
+// target, rec (B,N); windows = the float32 hann windows of every scale, concatenated.
+// Returns (loss[], d_rec (B,N) for unit upstream gradient, or an empty tensor).
+std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec_, at::IntArrayRef scales,
+                                        double overlap, const Tensor &windows_, bool need_grad) {
+    Tensor tgt = prep(target_, "target"), rec = prep(rec_, "rec"), win = prep(windows_, "windows");
+    TORCH_CHECK(tgt.dim() == 2 && rec.sizes() == tgt.sizes(), "mss_loss: target and rec must both be (B,N)");
+    const int64_t B = rec.size(0), N = rec.size(1);
+    const int ns = (int)scales.size();
+    TORCH_CHECK(ns >= 1 && ns <= 8, "mss_loss: 1..8 scales supported");
+    std::vector<int> sc(ns), hp(ns);
+    int64_t wsum = 0, tiles = 0, esum = 0, smax = 0;
+    for (int i = 0; i < ns; ++i) {
+        sc[i] = (int)scales[i];
+        hp[i] = (int)((double)scales[i] * (1.0 - overlap));     // int(s * (1 - overlap)), core.py:33
+        const int64_t t = ddsp_b200_mss_tiles(N, sc[i], hp[i]);
+        TORCH_CHECK(t > 0, "mss_loss: scale ", sc[i], " with hop ", hp[i], " unsupported for N=", N);
+        tiles += t * B;
+        wsum += sc[i];
+        esum += B * sc[i];
+        smax = std::max<int64_t>(smax, sc[i]);
+    }
+    TORCH_CHECK(win.numel() == wsum, "mss_loss: windows must hold sum(scales) values");
+    c10::cuda::CUDAGuard guard(rec.device());
+    Tensor tw = twiddle_table(rec.device(), std::max<int64_t>(4096, pow2_ge(smax)));
+    Tensor partial = at::empty({tiles, 2}, rec.options());
+    Tensor loss = at::empty({}, rec.options());
+    Tensor d_rec = need_grad ? at::empty_like(rec) : at::empty({0}, rec.options());
+    Tensor edge = need_grad ? at::empty({esum}, rec.options()) : Tensor();
+    void *st = cur_stream();
+    int64_t woff = 0, poff = 0, eoff = 0;
+    for (int i = 0; i < ns; ++i) {
+        check(ddsp_b200_mss_scale(fp(tgt), fp(rec), fp(win) + woff, fp(tw), (int)tw.size(0),
+                                  fpm(partial) + 2 * poff, need_grad ? fpm(d_rec) : nullptr,
+                                  need_grad ? fpm(edge) + eoff : nullptr, (int)B, N, sc[i], hp[i], i > 0, st),
+              "mss_scale");
+        woff += sc[i];
+        poff += ddsp_b200_mss_tiles(N, sc[i], hp[i]) * B;
+        eoff += B * sc[i];
+    }
+    check(ddsp_b200_mss_finish(fp(partial), need_grad ? fp(edge) : nullptr, need_grad ? fpm(d_rec) : nullptr,
+                               fpm(loss), (int)B, N, sc.data(), hp.data(), ns, st),
+          "mss_finish");
+    return {loss, d_rec};
+}
+
+int64_t abi_version() { return ddsp_b200_abi_version(); }
+
+}  // namespace
+
+TORCH_LIBRARY(ddsp_b200, m) {
+    m.def("abi_version() -> int", abi_version);
+    m.def("scale_function_fwd(Tensor x) -> Tensor");
+    m.def("scale_function_bwd(Tensor x, Tensor dy) -> Tensor");
+    m.def("remove_above_nyquist(Tensor amplitudes, Tensor f0, float sample_rate) -> Tensor");
+    m.def("harmonic_controls_fwd(Tensor amplitudes, Tensor harmonic_distribution, Tensor f0, float sample_rate) -> (Tensor, Tensor)");
+    m.def("harmonic_controls_bwd(Tensor amplitudes, Tensor harmonic_distribution, Tensor f0, Tensor d_amps, Tensor d_dist, float sample_rate) -> (Tensor, Tensor)");
+    m.def("harmonic_fwd(Tensor f0, Tensor weights, int block_size, float sample_rate, Tensor? phase0) -> (Tensor, Tensor, Tensor, Tensor)");
+    m.def("harmonic_bwd(Tensor grad_audio, Tensor weights, Tensor phi, Tensor delta, int block_size, float sample_rate, bool need_f0) -> (Tensor, Tensor)");
+    m.def("harmonic_ar_fwd(Tensor f0, Tensor amplitudes, float sample_rate) -> (Tensor, Tensor)");
+    m.def("harmonic_ar_bwd(Tensor grad_audio, Tensor amplitudes, Tensor phase, float sample_rate, bool need_f0) -> (Tensor, Tensor)");
+    m.def("amp_to_ir_fwd(Tensor amp, int target_size) -> Tensor");
+    m.def("amp_to_ir_bwd(Tensor d_ir, int n_bands) -> Tensor");
+    m.def("noise_fwd(Tensor magnitudes, Tensor noise) -> Tensor");
+    m.def("noise_bwd(Tensor grad_out, Tensor noise, int n_bands) -> Tensor");
+    m.def("fftconv_fwd(Tensor signal, Tensor kernel) -> Tensor");
+    m.def("fftconv_bwd(Tensor grad_out, Tensor signal, Tensor kernel, bool need_signal, bool need_kernel) -> (Tensor, Tensor)");
+    m.def("reverb_impulse_fwd(Tensor noise, Tensor decay, Tensor wet, Tensor t) -> Tensor");
+    m.def("reverb_impulse_bwd(Tensor d_impulse, Tensor noise, Tensor decay, Tensor wet, Tensor t) -> (Tensor, Tensor, Tensor)");
+    m.def("stft_mag_fwd(Tensor signal, Tensor window, int n_fft, int hop) -> Tensor");
+    m.def("stft_mag_bwd(Tensor signal, Tensor d_mag, Tensor window, int n_fft, int hop) -> Tensor");
+    m.def("mss_loss_fwd(Tensor target, Tensor rec, int[] scales, float overlap, Tensor windows, bool need_grad) -> (Tensor, Tensor)");
+}
+
+TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
+    m.impl("scale_function_fwd", scale_function_fwd);
+    m.impl("scale_function_bwd", scale_function_bwd);
+    m.impl("remove_above_nyquist", remove_above_nyquist);
+    m.impl("harmonic_controls_fwd", harmonic_controls_fwd);
+    m.impl("harmonic_controls_bwd", harmonic_controls_bwd);
+    m.impl("harmonic_fwd", harmonic_fwd);
+    m.impl("harmonic_bwd", harmonic_bwd);
+    m.impl("harmonic_ar_fwd", harmonic_ar_fwd);
+    m.impl("harmonic_ar_bwd", harmonic_ar_bwd);
+    m.impl("amp_to_ir_fwd", amp_to_ir_fwd);
+    m.impl("amp_to_ir_bwd", amp_to_ir_bwd);
+    m.impl("noise_fwd", noise_fwd);
+    m.impl("noise_bwd", noise_bwd);
+    m.impl("fftconv_fwd", fftconv_fwd);
+    m.impl("fftconv_bwd", fftconv_bwd);
+    m.impl("reverb_impulse_fwd", reverb_impulse_fwd);
+    m.impl("reverb_impulse_bwd", reverb_impulse_bwd);
+    m.impl("stft_mag_fwd", stft_mag_fwd);
+    m.impl("stft_mag_bwd", stft_mag_bwd);
+    m.impl("mss_loss_fwd", mss_loss_fwd);
+}

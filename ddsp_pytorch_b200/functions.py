@@ -1,0 +1,217 @@
+"""torch.autograd.Function wrappers around the ddsp_b200:: custom ops.
+
+Each Function pairs a ``*_fwd`` op with its hand-written ``*_bwd`` op.  The
+backward kernels are not differentiable again (``once_differentiable``).  Scripted / C++ inference
+calls the ``*_fwd`` ops directly and never touches this file.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from ._lib import get_ops
+
+_ops = get_ops()
+
+_WINDOWS = {}
+
+
+def hann_window_like_reference(n_fft: int, device) -> torch.Tensor:
+    """core.py:35 builds the window with ``torch.hann_window(s)`` on the CPU in float32 and then
+    moves it; doing the same keeps the window bit-identical to the reference's."""
+    key = (int(n_fft), str(device))
+    w = _WINDOWS.get(key)
+    if w is None:
+        w = torch.hann_window(int(n_fft)).to(device)
+        _WINDOWS[key] = w
+    return w
+
+
+class ScaleFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return _ops.scale_function_fwd(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return _ops.scale_function_bwd(x, dy).view_as(x)
+
+
+class RemoveAboveNyquist(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, amplitudes, f0, sample_rate):
+        ctx.save_for_backward(f0)
+        ctx.sample_rate = float(sample_rate)
+        return _ops.remove_above_nyquist(amplitudes, f0, ctx.sample_rate)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (f0,) = ctx.saved_tensors            # the mask has no gradient w.r.t. f0 (core.py:73)
+        return _ops.remove_above_nyquist(dy, f0, ctx.sample_rate), None, None
+
+
+class HarmonicControls(torch.autograd.Function):
+    """modules.py:44-67 fused: (amp_raw, dist_raw, f0) -> (amplitudes, normalised distribution)."""
+
+    @staticmethod
+    def forward(ctx, amp_raw, dist_raw, f0, sample_rate):
+        ctx.save_for_backward(amp_raw, dist_raw, f0)
+        ctx.sample_rate = float(sample_rate)
+        amps, dist = _ops.harmonic_controls_fwd(amp_raw, dist_raw, f0, ctx.sample_rate)
+        return amps, dist
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_amps, d_dist):
+        amp_raw, dist_raw, f0 = ctx.saved_tensors
+        da, dd = _ops.harmonic_controls_bwd(amp_raw, dist_raw, f0, d_amps, d_dist, ctx.sample_rate)
+        return da.view_as(amp_raw), dd.view_as(dist_raw), None, None
+
+
+class HarmonicFrames(torch.autograd.Function):
+    """modules.py:69-80 fused: frame-rate f0 (B,T,1) and weights (B,T,H) -> audio (B,T*bs,1)."""
+
+    @staticmethod
+    def forward(ctx, f0, weights, block_size, sample_rate, phase0):
+        audio, phase_end, phi, delta = _ops.harmonic_fwd(f0, weights, int(block_size),
+                                                         float(sample_rate), phase0)
+        ctx.save_for_backward(weights, phi, delta)
+        ctx.cfg = (int(block_size), float(sample_rate), f0.shape)
+        ctx.mark_non_differentiable(phase_end)
+        return audio, phase_end
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_audio, _g_phase):
+        weights, phi, delta = ctx.saved_tensors
+        bs, sr, f0_shape = ctx.cfg
+        need_f0 = ctx.needs_input_grad[0]
+        dw, df0 = _ops.harmonic_bwd(g_audio, weights, phi, delta, bs, sr, need_f0)
+        return (df0.view(f0_shape) if need_f0 else None), dw, None, None, None
+
+
+class HarmonicAudioRate(torch.autograd.Function):
+    """core.py:136-141: f0 (B,N,1), amplitudes (B,N,H) at audio rate -> (B,N,1)."""
+
+    @staticmethod
+    def forward(ctx, f0, amplitudes, sample_rate):
+        audio, phase = _ops.harmonic_ar_fwd(f0, amplitudes, float(sample_rate))
+        ctx.save_for_backward(amplitudes, phase)
+        ctx.cfg = (float(sample_rate), f0.shape)
+        return audio
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        amplitudes, phase = ctx.saved_tensors
+        sr, f0_shape = ctx.cfg
+        need_f0 = ctx.needs_input_grad[0]
+        da, df0 = _ops.harmonic_ar_bwd(g, amplitudes, phase, sr, need_f0)
+        return (df0.view(f0_shape) if need_f0 else None), da, None
+
+
+class AmpToImpulseResponse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, amp, target_size):
+        ctx.n_bands = amp.shape[-1]
+        return _ops.amp_to_ir_fwd(amp, int(target_size))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_ir):
+        return _ops.amp_to_ir_bwd(d_ir, ctx.n_bands), None
+
+
+class FilteredNoise(torch.autograd.Function):
+    """modules.py:116-128 fused, noise passed in: magnitudes (B,T,NB), noise (B,T,bs) -> (B,T*bs,1)."""
+
+    @staticmethod
+    def forward(ctx, magnitudes, noise):
+        ctx.save_for_backward(noise)
+        ctx.n_bands = magnitudes.shape[-1]
+        return _ops.noise_fwd(magnitudes, noise)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (noise,) = ctx.saved_tensors
+        return _ops.noise_bwd(g, noise, ctx.n_bands), None   # the draw itself has no gradient
+
+
+class FFTConvolve(torch.autograd.Function):
+    """core.py:169-176 on 2-D (rows, n) operands; kernel rows 1 (shared) or equal to signal rows."""
+
+    @staticmethod
+    def forward(ctx, signal, kernel):
+        ctx.save_for_backward(signal, kernel)
+        return _ops.fftconv_fwd(signal, kernel)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        signal, kernel = ctx.saved_tensors
+        ds, dk = _ops.fftconv_bwd(g, signal, kernel, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return (ds if ctx.needs_input_grad[0] else None), (dk if ctx.needs_input_grad[1] else None)
+
+
+class ReverbImpulse(torch.autograd.Function):
+    """modules.py:21-26: (noise (L,1), decay, wet, t (1,L,1)) -> impulse (1,L,1)."""
+
+    @staticmethod
+    def forward(ctx, noise, decay, wet, t):
+        ctx.save_for_backward(noise, decay, wet, t)
+        return _ops.reverb_impulse_fwd(noise, decay, wet, t)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_imp):
+        noise, decay, wet, t = ctx.saved_tensors
+        dn, dd, dw = _ops.reverb_impulse_bwd(d_imp, noise, decay, wet, t)
+        return dn.view_as(noise), dd.view_as(decay), dw.view_as(wet), None
+
+
+class StftMag(torch.autograd.Function):
+    """One scale of core.py:27-41: signal (B,N) -> |STFT| (B, s/2+1, 1+N//hop)."""
+
+    @staticmethod
+    def forward(ctx, signal, n_fft, hop):
+        window = hann_window_like_reference(n_fft, signal.device)
+        ctx.save_for_backward(signal, window)
+        ctx.cfg = (int(n_fft), int(hop))
+        return _ops.stft_mag_fwd(signal, window, int(n_fft), int(hop))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_mag):
+        signal, window = ctx.saved_tensors
+        n_fft, hop = ctx.cfg
+        return _ops.stft_mag_bwd(signal, d_mag, window, n_fft, hop), None, None
+
+
+class MultiScaleSpectralLoss(torch.autograd.Function):
+    """train.py:70-76 over core.py:27-41, fused: (target (B,N), rec (B,N)) -> scalar loss.
+    The gradient w.r.t. rec is produced by the forward launch itself (same FFTs); backward only
+    scales it.  target gets no gradient (train.py feeds data there)."""
+
+    @staticmethod
+    def forward(ctx, target, rec, scales, overlap):
+        scales = [int(s) for s in scales]
+        windows = torch.cat([hann_window_like_reference(s, rec.device) for s in scales])
+        need = bool(ctx.needs_input_grad[1])
+        loss, d_rec = _ops.mss_loss_fwd(target, rec, scales, float(overlap), windows, need)
+        if need:
+            ctx.save_for_backward(d_rec)
+        ctx.rec_shape = rec.shape
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (d_rec,) = ctx.saved_tensors
+        return None, (d_rec * g).view(ctx.rec_shape), None, None

@@ -1,0 +1,156 @@
+"""The synthesis hot path as one callable: decoder outputs -> audio -> multi-scale loss -> gradients.
+
+This is decoder.py:106-125 + train.py:92-103,129 without the control network: the stage the
+north star accelerates.  ``SynthStep`` owns static device buffers so that the whole forward +
+backward can be captured once in a CUDA graph and replayed (configs 1 and 3 are launch
+bound; one graph launch replaces ~30 kernel launches and all autograd bookkeeping).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import core
+from . import functions as F_
+
+
+@dataclass
+class SynthShapes:
+    batch: int
+    frames: int
+    block_size: int
+    n_harmonic: int
+    n_bands: int
+    sample_rate: int
+    reverb_length: Optional[int]            # None = no reverb (realtime export path)
+    scales: Sequence[int] = (4096, 2048, 1024, 512, 256, 128)
+    overlap: float = 0.75
+
+    @property
+    def samples(self) -> int:
+        return self.frames * self.block_size
+
+
+INPUT_NAMES = ("amp_raw", "dist_raw", "mag_raw", "pitch", "noise", "target")
+
+
+class SynthStep:
+    """Static-buffer runner of the hot path.  ``inputs`` are the decoder's raw outputs
+    (harmonic_proj / noise_proj rows), pitch, the uniform noise draw and the target audio."""
+
+    def __init__(self, shapes: SynthShapes, device="cuda", reverb_state: Optional[Dict[str, torch.Tensor]] = None):
+        s = self.shapes = shapes
+        dev = torch.device(device)
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.inputs = {
+            "amp_raw": torch.zeros(s.batch, s.frames, 1, **f32),
+            "dist_raw": torch.zeros(s.batch, s.frames, s.n_harmonic, **f32),
+            "mag_raw": torch.zeros(s.batch, s.frames, s.n_bands, **f32),
+            "pitch": torch.full((s.batch, s.frames, 1), 220.0, **f32),
+            "noise": torch.zeros(s.batch, s.frames, s.block_size, **f32),
+            "target": torch.zeros(s.batch, s.samples, **f32),
+        }
+        self.reverb = None
+        if s.reverb_length is not None:
+            from .models.modules import Reverb
+            self.reverb = Reverb(s.reverb_length, s.sample_rate).to(dev)
+            if reverb_state is not None:
+                self.reverb.load_state_dict(reverb_state)
+        self.leaves = [self.inputs[k] for k in ("amp_raw", "dist_raw", "mag_raw")]
+        for t in self.leaves:
+            t.requires_grad_(True)
+        if self.reverb is not None:
+            self.leaves += [self.reverb.noise, self.reverb.decay, self.reverb.wet]
+        self.loss = torch.zeros((), **f32)
+        self.signal = None
+        self.grads = None
+        self._graph = None
+        self._graph_fwd = None
+
+    # ---- the path -------------------------------------------------------------------------
+    def forward(self) -> torch.Tensor:
+        """decoder.py:110-125: controls -> harmonic + filtered noise (+ reverb).  (B,N,1)"""
+        i, s = self.inputs, self.shapes
+        amps, dist = F_.HarmonicControls.apply(i["amp_raw"], i["dist_raw"], i["pitch"], float(s.sample_rate))
+        weights = dist * amps
+        harmonic, _ = core.harmonic_synth_frames(i["pitch"], weights, s.block_size, s.sample_rate)
+        mags = core.scale_function(i["mag_raw"] + (-5.0))
+        noise = core.filtered_noise(mags, i["noise"])
+        signal = harmonic + noise
+        if self.reverb is not None:
+            signal = self.reverb(signal)
+        return signal
+
+    def forward_backward(self):
+        """train.py:89-103,129 on the synth part: loss and gradients of every leaf."""
+        s = self.shapes
+        signal = self.forward()
+        loss = core.multiscale_spectral_loss(self.inputs["target"], signal.squeeze(-1), list(s.scales), s.overlap)
+        grads = torch.autograd.grad(loss, self.leaves)
+        return signal, loss, grads
+
+    # ---- eager / graph execution ---------------------------------------------------------
+    def run(self):
+        self.signal, loss, self.grads = self.forward_backward()
+        self.loss = loss
+        return loss
+
+    def run_forward(self):
+        with torch.no_grad():
+            self.signal = self.forward()
+        return self.signal
+
+    def capture(self, forward_only: bool = False, warmup: int = 3):
+        """Capture the step in a CUDA graph (after a few eager runs on a side stream so that lazily
+        built tables and the allocator's pools exist before capture)."""
+        fn = self.run_forward if forward_only else self.run
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        if forward_only:
+            self._graph_fwd = graph
+        else:
+            self._graph = graph
+        return graph
+
+    def replay(self, forward_only: bool = False):
+        (self._graph_fwd if forward_only else self._graph).replay()
+
+    def load_inputs(self, host: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
+        """Copy a batch from (pinned) host tensors into the static buffers; returns bytes copied."""
+        n = 0
+        with torch.no_grad():
+            for k in INPUT_NAMES:
+                if k in host:
+                    self.inputs[k].copy_(host[k], non_blocking=non_blocking)
+                    n += host[k].numel() * host[k].element_size()
+        return n
+
+
+def synthetic_inputs(shapes: SynthShapes, seed: int = 0, pitch_lo: float = 36.0, pitch_hi: float = 84.0):
+    """SURVEY 8d synthetic inputs, drawn with the CPU generator (seeded), as CPU float32 tensors:
+    smooth pitch contours (MIDI note per voice + 5 Hz vibrato), N(0,1) decoder outputs, uniform
+    noise draw, 0.1*N(0,1) target audio."""
+    s = shapes
+    g = torch.Generator().manual_seed(seed)
+    midi = torch.rand(s.batch, 1, 1, generator=g) * (pitch_hi - pitch_lo) + pitch_lo
+    t = torch.arange(s.frames).view(1, -1, 1) * (s.block_size / s.sample_rate)
+    vib = 0.5 * torch.sin(2 * torch.pi * 5.0 * t + 2 * torch.pi * torch.rand(s.batch, 1, 1, generator=g))
+    pitch = 440.0 * torch.pow(2.0, (midi + vib - 69.0) / 12.0)
+    return {
+        "amp_raw": torch.randn(s.batch, s.frames, 1, generator=g),
+        "dist_raw": torch.randn(s.batch, s.frames, s.n_harmonic, generator=g),
+        "mag_raw": torch.randn(s.batch, s.frames, s.n_bands, generator=g),
+        "pitch": pitch.float().contiguous(),
+        "noise": torch.rand(s.batch, s.frames, s.block_size, generator=g) * 2 - 1,
+        "target": 0.1 * torch.randn(s.batch, s.samples, generator=g),
+    }

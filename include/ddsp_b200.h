@@ -1,0 +1,182 @@
+/*
+ * ddsp_b200.h -- C ABI of libddsp_b200.so: the DDSP synthesis hot path as hand-written
+ * sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary.  The reference
+ * (hugofloresgarcia/ddsp_pytorch) has no native code on this path: every entry point below
+ * replaces a chain of eager ATen calls in the reference's Python, cited per function as
+ * <file>:<lines> relative to the reference tree.  The TORCH_LIBRARY shim
+ * (ddsp_pytorch_b200/csrc/torch_ops.cpp) is the only in-repo caller; INTEGRATION.md shows the
+ * ctypes / libtorch bindings a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer to contiguous float32
+ *    (or the stated type) on the current CUDA device; nothing here allocates or frees device
+ *    memory or keeps state -- workspaces and constant tables are caller-owned;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - return value: 0 = launched; < 0 = argument error (DDSP_B200_E*); > 0 = cudaError_t of the
+ *    failed launch.  Nothing throws or aborts across this boundary;
+ *  - B = voices, T = frames, bs = block_size (samples per frame), N = T*bs, H = harmonics,
+ *    NB = noise bands, L = reverb taps.
+ */
+#ifndef DDSP_B200_H
+#define DDSP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDSP_B200_OK 0
+#define DDSP_B200_EINVAL (-1)      /* bad size / null pointer */
+#define DDSP_B200_EUNSUPPORTED (-2) /* shape outside what the kernels implement */
+
+int ddsp_b200_abi_version(void);
+const char *ddsp_b200_strerror(int status);
+/* kernels launched through this library since it was loaded (diagnostic counter) */
+uint64_t ddsp_b200_launch_count(void);
+
+/* ---- a1  scale_function: 2*sigmoid(x)^ln10 + 1e-7            (ddsp/core.py:77-78) ---------- */
+int ddsp_b200_scale_function_fwd(const float *x, float *y, int64_t n, void *stream);
+/* dx = dy * dy/dx, recomputed from x */
+int ddsp_b200_scale_function_bwd(const float *x, const float *dy, float *dx, int64_t n, void *stream);
+
+/* ---- a2  remove_above_nyquist                                 (ddsp/core.py:70-74) ---------- */
+/* out[r,k] = amp[r,k] * ((f0[r]*(k+1) < sample_rate/2) + 1e-4f);  rows = B*T.  With `grad` != 0
+ * the same call is the backward (amp := dy, out := dx): the mask does not depend on amp.       */
+int ddsp_b200_remove_above_nyquist(const float *amp, const float *f0, float *out, int64_t rows,
+                                   int H, float sample_rate, void *stream);
+
+/* ---- a3  HarmonicSynth.get_controls, fused          (ddsp/models/modules.py:44-67) ---------- */
+/* amp_raw[rows], dist_raw[rows,H], f0[rows]  ->  amps[rows] = scale(amp_raw),
+ * dist[rows,H] = normalise(scale(dist_raw) * nyquist_mask).                                    */
+int ddsp_b200_harmonic_controls_fwd(const float *amp_raw, const float *dist_raw, const float *f0,
+                                    float *amps, float *dist, int64_t rows, int H,
+                                    float sample_rate, void *stream);
+int ddsp_b200_harmonic_controls_bwd(const float *amp_raw, const float *dist_raw, const float *f0,
+                                    const float *d_amps, const float *d_dist, float *d_amp_raw,
+                                    float *d_dist_raw, int64_t rows, int H, float sample_rate,
+                                    void *stream);
+
+/* ---- a4+a5+a6  HarmonicSynth.forward, fused         (ddsp/models/modules.py:69-80,
+ *                upsample ddsp/core.py:64-67, harmonic_synth ddsp/core.py:136-141) ------------ */
+/* Phase workspace: phi[B*T], delta[B*T] uint64 = phase at the start of each frame and phase
+ * increment per sample, in turns as Q0.64 fixed point.  phase0[B] (may be NULL = 0) and
+ * phase_end[B] (may be NULL) are turns in [0,1) as double: the streaming carry. */
+int ddsp_b200_phase_scan(const float *f0, const double *phase0, uint64_t *phi, uint64_t *delta,
+                         double *phase_end, int B, int T, int block_size, double sample_rate,
+                         void *stream);
+/* weights[B,T,H] = harmonic_distribution * amplitudes;  audio[B, T*bs]. */
+int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_t *phi, const uint64_t *delta,
+                                  float *audio, int B, int T, int H, int block_size, void *stream);
+/* d_weights[B,T,H] = sum over the frame's samples of g * sin(k*phase). */
+int ddsp_b200_harmonic_frames_bwd_weights(const float *g_audio, const uint64_t *phi,
+                                          const uint64_t *delta, float *d_weights, int B, int T,
+                                          int H, int block_size, void *stream);
+/* d_f0[B,T] (only when f0 requires grad).  scratch: float[2*B*T]. */
+int ddsp_b200_harmonic_frames_bwd_f0(const float *g_audio, const float *weights,
+                                     const uint64_t *phi, const uint64_t *delta, float *scratch,
+                                     float *d_f0, int B, int T, int H, int block_size,
+                                     double sample_rate, void *stream);
+
+/* ---- a5  harmonic_synth at audio rate (generic signature)    (ddsp/core.py:136-141) -------- */
+/* f0[B,N], amps[B,N,H] -> audio[B,N];  phase[B*N] uint64 workspace (Q0.64 turns, inclusive). */
+int ddsp_b200_phase_scan_audio_rate(const float *f0, uint64_t *phase, int B, int64_t N,
+                                    double sample_rate, void *stream);
+int ddsp_b200_harmonic_audio_rate_fwd(const float *amps, const uint64_t *phase, float *audio, int B,
+                                      int64_t N, int H, void *stream);
+/* d_amps[B,N,H] and, if d_f0 != NULL, d_f0[B,N] (dphi[B*N] float workspace needed then). */
+int ddsp_b200_harmonic_audio_rate_bwd(const float *g_audio, const float *amps,
+                                      const uint64_t *phase, float *d_amps, float *dphi,
+                                      float *d_f0, int B, int64_t N, int H, double sample_rate,
+                                      void *stream);
+
+/* ---- a7  amp_to_impulse_response                             (ddsp/core.py:144-166) -------- */
+/* amp[rows,NB] -> ir[rows,target]: irfft (size 2(NB-1)), roll, periodic Hann, pad/crop, roll back */
+int ddsp_b200_amp_to_ir_fwd(const float *amp, float *ir, int64_t rows, int NB, int target,
+                            void *stream);
+int ddsp_b200_amp_to_ir_bwd(const float *d_ir, float *d_amp, int64_t rows, int NB, int target,
+                            void *stream);
+
+/* ---- a7+a8+a9  FilteredNoise.forward, fused        (ddsp/models/modules.py:116-128) -------- */
+/* mags[rows,NB], noise[rows,bs] (the uniform(-1,1) draw, an INPUT) -> out[rows*bs]; rows = B*T;
+ * requires bs >= 2(NB-1). */
+int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, float *out, int64_t rows,
+                                 int NB, int block_size, void *stream);
+int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise, float *d_mags,
+                                 int64_t rows, int NB, int block_size, void *stream);
+
+/* ---- FFT tables (caller-owned constant tables) --------------------------------------------- */
+/* table[m] = (cos, -sin)(2*pi*m/n), m in [0,n): n float2 = 2n floats; n a power of two.  One
+ * table of size n serves every transform whose size divides n (read with stride n/size).       */
+int ddsp_b200_twiddle_table(float *table, int n, void *stream);
+
+/* ---- a9 / a10  long FFT convolution = fft_convolve            (ddsp/core.py:169-176),
+ *                used by Reverb.forward                (ddsp/models/modules.py:28-35) ---------- */
+/* The reference pads to 2N and calls rfft/irfft; the result is the causal convolution truncated
+ * to the signal length, so any transform length n >= N + L - 1 is equivalent.  The transform is a
+ * four-step FFT of n = n1*n2 points held as `work[slot][k1][k2]` float2 (frequency k = k1 + n1*k2);
+ * spectra are multiplied in that layout and never transposed.  With `pair` != 0 a slot carries two
+ * real rows (re = row 2p, im = row 2p+1): a real filter acts on both parts independently.
+ * The host side composes (ddsp_pytorch_b200/csrc/torch_ops.cpp: fftconv_fwd / fftconv_bwd):
+ *   y  = cols_inv( rows_filter( cols_fwd(x),  H ) )            H = rows_spectrum(cols_fwd(h))
+ *   dx = cols_inv( rows_filter( cols_fwd(g),  H, conj ) )
+ *   dh = cols_inv( rows_correlate( cols_fwd(g), cols_fwd(x), reduce ) )                         */
+int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2);          /* host only: n1*n2 >= min_len */
+int ddsp_b200_fft4_cols_fwd(const float *x /*[rows,len]*/, int64_t rows, int64_t len, int pair,
+                            float *work, const float *twiddle /*size n1*n2*/, int n1, int n2,
+                            void *stream);
+int ddsp_b200_fft4_cols_inv(const float *work, float *out /*[rows,len]*/, int64_t rows, int64_t len,
+                            int pair, const float *twiddle, int n1, int n2, void *stream);
+int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const float *twiddle, int n1, int n2,
+                                 void *stream);
+/* h_slot_stride in complex elements between the filter spectra of successive slots (0 = shared) */
+int ddsp_b200_fft4_rows_filter(float *work, int64_t slots, const float *hspec, int64_t h_slot_stride,
+                               int conj_h, const float *twiddle, int n1, int n2, void *stream);
+/* out = rows of IFFT( FFT(g) * conj(FFT(x)) ), summed over slots into one slot when reduce != 0 */
+int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots, int reduce,
+                                  float *out, const float *twiddle, int n1, int n2, void *stream);
+
+/* ---- a10  Reverb.build_impulse                       (ddsp/models/modules.py:21-26) -------- */
+/* impulse[l] = noise[l]*exp(-softplus(-decay)*t[l]*500)*sigmoid(wet), impulse[0] = 1; l < L.
+ * decay, wet: device scalars; t: the module's (float32) time buffer.                            */
+int ddsp_b200_reverb_impulse_fwd(const float *noise, const float *decay, const float *wet,
+                                 const float *t, float *impulse, int L, void *stream);
+/* d_noise[L], d_decay[1], d_wet[1] from d_impulse[0..Lvalid) (taps >= Lvalid were cropped). */
+int ddsp_b200_reverb_impulse_bwd(const float *d_impulse, int Lvalid, const float *noise,
+                                 const float *decay, const float *wet, const float *t,
+                                 float *d_noise, float *d_decay, float *d_wet, int L, void *stream);
+
+/* ---- a11  multiscale_fft, one scale                           (ddsp/core.py:27-41) --------- */
+/* signal[B,N] -> mag[B, n_fft/2+1, frames], frames = 1 + N/hop (centred, reflect padded, periodic
+ * Hann, normalised).  window[n_fft] is the float32 torch.hann_window(n_fft) the reference builds on
+ * the CPU; twiddle is a table of size n_tab (a multiple of n_fft).                              */
+int ddsp_b200_stft_mag_fwd(const float *signal, const float *window, const float *twiddle, int n_tab,
+                           float *mag, int B, int64_t N, int n_fft, int hop, void *stream);
+/* d_signal[B,N] (=, or += when accumulate) from d_mag; the gradient of the reflect padding goes to
+ * edge[B, n_fft] and is folded in by ddsp_b200_stft_fold_edges.                                 */
+int ddsp_b200_stft_mag_bwd(const float *signal, const float *d_mag, const float *window,
+                           const float *twiddle, int n_tab, float *d_signal, float *edge, int B,
+                           int64_t N, int n_fft, int hop, int accumulate, void *stream);
+/* edge holds the blocks of `n_scales` scales back to back: [scale][B][n_fft]; scales: HOST array */
+int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int B, int64_t N,
+                              const int *scales, int n_scales, void *stream);
+
+/* ---- a11+a12  multiscale spectral loss, fused                 (train.py:70-76,92-103) ------ */
+/* Per scale: CTA tiles of one voice; partial[] receives 2 floats per CTA (sum |Sx-Sy|, sum
+ * |log(Sx+1e-7)-log(Sy+1e-7)|), ddsp_b200_mss_tiles(N,n_fft,hop)*B CTAs.  If d_rec != NULL the same
+ * launch also produces d(loss)/d(rec) for unit upstream gradient (= or += into d_rec[B,N], reflect
+ * padding part into edge[B,n_fft]).  ddsp_b200_mss_finish reduces the partials of all scales to
+ * loss[0] (layout: scales back to back) and folds the edges.  scales/hops: HOST arrays.         */
+int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop);
+int ddsp_b200_mss_scale(const float *target, const float *rec, const float *window,
+                        const float *twiddle, int n_tab, float *partial, float *d_rec, float *edge,
+                        int B, int64_t N, int n_fft, int hop, int accumulate, void *stream);
+int ddsp_b200_mss_finish(const float *partial, const float *edge, float *d_rec, float *loss, int B,
+                         int64_t N, const int *scales, const int *hops, int n_scales, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDSP_B200_H */

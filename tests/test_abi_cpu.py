@@ -1,0 +1,119 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, rejects bad arguments without touching a GPU, and the torch ops are registered with no
+CPU implementation.  No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import ddsp_pytorch_b200
+    return ddsp_pytorch_b200
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ddsp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ddsp_b200_\w+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(pkg):
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    names = declared_symbols()
+    assert len(names) >= 30
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in include/ddsp_b200.h but not exported: {missing}"
+
+
+def test_exported_symbols_are_declared(pkg):
+    """Nothing undocumented crosses the boundary."""
+    import subprocess
+    from ddsp_pytorch_b200._lib import CORE_PATH
+    out = subprocess.run(["nm", "-D", "--defined-only", CORE_PATH], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\bT (ddsp_b200_\w+)", out)))
+    assert exported == declared_symbols()
+
+
+def test_argument_errors_do_not_need_a_gpu(pkg):
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    lib.ddsp_b200_abi_version.restype = ctypes.c_int
+    assert lib.ddsp_b200_abi_version() == 1
+    fn = lib.ddsp_b200_scale_function_fwd
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    assert fn(None, None, 10, None) == -1
+    lib.ddsp_b200_strerror.restype = ctypes.c_char_p
+    assert b"invalid" in lib.ddsp_b200_strerror(-1)
+    n1, n2 = ctypes.c_int(), ctypes.c_int()
+    plan = lib.ddsp_b200_conv_plan
+    plan.argtypes = [ctypes.c_int64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    assert plan(64000 + 16000 - 1, n1, n2) == 0 and n1.value * n2.value == 1 << 17
+    assert plan(192000 + 48000 - 1, n1, n2) == 0 and n1.value * n2.value == 1 << 18
+    tiles = lib.ddsp_b200_mss_tiles
+    tiles.restype = ctypes.c_int64
+    tiles.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    assert tiles(64000, 4096, 1024) > 0
+    assert tiles(1000, 4096, 1024) == -1          # reflect padding needs n_fft/2 < N, like torch.stft
+
+
+def test_ops_registered_without_cpu_kernels(pkg):
+    ops = torch.ops.ddsp_b200
+    for name in ["harmonic_fwd", "harmonic_bwd", "noise_fwd", "noise_bwd", "fftconv_fwd", "fftconv_bwd",
+                 "stft_mag_fwd", "stft_mag_bwd", "mss_loss_fwd", "harmonic_controls_fwd", "reverb_impulse_fwd"]:
+        assert hasattr(ops, name)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ops.scale_function_fwd(torch.zeros(3))          # no CPU fallback: fails loudly
+
+
+def test_api_surface_matches_reference_names(pkg):
+    """every name ddsp/core.py exports is reachable with the same signature."""
+    import inspect
+    sigs = {
+        "safe_log": ["x"], "mean_std_loudness": ["dataset"], "multiscale_fft": ["signal", "scales", "overlap"],
+        "resample": ["x", "factor"], "upsample": ["signal", "factor"],
+        "remove_above_nyquist": ["amplitudes", "f0", "sample_rate"], "scale_function": ["x"],
+        "extract_loudness": ["signal", "sample_rate", "block_size", "n_fft"],
+        "extract_pitch": ["signal", "sample_rate", "block_size"], "mlp": ["in_size", "hidden_size", "n_layers"],
+        "gru": ["n_input", "hidden_size"], "harmonic_synth": ["f0", "amplitudes", "sample_rate"],
+        "amp_to_impulse_response": ["amp", "target_size"], "fft_convolve": ["signal", "kernel"],
+    }
+    for name, args in sigs.items():
+        assert list(inspect.signature(getattr(pkg, name)).parameters) == args, name
+    from ddsp_pytorch_b200.models.modules import FilteredNoise, HarmonicSynth, Reverb
+    assert list(inspect.signature(Reverb.__init__).parameters)[1:] == ["length", "sample_rate", "initial_wet", "initial_decay"]
+    assert list(inspect.signature(HarmonicSynth.__init__).parameters)[1:] == ["block_size", "sample_rate"]
+    assert list(inspect.signature(FilteredNoise.__init__).parameters)[1:] == ["block_size", "window_size", "initial_bias"]
+
+
+def test_state_dict_keys_match_reference_fixture(pkg):
+    from conftest import load_golden
+    from ddsp_pytorch_b200.models.decoder import DDSPDecoder
+    from ddsp_pytorch_b200.models.encoder import DDSPAutoencoder
+    kw = dict(hidden_size=16, n_harmonic=12, n_bands=65, sample_rate=16000, block_size=160, has_reverb=True)
+    for name, cls in [("model_decoder", DDSPDecoder), ("model_autoencoder", DDSPAutoencoder)]:
+        g = load_golden(name)
+        ref = {k[3:]: v.shape for k, v in g.items() if k.startswith("sd_")}
+        ours = {k: tuple(v.shape) for k, v in cls(**kw).state_dict().items()}
+        assert ours == ref
+
+
+def test_host_side_helpers_on_cpu(pkg):
+    """Functions that are stock torch (no kernel) behave like the reference on CPU tensors."""
+    x = torch.arange(12.0).reshape(1, 4, 3)
+    up = pkg.upsample(x, 5)
+    assert up.shape == (1, 20, 3) and torch.equal(up[0, 7], x[0, 1])
+    assert torch.allclose(pkg.safe_log(torch.ones(2)), torch.log(torch.ones(2) + 1e-7))
+    net = pkg.mlp(1, 8, 3)
+    assert [type(m).__name__ for m in net] == ["Linear", "LayerNorm", "LeakyReLU"] * 3
+    assert pkg.gru(2, 8).input_size == 16
+    m, s = pkg.mean_std_loudness([{"loudness": torch.tensor([1.0, 3.0])}, {"loudness": torch.tensor([2.0, 6.0])}])
+    assert abs(m - 3.0) < 1e-6
+    assert pkg.resample(torch.rand(2, 6, 3), 4).shape == (2, 24, 3)

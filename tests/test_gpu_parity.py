@@ -1,0 +1,409 @@
+"""GPU parity tests: the sm_100a kernels (through the TORCH_LIBRARY shim -> C ABI) against the CPU
+oracle evaluated in float64 and against the golden vectors made from the real reference.
+
+Tolerances (BASELINE.json north_star): audio <= 1e-4 max abs; gradients <= 1e-3 relative, per op
+with a fixed grad_output (never end to end); the MSS-loss gradient is judged against
+the reference float32 path's own deviation recorded in the fixture.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+AUDIO_TOL = 1e-4
+GRAD_REL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ddsp():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import ddsp_pytorch_b200 as pkg
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import ddsp_oracle
+    return ddsp_oracle
+
+
+def dev(a, grad=False):
+    t = torch.as_tensor(np.asarray(a), dtype=torch.float32).cuda()
+    return t.requires_grad_(True) if grad else t
+
+
+def t64(a, grad=False):
+    t = torch.as_tensor(np.asarray(a), dtype=torch.float64)
+    return t.requires_grad_(True) if grad else t
+
+
+def max_abs(got, ref):
+    return float((got.detach().double().cpu() - torch.as_tensor(np.asarray(ref)).double()).abs().max())
+
+
+def rel_err(got, ref):
+    ref = torch.as_tensor(np.asarray(ref)).double()
+    return float((got.detach().double().cpu() - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+def assert_audio(got, ref, tol=AUDIO_TOL):
+    e = max_abs(got, ref)
+    assert e <= tol, f"max abs error {e:.3e} > {tol:.1e}"
+
+
+def assert_grad(got, ref, tol=GRAD_REL):
+    e = rel_err(got, ref)
+    assert e <= tol, f"relative error {e:.3e} > {tol:.1e}"
+
+
+SYNTH = ["synth_c1_small", "synth_c3_buffer", "synth_h100"]
+
+
+# ------------------------------------------------------------------------------- a1, a2, a3
+def test_scale_function(ddsp, orc):
+    x = torch.linspace(-30, 30, 4001, dtype=torch.float64).requires_grad_(True)
+    y = orc.scale_function(x)
+    go = torch.randn(4001, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    (y * go).sum().backward()
+    xd = dev(x.detach(), grad=True)
+    yd = ddsp.scale_function(xd)
+    assert float(((yd.double().cpu() - y.detach()).abs() / y.detach()).max()) < 5e-6
+    (yd * dev(go)).sum().backward()
+    assert_grad(xd.grad, x.grad, 1e-5)
+
+
+def test_remove_above_nyquist_mask_is_float32_exact(ddsp, orc):
+    g = torch.Generator().manual_seed(1)
+    f0 = (torch.rand(3, 50, 1, generator=g) * 700 + 60)
+    f0[0, 0, 0] = 8000.0 / 7          # k*f0 lands next to Nyquist: the float32 product must decide
+    amp = torch.rand(3, 50, 40, generator=g)
+    ref = orc.remove_above_nyquist(amp, f0, 16000)             # float32 reference arithmetic
+    got = ddsp.remove_above_nyquist(amp.cuda(), f0.cuda(), 16000)
+    assert torch.equal(got.cpu(), ref), "mask must match the float32 reference bit for bit"
+    a = amp.cuda().requires_grad_(True)
+    ddsp.remove_above_nyquist(a, f0.cuda(), 16000).sum().backward()
+    assert torch.equal(a.grad.cpu(), orc.remove_above_nyquist(torch.ones_like(amp), f0, 16000))
+
+
+@pytest.mark.parametrize("name", SYNTH)
+def test_harmonic_controls(ddsp, orc, name):
+    g = load_golden(name)
+    sr = int(g["sr"])
+    from ddsp_pytorch_b200.models.modules import HarmonicSynth
+    hs = HarmonicSynth(int(g["bs"]), sr)
+    a, d = dev(g["amp_raw"], True), dev(g["dist_raw"], True)
+    c = hs.get_controls(a, d, dev(g["f0"]))
+    assert max_abs(c["amplitudes"], g["amps"]) < 2e-6
+    assert max_abs(c["harmonic_distribution"], g["dist"]) < 2e-6
+    # per-op gradient with a fixed grad_output, against float64 autograd of the oracle
+    gen = torch.Generator().manual_seed(5)
+    ga = torch.randn(g["amps"].shape, generator=gen, dtype=torch.float64)
+    gd = torch.randn(g["dist"].shape, generator=gen, dtype=torch.float64)
+    a64, d64 = t64(g["amp_raw"], True), t64(g["dist_raw"], True)
+    c64 = orc.harmonic_controls(a64, d64, t64(g["f0"]), sr)
+    ((c64["amplitudes"] * ga).sum() + (c64["harmonic_distribution"] * gd).sum()).backward()
+    ((c["amplitudes"] * dev(ga)).sum() + (c["harmonic_distribution"] * dev(gd)).sum()).backward()
+    assert_grad(a.grad, a64.grad, 1e-4)
+    assert_grad(d.grad, d64.grad, 1e-4)
+
+
+# ------------------------------------------------------------------------------- a4, a5, a6
+@pytest.mark.parametrize("name", SYNTH)
+def test_harmonic_frames_golden(ddsp, name):
+    g = load_golden(name)
+    bs, sr = int(g["bs"]), int(g["sr"])
+    w = dev(g["dist"] * g["amps"], True)
+    f0 = dev(g["f0"], True)
+    audio, _ = ddsp.harmonic_synth_frames(f0, w, bs, sr)
+    assert_audio(audio, g["harm"])
+    # the reference's own float32 path deviates more than we do from float64
+    assert max_abs(audio, g["harm"]) <= max(float(g["dev32_harm"]), 2e-5)
+    (audio * dev(g["g_harm"])).sum().backward()
+    # d weights: golden holds grads w.r.t. the raw controls; compare d_weights against the oracle
+    from oracle import ddsp_oracle as orc
+    w64 = t64(g["dist"] * g["amps"], True)
+    f64 = t64(g["f0"], True)
+    y64 = orc.harmonic_synth(orc.upsample(f64, bs), orc.upsample(w64, bs), sr)
+    (y64 * t64(g["g_harm"])).sum().backward()
+    assert_grad(w.grad, w64.grad)
+    assert_grad(f0.grad, f64.grad)
+    assert_grad(f0.grad, g["d_f0"])
+
+
+def test_harmonic_module_chain_grads(ddsp):
+    """controls -> in-place scaling -> fused synth, gradients w.r.t. the raw decoder outputs."""
+    g = load_golden("synth_c1_small")
+    from ddsp_pytorch_b200.models.modules import HarmonicSynth
+    hs = HarmonicSynth(int(g["bs"]), int(g["sr"]))
+    a, d = dev(g["amp_raw"], True), dev(g["dist_raw"], True)
+    c = hs.get_controls(a, d, dev(g["f0"]))
+    y = hs(**c)
+    assert_audio(y, g["harm"])
+    # after forward the dict holds distribution x amplitude
+    assert max_abs(c["harmonic_distribution"], g["dist"] * g["amps"]) < 2e-6
+    (y * dev(g["g_harm"])).sum().backward()
+    assert_grad(a.grad, g["d_amp_raw"])
+    assert_grad(d.grad, g["d_dist_raw"])
+
+
+def test_harmonic_frames_config1_shapes(ddsp, orc):
+    """B=2 slice of config 1 (16 kHz, block 160, 100 harmonics, 4 s) against the float64 oracle."""
+    gen = torch.Generator().manual_seed(3)
+    B, T, bs, H, sr = 2, 400, 160, 100, 16000
+    f0 = torch.rand(B, T, 1, generator=gen) * 700 + 80
+    w = torch.rand(B, T, H, generator=gen) * (2.0 / H)
+    ref = orc.harmonic_synth(orc.upsample(f0.double(), bs), orc.upsample(w.double(), bs), sr)
+    got, phase_end = ddsp.harmonic_synth_frames(f0.cuda(), w.cuda(), bs, sr)
+    assert_audio(got, ref)
+    ref32 = orc.harmonic_synth(orc.upsample(f0, bs), orc.upsample(w, bs), sr)
+    assert max_abs(got, ref) < max_abs(ref32, ref), "must beat the reference's float32 phase error"
+    turns = (f0.double()[..., 0] / sr).sum(1) * bs
+    d = (phase_end.cpu() - (turns - turns.floor())).abs()
+    assert float(torch.minimum(d, 1 - d).max()) < 1e-9
+
+
+def test_harmonic_frames_config4_shapes_and_reseed(ddsp, orc):
+    """48 kHz, block 512, 256 harmonics (crosses the recurrence re-seed at harmonic 129)."""
+    gen = torch.Generator().manual_seed(4)
+    B, T, bs, H, sr = 1, 24, 512, 256, 48000
+    f0 = torch.rand(B, T, 1, generator=gen) * 120 + 40
+    w = torch.rand(B, T, H, generator=gen) * (2.0 / H)
+    ref = orc.harmonic_synth(orc.upsample(f0.double(), bs), orc.upsample(w.double(), bs), sr)
+    wd = w.cuda().requires_grad_(True)
+    got, _ = ddsp.harmonic_synth_frames(f0.cuda(), wd, bs, sr)
+    assert_audio(got, ref)
+    go = torch.randn(B, T * bs, 1, generator=gen)
+    (got * go.cuda()).sum().backward()
+    w64 = w.double().requires_grad_(True)
+    y = orc.harmonic_synth(orc.upsample(f0.double(), bs), orc.upsample(w64, bs), sr)
+    (y * go.double()).sum().backward()
+    assert_grad(wd.grad, w64.grad)
+
+
+def test_harmonic_frames_odd_block_and_streaming(ddsp, orc):
+    """block sizes that are not multiples of 4 / 2, and phase carry across two calls."""
+    gen = torch.Generator().manual_seed(6)
+    for bs in (6, 50, 37):
+        B, T, H, sr = 2, 9, 7, 8000
+        f0 = torch.rand(B, T, 1, generator=gen) * 300 + 50
+        w = torch.rand(B, T, H, generator=gen)
+        ref = orc.harmonic_synth(orc.upsample(f0.double(), bs), orc.upsample(w.double(), bs), sr)
+        got, _ = ddsp.harmonic_synth_frames(f0.cuda(), w.cuda(), bs, sr)
+        assert_audio(got, ref, 2e-5 * H)
+        a, pe = ddsp.harmonic_synth_frames(f0[:, :4].cuda(), w[:, :4].cuda(), bs, sr)
+        b, _ = ddsp.harmonic_synth_frames(f0[:, 4:].cuda(), w[:, 4:].cuda(), bs, sr, pe)
+        assert_audio(torch.cat([a, b], 1), ref, 2e-5 * H)
+
+
+def test_harmonic_audio_rate_golden(ddsp):
+    g = load_golden("harmonic_audio_rate")
+    f0, amps = dev(g["f0"], True), dev(g["amps"], True)
+    y = ddsp.harmonic_synth(f0, amps, int(g["sr"]))
+    assert y.shape == g["y"].shape
+    assert_audio(y, g["y"])
+    (y * dev(g["go"])).sum().backward()
+    assert_grad(amps.grad, g["d_amps"])
+    assert_grad(f0.grad, g["d_f0"])
+
+
+def test_harmonic_audio_rate_equals_frames(ddsp):
+    gen = torch.Generator().manual_seed(7)
+    B, T, bs, H, sr = 2, 20, 160, 100, 16000
+    f0 = (torch.rand(B, T, 1, generator=gen) * 700 + 80).cuda()
+    w = (torch.rand(B, T, H, generator=gen) / H).cuda()
+    a, _ = ddsp.harmonic_synth_frames(f0, w, bs, sr)
+    b = ddsp.harmonic_synth(ddsp.upsample(f0, bs), ddsp.upsample(w, bs), sr)
+    assert max_abs(a, b.cpu()) < 2e-5
+
+
+# ------------------------------------------------------------------------------- a7, a8, a9
+@pytest.mark.parametrize("name", SYNTH)
+def test_filtered_noise_golden(ddsp, name):
+    g = load_golden(name)
+    from ddsp_pytorch_b200.models.modules import FilteredNoise
+    fn = FilteredNoise(int(g["bs"]), int(g["NB"]))
+    m = dev(g["mag_raw"], True)
+    mags = fn.get_controls(m)["magnitudes"]
+    assert max_abs(mags, g["mags"]) < 1e-6
+    y = fn(mags, noise=dev(g["noise"]))
+    assert y.shape == g["nz"].shape
+    assert_audio(y, g["nz"], 1e-6)
+    (y * dev(g["g_noise"])).sum().backward()
+    assert_grad(m.grad, g["d_mag_raw"])
+
+
+def test_filtered_noise_draw_matches_reference_generator(ddsp, orc):
+    from ddsp_pytorch_b200.models.modules import FilteredNoise
+    fn = FilteredNoise(160, 65)
+    mags = torch.rand(2, 5, 65).cuda()
+    torch.manual_seed(123)
+    y = fn(mags)
+    torch.manual_seed(123)
+    noise = orc.draw_noise(2, 5, 160)
+    ref = orc.filtered_noise(mags.double().cpu(), noise.double(), 160)
+    assert_audio(y, ref, 1e-6)
+
+
+def test_amp_to_impulse_response_golden(ddsp):
+    g = load_golden("impulse_response")
+    for tag in "abcd":
+        amp = dev(g[f"{tag}_amp"], True)
+        ir = ddsp.amp_to_impulse_response(amp, int(g[f"{tag}_ts"]))
+        assert ir.shape == g[f"{tag}_ir"].shape
+        assert_audio(ir, g[f"{tag}_ir"], 1e-6)
+        (ir * dev(g[f"{tag}_go"])).sum().backward()
+        assert_grad(amp.grad, g[f"{tag}_damp"], 1e-4)
+
+
+def test_fft_convolve_golden(ddsp):
+    g = load_golden("fft_convolve")
+    for tag in "abc":
+        s, k = dev(g[f"{tag}_s"], True), dev(g[f"{tag}_k"], True)
+        y = ddsp.fft_convolve(s, k)
+        assert y.shape == g[f"{tag}_y"].shape
+        scale = max(1.0, float(np.abs(g[f"{tag}_y"]).max()))
+        assert_audio(y, g[f"{tag}_y"], 2e-5 * scale)
+        (y * dev(g[f"{tag}_go"])).sum().backward()
+        assert_grad(s.grad, g[f"{tag}_ds"], 1e-4)
+        assert_grad(k.grad, g[f"{tag}_dk"], 1e-4)
+
+
+# ------------------------------------------------------------------------------- a10
+@pytest.mark.parametrize("name", ["reverb_pad", "reverb_crop"])
+def test_reverb_golden(ddsp, name):
+    g = load_golden(name)
+    from ddsp_pytorch_b200.models.modules import Reverb
+    rv = Reverb(int(g["L"]), int(g["sr"]))
+    rv.load_state_dict({"noise": torch.as_tensor(g["noise"]).float(), "decay": torch.as_tensor(g["decay"]).float(),
+                        "wet": torch.as_tensor(g["wet"]).float(), "t": torch.as_tensor(g["t"]).float()})
+    rv.cuda()
+    assert max_abs(rv.build_impulse(), g["impulse"]) < 1e-6
+    x = dev(g["x"], True)
+    y = rv(x)
+    assert y.shape == g["y"].shape
+    assert_audio(y, g["y"], 2e-5 * max(1.0, float(np.abs(g["y"]).max())))
+    (y * dev(g["go"])).sum().backward()
+    assert_grad(x.grad, g["d_x"], 1e-4)
+    assert_grad(rv.noise.grad, g["d_noise"], 1e-4)
+    assert abs(float(rv.decay.grad) - float(g["d_decay"])) <= 1e-3 * abs(float(g["d_decay"])) + 1e-6
+    assert abs(float(rv.wet.grad) - float(g["d_wet"])) <= 1e-3 * abs(float(g["d_wet"])) + 1e-6
+
+
+def test_reverb_config1_shapes(ddsp, orc):
+    """L = sr = 16000 taps over 4 s, B = 3 (odd: exercises the unpaired voice)."""
+    torch.manual_seed(0)
+    from ddsp_pytorch_b200.models.modules import Reverb
+    rv = Reverb(16000, 16000, initial_wet=1.0, initial_decay=3.0)
+    x = torch.randn(3, 64000, 1) * 0.1
+    ref = orc.reverb(x.double(), rv.noise.detach().double(), rv.decay.detach().double(),
+                     rv.wet.detach().double(), rv.t.double())
+    y = rv.cuda()(x.cuda())
+    assert_audio(y, ref, 1e-4)
+
+
+# ------------------------------------------------------------------------------- a11, a12
+@pytest.mark.parametrize("name", ["mss_full_scales", "mss_small"])
+def test_multiscale_fft_golden(ddsp, name):
+    g = load_golden(name)
+    scales, ov = [int(s) for s in g["scales"]], float(g["overlap"])
+    rec = dev(g["rec"], True)
+    mags = ddsp.multiscale_fft(rec, scales, ov)
+    for s, m in zip(scales, mags):
+        assert m.shape == g[f"mag_rec_{s}"].shape
+        assert_audio(m, g[f"mag_rec_{s}"], 2e-6)
+        (gr,) = torch.autograd.grad((m * dev(g[f"go_{s}"])).sum(), rec, retain_graph=True)
+        assert_grad(gr, g[f"d_rec_{s}"], 1e-4)
+
+
+@pytest.mark.parametrize("name", ["mss_full_scales", "mss_small"])
+def test_mss_loss_fused_golden(ddsp, name):
+    g = load_golden(name)
+    scales, ov = [int(s) for s in g["scales"]], float(g["overlap"])
+    rec = dev(g["rec"], True)
+    loss = ddsp.multiscale_spectral_loss(dev(g["tgt"]), rec, scales, ov)
+    assert abs(float(loss) - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+    loss.backward()
+    # L1 sign ties: the reference's own float32 gradient is this far from float64
+    bound = max(GRAD_REL, 1.5 * float(g["dev32_d_rec_rel"]))
+    assert_grad(rec.grad, g["d_rec"], bound)
+    # list API + train.py's loss give the same number
+    mt = ddsp.multiscale_fft(dev(g["tgt"]), scales, ov)
+    mr = ddsp.multiscale_fft(rec.detach(), scales, ov)
+    l2 = sum((a - b).abs().mean() + (ddsp.safe_log(a) - ddsp.safe_log(b)).abs().mean() for a, b in zip(mt, mr))
+    assert abs(float(l2) - float(g["loss"])) <= 2e-6 * abs(float(g["loss"]))
+
+
+def test_mss_loss_config_shapes_and_determinism(ddsp, orc):
+    gen = torch.Generator().manual_seed(11)
+    B, N = 2, 64000
+    scales, ov = [4096, 2048, 1024, 512, 256, 128], 0.75
+    tgt = 0.1 * torch.randn(B, N, generator=gen)
+    rec = 0.1 * torch.randn(B, N, generator=gen)
+    r64 = rec.double().requires_grad_(True)
+    ref = orc.mss_loss(tgt.double(), r64, scales, ov)
+    ref.backward()
+    r = rec.cuda().requires_grad_(True)
+    loss = ddsp.multiscale_spectral_loss(tgt.cuda(), r, scales, ov)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 5e-6 * abs(float(ref))
+    r32 = rec.clone().requires_grad_(True)
+    orc.mss_loss(tgt, r32, scales, ov).backward()
+    ref32_dev = float((r32.grad.double() - r64.grad).norm() / r64.grad.norm())
+    assert_grad(r.grad, r64.grad, max(GRAD_REL, 1.5 * ref32_dev))
+    r2 = rec.cuda().requires_grad_(True)
+    loss2 = ddsp.multiscale_spectral_loss(tgt.cuda(), r2, scales, ov)
+    loss2.backward()
+    assert torch.equal(loss, loss2) and torch.equal(r.grad, r2.grad), "no atomics: bit-reproducible"
+
+
+# ------------------------------------------------------------------------------- a14 models
+@pytest.mark.parametrize("name,cls", [("model_decoder", "DDSPDecoder"), ("model_autoencoder", "DDSPAutoencoder")])
+def test_model_forward_matches_reference(ddsp, name, cls):
+    g = load_golden(name)
+    from ddsp_pytorch_b200.models import decoder, encoder
+    ctor = getattr(decoder, cls, None) or getattr(encoder, cls)
+    model = ctor(hidden_size=16, n_harmonic=12, n_bands=65, sample_rate=16000, block_size=160, has_reverb=True)
+    sd = {k[3:]: torch.as_tensor(v) for k, v in g.items() if k.startswith("sd_")}
+    assert set(sd) == set(model.state_dict()), "state_dict keys must equal the reference's"
+    model.load_state_dict(sd)
+    model.cuda()
+    batch = {k[3:]: torch.as_tensor(v).cuda() for k, v in g.items() if k.startswith("in_")}
+    torch.manual_seed(int(g["noise_seed"]))
+    out = model(batch)
+    for key in ["signal", "noise", "harmonic_audio"]:
+        assert out[key].shape == g["out_" + key].shape
+        assert_audio(out[key], g["out_" + key], 1e-4)
+    assert max_abs(out["harmonic_ctrls"]["harmonic_distribution"], g["out_harmonic_distribution"]) < 1e-5
+    assert max_abs(out["noise_ctrls"]["magnitudes"], g["out_magnitudes"]) < 1e-5
+    assert set(out) >= {"f0", "loudness", "signal", "noise", "harmonic_audio", "noise_ctrls", "harmonic_ctrls"}
+    out["signal"].square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for n, p in model.named_parameters()
+               if not n.startswith("decoder.z") or True)
+
+
+# ------------------------------------------------------------------------------- C ABI, direct
+def test_c_abi_direct_call(ddsp):
+    import ctypes
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    x = torch.linspace(-4, 4, 1000).cuda()
+    y = torch.empty_like(x)
+    fn = lib.ddsp_b200_scale_function_fwd
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    st = torch.cuda.current_stream().cuda_stream
+    assert fn(x.data_ptr(), y.data_ptr(), x.numel(), st) == 0
+    torch.cuda.synchronize()
+    ref = 2 * torch.sigmoid(x.double().cpu()) ** math.log(10) + 1e-7
+    assert max_abs(y, ref) < 1e-6
+    assert fn(None, y.data_ptr(), 3, st) == -1, "argument errors are negative status codes"
+
+
+def test_no_cpu_fallback(ddsp):
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        ddsp.scale_function(torch.zeros(4))
