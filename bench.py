@@ -275,9 +275,17 @@ def run_b200(args, rank, world):
     step.run()
     launches = int(lib.ddsp_b200_launch_count() - c0)
     use_graph = not args.no_graph
+    graph_note = "CUDA graph replay"
     if use_graph:
-        step.capture(forward_only=False)
-        step.capture(forward_only=True)
+        try:
+            step.capture(forward_only=False)
+            step.capture(forward_only=True)
+        except Exception as e:                      # stay measurable: fall back to eager launches
+            use_graph = False
+            graph_note = f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+    else:
+        graph_note = "eager"
     run_step = (lambda: step.replay()) if use_graph else step.run
     run_fwd = (lambda: step.replay(True)) if use_graph else step.run_forward
 
@@ -374,7 +382,7 @@ def run_b200(args, rank, world):
                        "samples_per_voice": shapes.samples, "parallelism": f"voices sharded x{world}, NCCL "
                        f"all-reduce of {n_param} reverb-parameter grads" if world > 1 else "single GPU",
                        "l2": "256 MiB memset between timed steps (outside the event pairs)",
-                       "launch": "CUDA graph replay" if use_graph else "eager"},
+                       "launch": graph_note},
             "fwd": {"value": samples_per_step / (fwd_ms * 1e-3), "unit": UNIT, "ms_per_step": fwd_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": 1e3 * float(te) / e2e_steps, "loss": loss_host},

@@ -17,6 +17,7 @@
 // Gradient of the samples in the reflect padding goes to a small per-voice edge buffer and is folded
 // back by ddsp_b200_stft_fold_edges (again a gather).
 #include "fft.cuh"
+#include "regfft.cuh"
 
 namespace {
 
@@ -198,6 +199,194 @@ mss_scale_kernel(const float *__restrict__ target, const float *__restrict__ rec
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused loss, register-tiled FFT version (n_fft = 64 .. 4096; regfft.cuh).  Same tiling and maths as
+// mss_scale_kernel above; what changes is the transform: T = n_fft/16 threads per frame, 16 values
+// per thread in registers, 2 or 3 shared-memory round trips per transform instead of log4(n_fft).
+// A batch is NF = 2G frame slots (G = transforms the CTA runs at once): two forward rounds, then ONE
+// round of G inverse transforms, each carrying the gradient spectra of slots p (re) and p+G (im).
+// ---------------------------------------------------------------------------------------------
+template <int LG>
+struct RegCfg {
+    using P = regfft::Plan<LG>;
+    static constexpr int G = (kStftThreads / P::T) > 32 ? 32 : (kStftThreads / P::T);
+    static constexpr int NF = 2 * G;
+};
+
+// one full transform pass over the CTA's two slot groups (forward) or one (inverse) is written out
+// phase by phase in the kernel; this helper only hides the 2- vs 3-stage difference.
+template <int LG, bool INV>
+__device__ __forceinline__ void reg_stages_after0(float2 (&xa)[16], float2 (&xb)[16], float2 *bufa,
+                                                  float2 *bufb, bool act_a, bool act_b, int t,
+                                                  const float2 *__restrict__ tw, int tws) {
+    using namespace regfft;
+    __syncthreads();
+    if (act_a) stage_load<LG, 1>(xa, bufa, t);
+    if (act_b) stage_load<LG, 1>(xb, bufb, t);
+    __syncthreads();
+    if (act_a) stage_compute_store<LG, 1, INV>(xa, bufa, t, tw, tws);
+    if (act_b) stage_compute_store<LG, 1, INV>(xb, bufb, t, tw, tws);
+    if (Plan<LG>::STAGES == 3) {
+        __syncthreads();
+        if (act_a) stage_load<LG, 2>(xa, bufa, t);
+        if (act_b) stage_load<LG, 2>(xb, bufb, t);
+        __syncthreads();
+        if (act_a) stage_compute_store<LG, 2, INV>(xa, bufa, t, tw, tws);
+        if (act_b) stage_compute_store<LG, 2, INV>(xb, bufb, t, tw, tws);
+    }
+    __syncthreads();
+}
+
+template <int LG, bool GRAD>
+__global__ void __launch_bounds__(kStftThreads, 2)
+mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__ rec,
+                     const float *__restrict__ window, const float2 *__restrict__ tw, int tws,
+                     float *__restrict__ partial, float *__restrict__ d_rec, float *__restrict__ edge,
+                     TileGeom g, int accumulate, float inv_cnt) {
+    using namespace regfft;
+    using P = Plan<LG>;
+    using C = RegCfg<LG>;
+    constexpr int N = P::N, T = P::T, G = C::G, NF = C::NF, PITCH = P::PITCH;
+    constexpr int HS = N / 2, BINS = HS + 1;
+    extern __shared__ __align__(16) float smem[];
+    float2 *buf = reinterpret_cast<float2 *>(smem);                       // [NF][PITCH]
+    float *ola = reinterpret_cast<float *>(buf + (size_t)NF * PITCH);     // [FT*hop]
+    __shared__ float red[2][kStftThreads / 32];
+
+    const int tid = threadIdx.x;
+    const int grp = tid / T, t = tid - grp * T;
+    const bool act = grp < G;
+    const int b = blockIdx.y;
+    const int f0 = blockIdx.x * g.FT;
+    const int64_t P0 = (int64_t)f0 * g.hop;
+    const int owned = g.FT * g.hop;
+    const int fs = GRAD ? max(0, f0 - g.ov) : min(f0, g.frames);
+    const int fe = min(f0 + g.FT, g.frames);
+    const float *xr = rec + (size_t)b * g.N;
+    const float *xt = target + (size_t)b * g.N;
+    const float rs = rsqrtf((float)N);
+    const int Ni = (int)g.N;
+
+    if (GRAD)
+        for (int i = tid; i < owned; i += kStftThreads) ola[i] = 0.f;
+    float lin = 0.f, lgs = 0.f;
+
+    for (int fb = fs; fb < fe; fb += NF) {
+        __syncthreads();                       // previous batch fully consumed
+        float2 xa[16], xb[16];
+        float2 *bufa = buf + (size_t)grp * PITCH, *bufb = buf + (size_t)(grp + G) * PITCH;
+        // ---- forward: slot grp (round 0) and slot grp+G (round 1); stage 0 straight from global
+        if (act) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int f = fb + grp + e * G;
+                float2 (&x)[16] = e ? xb : xa;
+                if (f < fe) {
+                    const int base = f * g.hop - HS + t;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        int m = base + r * T;
+                        m = m < 0 ? -m : m;
+                        m = m >= Ni ? 2 * (Ni - 1) - m : m;
+                        const float w = __ldg(window + t + r * T);
+                        x[r] = make_float2(__ldg(xr + m) * w, __ldg(xt + m) * w);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) x[r] = make_float2(0.f, 0.f);
+                }
+                stage_compute_store<LG, 0, false>(x, e ? bufb : bufa, t, tw, tws);
+            }
+        }
+        reg_stages_after0<LG, false>(xa, xb, bufa, bufb, act, act, t, tw, tws);
+
+        // ---- per bin: magnitudes, loss, gradient spectra of the pair (slot p, slot p+G)
+        for (int idx = tid; idx < G * BINS; idx += kStftThreads) {
+            const int p = idx / BINS, k = idx - p * BINS;
+            const int km = (N - k) & (N - 1);
+            float2 u[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int f = fb + p + e * G;
+                u[e] = make_float2(0.f, 0.f);
+                if (f < fe) {
+                    const float2 *Z = buf + (size_t)(p + e * G) * PITCH;
+                    const float2 zk = Z[pad16(k)], zm = Z[pad16(km)];
+                    const float2 Y = untangle_re(zk, zm);     // rec spectrum
+                    const float2 X = untangle_im(zk, zm);     // target spectrum
+                    const float ay = sqrtf(fmaf(Y.x, Y.x, Y.y * Y.y));
+                    const float ax = sqrtf(fmaf(X.x, X.x, X.y * X.y));
+                    const float sy = ay * rs, sx = ax * rs;
+                    const float d = sy - sx;
+                    if (f >= f0) {                              // loss counted by the owning tile only
+                        lin += fabsf(d);
+                        lgs += fabsf(__logf((sy + 1e-7f) / (sx + 1e-7f)));
+                    }
+                    if (GRAD && ay > 0.f) {
+                        // log is monotonic: sign(log(sy+eps) - log(sx+eps)) == sign(sy - sx)
+                        const float sg = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+                        const float c = (sg + sg / (sy + 1e-7f)) * inv_cnt * rs / ay;
+                        u[e] = make_float2(c * Y.x, c * Y.y);
+                    }
+                }
+            }
+            if (GRAD) {
+                float2 *dst = buf + (size_t)p * PITCH;
+                if (k == 0 || k == HS) {
+                    dst[pad16(k)] = make_float2(u[0].x, u[1].x);
+                } else {
+                    dst[pad16(k)] = make_float2(0.5f * (u[0].x - u[1].y), 0.5f * (u[0].y + u[1].x));
+                    dst[pad16(km)] = make_float2(0.5f * (u[0].x + u[1].y), 0.5f * (-u[0].y + u[1].x));
+                }
+            }
+        }
+        if (GRAD) {
+            // ---- inverse: one transform per pair, in place in slot p
+            __syncthreads();
+            if (act) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) xa[r] = bufa[pad16(t + r * T)];
+            }
+            __syncthreads();
+            if (act) stage_compute_store<LG, 0, true>(xa, bufa, t, tw, tws);
+            reg_stages_after0<LG, true>(xa, xb, bufa, bufb, act, false, t, tw, tws);
+            // ---- ordered gather overlap-add of this batch's frames into the owned positions
+            const int last = min(fb + NF, fe) - 1;
+            const int lo = max(0, (int)((int64_t)fb * g.hop - P0));
+            const int hi = min(owned, (int)((int64_t)last * g.hop + N - P0));
+            for (int i = lo + tid; i < hi; i += kStftThreads) {
+                const int pos = (int)(P0 + i);                  // padded position
+                int flo = pos - N + 1 <= 0 ? 0 : (pos - N + g.hop) / g.hop;
+                int fhi = pos / g.hop;
+                flo = max(flo, fb);
+                fhi = min(fhi, last);
+                float acc = ola[i];
+                for (int f = flo; f <= fhi; ++f) {
+                    const int q = f - fb;
+                    const int n = pos - f * g.hop;
+                    const float2 v = buf[(size_t)(q >= G ? q - G : q) * PITCH + pad16(n)];
+                    acc = fmaf(__ldg(window + n), q >= G ? v.y : v.x, acc);
+                }
+                ola[i] = acc;
+            }
+        }
+    }
+    __syncthreads();
+    if (GRAD) store_owned(ola, d_rec + (size_t)b * g.N, edge + (size_t)b * g.s, g, P0, accumulate, tid);
+
+    lin = ddsp_warp_sum(lin);
+    lgs = ddsp_warp_sum(lgs);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = lin; red[1][tid >> 5] = lgs; }
+    __syncthreads();
+    if (tid == 0) {
+        float a = 0.f, c = 0.f;
+        for (int i = 0; i < kStftThreads / 32; ++i) { a += red[0][i]; c += red[1][i]; }
+        float *pp = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+        pp[0] = a;
+        pp[1] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // |STFT| forward (API path of multiscale_fft): two frames of the signal per complex FFT.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kStftThreads)
@@ -371,6 +560,38 @@ struct HostGeom {
     size_t smem_loss, smem_mag_fwd, smem_mag_bwd;
 };
 
+bool reg_path(int n_fft) { return n_fft >= 64 && n_fft <= 4096; }
+
+// geometry of the register-FFT loss kernel: NF = 2G frame slots per batch, tiles of TF = FT + ov frames
+int make_geom_reg(int64_t N, int n_fft, int hop, HostGeom *out) {
+    if (n_fft & (n_fft - 1)) return DDSP_B200_EUNSUPPORTED;
+    if (hop < 1 || hop > n_fft) return DDSP_B200_EUNSUPPORTED;
+    if (N <= n_fft / 2 || N >= (1ll << 30)) return DDSP_B200_EUNSUPPORTED;
+    TileGeom g;
+    g.s = n_fft; g.lg = ddsp_ilog2(n_fft); g.hop = hop; g.N = N;
+    g.frames = 1 + (int)(N / hop);
+    g.ov = (n_fft + hop - 1) / hop - 1;
+    const int T = n_fft / 16;
+    int G = kStftThreads / T;
+    if (G > 32) G = 32;
+    const int nf = 2 * G;
+    g.NF = nf;
+    const size_t pitch = ((size_t)n_fft + (n_fft >> 4) + 1) & ~(size_t)1;
+    int tf = nf * ((16 + nf - 1) / nf);
+    while (tf - g.ov < 1) tf += nf;
+    auto total = [&](int tf_) {
+        return (size_t)nf * pitch * sizeof(float2) + (size_t)(tf_ - g.ov) * hop * sizeof(float);
+    };
+    while (total(tf) > 113 * 1024 && tf - nf - g.ov >= 1) tf -= nf;     // two CTAs per SM when possible
+    if (total(tf) > 220 * 1024) return DDSP_B200_EUNSUPPORTED;
+    g.FT = tf - g.ov;
+    out->g = g;
+    out->smem_loss = total(tf);
+    out->smem_mag_fwd = out->smem_mag_bwd = 0;
+    out->tiles = (int)ddsp_ceil_div(N + n_fft, (int64_t)g.FT * hop);
+    return DDSP_B200_OK;
+}
+
 int make_geom(int64_t N, int n_fft, int hop, bool with_overlap, HostGeom *out) {
     if (n_fft < 8 || (n_fft & (n_fft - 1)) || n_fft > 8192) return DDSP_B200_EUNSUPPORTED;
     if (hop < 1 || hop > n_fft) return DDSP_B200_EUNSUPPORTED;
@@ -415,11 +636,33 @@ int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
+int loss_geom(int64_t N, int n_fft, int hop, HostGeom *hg) {
+    return reg_path(n_fft) ? make_geom_reg(N, n_fft, hop, hg) : make_geom(N, n_fft, hop, true, hg);
+}
+
+template <int LG>
+int launch_reg(const float *target, const float *rec, const float *window, const float2 *tw, int tws,
+               float *partial, float *d_rec, float *edge, const HostGeom &hg, int B, int accumulate,
+               float inv_cnt, cudaStream_t st) {
+    dim3 grid(hg.tiles, B);
+    int s;
+    if (d_rec) {
+        if ((s = set_smem(mss_scale_reg_kernel<LG, true>, hg.smem_loss))) return s;
+        mss_scale_reg_kernel<LG, true><<<grid, kStftThreads, hg.smem_loss, st>>>(
+            target, rec, window, tw, tws, partial, d_rec, edge, hg.g, accumulate, inv_cnt);
+    } else {
+        if ((s = set_smem(mss_scale_reg_kernel<LG, false>, hg.smem_loss))) return s;
+        mss_scale_reg_kernel<LG, false><<<grid, kStftThreads, hg.smem_loss, st>>>(
+            target, rec, window, tw, tws, partial, nullptr, nullptr, hg.g, accumulate, inv_cnt);
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop) {
     HostGeom hg;
-    if (make_geom(N, n_fft, hop, true, &hg)) return -1;
+    if (loss_geom(N, n_fft, hop, &hg)) return -1;
     return hg.tiles;
 }
 
@@ -431,12 +674,27 @@ extern "C" int ddsp_b200_mss_scale(const float *target, const float *rec, const 
     DDSP_REQUIRE(!d_rec || edge);
     DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
     HostGeom hg;
-    int s = make_geom(N, n_fft, hop, true, &hg);
+    int s = loss_geom(N, n_fft, hop, &hg);
     if (s) return s;
     const float inv_cnt = 1.0f / ((float)B * (float)(n_fft / 2 + 1) * (float)hg.g.frames);
     dim3 grid(hg.tiles, B);
     const float2 *tw = reinterpret_cast<const float2 *>(twiddle);
     cudaStream_t st = (cudaStream_t)stream;
+    if (reg_path(n_fft)) {
+        const int tws = n_tab / n_fft;
+#define DDSP_REG_CASE(LG)                                                                            \
+    case LG:                                                                                         \
+        s = launch_reg<LG>(target, rec, window, tw, tws, partial, d_rec, edge, hg, B, accumulate,    \
+                           inv_cnt, st);                                                             \
+        break;
+        switch (hg.g.lg) {
+            DDSP_REG_CASE(6) DDSP_REG_CASE(7) DDSP_REG_CASE(8) DDSP_REG_CASE(9) DDSP_REG_CASE(10)
+            DDSP_REG_CASE(11) DDSP_REG_CASE(12)
+            default: return DDSP_B200_EUNSUPPORTED;
+        }
+#undef DDSP_REG_CASE
+        return s ? s : ddsp_launch_status();
+    }
     if (d_rec) {
         if ((s = set_smem(mss_scale_kernel<true>, hg.smem_loss))) return s;
         mss_scale_kernel<true><<<grid, kStftThreads, hg.smem_loss, st>>>(
@@ -460,7 +718,7 @@ extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, flo
     int64_t poff = 0, eoff = 0;
     for (int i = 0; i < n_scales; ++i) {
         HostGeom hg;
-        int s = make_geom(N, scales[i], hops[i], true, &hg);
+        int s = loss_geom(N, scales[i], hops[i], &hg);
         if (s) return s;
         fin.off[i] = poff;
         fin.cnt[i] = (int64_t)hg.tiles * B;

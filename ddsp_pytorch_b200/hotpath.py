@@ -58,11 +58,6 @@ class SynthStep:
             self.reverb = Reverb(s.reverb_length, s.sample_rate).to(dev)
             if reverb_state is not None:
                 self.reverb.load_state_dict(reverb_state)
-        self.leaves = [self.inputs[k] for k in ("amp_raw", "dist_raw", "mag_raw")]
-        for t in self.leaves:
-            t.requires_grad_(True)
-        if self.reverb is not None:
-            self.leaves += [self.reverb.noise, self.reverb.decay, self.reverb.wet]
         self.loss = torch.zeros((), **f32)
         self.signal = None
         self.grads = None
@@ -70,25 +65,43 @@ class SynthStep:
         self._graph_fwd = None
 
     # ---- the path -------------------------------------------------------------------------
-    def forward(self) -> torch.Tensor:
+    def _leaves(self):
+        """Fresh leaf aliases of the differentiable buffers.  New leaves every call keep autograd's
+        per-leaf bookkeeping on the stream of the current call, which CUDA-graph capture requires."""
+        leaves = [self.inputs[k].detach().requires_grad_(True) for k in ("amp_raw", "dist_raw", "mag_raw")]
+        if self.reverb is not None:
+            leaves += [p.detach().requires_grad_(True) for p in
+                       (self.reverb.noise, self.reverb.decay, self.reverb.wet)]
+        return leaves
+
+    def forward(self, leaves=None) -> torch.Tensor:
         """decoder.py:110-125: controls -> harmonic + filtered noise (+ reverb).  (B,N,1)"""
         i, s = self.inputs, self.shapes
-        amps, dist = F_.HarmonicControls.apply(i["amp_raw"], i["dist_raw"], i["pitch"], float(s.sample_rate))
+        if leaves is None:
+            leaves = [i["amp_raw"], i["dist_raw"], i["mag_raw"]]
+            if self.reverb is not None:
+                leaves += [self.reverb.noise, self.reverb.decay, self.reverb.wet]
+        amps, dist = F_.HarmonicControls.apply(leaves[0], leaves[1], i["pitch"], float(s.sample_rate))
         weights = dist * amps
         harmonic, _ = core.harmonic_synth_frames(i["pitch"], weights, s.block_size, s.sample_rate)
-        mags = core.scale_function(i["mag_raw"] + (-5.0))
+        mags = core.scale_function(leaves[2] + (-5.0))
         noise = core.filtered_noise(mags, i["noise"])
         signal = harmonic + noise
         if self.reverb is not None:
-            signal = self.reverb(signal)
+            impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
+            taps = min(s.samples, s.reverb_length)
+            kernel = impulse.reshape(1, s.reverb_length)[:, :taps]
+            signal = F_.FFTConvolve.apply(signal.squeeze(-1), kernel).unsqueeze(-1)
         return signal
 
     def forward_backward(self):
-        """train.py:89-103,129 on the synth part: loss and gradients of every leaf."""
+        """train.py:89-103,129 on the synth part: loss and gradients of every leaf
+        (amp_raw, dist_raw, mag_raw, reverb.noise, reverb.decay, reverb.wet)."""
         s = self.shapes
-        signal = self.forward()
+        leaves = self._leaves()
+        signal = self.forward(leaves)
         loss = core.multiscale_spectral_loss(self.inputs["target"], signal.squeeze(-1), list(s.scales), s.overlap)
-        grads = torch.autograd.grad(loss, self.leaves)
+        grads = torch.autograd.grad(loss, leaves)
         return signal, loss, grads
 
     # ---- eager / graph execution ---------------------------------------------------------
