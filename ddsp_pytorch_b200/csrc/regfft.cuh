@@ -106,12 +106,22 @@ template <int LG, int S> struct Stage {
     static constexpr int NS = S == 0 ? 1 : (S == 1 ? 16 : 256);
 };
 
+// Per-size twiddle table ("stage table"), built by ddsp_b200_stft_stage_twiddles:
+//   stage 1: (R1-1) x 16  entries  exp(-2 pi i r k / (16 R1)),   [r-1][k]
+//   stage 2: (R2-1) x 256 entries  exp(-2 pi i r k / (256 R2)),  [r-1][k]   (3-stage sizes only)
+// A warp's lanes hold consecutive k, so every table read is one or two wavefronts (the generic
+// exp(-2 pi i m / N) table read with stride r*k*... touched 16 cache lines per read).
+template <int LG> DDSP_HD constexpr int stage_table_offset2() { return (Plan<LG>::R1 - 1) * 16; }
+template <int LG> DDSP_HD constexpr int stage_table_size() {
+    return (Plan<LG>::R1 - 1) * 16 + (Plan<LG>::STAGES == 3 ? (Plan<LG>::R2 - 1) * 256 : 0);
+}
+
 // Stage S of the transform, for thread t (0 <= t < T) of the group working on `buf`.
 // On entry x[m*R + r] = stage input (j_m + r*N/R), j_m = t + m*T, m < 16/R.
 // Applies the stage's twiddles and butterflies and stores to the autosort positions of buf.
-// tw[i*tws] = exp(-2 pi i * i / N).
+// tw = the stage table of this size.
 template <int LG, int S, bool INV>
-DDSP_HD void stage_compute_store(float2 (&x)[16], float2 *buf, int t, const float2 *tw, int tws) {
+DDSP_HD void stage_compute_store(float2 (&x)[16], float2 *buf, int t, const float2 *tw) {
     using P = Plan<LG>;
     constexpr int R = Stage<LG, S>::R;
     constexpr int NS = Stage<LG, S>::NS;
@@ -121,13 +131,14 @@ DDSP_HD void stage_compute_store(float2 (&x)[16], float2 *buf, int t, const floa
         const int j = t + m * P::T;
         const int k = j & (NS - 1);
         if (S > 0) {
-            const int step = k * (P::N / (NS * R)) * tws;
+            // stage table laid out [r-1][k]: lanes (consecutive k) read consecutive entries
+            const float2 *tab = tw + (S == 1 ? 0 : stage_table_offset2<LG>());
 #pragma unroll
             for (int r = 1; r < R; ++r) {
 #ifdef __CUDA_ARCH__
-                float2 w = __ldg(tw + r * step);
+                float2 w = __ldg(tab + (r - 1) * NS + k);
 #else
-                float2 w = tw[r * step];
+                float2 w = tab[(r - 1) * NS + k];
 #endif
                 if (INV) w.y = -w.y;
                 x[m * R + r] = c_mul(x[m * R + r], w);

@@ -217,21 +217,21 @@ struct RegCfg {
 template <int LG, bool INV>
 __device__ __forceinline__ void reg_stages_after0(float2 (&xa)[16], float2 (&xb)[16], float2 *bufa,
                                                   float2 *bufb, bool act_a, bool act_b, int t,
-                                                  const float2 *__restrict__ tw, int tws) {
+                                                  const float2 *__restrict__ tw) {
     using namespace regfft;
     __syncthreads();
     if (act_a) stage_load<LG, 1>(xa, bufa, t);
     if (act_b) stage_load<LG, 1>(xb, bufb, t);
     __syncthreads();
-    if (act_a) stage_compute_store<LG, 1, INV>(xa, bufa, t, tw, tws);
-    if (act_b) stage_compute_store<LG, 1, INV>(xb, bufb, t, tw, tws);
+    if (act_a) stage_compute_store<LG, 1, INV>(xa, bufa, t, tw);
+    if (act_b) stage_compute_store<LG, 1, INV>(xb, bufb, t, tw);
     if (Plan<LG>::STAGES == 3) {
         __syncthreads();
         if (act_a) stage_load<LG, 2>(xa, bufa, t);
         if (act_b) stage_load<LG, 2>(xb, bufb, t);
         __syncthreads();
-        if (act_a) stage_compute_store<LG, 2, INV>(xa, bufa, t, tw, tws);
-        if (act_b) stage_compute_store<LG, 2, INV>(xb, bufb, t, tw, tws);
+        if (act_a) stage_compute_store<LG, 2, INV>(xa, bufa, t, tw);
+        if (act_b) stage_compute_store<LG, 2, INV>(xb, bufb, t, tw);
     }
     __syncthreads();
 }
@@ -239,7 +239,7 @@ __device__ __forceinline__ void reg_stages_after0(float2 (&xa)[16], float2 (&xb)
 template <int LG, bool GRAD>
 __global__ void __launch_bounds__(kStftThreads, 2)
 mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__ rec,
-                     const float *__restrict__ window, const float2 *__restrict__ tw, int tws,
+                     const float *__restrict__ window, const float2 *__restrict__ tw,
                      float *__restrict__ partial, float *__restrict__ d_rec, float *__restrict__ edge,
                      TileGeom g, int accumulate, float inv_cnt) {
     using namespace regfft;
@@ -282,22 +282,30 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
                 float2 (&x)[16] = e ? xb : xa;
                 if (f < fe) {
                     const int base = f * g.hop - HS + t;
+                    if (f * g.hop - HS >= 0 && f * g.hop - HS + N <= Ni) {      // interior frame: no reflection
 #pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        int m = base + r * T;
-                        m = m < 0 ? -m : m;
-                        m = m >= Ni ? 2 * (Ni - 1) - m : m;
-                        const float w = __ldg(window + t + r * T);
-                        x[r] = make_float2(__ldg(xr + m) * w, __ldg(xt + m) * w);
+                        for (int r = 0; r < 16; ++r) {
+                            const float w = __ldg(window + t + r * T);
+                            x[r] = make_float2(__ldg(xr + base + r * T) * w, __ldg(xt + base + r * T) * w);
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            int m = base + r * T;
+                            m = m < 0 ? -m : m;
+                            m = m >= Ni ? 2 * (Ni - 1) - m : m;
+                            const float w = __ldg(window + t + r * T);
+                            x[r] = make_float2(__ldg(xr + m) * w, __ldg(xt + m) * w);
+                        }
                     }
                 } else {
 #pragma unroll
                     for (int r = 0; r < 16; ++r) x[r] = make_float2(0.f, 0.f);
                 }
-                stage_compute_store<LG, 0, false>(x, e ? bufb : bufa, t, tw, tws);
+                stage_compute_store<LG, 0, false>(x, e ? bufb : bufa, t, tw);
             }
         }
-        reg_stages_after0<LG, false>(xa, xb, bufa, bufb, act, act, t, tw, tws);
+        reg_stages_after0<LG, false>(xa, xb, bufa, bufb, act, act, t, tw);
 
         // ---- per bin: magnitudes, loss, gradient spectra of the pair (slot p, slot p+G)
         for (int idx = tid; idx < G * BINS; idx += kStftThreads) {
@@ -307,36 +315,34 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int f = fb + p + e * G;
-                u[e] = make_float2(0.f, 0.f);
-                if (f < fe) {
-                    const float2 *Z = buf + (size_t)(p + e * G) * PITCH;
-                    const float2 zk = Z[pad16(k)], zm = Z[pad16(km)];
-                    const float2 Y = untangle_re(zk, zm);     // rec spectrum
-                    const float2 X = untangle_im(zk, zm);     // target spectrum
-                    const float ay = sqrtf(fmaf(Y.x, Y.x, Y.y * Y.y));
-                    const float ax = sqrtf(fmaf(X.x, X.x, X.y * X.y));
-                    const float sy = ay * rs, sx = ax * rs;
-                    const float d = sy - sx;
-                    if (f >= f0) {                              // loss counted by the owning tile only
-                        lin += fabsf(d);
-                        lgs += fabsf(__logf((sy + 1e-7f) / (sx + 1e-7f)));
-                    }
-                    if (GRAD && ay > 0.f) {
-                        // log is monotonic: sign(log(sy+eps) - log(sx+eps)) == sign(sy - sx)
-                        const float sg = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
-                        const float c = (sg + sg / (sy + 1e-7f)) * inv_cnt * rs / ay;
-                        u[e] = make_float2(c * Y.x, c * Y.y);
-                    }
-                }
+                const float2 *Z = buf + (size_t)(p + e * G) * PITCH;
+                const float2 zk = Z[pad16(k)], zm = Z[pad16(km)];
+                const float2 Y = untangle_re(zk, zm);         // rec spectrum
+                const float2 X = untangle_im(zk, zm);         // target spectrum
+                const float yy = fmaf(Y.x, Y.x, Y.y * Y.y), xx = fmaf(X.x, X.x, X.y * X.y);
+                const float ry = rsqrtf(fmaxf(yy, 1e-37f));   // 1/|Y| (|Y| = 0 -> gradient 0 below)
+                const float sy = sqrtf(yy) * rs, sx = sqrtf(xx) * rs;
+                const float d = sy - sx;
+                const float iy = __fdividef(1.0f, sy + 1e-7f);
+                // loss is counted by the owning tile only, and only for frames that exist
+                const float own = (f >= f0 && f < fe) ? 1.f : 0.f;
+                lin = fmaf(own, fabsf(d), lin);
+                lgs = fmaf(own, fabsf(__logf((sx + 1e-7f) * iy)), lgs);
+                // log is monotonic: sign(log(sy+eps) - log(sx+eps)) == sign(sy - sx)
+                const float sg = (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f);
+                float c = fmaf(sg, iy, sg) * (inv_cnt * rs) * ry;
+                c = (f < fe && yy > 0.f) ? c : 0.f;
+                u[e] = make_float2(c * Y.x, c * Y.y);
             }
             if (GRAD) {
                 float2 *dst = buf + (size_t)p * PITCH;
-                if (k == 0 || k == HS) {
-                    dst[pad16(k)] = make_float2(u[0].x, u[1].x);
-                } else {
-                    dst[pad16(k)] = make_float2(0.5f * (u[0].x - u[1].y), 0.5f * (u[0].y + u[1].x));
+                // Zi[k] = (Ua + i Ub)/2 ; Zi[N-k] = (conj Ua + i conj Ub)/2 ; real-only at k = 0, N/2
+                const bool edge_bin = (k == 0) | (k == HS);
+                const float2 a = edge_bin ? make_float2(u[0].x, u[1].x)
+                                          : make_float2(0.5f * (u[0].x - u[1].y), 0.5f * (u[0].y + u[1].x));
+                dst[pad16(k)] = a;
+                if (!edge_bin)
                     dst[pad16(km)] = make_float2(0.5f * (u[0].x + u[1].y), 0.5f * (-u[0].y + u[1].x));
-                }
             }
         }
         if (GRAD) {
@@ -347,26 +353,47 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
                 for (int r = 0; r < 16; ++r) xa[r] = bufa[pad16(t + r * T)];
             }
             __syncthreads();
-            if (act) stage_compute_store<LG, 0, true>(xa, bufa, t, tw, tws);
-            reg_stages_after0<LG, true>(xa, xb, bufa, bufb, act, false, t, tw, tws);
-            // ---- ordered gather overlap-add of this batch's frames into the owned positions
-            const int last = min(fb + NF, fe) - 1;
-            const int lo = max(0, (int)((int64_t)fb * g.hop - P0));
-            const int hi = min(owned, (int)((int64_t)last * g.hop + N - P0));
-            for (int i = lo + tid; i < hi; i += kStftThreads) {
-                const int pos = (int)(P0 + i);                  // padded position
-                int flo = pos - N + 1 <= 0 ? 0 : (pos - N + g.hop) / g.hop;
-                int fhi = pos / g.hop;
-                flo = max(flo, fb);
-                fhi = min(fhi, last);
-                float acc = ola[i];
-                for (int f = flo; f <= fhi; ++f) {
-                    const int q = f - fb;
-                    const int n = pos - f * g.hop;
-                    const float2 v = buf[(size_t)(q >= G ? q - G : q) * PITCH + pad16(n)];
-                    acc = fmaf(__ldg(window + n), q >= G ? v.y : v.x, acc);
+            if (act) stage_compute_store<LG, 0, true>(xa, bufa, t, tw);
+            reg_stages_after0<LG, true>(xa, xb, bufa, bufb, act, false, t, tw);
+            // ---- ordered overlap-add.  Frames f and f + (ov+1) never overlap, so the batch is added in
+            // ov+1 phases (one residue class of frames per phase, all its frames in parallel); every owned
+            // position receives its <= ov+1 contributions in class order: deterministic, no atomics.
+            const int ncls = g.ov + 1;
+            const bool vec4 = (g.hop & 3) == 0;            // then every frame start is 16-byte aligned in ola
+            for (int c = 0; c < ncls; ++c) {
+                // frames fb + c, fb + c + ncls, ... of this batch
+                const int nfr = (NF - c + ncls - 1) / ncls;
+                if (vec4) {
+                    for (int idx = tid; idx < nfr * (N / 4); idx += kStftThreads) {
+                        const int q = c + (idx >> (LG - 2)) * ncls, n = (idx & (N / 4 - 1)) * 4;
+                        const int f = fb + q;
+                        const int i = f * g.hop + n - (int)P0;
+                        if (f < fe && i >= 0 && i < owned) {       // owned % 4 == 0: all four or none
+                            const float2 *src = buf + (size_t)(q >= G ? q - G : q) * PITCH + pad16(n);
+                            // (the padded index may be odd: 8-byte loads only)
+                            const float2 v0 = src[0], v1 = src[1], v2 = src[2], v3 = src[3];
+                            const float4 w = __ldg(reinterpret_cast<const float4 *>(window + n));
+                            float4 o = *reinterpret_cast<float4 *>(ola + i);
+                            const bool im = q >= G;
+                            o.x = fmaf(w.x, im ? v0.y : v0.x, o.x);
+                            o.y = fmaf(w.y, im ? v1.y : v1.x, o.y);
+                            o.z = fmaf(w.z, im ? v2.y : v2.x, o.z);
+                            o.w = fmaf(w.w, im ? v3.y : v3.x, o.w);
+                            *reinterpret_cast<float4 *>(ola + i) = o;
+                        }
+                    }
+                } else {
+                    for (int idx = tid; idx < nfr * N; idx += kStftThreads) {
+                        const int q = c + (idx >> LG) * ncls, n = idx & (N - 1);
+                        const int f = fb + q;
+                        const int i = f * g.hop + n - (int)P0;
+                        if (f < fe && i >= 0 && i < owned) {
+                            const float2 v = buf[(size_t)(q >= G ? q - G : q) * PITCH + pad16(n)];
+                            ola[i] = fmaf(__ldg(window + n), q >= G ? v.y : v.x, ola[i]);
+                        }
+                    }
                 }
-                ola[i] = acc;
+                __syncthreads();
             }
         }
     }
@@ -562,6 +589,20 @@ struct HostGeom {
 
 bool reg_path(int n_fft) { return n_fft >= 64 && n_fft <= 4096; }
 
+// regfft.cuh stage table: stage 1 [r-1][k] (k < 16), then stage 2 [r-1][k] (k < 256)
+__global__ void stage_twiddle_kernel(float2 *__restrict__ tab, int n_fft, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r1 = n_fft <= 256 ? n_fft / 16 : 16, r2 = n_fft <= 256 ? 1 : n_fft / 256;
+    const int n1 = (r1 - 1) * 16;
+    int r, k, denom;
+    if (i < n1) { r = i / 16 + 1; k = i % 16; denom = 16 * r1; }
+    else { r = (i - n1) / 256 + 1; k = (i - n1) % 256; denom = 256 * r2; }
+    double sn, cs;
+    sincospi(2.0 * (double)((long long)r * k % denom) / (double)denom, &sn, &cs);
+    tab[i] = make_float2((float)cs, (float)(-sn));
+}
+
 // geometry of the register-FFT loss kernel: NF = 2G frame slots per batch, tiles of TF = FT + ov frames
 int make_geom_reg(int64_t N, int n_fft, int hop, HostGeom *out) {
     if (n_fft & (n_fft - 1)) return DDSP_B200_EUNSUPPORTED;
@@ -577,12 +618,14 @@ int make_geom_reg(int64_t N, int n_fft, int hop, HostGeom *out) {
     const int nf = 2 * G;
     g.NF = nf;
     const size_t pitch = ((size_t)n_fft + (n_fft >> 4) + 1) & ~(size_t)1;
-    int tf = nf * ((16 + nf - 1) / nf);
-    while (tf - g.ov < 1) tf += nf;
     auto total = [&](int tf_) {
         return (size_t)nf * pitch * sizeof(float2) + (size_t)(tf_ - g.ov) * hop * sizeof(float);
     };
-    while (total(tf) > 113 * 1024 && tf - nf - g.ov >= 1) tf -= nf;     // two CTAs per SM when possible
+    // frames per tile (a whole number of batches): as many as keep two CTAs per SM (<= 113 KB each),
+    // up to 64 (228 KB per SM, 1 KB reserved per CTA, a few static bytes) -- the ov frames a tile recomputes are then a small fraction
+    int tf = nf;
+    while (tf - g.ov < 1) tf += nf;
+    while (tf + nf <= 64 && total(tf + nf) <= 110 * 1024) tf += nf;
     if (total(tf) > 220 * 1024) return DDSP_B200_EUNSUPPORTED;
     g.FT = tf - g.ov;
     out->g = g;
@@ -641,7 +684,7 @@ int loss_geom(int64_t N, int n_fft, int hop, HostGeom *hg) {
 }
 
 template <int LG>
-int launch_reg(const float *target, const float *rec, const float *window, const float2 *tw, int tws,
+int launch_reg(const float *target, const float *rec, const float *window, const float2 *tw,
                float *partial, float *d_rec, float *edge, const HostGeom &hg, int B, int accumulate,
                float inv_cnt, cudaStream_t st) {
     dim3 grid(hg.tiles, B);
@@ -649,16 +692,30 @@ int launch_reg(const float *target, const float *rec, const float *window, const
     if (d_rec) {
         if ((s = set_smem(mss_scale_reg_kernel<LG, true>, hg.smem_loss))) return s;
         mss_scale_reg_kernel<LG, true><<<grid, kStftThreads, hg.smem_loss, st>>>(
-            target, rec, window, tw, tws, partial, d_rec, edge, hg.g, accumulate, inv_cnt);
+            target, rec, window, tw, partial, d_rec, edge, hg.g, accumulate, inv_cnt);
     } else {
         if ((s = set_smem(mss_scale_reg_kernel<LG, false>, hg.smem_loss))) return s;
         mss_scale_reg_kernel<LG, false><<<grid, kStftThreads, hg.smem_loss, st>>>(
-            target, rec, window, tw, tws, partial, nullptr, nullptr, hg.g, accumulate, inv_cnt);
+            target, rec, window, tw, partial, nullptr, nullptr, hg.g, accumulate, inv_cnt);
     }
     return 0;
 }
 
 }  // namespace
+
+extern "C" int64_t ddsp_b200_stft_stage_twiddles_size(int n_fft) {
+    if (!reg_path(n_fft) || (n_fft & (n_fft - 1))) return 0;
+    const int r1 = n_fft <= 256 ? n_fft / 16 : 16, r2 = n_fft <= 256 ? 1 : n_fft / 256;
+    return (int64_t)(r1 - 1) * 16 + (n_fft > 256 ? (int64_t)(r2 - 1) * 256 : 0);
+}
+
+extern "C" int ddsp_b200_stft_stage_twiddles(float *table, int n_fft, void *stream) {
+    DDSP_REQUIRE(table && reg_path(n_fft) && (n_fft & (n_fft - 1)) == 0);
+    const int total = (int)ddsp_b200_stft_stage_twiddles_size(n_fft);
+    stage_twiddle_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float2 *>(table), n_fft, total);
+    return ddsp_launch_status();
+}
 
 extern "C" int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop) {
     HostGeom hg;
@@ -667,9 +724,9 @@ extern "C" int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop) {
 }
 
 extern "C" int ddsp_b200_mss_scale(const float *target, const float *rec, const float *window,
-                                   const float *twiddle, int n_tab, float *partial, float *d_rec,
-                                   float *edge, int B, int64_t N, int n_fft, int hop, int accumulate,
-                                   void *stream) {
+                                   const float *twiddle, int n_tab, const float *stage_twiddle,
+                                   float *partial, float *d_rec, float *edge, int B, int64_t N,
+                                   int n_fft, int hop, int accumulate, void *stream) {
     DDSP_REQUIRE(target && rec && window && twiddle && partial && B > 0 && B <= 65535);
     DDSP_REQUIRE(!d_rec || edge);
     DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
@@ -681,10 +738,11 @@ extern "C" int ddsp_b200_mss_scale(const float *target, const float *rec, const 
     const float2 *tw = reinterpret_cast<const float2 *>(twiddle);
     cudaStream_t st = (cudaStream_t)stream;
     if (reg_path(n_fft)) {
-        const int tws = n_tab / n_fft;
+        if (!stage_twiddle) return DDSP_B200_EINVAL;
+        const float2 *stw = reinterpret_cast<const float2 *>(stage_twiddle);
 #define DDSP_REG_CASE(LG)                                                                            \
     case LG:                                                                                         \
-        s = launch_reg<LG>(target, rec, window, tw, tws, partial, d_rec, edge, hg, B, accumulate,    \
+        s = launch_reg<LG>(target, rec, window, stw, partial, d_rec, edge, hg, B, accumulate,        \
                            inv_cnt, st);                                                             \
         break;
         switch (hg.g.lg) {

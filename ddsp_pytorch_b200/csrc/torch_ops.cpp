@@ -53,6 +53,23 @@ Tensor twiddle_table(const at::Device &dev, int64_t n) {
     return t;
 }
 
+Tensor stage_twiddle_table(const at::Device &dev, int64_t n_fft) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int64_t>, Tensor> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair((int)dev.index(), n_fft);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const int64_t n = ddsp_b200_stft_stage_twiddles_size((int)n_fft);
+    Tensor t;
+    if (n > 0) {
+        t = at::empty({n, 2}, at::TensorOptions().device(dev).dtype(at::kFloat));
+        check(ddsp_b200_stft_stage_twiddles(fpm(t), (int)n_fft, cur_stream()), "stft_stage_twiddles");
+    }
+    cache[key] = t;
+    return t;
+}
+
 // ---------------------------------------------------------------------------------------- a1-a3
 Tensor scale_function_fwd(const Tensor &x_) {
     Tensor x = prep(x_, "x");
@@ -443,8 +460,9 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
     void *st = cur_stream();
     int64_t woff = 0, poff = 0, eoff = 0;
     for (int i = 0; i < ns; ++i) {
+        Tensor stw = stage_twiddle_table(rec.device(), sc[i]);
         check(ddsp_b200_mss_scale(fp(tgt), fp(rec), fp(win) + woff, fp(tw), (int)tw.size(0),
-                                  fpm(partial) + 2 * poff, need_grad ? fpm(d_rec) : nullptr,
+                                  stw.defined() ? fp(stw) : nullptr, fpm(partial) + 2 * poff, need_grad ? fpm(d_rec) : nullptr,
                                   need_grad ? fpm(edge) + eoff : nullptr, (int)B, N, sc[i], hp[i], i > 0, st),
               "mss_scale");
         woff += sc[i];

@@ -170,9 +170,14 @@ int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int B, int64_t
  * padding part into edge[B,n_fft]).  ddsp_b200_mss_finish reduces the partials of all scales to
  * loss[0] (layout: scales back to back) and folds the edges.  scales/hops: HOST arrays.         */
 int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop);
+/* per-size constant table of the register-tiled FFT (64 <= n_fft <= 4096): `size` float2 entries */
+int64_t ddsp_b200_stft_stage_twiddles_size(int n_fft);
+int ddsp_b200_stft_stage_twiddles(float *table, int n_fft, void *stream);
+/* stage_twiddle: the table above for n_fft (may be NULL outside 64..4096, where `twiddle` is used) */
 int ddsp_b200_mss_scale(const float *target, const float *rec, const float *window,
-                        const float *twiddle, int n_tab, float *partial, float *d_rec, float *edge,
-                        int B, int64_t N, int n_fft, int hop, int accumulate, void *stream);
+                        const float *twiddle, int n_tab, const float *stage_twiddle, float *partial,
+                        float *d_rec, float *edge, int B, int64_t N, int n_fft, int hop, int accumulate,
+                        void *stream);
 int ddsp_b200_mss_finish(const float *partial, const float *edge, float *d_rec, float *loss, int B,
                          int64_t N, const int *scales, const int *hops, int n_scales, void *stream);
 

@@ -14,10 +14,19 @@ template <int LG, bool INV>
 double check() {
     using P = Plan<LG>;
     const int N = P::N, T = P::T;
-    const int NT = 4096, tws = NT / N;
-    std::vector<float2> tw(NT);
-    for (int m = 0; m < NT; ++m)
-        tw[m] = make_float2((float)cos(2 * M_PI * m / NT), (float)(-sin(2 * M_PI * m / NT)));
+    // stage table as ddsp_b200_stft_stage_twiddles builds it
+    std::vector<float2> tw(stage_table_size<LG>() + 1);
+    for (int r = 1; r < P::R1; ++r)
+        for (int k = 0; k < 16; ++k) {
+            const double a = -2 * M_PI * r * k / (16.0 * P::R1);
+            tw[(r - 1) * 16 + k] = make_float2((float)cos(a), (float)sin(a));
+        }
+    if (P::STAGES == 3)
+        for (int r = 1; r < P::R2; ++r)
+            for (int k = 0; k < 256; ++k) {
+                const double a = -2 * M_PI * r * k / (256.0 * P::R2);
+                tw[stage_table_offset2<LG>() + (r - 1) * 256 + k] = make_float2((float)cos(a), (float)sin(a));
+            }
     std::vector<float2> in(N), buf(P::PITCH);
     srand(LG * 2 + INV);
     for (auto &v : in) v = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
@@ -25,12 +34,12 @@ double check() {
     std::vector<Regs> x(T);
     for (int t = 0; t < T; ++t)
         for (int r = 0; r < 16; ++r) x[t].v[r] = in[t + r * T];
-    for (int t = 0; t < T; ++t) stage_compute_store<LG, 0, INV>(x[t].v, buf.data(), t, tw.data(), tws);
+    for (int t = 0; t < T; ++t) stage_compute_store<LG, 0, INV>(x[t].v, buf.data(), t, tw.data());
     for (int t = 0; t < T; ++t) stage_load<LG, 1>(x[t].v, buf.data(), t);
-    for (int t = 0; t < T; ++t) stage_compute_store<LG, 1, INV>(x[t].v, buf.data(), t, tw.data(), tws);
+    for (int t = 0; t < T; ++t) stage_compute_store<LG, 1, INV>(x[t].v, buf.data(), t, tw.data());
     if (P::STAGES == 3) {
         for (int t = 0; t < T; ++t) stage_load<LG, 2>(x[t].v, buf.data(), t);
-        for (int t = 0; t < T; ++t) stage_compute_store<LG, 2, INV>(x[t].v, buf.data(), t, tw.data(), tws);
+        for (int t = 0; t < T; ++t) stage_compute_store<LG, 2, INV>(x[t].v, buf.data(), t, tw.data());
     }
     double worst = 0, scale = 0;
     for (int k = 0; k < N; ++k) {
