@@ -19,12 +19,16 @@
 #include <atomic>
 
 #include "fft.cuh"
+#include "regfft.cuh"
 
 namespace {
 
-constexpr int kCW = 8;            // adjacent columns per CTA in the column passes (64 B runs)
-constexpr int kColThreads = 256;
-constexpr int kRowThreads = 128;
+using namespace regfft;
+
+// Columns per CTA in the column passes: 16 adjacent columns = 64 B runs of the real inputs and
+// 128 B runs of the complex work buffer; a column transform uses n1/16 threads, so a CTA has n1 threads.
+constexpr int kCols = 16;
+constexpr int kRowThreads = 256;      // row passes: 256/(n2/16) rows per CTA
 
 __global__ void twiddle_kernel(float2 *__restrict__ tab, int n) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,151 +38,251 @@ __global__ void twiddle_kernel(float2 *__restrict__ tab, int n) {
     tab[m] = make_float2((float)c, (float)(-s));
 }
 
-__device__ __forceinline__ int col_pitch(int n1) { return fpad_size(n1) + 1; }   // odd: columns land on distinct banks
+// The inter-step twiddle W_n^(a*b) for one fixed a (a column index or a row index) and b = 0..len-1 is
+// served from two small shared tables: W^(a*b) = hi[b >> 4] * lo[b & 15],  hi[j] = W^(16 a j), lo[j] = W^(a j)
+// (one extra rounding instead of a scattered read of the n-entry table per element).
+struct StepTwiddle {
+    const float2 *hi, *lo;
+    __device__ __forceinline__ float2 at(int b, bool conj) const {
+        const float2 h = hi[b >> 4], l = lo[b & 15];
+        float2 w = make_float2(h.x * l.x - h.y * l.y, h.x * l.y + h.y * l.x);
+        if (conj) w.y = -w.y;
+        return w;
+    }
+};
 
-// A: x rows -> work[slot][k1][i2]
-__global__ void __launch_bounds__(kColThreads)
-cols_fwd_kernel(const float *__restrict__ x, int64_t rows, int64_t len, int pair,
-                float2 *__restrict__ work, const float2 *__restrict__ tw, int n1, int lg1, int n2) {
+// fill hi[0..len/16), lo[0..16) for fixed a; a*b < n for all b < len (a < other factor)
+__device__ __forceinline__ void fill_step_twiddle(float2 *hi, float2 *lo, const float2 *__restrict__ twn,
+                                                  int a, int len, int t, int nthr) {
+    for (int j = t; j < len / 16; j += nthr) hi[j] = __ldg(twn + (size_t)a * 16 * j);
+    for (int j = t; j < 16; j += nthr) lo[j] = __ldg(twn + (size_t)a * j);
+}
+
+template <int LG, bool INV>
+__device__ __forceinline__ void mid_stages(float2 (&x)[16], float2 *buf, int t, const float2 *__restrict__ stw,
+                                           bool act) {
+    // stages 1 .. last-1 (i.e. stage 1 of a 3-stage transform), each: sync, load, sync, compute+store
+    if (Plan<LG>::STAGES == 3) {
+        __syncthreads();
+        if (act) stage_load<LG, 1>(x, buf, t);
+        __syncthreads();
+        if (act) stage_compute_store<LG, 1, INV>(x, buf, t, stw);
+    }
+    __syncthreads();
+    if (act) stage_load<LG, Plan<LG>::STAGES - 1>(x, buf, t);
+    __syncthreads();
+}
+
+// ---- A: real rows -> column FFT over i1 -> * W_n^(i2 k1) -> work[slot][k1][i2] -------------------
+template <int LG1>
+__global__ void __launch_bounds__((1 << LG1))
+cols_fwd_kernel(const float *__restrict__ x, int64_t rows, int64_t len, int pair, float2 *__restrict__ work,
+                const float2 *__restrict__ twn, const float2 *__restrict__ stw, int n2) {
+    using P = Plan<LG1>;
+    constexpr int n1 = P::N, T = P::T, PITCH = P::PITCH + 1;     // odd pitch: the 16 columns hit 16 banks
     extern __shared__ __align__(16) float smem[];
-    const int pitch = col_pitch(n1);
-    float2 *bufA = reinterpret_cast<float2 *>(smem);
-    float2 *bufB = bufA + kCW * pitch;
-    const int tid = threadIdx.x;
+    float2 *bufs = reinterpret_cast<float2 *>(smem);              // [kCols][PITCH]
+    float2 *thi = bufs + kCols * PITCH;                           // [kCols][n1/16]
+    float2 *tlo = thi + kCols * (n1 / 16);                        // [kCols][16]
+    const int tid = threadIdx.x, c = tid & (kCols - 1), t = tid >> 4;
     const int64_t p = blockIdx.y;
-    const int c0 = blockIdx.x * kCW;
+    const int col = blockIdx.x * kCols + c;
     const int64_t rre = pair ? 2 * p : p, rim = pair ? 2 * p + 1 : rows;
     const float *xr = x + rre * len;
     const float *xi = rim < rows ? x + rim * len : nullptr;
-    for (int idx = tid; idx < kCW * n1; idx += kColThreads) {
-        const int i1 = idx / kCW, c = idx - i1 * kCW;
-        const int64_t pos = (int64_t)i1 * n2 + c0 + c;
-        float2 v = make_float2(0.f, 0.f);
+    fill_step_twiddle(thi + c * (n1 / 16), tlo + c * 16, twn, col, n1, t, T);
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int64_t pos = (int64_t)(t + r * T) * n2 + col;
+        v[r] = make_float2(0.f, 0.f);
         if (pos < len) {
-            v.x = __ldg(xr + pos);
-            if (xi) v.y = __ldg(xi + pos);
+            v[r].x = __ldg(xr + pos);
+            if (xi) v[r].y = __ldg(xi + pos);
         }
-        bufA[c * pitch + fpad(i1)] = v;
     }
-    __syncthreads();
-    const float2 *Z = cta_fft<false>(bufA, bufB, pitch, kCW, n1, lg1, tw, n2, tid, kColThreads);
-    float2 *w = work + (size_t)p * n1 * n2;
-    for (int idx = tid; idx < kCW * n1; idx += kColThreads) {
-        const int k1 = idx / kCW, c = idx - k1 * kCW;
-        const float2 t = __ldg(tw + (size_t)(c0 + c) * k1);
-        w[(size_t)k1 * n2 + c0 + c] = cmul(Z[c * pitch + fpad(k1)], t);
-    }
+    float2 *buf = bufs + c * PITCH;
+    stage_compute_store<LG1, 0, false>(v, buf, t, stw);
+    mid_stages<LG1, false>(v, buf, t, stw, true);
+    const StepTwiddle st{thi + c * (n1 / 16), tlo + c * 16};
+    float2 *w = work + (size_t)p * n1 * n2 + col;
+    stage_compute_sink<LG1, P::STAGES - 1, false>(v, t, stw, [&](int k1, float2 val) {
+        w[(size_t)k1 * n2] = c_mul(val, st.at(k1, false));
+    });
 }
 
-// C: work[slot][k1][i2] -> real rows (first len samples), scaled by 1/n
-__global__ void __launch_bounds__(kColThreads)
-cols_inv_kernel(const float2 *__restrict__ work, float *__restrict__ out, int64_t rows, int64_t len,
-                int pair, const float2 *__restrict__ tw, int n1, int lg1, int n2) {
+// ---- C: work[slot][k1][i2] -> inverse column FFT over k1 -> real rows, scaled 1/n ------------------
+template <int LG1>
+__global__ void __launch_bounds__((1 << LG1))
+cols_inv_kernel(const float2 *__restrict__ work, float *__restrict__ out, int64_t rows, int64_t len, int pair,
+                const float2 *__restrict__ stw, int n2) {
+    using P = Plan<LG1>;
+    constexpr int n1 = P::N, T = P::T, PITCH = P::PITCH + 1;
     extern __shared__ __align__(16) float smem[];
-    const int pitch = col_pitch(n1);
-    float2 *bufA = reinterpret_cast<float2 *>(smem);
-    float2 *bufB = bufA + kCW * pitch;
-    const int tid = threadIdx.x;
+    float2 *bufs = reinterpret_cast<float2 *>(smem);
+    const int tid = threadIdx.x, c = tid & (kCols - 1), t = tid >> 4;
     const int64_t p = blockIdx.y;
-    const int c0 = blockIdx.x * kCW;
-    const float2 *w = work + (size_t)p * n1 * n2;
-    for (int idx = tid; idx < kCW * n1; idx += kColThreads) {
-        const int k1 = idx / kCW, c = idx - k1 * kCW;
-        bufA[c * pitch + fpad(k1)] = w[(size_t)k1 * n2 + c0 + c];
-    }
-    __syncthreads();
-    const float2 *Y = cta_fft<true>(bufA, bufB, pitch, kCW, n1, lg1, tw, n2, tid, kColThreads);
+    const int col = blockIdx.x * kCols + c;
+    const float2 *w = work + (size_t)p * n1 * n2 + col;
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = w[(size_t)(t + r * T) * n2];
+    float2 *buf = bufs + c * PITCH;
+    stage_compute_store<LG1, 0, true>(v, buf, t, stw);
+    mid_stages<LG1, true>(v, buf, t, stw, true);
     const float sc = 1.0f / ((float)n1 * (float)n2);
     const int64_t rre = pair ? 2 * p : p, rim = pair ? 2 * p + 1 : rows;
     float *yr = out + rre * len;
     float *yi = rim < rows ? out + rim * len : nullptr;
-    for (int idx = tid; idx < kCW * n1; idx += kColThreads) {
-        const int i1 = idx / kCW, c = idx - i1 * kCW;
-        const int64_t pos = (int64_t)i1 * n2 + c0 + c;
+    stage_compute_sink<LG1, P::STAGES - 1, true>(v, t, stw, [&](int i1, float2 val) {
+        const int64_t pos = (int64_t)i1 * n2 + col;
         if (pos < len) {
-            const float2 v = Y[c * pitch + fpad(i1)];
-            yr[pos] = v.x * sc;
-            if (yi) yi[pos] = v.y * sc;
+            yr[pos] = val.x * sc;
+            if (yi) yi[pos] = val.y * sc;
         }
-    }
+    });
 }
 
-// B, three flavours on one row (k1) of one slot:
-//   MODE 0 spectrum : row FFT, write
-//   MODE 1 filter   : row FFT, * H (or conj H), inverse row FFT, * W_n^(-i2 k1), write in place
-template <int MODE>
+// ---- B: row passes.  A CTA works on ROWS = 256/(n2/16) consecutive rows k1 of one slot. ----------------
+template <int LG2> struct RowCfg {
+    using P = Plan<LG2>;
+    static constexpr int ROWS = kRowThreads / P::T;
+};
+
+// MODE 0 spectrum: row FFT, write.   MODE 1 filter: row FFT, * H (or conj H), inverse row FFT,
+// * W_n^(-i2 k1), write in place.
+template <int LG2, int MODE>
 __global__ void __launch_bounds__(kRowThreads)
-rows_kernel(float2 *__restrict__ work, const float2 *__restrict__ hspec, int64_t h_slot_stride,
-            int conj_h, const float2 *__restrict__ tw, int n1, int n2, int lg2) {
+rows_kernel(float2 *__restrict__ work, const float2 *__restrict__ hspec, int64_t h_slot_stride, int conj_h,
+            const float2 *__restrict__ twn, const float2 *__restrict__ stw, int n1) {
+    using P = Plan<LG2>;
+    constexpr int n2 = P::N, T = P::T, PITCH = P::PITCH, ROWS = RowCfg<LG2>::ROWS;
     extern __shared__ __align__(16) float smem[];
-    const int pitch = fpad_size(n2);
-    float2 *bufA = reinterpret_cast<float2 *>(smem);
-    float2 *bufB = bufA + pitch;
-    const int tid = threadIdx.x;
-    const int k1 = blockIdx.x;
+    float2 *bufs = reinterpret_cast<float2 *>(smem);              // [ROWS][PITCH]
+    float2 *thi = bufs + ROWS * PITCH;                            // [ROWS][n2/16]
+    float2 *tlo = thi + ROWS * (n2 / 16);                         // [ROWS][16]
+    const int tid = threadIdx.x, g = tid / T, t = tid - g * T;
+    const int k1 = blockIdx.x * ROWS + g;
     const int64_t p = blockIdx.y;
     float2 *row = work + ((size_t)p * n1 + k1) * n2;
-    for (int i = tid; i < n2; i += kRowThreads) bufA[fpad(i)] = row[i];
-    __syncthreads();
-    float2 *S = cta_fft<false>(bufA, bufB, pitch, 1, n2, lg2, tw, n1, tid, kRowThreads);
+    float2 *buf = bufs + g * PITCH;
+    if (MODE == 1) fill_step_twiddle(thi + g * (n2 / 16), tlo + g * 16, twn, k1, n2, t, T);
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = row[t + r * T];
+    stage_compute_store<LG2, 0, false>(v, buf, t, stw);
+    mid_stages<LG2, false>(v, buf, t, stw, true);
     if (MODE == 0) {
-        for (int i = tid; i < n2; i += kRowThreads) row[i] = S[fpad(i)];
+        stage_compute_sink<LG2, P::STAGES - 1, false>(v, t, stw, [&](int k2, float2 val) { row[k2] = val; });
         return;
     }
-    float2 *other = (S == bufA) ? bufB : bufA;
     const float2 *h = hspec + (size_t)p * h_slot_stride + (size_t)k1 * n2;
-    for (int i = tid; i < n2; i += kRowThreads) {
-        const float2 hv = __ldg(h + i);
-        S[fpad(i)] = conj_h ? cmulc(S[fpad(i)], hv) : cmul(S[fpad(i)], hv);
-    }
+    stage_compute_sink<LG2, P::STAGES - 1, false>(v, t, stw, [&](int k2, float2 val) {
+        float2 hv = __ldg(h + k2);
+        if (conj_h) hv.y = -hv.y;
+        buf[pad16(k2)] = c_mul(val, hv);
+    });
     __syncthreads();
-    const float2 *Y = cta_fft<true>(S, other, pitch, 1, n2, lg2, tw, n1, tid, kRowThreads);
-    for (int i = tid; i < n2; i += kRowThreads) {
-        float2 t = __ldg(tw + (size_t)i * k1);
-        t.y = -t.y;
-        row[i] = cmul(Y[fpad(i)], t);
-    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = buf[pad16(t + r * T)];
+    __syncthreads();
+    stage_compute_store<LG2, 0, true>(v, buf, t, stw);
+    mid_stages<LG2, true>(v, buf, t, stw, true);
+    const StepTwiddle st{thi + g * (n2 / 16), tlo + g * 16};
+    stage_compute_sink<LG2, P::STAGES - 1, true>(v, t, stw, [&](int i2, float2 val) {
+        row[i2] = c_mul(val, st.at(i2, true));
+    });
 }
 
-// Correlation rows: out[k1] = IFFT_row( sum_slots FFT_row(G) * conj(FFT_row(X)) ) * W_n^(-i2 k1).
-// reduce != 0: one output slot (sum over all slots); else one output slot per input slot.
+// Correlation, phase 1: partial[split][k1][k2] = sum over the slots of this split of
+// FFT_row(G)[k2] * conj(FFT_row(X)[k2]).  The accumulator lives in registers (same positions as the
+// last stage's outputs).
+template <int LG2>
 __global__ void __launch_bounds__(kRowThreads)
 rows_corr_kernel(const float2 *__restrict__ work_g, const float2 *__restrict__ work_x, int64_t slots,
-                 int reduce, float2 *__restrict__ out, const float2 *__restrict__ tw, int n1, int n2,
-                 int lg2) {
+                 int nsplit, float2 *__restrict__ partial, const float2 *__restrict__ stw, int n1) {
+    using P = Plan<LG2>;
+    constexpr int n2 = P::N, T = P::T, PITCH = P::PITCH, ROWS = RowCfg<LG2>::ROWS;
+    constexpr int R = Stage<LG2, P::STAGES - 1>::R, M = 16 / R;
     extern __shared__ __align__(16) float smem[];
-    const int pitch = fpad_size(n2);
-    float2 *bufA = reinterpret_cast<float2 *>(smem);          // [2][pitch]
-    float2 *bufB = bufA + 2 * pitch;                          // [2][pitch]
-    float2 *acc = bufB + 2 * pitch;                           // [pitch]
-    float2 *scr = acc + pitch;                                // [pitch]
-    const int tid = threadIdx.x;
-    const int k1 = blockIdx.x;
-    const int64_t p0 = reduce ? 0 : blockIdx.y, p1 = reduce ? slots : p0 + 1;
-    for (int i = tid; i < n2; i += kRowThreads) acc[fpad(i)] = make_float2(0.f, 0.f);
-    for (int64_t p = p0; p < p1; ++p) {
+    float2 *bufs = reinterpret_cast<float2 *>(smem);              // [ROWS][PITCH]
+    const int tid = threadIdx.x, g = tid / T, t = tid - g * T;
+    const int k1 = blockIdx.x * ROWS + g;
+    const int split = blockIdx.y;
+    float2 *buf = bufs + g * PITCH;
+    float2 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
+    float2 v[16];
+    for (int64_t p = split; p < slots; p += nsplit) {
         const float2 *rg = work_g + ((size_t)p * n1 + k1) * n2;
         const float2 *rx = work_x + ((size_t)p * n1 + k1) * n2;
+        // spectrum of the G row into shared memory
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = rg[t + r * T];
+        __syncthreads();                                  // previous slot's spectrum fully consumed
+        stage_compute_store<LG2, 0, false>(v, buf, t, stw);
+        mid_stages<LG2, false>(v, buf, t, stw, true);
+        stage_compute_store<LG2, P::STAGES - 1, false>(v, buf, t, stw);
         __syncthreads();
-        for (int i = tid; i < n2; i += kRowThreads) {
-            bufA[fpad(i)] = rg[i];
-            bufA[pitch + fpad(i)] = rx[i];
-        }
+        // this thread's part of the G spectrum (the positions its last stage produces), to registers
+        float2 gs[16];
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                gs[m * R + r] = buf[pad16(stage_out_index<LG2, P::STAGES - 1>(t, m, r))];
+        // spectrum of the X row, consumed straight from the last stage's registers
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = rx[t + r * T];
         __syncthreads();
-        const float2 *S = cta_fft<false>(bufA, bufB, pitch, 2, n2, lg2, tw, n1, tid, kRowThreads);
-        for (int i = tid; i < n2; i += kRowThreads) {          // same thread owns acc[i] throughout
-            const float2 v = cmulc(S[fpad(i)], S[pitch + fpad(i)]);
-            acc[fpad(i)] = cadd(acc[fpad(i)], v);
+        stage_compute_store<LG2, 0, false>(v, buf, t, stw);
+        mid_stages<LG2, false>(v, buf, t, stw, true);
+        stage_compute_regs<LG2, P::STAGES - 1, false>(v, t, stw);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                       // g * conj(x)
+            acc[i].x += gs[i].x * v[i].x + gs[i].y * v[i].y;
+            acc[i].y += gs[i].y * v[i].x - gs[i].x * v[i].y;
         }
     }
-    __syncthreads();
-    const float2 *Y = cta_fft<true>(acc, scr, pitch, 1, n2, lg2, tw, n1, tid, kRowThreads);
-    float2 *row = out + ((size_t)(reduce ? 0 : p0) * n1 + k1) * n2;
-    for (int i = tid; i < n2; i += kRowThreads) {
-        float2 t = __ldg(tw + (size_t)i * k1);
-        t.y = -t.y;
-        row[i] = cmul(Y[fpad(i)], t);
+    float2 *out = partial + ((size_t)split * n1 + k1) * n2;
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int r = 0; r < R; ++r) out[stage_out_index<LG2, P::STAGES - 1>(t, m, r)] = acc[m * R + r];
+}
+
+// Correlation, phase 2: out[o][k1] = IFFT_row(sum of `nsum` partial spectra) * W_n^(-i2 k1)
+template <int LG2>
+__global__ void __launch_bounds__(kRowThreads)
+rows_corr_finish_kernel(const float2 *__restrict__ partial, int nsum, float2 *__restrict__ out,
+                        const float2 *__restrict__ twn, const float2 *__restrict__ stw, int n1) {
+    using P = Plan<LG2>;
+    constexpr int n2 = P::N, T = P::T, PITCH = P::PITCH, ROWS = RowCfg<LG2>::ROWS;
+    extern __shared__ __align__(16) float smem[];
+    float2 *bufs = reinterpret_cast<float2 *>(smem);
+    float2 *thi = bufs + ROWS * PITCH;
+    float2 *tlo = thi + ROWS * (n2 / 16);
+    const int tid = threadIdx.x, g = tid / T, t = tid - g * T;
+    const int k1 = blockIdx.x * ROWS + g;
+    const int64_t o = blockIdx.y;
+    float2 *buf = bufs + g * PITCH;
+    fill_step_twiddle(thi + g * (n2 / 16), tlo + g * 16, twn, k1, n2, t, T);
+    float2 v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+    for (int s = 0; s < nsum; ++s) {
+        const float2 *src = partial + (((size_t)o * nsum + s) * n1 + k1) * n2;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = c_add(v[r], src[t + r * T]);
     }
+    stage_compute_store<LG2, 0, true>(v, buf, t, stw);
+    mid_stages<LG2, true>(v, buf, t, stw, true);
+    const StepTwiddle st{thi + g * (n2 / 16), tlo + g * 16};
+    float2 *row = out + ((size_t)o * n1 + k1) * n2;
+    stage_compute_sink<LG2, P::STAGES - 1, true>(v, t, stw, [&](int i2, float2 val) {
+        row[i2] = c_mul(val, st.at(i2, true));
+    });
 }
 
 // ---- Reverb impulse (modules.py:21-26) -------------------------------------------------------
@@ -238,12 +342,37 @@ int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
-bool plan_ok(int n1, int n2) {
-    auto p2 = [](int v) { return v > 0 && (v & (v - 1)) == 0; };
-    return p2(n1) && p2(n2) && n1 >= 4 && n1 <= 1024 && n2 >= kCW && n2 <= 4096;
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+// n1 (column transform, one CTA of n1 threads per 16 columns): 64..512; n2 (row transform): 64..4096
+bool plan_ok(int n1, int n2) { return pow2(n1) && pow2(n2) && n1 >= 64 && n1 <= 512 && n2 >= 64 && n2 <= 4096; }
+
+template <int LG> size_t col_smem() {
+    return (size_t)kCols * (Plan<LG>::PITCH + 1 + Plan<LG>::N / 16 + 16) * sizeof(float2);
+}
+template <int LG> size_t row_smem() {
+    return (size_t)RowCfg<LG>::ROWS * (Plan<LG>::PITCH + Plan<LG>::N / 16 + 16) * sizeof(float2);
 }
 
-size_t col_smem(int n1) { return 2 * (size_t)kCW * (fpad_size(n1) + 1) * sizeof(float2); }
+// compile-time dispatch on log2 of a transform size (columns 64..512, rows 64..4096)
+#define DDSP_LG_SWITCH_COLS(lg, CALL) \
+    switch (lg) {                     \
+        case 6: CALL(6); break;       \
+        case 7: CALL(7); break;       \
+        case 8: CALL(8); break;       \
+        case 9: CALL(9); break;       \
+        default: break;               \
+    }
+#define DDSP_LG_SWITCH_ROWS(lg, CALL) \
+    switch (lg) {                     \
+        case 6: CALL(6); break;       \
+        case 7: CALL(7); break;       \
+        case 8: CALL(8); break;       \
+        case 9: CALL(9); break;       \
+        case 10: CALL(10); break;     \
+        case 11: CALL(11); break;     \
+        case 12: CALL(12); break;     \
+        default: break;               \
+    }
 
 }  // namespace
 
@@ -256,79 +385,115 @@ extern "C" int ddsp_b200_twiddle_table(float *table, int n, void *stream) {
 extern "C" int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2) {
     DDSP_REQUIRE(n1 && n2 && min_len >= 1);
     int lg = ddsp_ilog2(min_len);
-    if (lg < 5) lg = 5;
-    const int lg1 = lg / 2, lg2 = lg - lg1;
+    if (lg < 12) lg = 12;
+    int lg1 = lg / 2;
+    if (lg1 > 9) lg1 = 9;
+    const int lg2 = lg - lg1;
+    if (lg2 > 12) return DDSP_B200_EUNSUPPORTED;
     *n1 = 1 << lg1;
     *n2 = 1 << lg2;
     return plan_ok(*n1, *n2) ? DDSP_B200_OK : DDSP_B200_EUNSUPPORTED;
 }
 
 extern "C" int ddsp_b200_fft4_cols_fwd(const float *x, int64_t rows, int64_t len, int pair, float *work,
-                                       const float *twiddle, int n1, int n2, void *stream) {
-    DDSP_REQUIRE(x && work && twiddle && rows > 0 && len > 0 && plan_ok(n1, n2));
+                                       const float *twiddle, const float *stage1, int n1, int n2,
+                                       void *stream) {
+    DDSP_REQUIRE(x && work && twiddle && stage1 && rows > 0 && len > 0 && plan_ok(n1, n2));
     DDSP_REQUIRE(len <= (int64_t)n1 * n2);
     const int64_t slots = pair ? (rows + 1) / 2 : rows;
     DDSP_REQUIRE(slots <= 65535);
-    const size_t smem = col_smem(n1);
-    int s = set_smem(cols_fwd_kernel, smem);
-    if (s) return s;
-    cols_fwd_kernel<<<dim3(n2 / kCW, (unsigned)slots), kColThreads, smem, (cudaStream_t)stream>>>(
-        x, rows, len, pair, reinterpret_cast<float2 *>(work), reinterpret_cast<const float2 *>(twiddle),
-        n1, ddsp_ilog2(n1), n2);
-    return ddsp_launch_status();
+    int s = DDSP_B200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(n2 / kCols, (unsigned)slots);
+#define CALL(LG)                                                                                        \
+    if (!(s = set_smem(cols_fwd_kernel<LG>, col_smem<LG>())))                                           \
+        cols_fwd_kernel<LG><<<grid, 1 << LG, col_smem<LG>(), st>>>(                                      \
+            x, rows, len, pair, reinterpret_cast<float2 *>(work), reinterpret_cast<const float2 *>(twiddle), \
+            reinterpret_cast<const float2 *>(stage1), n2)
+    DDSP_LG_SWITCH_COLS(ddsp_ilog2(n1), CALL)
+#undef CALL
+    return s ? s : ddsp_launch_status();
 }
 
 extern "C" int ddsp_b200_fft4_cols_inv(const float *work, float *out, int64_t rows, int64_t len, int pair,
-                                       const float *twiddle, int n1, int n2, void *stream) {
-    DDSP_REQUIRE(work && out && twiddle && rows > 0 && len > 0 && plan_ok(n1, n2));
+                                       const float *stage1, int n1, int n2, void *stream) {
+    DDSP_REQUIRE(work && out && stage1 && rows > 0 && len > 0 && plan_ok(n1, n2));
     DDSP_REQUIRE(len <= (int64_t)n1 * n2);
     const int64_t slots = pair ? (rows + 1) / 2 : rows;
     DDSP_REQUIRE(slots <= 65535);
-    const size_t smem = col_smem(n1);
-    int s = set_smem(cols_inv_kernel, smem);
-    if (s) return s;
-    cols_inv_kernel<<<dim3(n2 / kCW, (unsigned)slots), kColThreads, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2 *>(work), out, rows, len, pair,
-        reinterpret_cast<const float2 *>(twiddle), n1, ddsp_ilog2(n1), n2);
-    return ddsp_launch_status();
+    int s = DDSP_B200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(n2 / kCols, (unsigned)slots);
+#define CALL(LG)                                                                                        \
+    if (!(s = set_smem(cols_inv_kernel<LG>, col_smem<LG>())))                                           \
+        cols_inv_kernel<LG><<<grid, 1 << LG, col_smem<LG>(), st>>>(                                      \
+            reinterpret_cast<const float2 *>(work), out, rows, len, pair,                               \
+            reinterpret_cast<const float2 *>(stage1), n2)
+    DDSP_LG_SWITCH_COLS(ddsp_ilog2(n1), CALL)
+#undef CALL
+    return s ? s : ddsp_launch_status();
 }
 
-extern "C" int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const float *twiddle, int n1,
-                                            int n2, void *stream) {
-    DDSP_REQUIRE(work && twiddle && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
-    const size_t smem = 2 * (size_t)fpad_size(n2) * sizeof(float2);
-    int s = set_smem(rows_kernel<0>, smem);
-    if (s) return s;
-    rows_kernel<0><<<dim3(n1, (unsigned)slots), kRowThreads, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<float2 *>(work), nullptr, 0, 0, reinterpret_cast<const float2 *>(twiddle), n1, n2,
-        ddsp_ilog2(n2));
-    return ddsp_launch_status();
+extern "C" int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const float *twiddle,
+                                            const float *stage2, int n1, int n2, void *stream) {
+    DDSP_REQUIRE(work && twiddle && stage2 && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
+    int s = DDSP_B200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(LG)                                                                                        \
+    if (!(s = set_smem(rows_kernel<LG, 0>, row_smem<LG>())))                                            \
+        rows_kernel<LG, 0><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
+            reinterpret_cast<float2 *>(work), nullptr, 0, 0, reinterpret_cast<const float2 *>(twiddle),  \
+            reinterpret_cast<const float2 *>(stage2), n1)
+    DDSP_LG_SWITCH_ROWS(ddsp_ilog2(n2), CALL)
+#undef CALL
+    return s ? s : ddsp_launch_status();
 }
 
 extern "C" int ddsp_b200_fft4_rows_filter(float *work, int64_t slots, const float *hspec,
-                                          int64_t h_slot_stride, int conj_h, const float *twiddle, int n1,
-                                          int n2, void *stream) {
-    DDSP_REQUIRE(work && hspec && twiddle && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
-    const size_t smem = 2 * (size_t)fpad_size(n2) * sizeof(float2);
-    int s = set_smem(rows_kernel<1>, smem);
-    if (s) return s;
-    rows_kernel<1><<<dim3(n1, (unsigned)slots), kRowThreads, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<float2 *>(work), reinterpret_cast<const float2 *>(hspec), h_slot_stride, conj_h,
-        reinterpret_cast<const float2 *>(twiddle), n1, n2, ddsp_ilog2(n2));
-    return ddsp_launch_status();
+                                          int64_t h_slot_stride, int conj_h, const float *twiddle,
+                                          const float *stage2, int n1, int n2, void *stream) {
+    DDSP_REQUIRE(work && hspec && twiddle && stage2 && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
+    int s = DDSP_B200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(LG)                                                                                        \
+    if (!(s = set_smem(rows_kernel<LG, 1>, row_smem<LG>())))                                            \
+        rows_kernel<LG, 1><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
+            reinterpret_cast<float2 *>(work), reinterpret_cast<const float2 *>(hspec), h_slot_stride,   \
+            conj_h, reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1)
+    DDSP_LG_SWITCH_ROWS(ddsp_ilog2(n2), CALL)
+#undef CALL
+    return s ? s : ddsp_launch_status();
+}
+
+extern "C" int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce) {
+    if (!reduce) return slots;
+    return slots < 8 ? slots : 8;
 }
 
 extern "C" int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots,
-                                             int reduce, float *out, const float *twiddle, int n1, int n2,
-                                             void *stream) {
-    DDSP_REQUIRE(work_g && work_x && out && twiddle && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
-    const size_t smem = 6 * (size_t)fpad_size(n2) * sizeof(float2);
-    int s = set_smem(rows_corr_kernel, smem);
-    if (s) return s;
-    rows_corr_kernel<<<dim3(n1, reduce ? 1u : (unsigned)slots), kRowThreads, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float2 *>(work_g), reinterpret_cast<const float2 *>(work_x), slots, reduce,
-        reinterpret_cast<float2 *>(out), reinterpret_cast<const float2 *>(twiddle), n1, n2, ddsp_ilog2(n2));
-    return ddsp_launch_status();
+                                             int reduce, float *scratch, float *out, const float *twiddle,
+                                             const float *stage2, int n1, int n2, void *stream) {
+    DDSP_REQUIRE(work_g && work_x && scratch && out && twiddle && stage2 && slots > 0 && slots <= 65535);
+    DDSP_REQUIRE(plan_ok(n1, n2));
+    const int nsplit = (int)ddsp_b200_fft4_correlate_splits(slots, reduce);
+    const int nsum = reduce ? nsplit : 1;
+    const int nout = reduce ? 1 : (int)slots;
+    int s = DDSP_B200_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(LG)                                                                                        \
+    if (!(s = set_smem(rows_corr_kernel<LG>, row_smem<LG>())) &&                                        \
+        !(s = set_smem(rows_corr_finish_kernel<LG>, row_smem<LG>()))) {                                 \
+        rows_corr_kernel<LG><<<dim3(n1 / RowCfg<LG>::ROWS, nsplit), kRowThreads, row_smem<LG>(), st>>>(  \
+            reinterpret_cast<const float2 *>(work_g), reinterpret_cast<const float2 *>(work_x), slots,  \
+            nsplit, reinterpret_cast<float2 *>(scratch), reinterpret_cast<const float2 *>(stage2), n1); \
+        if (!(s = ddsp_launch_status()))                                                                \
+            rows_corr_finish_kernel<LG><<<dim3(n1 / RowCfg<LG>::ROWS, nout), kRowThreads, row_smem<LG>(), st>>>( \
+                reinterpret_cast<const float2 *>(scratch), nsum, reinterpret_cast<float2 *>(out),       \
+                reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1); \
+    }
+    DDSP_LG_SWITCH_ROWS(ddsp_ilog2(n2), CALL)
+#undef CALL
+    return s ? s : ddsp_launch_status();
 }
 
 extern "C" int ddsp_b200_reverb_impulse_fwd(const float *noise, const float *decay, const float *wet,

@@ -120,8 +120,14 @@ template <int LG> DDSP_HD constexpr int stage_table_size() {
 // On entry x[m*R + r] = stage input (j_m + r*N/R), j_m = t + m*T, m < 16/R.
 // Applies the stage's twiddles and butterflies and stores to the autosort positions of buf.
 // tw = the stage table of this size.
+struct SmemStore {           // default sink of a stage: the transform's padded shared buffer
+    float2 *buf;
+    DDSP_HD void operator()(int idx, float2 v) const { buf[pad16(idx)] = v; }
+};
+
+// twiddle + butterflies of stage S, results left in x: x[m*R + r] is output (j_m - k)*R + k + r*NS
 template <int LG, int S, bool INV>
-DDSP_HD void stage_compute_store(float2 (&x)[16], float2 *buf, int t, const float2 *tw) {
+DDSP_HD void stage_compute_regs(float2 (&x)[16], int t, const float2 *tw) {
     using P = Plan<LG>;
     constexpr int R = Stage<LG, S>::R;
     constexpr int NS = Stage<LG, S>::NS;
@@ -145,10 +151,33 @@ DDSP_HD void stage_compute_store(float2 (&x)[16], float2 *buf, int t, const floa
             }
         }
         dft_r<R, INV>(&x[m * R]);
-        const int base = (j - k) * R + k;
-#pragma unroll
-        for (int r = 0; r < R; ++r) buf[pad16(base + r * NS)] = x[m * R + r];
     }
+}
+
+// output index of register slot m*R + r of stage S for thread t
+template <int LG, int S>
+DDSP_HD int stage_out_index(int t, int m, int r) {
+    constexpr int R = Stage<LG, S>::R;
+    constexpr int NS = Stage<LG, S>::NS;
+    const int j = t + m * Plan<LG>::T;
+    const int k = j & (NS - 1);
+    return (j - k) * R + k + r * NS;
+}
+
+template <int LG, int S, bool INV, typename Store>
+DDSP_HD void stage_compute_sink(float2 (&x)[16], int t, const float2 *tw, const Store &store) {
+    constexpr int R = Stage<LG, S>::R;
+    constexpr int M = 16 / R;
+    stage_compute_regs<LG, S, INV>(x, t, tw);
+#pragma unroll
+    for (int m = 0; m < M; ++m)
+#pragma unroll
+        for (int r = 0; r < R; ++r) store(stage_out_index<LG, S>(t, m, r), x[m * R + r]);
+}
+
+template <int LG, int S, bool INV>
+DDSP_HD void stage_compute_store(float2 (&x)[16], float2 *buf, int t, const float2 *tw) {
+    stage_compute_sink<LG, S, INV>(x, t, tw, SmemStore{buf});
 }
 
 // Load the inputs of stage S (S >= 1) from buf into registers.

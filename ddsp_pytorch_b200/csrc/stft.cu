@@ -538,14 +538,19 @@ struct FoldArgs {
 };
 
 __global__ void stft_fold_kernel(const float *__restrict__ edge, float *__restrict__ d_sig, int B,
-                                 int64_t N, FoldArgs fa) {
+                                 int64_t N, FoldArgs fa, int hs_max) {
+    // only samples 1..hs_max and N-1-hs_max..N-2 mirror into the padding; when the two ranges would
+    // overlap (short signals) every sample is visited instead
     const int b = blockIdx.y;
-    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N;
-         m += (int64_t)gridDim.x * blockDim.x) {
+    const bool full = 2 * (int64_t)hs_max + 2 >= N;
+    const int64_t count = full ? N : 2 * (int64_t)hs_max;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = full ? i : (i < hs_max ? 1 + i : N - 1 - hs_max + (i - hs_max));
         float acc = 0.f;
-        for (int i = 0; i < fa.n_scales; ++i) {
-            const int hs = fa.s[i] >> 1;
-            const float *e = edge + fa.off[i] + (size_t)b * fa.s[i];
+        for (int k = 0; k < fa.n_scales; ++k) {
+            const int hs = fa.s[k] >> 1;
+            const float *e = edge + fa.off[k] + (size_t)b * fa.s[k];
             if (m >= 1 && m <= hs) acc += e[hs - m];                         // left pad: i = hs - m
             if (m <= N - 2 && m >= N - 1 - hs) acc += e[hs + (N - 2 - m)];   // right pad
         }
@@ -703,15 +708,15 @@ int launch_reg(const float *target, const float *rec, const float *window, const
 
 }  // namespace
 
-extern "C" int64_t ddsp_b200_stft_stage_twiddles_size(int n_fft) {
+extern "C" int64_t ddsp_b200_fft_stage_twiddles_size(int n_fft) {
     if (!reg_path(n_fft) || (n_fft & (n_fft - 1))) return 0;
     const int r1 = n_fft <= 256 ? n_fft / 16 : 16, r2 = n_fft <= 256 ? 1 : n_fft / 256;
     return (int64_t)(r1 - 1) * 16 + (n_fft > 256 ? (int64_t)(r2 - 1) * 256 : 0);
 }
 
-extern "C" int ddsp_b200_stft_stage_twiddles(float *table, int n_fft, void *stream) {
+extern "C" int ddsp_b200_fft_stage_twiddles(float *table, int n_fft, void *stream) {
     DDSP_REQUIRE(table && reg_path(n_fft) && (n_fft & (n_fft - 1)) == 0);
-    const int total = (int)ddsp_b200_stft_stage_twiddles_size(n_fft);
+    const int total = (int)ddsp_b200_fft_stage_twiddles_size(n_fft);
     stage_twiddle_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float2 *>(table), n_fft, total);
     return ddsp_launch_status();
@@ -790,9 +795,11 @@ extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, flo
     mss_finalize_kernel<<<1, 256, 0, st>>>(partial, loss, fin);
     int s = ddsp_launch_status();
     if (s || !d_rec) return s;
-    int gx = (int)ddsp_ceil_div(N, 256);
+    int hs_max = 0;
+    for (int i = 0; i < n_scales; ++i) hs_max = scales[i] / 2 > hs_max ? scales[i] / 2 : hs_max;
+    int gx = (int)ddsp_ceil_div(2 * (int64_t)hs_max + 2 >= N ? N : 2 * (int64_t)hs_max, 256);
     if (gx > 1024) gx = 1024;
-    stft_fold_kernel<<<dim3(gx, B), 256, 0, st>>>(edge, d_rec, B, N, fold);
+    stft_fold_kernel<<<dim3(gx, B), 256, 0, st>>>(edge, d_rec, B, N, fold, hs_max);
     return ddsp_launch_status();
 }
 
@@ -837,8 +844,10 @@ extern "C" int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int
         fold.off[i] = eoff;
         eoff += (int64_t)B * scales[i];
     }
-    int gx = (int)ddsp_ceil_div(N, 256);
+    int hs_max = 0;
+    for (int i = 0; i < n_scales; ++i) hs_max = scales[i] / 2 > hs_max ? scales[i] / 2 : hs_max;
+    int gx = (int)ddsp_ceil_div(2 * (int64_t)hs_max + 2 >= N ? N : 2 * (int64_t)hs_max, 256);
     if (gx > 1024) gx = 1024;
-    stft_fold_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(edge, d_signal, B, N, fold);
+    stft_fold_kernel<<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(edge, d_signal, B, N, fold, hs_max);
     return ddsp_launch_status();
 }

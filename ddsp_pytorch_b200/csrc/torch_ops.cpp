@@ -60,11 +60,11 @@ Tensor stage_twiddle_table(const at::Device &dev, int64_t n_fft) {
     auto key = std::make_pair((int)dev.index(), n_fft);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    const int64_t n = ddsp_b200_stft_stage_twiddles_size((int)n_fft);
+    const int64_t n = ddsp_b200_fft_stage_twiddles_size((int)n_fft);
     Tensor t;
     if (n > 0) {
         t = at::empty({n, 2}, at::TensorOptions().device(dev).dtype(at::kFloat));
-        check(ddsp_b200_stft_stage_twiddles(fpm(t), (int)n_fft, cur_stream()), "stft_stage_twiddles");
+        check(ddsp_b200_fft_stage_twiddles(fpm(t), (int)n_fft, cur_stream()), "stft_stage_twiddles");
     }
     cache[key] = t;
     return t;
@@ -285,7 +285,7 @@ Tensor noise_bwd(const Tensor &g_, const Tensor &noise_, int64_t NB) {
 struct ConvPlan {
     int n1, n2;
     int64_t n;
-    Tensor tw;
+    Tensor tw, st1, st2;       // W_n table and the stage tables of the two sub-transforms
 };
 
 ConvPlan conv_plan(const at::Device &dev, int64_t min_len) {
@@ -293,6 +293,8 @@ ConvPlan conv_plan(const at::Device &dev, int64_t min_len) {
     check(ddsp_b200_conv_plan(min_len, &p.n1, &p.n2), "conv_plan");
     p.n = (int64_t)p.n1 * p.n2;
     p.tw = twiddle_table(dev, p.n);
+    p.st1 = stage_twiddle_table(dev, p.n1);
+    p.st2 = stage_twiddle_table(dev, p.n2);
     return p;
 }
 
@@ -312,13 +314,13 @@ Tensor fftconv_fwd(const Tensor &signal_, const Tensor &kernel_) {
     const int64_t slots = pair ? (R + 1) / 2 : R;
     void *st = cur_stream();
     Tensor hspec = at::empty({Rk, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(h)");
-    check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), p.n1, p.n2, st), "fft4_rows_spectrum");
+    check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+    check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
     Tensor work = at::empty({slots, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(x)");
-    check(ddsp_b200_fft4_rows_filter(fpm(work), slots, fp(hspec), pair ? 0 : p.n, 0, fp(p.tw), p.n1, p.n2, st),
+    check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(x)");
+    check(ddsp_b200_fft4_rows_filter(fpm(work), slots, fp(hspec), pair ? 0 : p.n, 0, fp(p.tw), fp(p.st2), p.n1, p.n2, st),
           "fft4_rows_filter");
-    check(ddsp_b200_fft4_cols_inv(fp(work), fpm(out), R, n, pair, fp(p.tw), p.n1, p.n2, st), "fft4_cols_inv");
+    check(ddsp_b200_fft4_cols_inv(fp(work), fpm(out), R, n, pair, fp(p.st1), p.n1, p.n2, st), "fft4_cols_inv");
     return out;
 }
 
@@ -338,27 +340,27 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
     const int64_t slots = pair ? (R + 1) / 2 : R;
     void *st = cur_stream();
     Tensor work_g = at::empty({slots, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(g)");
+    check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(g)");
     if (need_kernel) {
         Tensor work_x = at::empty({slots, p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), p.n1, p.n2, st),
+        check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), fp(p.st1), p.n1, p.n2, st),
               "fft4_cols_fwd(x)");
         Tensor corr = at::empty({Rk, p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_rows_correlate(fp(work_g), fp(work_x), slots, pair, fpm(corr), fp(p.tw), p.n1, p.n2,
-                                            st),
+        Tensor scratch = at::empty({ddsp_b200_fft4_correlate_splits(slots, pair), p.n, 2}, sig.options());
+        check(ddsp_b200_fft4_rows_correlate(fp(work_g), fp(work_x), slots, pair, fpm(scratch), fpm(corr),
+                                            fp(p.tw), fp(p.st2), p.n1, p.n2, st),
               "fft4_rows_correlate");
         Tensor dk = Lc == Lk ? d_ker : at::empty({Rk, Lc}, sig.options());
-        check(ddsp_b200_fft4_cols_inv(fp(corr), fpm(dk), Rk, Lc, 0, fp(p.tw), p.n1, p.n2, st), "fft4_cols_inv(dh)");
+        check(ddsp_b200_fft4_cols_inv(fp(corr), fpm(dk), Rk, Lc, 0, fp(p.st1), p.n1, p.n2, st), "fft4_cols_inv(dh)");
         if (Lc != Lk) d_ker.narrow(1, 0, Lc).copy_(dk);
     }
     if (need_signal) {
         Tensor hspec = at::empty({Rk, p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), p.n1, p.n2, st), "fft4_cols_fwd(h)");
-        check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), p.n1, p.n2, st), "fft4_rows_spectrum");
-        check(ddsp_b200_fft4_rows_filter(fpm(work_g), slots, fp(hspec), pair ? 0 : p.n, 1, fp(p.tw), p.n1, p.n2,
-                                         st),
+        check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+        check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
+        check(ddsp_b200_fft4_rows_filter(fpm(work_g), slots, fp(hspec), pair ? 0 : p.n, 1, fp(p.tw), fp(p.st2), p.n1, p.n2, st),
               "fft4_rows_filter(conj)");
-        check(ddsp_b200_fft4_cols_inv(fp(work_g), fpm(d_sig), R, n, pair, fp(p.tw), p.n1, p.n2, st),
+        check(ddsp_b200_fft4_cols_inv(fp(work_g), fpm(d_sig), R, n, pair, fp(p.st1), p.n1, p.n2, st),
               "fft4_cols_inv(dx)");
     }
     return {d_sig, d_ker};

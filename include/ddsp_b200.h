@@ -111,6 +111,10 @@ int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise, float *
 /* table[m] = (cos, -sin)(2*pi*m/n), m in [0,n): n float2 = 2n floats; n a power of two.  One
  * table of size n serves every transform whose size divides n (read with stride n/size).       */
 int ddsp_b200_twiddle_table(float *table, int n, void *stream);
+/* per-size constant table of the register-tiled FFT (ddsp_pytorch_b200/csrc/regfft.cuh), sizes
+ * 64..4096: `size` float2 entries, laid out per stage as [r-1][k] so a warp reads them coalesced. */
+int64_t ddsp_b200_fft_stage_twiddles_size(int n_fft);
+int ddsp_b200_fft_stage_twiddles(float *table, int n_fft, void *stream);
 
 /* ---- a9 / a10  long FFT convolution = fft_convolve            (ddsp/core.py:169-176),
  *                used by Reverb.forward                (ddsp/models/modules.py:28-35) ---------- */
@@ -124,19 +128,25 @@ int ddsp_b200_twiddle_table(float *table, int n, void *stream);
  *   dx = cols_inv( rows_filter( cols_fwd(g),  H, conj ) )
  *   dh = cols_inv( rows_correlate( cols_fwd(g), cols_fwd(x), reduce ) )                         */
 int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2);          /* host only: n1*n2 >= min_len */
+/* twiddle: ddsp_b200_twiddle_table of size n1*n2; stage1 / stage2: ddsp_b200_fft_stage_twiddles of
+ * size n1 / n2 (constant tables of the register-tiled sub-transforms).                            */
 int ddsp_b200_fft4_cols_fwd(const float *x /*[rows,len]*/, int64_t rows, int64_t len, int pair,
-                            float *work, const float *twiddle /*size n1*n2*/, int n1, int n2,
+                            float *work, const float *twiddle, const float *stage1, int n1, int n2,
                             void *stream);
 int ddsp_b200_fft4_cols_inv(const float *work, float *out /*[rows,len]*/, int64_t rows, int64_t len,
-                            int pair, const float *twiddle, int n1, int n2, void *stream);
-int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const float *twiddle, int n1, int n2,
-                                 void *stream);
+                            int pair, const float *stage1, int n1, int n2, void *stream);
+int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const float *twiddle, const float *stage2,
+                                 int n1, int n2, void *stream);
 /* h_slot_stride in complex elements between the filter spectra of successive slots (0 = shared) */
 int ddsp_b200_fft4_rows_filter(float *work, int64_t slots, const float *hspec, int64_t h_slot_stride,
-                               int conj_h, const float *twiddle, int n1, int n2, void *stream);
-/* out = rows of IFFT( FFT(g) * conj(FFT(x)) ), summed over slots into one slot when reduce != 0 */
+                               int conj_h, const float *twiddle, const float *stage2, int n1, int n2,
+                               void *stream);
+/* out = rows of IFFT( FFT(g) * conj(FFT(x)) ), summed over slots into one slot when reduce != 0.
+ * scratch: ddsp_b200_fft4_correlate_splits(slots, reduce) * n1*n2 complex (partial spectra).      */
+int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce);
 int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots, int reduce,
-                                  float *out, const float *twiddle, int n1, int n2, void *stream);
+                                  float *scratch, float *out, const float *twiddle, const float *stage2,
+                                  int n1, int n2, void *stream);
 
 /* ---- a10  Reverb.build_impulse                       (ddsp/models/modules.py:21-26) -------- */
 /* impulse[l] = noise[l]*exp(-softplus(-decay)*t[l]*500)*sigmoid(wet), impulse[0] = 1; l < L.
@@ -170,9 +180,6 @@ int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int B, int64_t
  * padding part into edge[B,n_fft]).  ddsp_b200_mss_finish reduces the partials of all scales to
  * loss[0] (layout: scales back to back) and folds the edges.  scales/hops: HOST arrays.         */
 int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop);
-/* per-size constant table of the register-tiled FFT (64 <= n_fft <= 4096): `size` float2 entries */
-int64_t ddsp_b200_stft_stage_twiddles_size(int n_fft);
-int ddsp_b200_stft_stage_twiddles(float *table, int n_fft, void *stream);
 /* stage_twiddle: the table above for n_fft (may be NULL outside 64..4096, where `twiddle` is used) */
 int ddsp_b200_mss_scale(const float *target, const float *rec, const float *window,
                         const float *twiddle, int n_tab, const float *stage_twiddle, float *partial,
