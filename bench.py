@@ -192,11 +192,9 @@ def kernel_table(step, shapes, flush, peaks):
     i = {k: v.detach() for k, v in step.inputs.items()}
     B, T, bs, H, NB, N = shapes.batch, shapes.frames, shapes.block_size, shapes.n_harmonic, shapes.n_bands, shapes.samples
     sr = float(shapes.sample_rate)
-    amps, dist = ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr)
-    w = (dist * amps).contiguous()
+    amps, dist, w = ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr, True)
     audio, _, phi, delta = ops.harmonic_fwd(i["pitch"], w, bs, sr, None)
     g = torch.randn_like(audio)
-    mags = ops.scale_function_fwd(i["mag_raw"] - 5.0)
     sig2 = audio.squeeze(-1).contiguous()
     imp = step.reverb.build_impulse().detach().reshape(1, -1)
     from ddsp_pytorch_b200.functions import hann_window_like_reference
@@ -221,15 +219,15 @@ def kernel_table(step, shapes, flush, peaks):
     add("K1 harmonic_frames_fwd", lambda: ops.harmonic_fwd(i["pitch"], w, bs, sr, None), fma_ops=2 * hs,
         note="SURVEY 8d: 2 FMA per harmonic-sample (recurrence + weighted sum) vs 148 SM x 128 lanes x max clock")
     add("K1 harmonic_frames_bwd", lambda: ops.harmonic_bwd(g, w, phi, delta, bs, sr, False), fma_ops=2 * hs)
-    add("K2 filtered_noise_fwd", lambda: ops.noise_fwd(mags, i["noise"]), alg_bytes=4 * B * T * (NB + 2 * bs))
-    add("K2 filtered_noise_bwd", lambda: ops.noise_bwd(g, i["noise"], NB), alg_bytes=4 * B * T * (NB + 2 * bs))
+    add("K2 filtered_noise_fwd", lambda: ops.noise_fwd(i["mag_raw"], i["noise"], audio, True, -5.0), alg_bytes=4 * B * T * (NB + 3 * bs))
+    add("K2 filtered_noise_bwd", lambda: ops.noise_bwd(g, i["noise"], i["mag_raw"], NB, True, -5.0), alg_bytes=4 * B * T * (NB + 2 * bs))
     add("K3 reverb fftconv_fwd (5 launches)", lambda: ops.fftconv_fwd(sig2, imp), alg_bytes=4 * (2 * B * N + imp.numel()))
     add("K3 reverb fftconv_bwd (8 launches)", lambda: ops.fftconv_bwd(sig2, sig2, imp, True, True),
         alg_bytes=4 * (3 * B * N + 2 * imp.numel()))
     add("K4L mss_loss fwd+grad (6 scales + finish)",
         lambda: ops.mss_loss_fwd(i["target"], sig2, list(shapes.scales), shapes.overlap, windows, True),
         alg_bytes=4 * 3 * B * N, note="SURVEY 8d: read rec+target, write grad")
-    add("K0 harmonic_controls_fwd", lambda: ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr),
+    add("K0 harmonic_controls_fwd", lambda: ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr, True),
         alg_bytes=4 * B * T * (2 * H + 3))
     return rows
 
@@ -332,17 +330,27 @@ def run_b200(args, rank, world):
         dist.all_reduce(tf, op=dist.ReduceOp.MAX)
     fwd_ms = float(tf)
 
-    # end to end: pinned host inputs -> H2D -> step -> loss read back, every step
+    # end to end through the public API with HOST buffers: every step copies its inputs from pinned
+    # host memory (the copy of step k+1 is queued before step k is waited for, as a prefetching data
+    # loader does), runs, and reads the loss back to the host.
     barrier()
     e2e_steps = max(10, args.steps // 2)
-    for _ in range(3):
-        step.load_inputs(host); full_step(); float(step.loss)
+    hosts = [host, {k: v.clone().pin_memory() for k, v in host.items()}]
+
+    def e2e_loop(n):
+        step.prefetch(hosts[0])
+        last = 0.0
+        for k in range(n):
+            step.step_prefetched()
+            allreduce_grads()
+            step.prefetch(hosts[(k + 1) & 1])                    # H2D of the next batch, overlapped
+            last = float(step.loss.detach())                     # D2H + sync of this step's result
+        return last
+
+    e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step.load_inputs(host)
-        full_step()
-        loss_host = float(step.loss)                                 # D2H + sync
+    loss_host = e2e_loop(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -385,7 +393,9 @@ def run_b200(args, rank, world):
                        "launch": graph_note},
             "fwd": {"value": samples_per_step / (fwd_ms * 1e-3), "unit": UNIT, "ms_per_step": fwd_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
-                    "ms_per_step": 1e3 * float(te) / e2e_steps, "loss": loss_host},
+                    "ms_per_step": 1e3 * float(te) / e2e_steps, "loss": loss_host,
+                    "how": "pinned host -> H2D (copy stream, next batch prefetched during the step) -> D2D into "
+                           "the graph inputs -> step -> loss.item(); wall clock between synchronisations"},
             "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "clocks": clocks.summary(), "wall_s_timed_loop": t_wall,
         }

@@ -71,6 +71,18 @@ struct ddsp_osc {
     }
 };
 
+// scale_function of the reference (ddsp/core.py:77-78): 2*sigmoid(x)^ln10 + 1e-7, and its derivative
+__device__ __forceinline__ float ddsp_softplus_neg(float x) {          // log(1 + exp(-x)), stable
+    return fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
+}
+__device__ __forceinline__ float ddsp_scale_core(float x) {
+    return 2.f * expf(-2.302585092994046f * ddsp_softplus_neg(x));      // 2*sigmoid(x)^ln10
+}
+__device__ __forceinline__ float ddsp_scale_fn(float x) { return ddsp_scale_core(x) + 1e-7f; }
+__device__ __forceinline__ float ddsp_scale_grad(float x) {             // ln10 * 2 sigmoid^ln10 * (1 - sigmoid)
+    return 2.302585092994046f * ddsp_scale_core(x) * (1.f / (1.f + expf(x)));
+}
+
 #define DDSP_PI_F 3.14159265358979323846f
 #define DDSP_2PI_F 6.28318530717958647692f
 

@@ -10,19 +10,8 @@
 
 namespace {
 
-constexpr float kLn10 = 2.302585092994046f;
-
-// softplus(-x) = log(1 + exp(-x)), stable for both signs
-__device__ __forceinline__ float softplus_neg(float x) {
-    return fmaxf(-x, 0.f) + log1pf(expf(-fabsf(x)));
-}
-// sigmoid(x)^ln10 * 2  ( = exp(-ln10 * softplus(-x)) * 2 )
-__device__ __forceinline__ float scale_core(float x) { return 2.f * expf(-kLn10 * softplus_neg(x)); }
-__device__ __forceinline__ float scale_fn(float x) { return scale_core(x) + 1e-7f; }
-// d/dx scale_fn = ln10 * 2 sigmoid^ln10 * (1 - sigmoid(x))
-__device__ __forceinline__ float scale_grad(float x) {
-    return kLn10 * scale_core(x) * (1.f / (1.f + expf(x)));
-}
+__device__ __forceinline__ float scale_fn(float x) { return ddsp_scale_fn(x); }
+__device__ __forceinline__ float scale_grad(float x) { return ddsp_scale_grad(x); }
 // (mask.float() + 1e-4) of core.py:73: both branches are float32 sums
 __device__ __forceinline__ float nyquist_mask(float f0, int k1, float nyq) {
     return (__fmul_rn(f0, (float)k1) < nyq) ? (1.0f + 1e-4f) : 1e-4f;   // single rounded product
@@ -55,7 +44,8 @@ constexpr int kRowWarps = 8;
 __global__ void __launch_bounds__(kRowWarps * 32)
 controls_fwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__ dist_raw,
                     const float *__restrict__ f0, float *__restrict__ amps,
-                    float *__restrict__ dist, int64_t rows, int H, float nyq) {
+                    float *__restrict__ dist, float *__restrict__ weights, int64_t rows, int H,
+                    float nyq) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -69,35 +59,49 @@ controls_fwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__
         sum += v;
     }
     sum = ddsp_warp_sum(sum);
-    for (int k = lane; k < H; k += 32) dn[k] = dn[k] / sum;     // same thread re-reads its own write
-    if (lane == 0) amps[row] = scale_fn(amp_raw[row]);
+    const float amp = scale_fn(amp_raw[row]);
+    for (int k = lane; k < H; k += 32) {
+        const float n = dn[k] / sum;                            // same thread re-reads its own write
+        dn[k] = n;
+        if (weights) weights[row * H + k] = n * amp;            // modules.py:73: distribution *= amplitudes
+    }
+    if (lane == 0) amps[row] = amp;
 }
 
 __global__ void __launch_bounds__(kRowWarps * 32)
 controls_bwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__ dist_raw,
                     const float *__restrict__ f0, const float *__restrict__ d_amps,
-                    const float *__restrict__ d_dist, float *__restrict__ d_amp_raw,
-                    float *__restrict__ d_dist_raw, int64_t rows, int H, float nyq) {
+                    const float *__restrict__ d_dist, const float *__restrict__ d_weights,
+                    float *__restrict__ d_amp_raw, float *__restrict__ d_dist_raw, int64_t rows, int H,
+                    float nyq) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kRowWarps + (threadIdx.x >> 5);
     if (row >= rows) return;
     const float f = f0[row];
     const float *dr = dist_raw + row * H;
-    const float *gd = d_dist + row * H;
+    const float *gd = d_dist ? d_dist + row * H : nullptr;
+    const float *gw = d_weights ? d_weights + row * H : nullptr;
     float *out = d_dist_raw + row * H;
-    // n_k = v_k / S  ->  dv_k = (g_k - sum_j g_j n_j) / S
-    float sum = 0.f, dot = 0.f;
+    const float amp = scale_fn(amp_raw[row]);
+    // n_k = v_k / S;  total gradient on n_k:  g_k = d_dist_k + d_weights_k * amp
+    //   dv_k = (g_k - sum_j g_j n_j) / S ;   d amp = d_amps + sum_k d_weights_k n_k
+    float sum = 0.f, dot = 0.f, wdot = 0.f;
     for (int k = lane; k < H; k += 32) {
         const float v = scale_fn(dr[k]) * nyquist_mask(f, k + 1, nyq);
+        const float g = (gd ? gd[k] : 0.f) + (gw ? gw[k] * amp : 0.f);
         sum += v;
-        dot = fmaf(gd[k], v, dot);
+        dot = fmaf(g, v, dot);
+        if (gw) wdot = fmaf(gw[k], v, wdot);
     }
     sum = ddsp_warp_sum(sum);
-    dot = ddsp_warp_sum(dot) / sum;                   // sum_j g_j n_j
     const float inv = 1.f / sum;
-    for (int k = lane; k < H; k += 32)
-        out[k] = (gd[k] - dot) * inv * nyquist_mask(f, k + 1, nyq) * scale_grad(dr[k]);
-    if (lane == 0) d_amp_raw[row] = d_amps[row] * scale_grad(amp_raw[row]);
+    dot = ddsp_warp_sum(dot) * inv;                   // sum_j g_j n_j
+    wdot = ddsp_warp_sum(wdot) * inv;                 // sum_k d_weights_k n_k
+    for (int k = lane; k < H; k += 32) {
+        const float g = (gd ? gd[k] : 0.f) + (gw ? gw[k] * amp : 0.f);
+        out[k] = (g - dot) * inv * nyquist_mask(f, k + 1, nyq) * scale_grad(dr[k]);
+    }
+    if (lane == 0) d_amp_raw[row] = ((d_amps ? d_amps[row] : 0.f) + wdot) * scale_grad(amp_raw[row]);
 }
 
 inline int ew_blocks(int64_t n) {
@@ -135,26 +139,26 @@ extern "C" int ddsp_b200_remove_above_nyquist(const float *amp, const float *f0,
 
 extern "C" int ddsp_b200_harmonic_controls_fwd(const float *amp_raw, const float *dist_raw,
                                                const float *f0, float *amps, float *dist,
-                                               int64_t rows, int H, float sample_rate,
+                                               float *weights, int64_t rows, int H, float sample_rate,
                                                void *stream) {
     DDSP_REQUIRE(amp_raw && dist_raw && f0 && amps && dist && rows >= 0 && H > 0);
     if (rows == 0) return DDSP_B200_OK;
     controls_fwd_kernel<<<(unsigned)ddsp_ceil_div(rows, kRowWarps), kRowWarps * 32, 0,
-                          (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, amps, dist, rows, H,
-                                                  sample_rate * 0.5f);
+                          (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, amps, dist, weights, rows,
+                                                  H, sample_rate * 0.5f);
     return ddsp_launch_status();
 }
 
 extern "C" int ddsp_b200_harmonic_controls_bwd(const float *amp_raw, const float *dist_raw,
                                                const float *f0, const float *d_amps,
-                                               const float *d_dist, float *d_amp_raw,
-                                               float *d_dist_raw, int64_t rows, int H,
+                                               const float *d_dist, const float *d_weights,
+                                               float *d_amp_raw, float *d_dist_raw, int64_t rows, int H,
                                                float sample_rate, void *stream) {
-    DDSP_REQUIRE(amp_raw && dist_raw && f0 && d_amps && d_dist && d_amp_raw && d_dist_raw);
+    DDSP_REQUIRE(amp_raw && dist_raw && f0 && d_amp_raw && d_dist_raw);
     DDSP_REQUIRE(rows >= 0 && H > 0);
     if (rows == 0) return DDSP_B200_OK;
     controls_bwd_kernel<<<(unsigned)ddsp_ceil_div(rows, kRowWarps), kRowWarps * 32, 0,
-                          (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, d_amps, d_dist, d_amp_raw,
-                                                  d_dist_raw, rows, H, sample_rate * 0.5f);
+                          (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, d_amps, d_dist, d_weights,
+                                                  d_amp_raw, d_dist_raw, rows, H, sample_rate * 0.5f);
     return ddsp_launch_status();
 }

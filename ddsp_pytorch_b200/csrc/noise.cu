@@ -138,7 +138,8 @@ struct NoiseLayout {
 
 __global__ void __launch_bounds__(kNoiseThreads)
 filtered_noise_fwd_kernel(const float *__restrict__ mags, const float *__restrict__ noise,
-                          float *__restrict__ out, int64_t rows, int NB, int bs, int RPC) {
+                          const float *__restrict__ add, float *__restrict__ out, int64_t rows, int NB,
+                          int bs, int RPC, int apply_scale, float bias) {
     extern __shared__ __align__(16) float smem[];
     const NoiseLayout L(NB, bs);
     const int half = L.half, F = L.F;
@@ -154,7 +155,9 @@ filtered_noise_fwd_kernel(const float *__restrict__ mags, const float *__restric
         // ---- stage mags and noise (coalesced over the CTA's rows)
         for (int i = tid; i < nr * NB; i += kNoiseThreads) {
             const int r = i / NB, k = i - r * NB;
-            rowbase[r * L.stride + L.m() + k] = __ldg(mags + (r0 + r) * NB + k);
+            const float m = __ldg(mags + (r0 + r) * NB + k);
+            // modules.py:111-114 folded in: magnitudes = scale_function(raw + initial_bias)
+            rowbase[r * L.stride + L.m() + k] = apply_scale ? ddsp_scale_fn(m + bias) : m;
         }
         for (int i = tid; i < nr * (half + bs); i += kNoiseThreads) {
             const int r = i / (half + bs), j = i - r * (half + bs);
@@ -217,7 +220,9 @@ filtered_noise_fwd_kernel(const float *__restrict__ mags, const float *__restric
         __syncthreads();
         for (int i = tid; i < nr * bs; i += kNoiseThreads) {
             const int r = i / bs, j = i - r * bs;
-            out[(r0 + r) * bs + j] = rowbase[r * L.stride + L.ys() + j];
+            float y = rowbase[r * L.stride + L.ys() + j];
+            if (add) y += __ldg(add + (r0 + r) * bs + j);       // decoder.py:121: harmonic + noise
+            out[(r0 + r) * bs + j] = y;
         }
     }
 }
@@ -227,7 +232,8 @@ filtered_noise_fwd_kernel(const float *__restrict__ mags, const float *__restric
 // ys area is reused for g; taps area receives d taps; h area receives dh.
 __global__ void __launch_bounds__(kNoiseThreads)
 filtered_noise_bwd_kernel(const float *__restrict__ g_out, const float *__restrict__ noise,
-                          float *__restrict__ d_mags, int64_t rows, int NB, int bs, int RPC) {
+                          const float *__restrict__ mags_raw, float *__restrict__ d_mags, int64_t rows,
+                          int NB, int bs, int RPC, int apply_scale, float bias) {
     extern __shared__ __align__(16) float smem[];
     const NoiseLayout L(NB, bs);
     const int half = L.half, F = L.F;
@@ -293,7 +299,9 @@ filtered_noise_bwd_kernel(const float *__restrict__ g_out, const float *__restri
         __syncthreads();
         for (int i = tid; i < nr * NB; i += kNoiseThreads) {
             const int r = i / NB, k = i - r * NB;
-            d_mags[(r0 + r) * NB + k] = rowbase[r * L.stride + L.m() + k];
+            float d = rowbase[r * L.stride + L.m() + k];
+            if (apply_scale) d *= ddsp_scale_grad(__ldg(mags_raw + (r0 + r) * NB + k) + bias);
+            d_mags[(r0 + r) * NB + k] = d;
         }
     }
 }
@@ -343,8 +351,9 @@ static int noise_launch_cfg(int64_t rows, int NB, int bs, int *rpc, size_t *smem
     return DDSP_B200_OK;
 }
 
-extern "C" int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, float *out,
-                                            int64_t rows, int NB, int block_size, void *stream) {
+extern "C" int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, const float *add,
+                                            float *out, int64_t rows, int NB, int block_size,
+                                            int apply_scale, float bias, void *stream) {
     DDSP_REQUIRE(mags && noise && out && rows >= 0);
     if (rows == 0) return DDSP_B200_OK;
     int rpc, grid;
@@ -355,13 +364,14 @@ extern "C" int ddsp_b200_filtered_noise_fwd(const float *mags, const float *nois
         cudaFuncSetAttribute(filtered_noise_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
     filtered_noise_fwd_kernel<<<grid, kNoiseThreads, smem, (cudaStream_t)stream>>>(
-        mags, noise, out, rows, NB, block_size, rpc);
+        mags, noise, add, out, rows, NB, block_size, rpc, apply_scale, bias);
     return ddsp_launch_status();
 }
 
-extern "C" int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise, float *d_mags,
-                                            int64_t rows, int NB, int block_size, void *stream) {
-    DDSP_REQUIRE(g_out && noise && d_mags && rows >= 0);
+extern "C" int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise,
+                                            const float *mags_raw, float *d_mags, int64_t rows, int NB,
+                                            int block_size, int apply_scale, float bias, void *stream) {
+    DDSP_REQUIRE(g_out && noise && d_mags && rows >= 0 && (!apply_scale || mags_raw));
     if (rows == 0) return DDSP_B200_OK;
     int rpc, grid;
     size_t smem;
@@ -371,6 +381,6 @@ extern "C" int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noi
         cudaFuncSetAttribute(filtered_noise_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
     filtered_noise_bwd_kernel<<<grid, kNoiseThreads, smem, (cudaStream_t)stream>>>(
-        g_out, noise, d_mags, rows, NB, block_size, rpc);
+        g_out, noise, mags_raw, d_mags, rows, NB, block_size, rpc, apply_scale, bias);
     return ddsp_launch_status();
 }

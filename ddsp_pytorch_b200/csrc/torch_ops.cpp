@@ -101,32 +101,46 @@ Tensor remove_above_nyquist(const Tensor &amp_, const Tensor &f0_, double sample
     return out;
 }
 
-std::tuple<Tensor, Tensor> harmonic_controls_fwd(const Tensor &amp_raw_, const Tensor &dist_raw_,
-                                                 const Tensor &f0_, double sample_rate) {
+Tensor opt_prep(const c10::optional<Tensor> &t, const char *name) {
+    return (t.has_value() && t->defined()) ? prep(*t, name) : Tensor();
+}
+const float *opt_fp(const Tensor &t) { return t.defined() ? t.data_ptr<float>() : nullptr; }
+
+// (amps, dist, weights = dist*amps)
+std::tuple<Tensor, Tensor, Tensor> harmonic_controls_fwd(const Tensor &amp_raw_, const Tensor &dist_raw_,
+                                                         const Tensor &f0_, double sample_rate,
+                                                         bool with_weights) {
     Tensor a = prep(amp_raw_, "amplitudes"), d = prep(dist_raw_, "harmonic_distribution"),
            f = prep(f0_, "f0");
     const int64_t H = d.size(-1), rows = d.numel() / H;
     TORCH_CHECK(a.numel() == rows && f.numel() == rows, "harmonic_controls: shape mismatch");
     c10::cuda::CUDAGuard guard(d.device());
     Tensor amps = at::empty_like(a), dist = at::empty_like(d);
-    check(ddsp_b200_harmonic_controls_fwd(fp(a), fp(d), fp(f), fpm(amps), fpm(dist), rows, (int)H,
+    Tensor weights = with_weights ? at::empty_like(d) : at::empty({0}, d.options());
+    check(ddsp_b200_harmonic_controls_fwd(fp(a), fp(d), fp(f), fpm(amps), fpm(dist),
+                                          with_weights ? fpm(weights) : nullptr, rows, (int)H,
                                           (float)sample_rate, cur_stream()),
           "harmonic_controls_fwd");
-    return {amps, dist};
+    return {amps, dist, weights};
 }
 
 std::tuple<Tensor, Tensor> harmonic_controls_bwd(const Tensor &amp_raw_, const Tensor &dist_raw_,
-                                                 const Tensor &f0_, const Tensor &d_amps_,
-                                                 const Tensor &d_dist_, double sample_rate) {
+                                                 const Tensor &f0_, const c10::optional<Tensor> &d_amps_,
+                                                 const c10::optional<Tensor> &d_dist_,
+                                                 const c10::optional<Tensor> &d_weights_,
+                                                 double sample_rate) {
     Tensor a = prep(amp_raw_, "amplitudes"), d = prep(dist_raw_, "harmonic_distribution"),
-           f = prep(f0_, "f0"), ga = prep(d_amps_, "d_amps"), gd = prep(d_dist_, "d_dist");
+           f = prep(f0_, "f0");
+    Tensor ga = opt_prep(d_amps_, "d_amps"), gd = opt_prep(d_dist_, "d_dist"),
+           gw = opt_prep(d_weights_, "d_weights");
     const int64_t H = d.size(-1), rows = d.numel() / H;
-    TORCH_CHECK(a.numel() == rows && f.numel() == rows && ga.numel() == rows && gd.numel() == d.numel(),
+    TORCH_CHECK(a.numel() == rows && f.numel() == rows && (!ga.defined() || ga.numel() == rows) &&
+                    (!gd.defined() || gd.numel() == d.numel()) && (!gw.defined() || gw.numel() == d.numel()),
                 "harmonic_controls_bwd: shape mismatch");
     c10::cuda::CUDAGuard guard(d.device());
     Tensor da = at::empty_like(a), dd = at::empty_like(d);
-    check(ddsp_b200_harmonic_controls_bwd(fp(a), fp(d), fp(f), fp(ga), fp(gd), fpm(da), fpm(dd), rows,
-                                          (int)H, (float)sample_rate, cur_stream()),
+    check(ddsp_b200_harmonic_controls_bwd(fp(a), fp(d), fp(f), opt_fp(ga), opt_fp(gd), opt_fp(gw), fpm(da),
+                                          fpm(dd), rows, (int)H, (float)sample_rate, cur_stream()),
           "harmonic_controls_bwd");
     return {da, dd};
 }
@@ -257,26 +271,33 @@ Tensor amp_to_ir_bwd(const Tensor &d_ir_, int64_t NB) {
     return d_amp;
 }
 
-Tensor noise_fwd(const Tensor &mags_, const Tensor &noise_) {
-    Tensor mags = prep(mags_, "magnitudes"), noise = prep(noise_, "noise");
+Tensor noise_fwd(const Tensor &mags_, const Tensor &noise_, const c10::optional<Tensor> &add_, bool apply_scale,
+                 double bias) {
+    Tensor mags = prep(mags_, "magnitudes"), noise = prep(noise_, "noise"), add = opt_prep(add_, "add");
     TORCH_CHECK(mags.dim() == 3 && noise.dim() == 3 && mags.size(0) == noise.size(0) &&
                     mags.size(1) == noise.size(1),
                 "filtered noise: magnitudes (B,T,NB) and noise (B,T,block) expected");
     const int64_t B = mags.size(0), T = mags.size(1), NB = mags.size(2), bs = noise.size(2);
+    TORCH_CHECK(!add.defined() || add.numel() == B * T * bs, "filtered noise: `add` must be (B,T*block,1)");
     c10::cuda::CUDAGuard guard(mags.device());
     Tensor out = at::empty({B, T * bs, 1}, mags.options());
-    check(ddsp_b200_filtered_noise_fwd(fp(mags), fp(noise), fpm(out), B * T, (int)NB, (int)bs, cur_stream()),
+    check(ddsp_b200_filtered_noise_fwd(fp(mags), fp(noise), opt_fp(add), fpm(out), B * T, (int)NB, (int)bs,
+                                       apply_scale, (float)bias, cur_stream()),
           "filtered_noise_fwd");
     return out;
 }
 
-Tensor noise_bwd(const Tensor &g_, const Tensor &noise_, int64_t NB) {
-    Tensor g = prep(g_, "grad_out"), noise = prep(noise_, "noise");
+Tensor noise_bwd(const Tensor &g_, const Tensor &noise_, const c10::optional<Tensor> &mags_raw_, int64_t NB,
+                 bool apply_scale, double bias) {
+    Tensor g = prep(g_, "grad_out"), noise = prep(noise_, "noise"), raw = opt_prep(mags_raw_, "mags_raw");
     const int64_t B = noise.size(0), T = noise.size(1), bs = noise.size(2);
     TORCH_CHECK(g.numel() == B * T * bs, "filtered noise backward: shape mismatch");
+    TORCH_CHECK(!apply_scale || (raw.defined() && raw.numel() == B * T * NB),
+                "filtered noise backward: raw magnitudes needed when the scale function is fused");
     c10::cuda::CUDAGuard guard(noise.device());
     Tensor d_mags = at::empty({B, T, NB}, noise.options());
-    check(ddsp_b200_filtered_noise_bwd(fp(g), fp(noise), fpm(d_mags), B * T, (int)NB, (int)bs, cur_stream()),
+    check(ddsp_b200_filtered_noise_bwd(fp(g), fp(noise), opt_fp(raw), fpm(d_mags), B * T, (int)NB, (int)bs,
+                                       apply_scale, (float)bias, cur_stream()),
           "filtered_noise_bwd");
     return d_mags;
 }
@@ -486,16 +507,16 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("scale_function_fwd(Tensor x) -> Tensor");
     m.def("scale_function_bwd(Tensor x, Tensor dy) -> Tensor");
     m.def("remove_above_nyquist(Tensor amplitudes, Tensor f0, float sample_rate) -> Tensor");
-    m.def("harmonic_controls_fwd(Tensor amplitudes, Tensor harmonic_distribution, Tensor f0, float sample_rate) -> (Tensor, Tensor)");
-    m.def("harmonic_controls_bwd(Tensor amplitudes, Tensor harmonic_distribution, Tensor f0, Tensor d_amps, Tensor d_dist, float sample_rate) -> (Tensor, Tensor)");
+    m.def("harmonic_controls_fwd(Tensor amplitudes, Tensor harmonic_distribution, Tensor f0, float sample_rate, bool with_weights) -> (Tensor, Tensor, Tensor)");
+    m.def("harmonic_controls_bwd(Tensor amplitudes, Tensor harmonic_distribution, Tensor f0, Tensor? d_amps, Tensor? d_dist, Tensor? d_weights, float sample_rate) -> (Tensor, Tensor)");
     m.def("harmonic_fwd(Tensor f0, Tensor weights, int block_size, float sample_rate, Tensor? phase0) -> (Tensor, Tensor, Tensor, Tensor)");
     m.def("harmonic_bwd(Tensor grad_audio, Tensor weights, Tensor phi, Tensor delta, int block_size, float sample_rate, bool need_f0) -> (Tensor, Tensor)");
     m.def("harmonic_ar_fwd(Tensor f0, Tensor amplitudes, float sample_rate) -> (Tensor, Tensor)");
     m.def("harmonic_ar_bwd(Tensor grad_audio, Tensor amplitudes, Tensor phase, float sample_rate, bool need_f0) -> (Tensor, Tensor)");
     m.def("amp_to_ir_fwd(Tensor amp, int target_size) -> Tensor");
     m.def("amp_to_ir_bwd(Tensor d_ir, int n_bands) -> Tensor");
-    m.def("noise_fwd(Tensor magnitudes, Tensor noise) -> Tensor");
-    m.def("noise_bwd(Tensor grad_out, Tensor noise, int n_bands) -> Tensor");
+    m.def("noise_fwd(Tensor magnitudes, Tensor noise, Tensor? add, bool apply_scale, float bias) -> Tensor");
+    m.def("noise_bwd(Tensor grad_out, Tensor noise, Tensor? magnitudes_raw, int n_bands, bool apply_scale, float bias) -> Tensor");
     m.def("fftconv_fwd(Tensor signal, Tensor kernel) -> Tensor");
     m.def("fftconv_bwd(Tensor grad_out, Tensor signal, Tensor kernel, bool need_signal, bool need_kernel) -> (Tensor, Tensor)");
     m.def("reverb_impulse_fwd(Tensor noise, Tensor decay, Tensor wet, Tensor t) -> Tensor");

@@ -63,14 +63,33 @@ class HarmonicControls(torch.autograd.Function):
     def forward(ctx, amp_raw, dist_raw, f0, sample_rate):
         ctx.save_for_backward(amp_raw, dist_raw, f0)
         ctx.sample_rate = float(sample_rate)
-        amps, dist = _ops.harmonic_controls_fwd(amp_raw, dist_raw, f0, ctx.sample_rate)
+        amps, dist, _ = _ops.harmonic_controls_fwd(amp_raw, dist_raw, f0, ctx.sample_rate, False)
         return amps, dist
 
     @staticmethod
     @once_differentiable
     def backward(ctx, d_amps, d_dist):
         amp_raw, dist_raw, f0 = ctx.saved_tensors
-        da, dd = _ops.harmonic_controls_bwd(amp_raw, dist_raw, f0, d_amps, d_dist, ctx.sample_rate)
+        da, dd = _ops.harmonic_controls_bwd(amp_raw, dist_raw, f0, d_amps, d_dist, None, ctx.sample_rate)
+        return da.view_as(amp_raw), dd.view_as(dist_raw), None, None
+
+
+class HarmonicControlsWeights(torch.autograd.Function):
+    """get_controls + the in-place ``distribution *= amplitudes`` of HarmonicSynth.forward
+    (modules.py:44-67,73) in one launch: -> (amplitudes, distribution, weights = distribution*amplitudes)."""
+
+    @staticmethod
+    def forward(ctx, amp_raw, dist_raw, f0, sample_rate):
+        ctx.save_for_backward(amp_raw, dist_raw, f0)
+        ctx.sample_rate = float(sample_rate)
+        ctx.set_materialize_grads(False)
+        return _ops.harmonic_controls_fwd(amp_raw, dist_raw, f0, ctx.sample_rate, True)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d_amps, d_dist, d_weights):
+        amp_raw, dist_raw, f0 = ctx.saved_tensors
+        da, dd = _ops.harmonic_controls_bwd(amp_raw, dist_raw, f0, d_amps, d_dist, d_weights, ctx.sample_rate)
         return da.view_as(amp_raw), dd.view_as(dist_raw), None, None
 
 
@@ -135,13 +154,31 @@ class FilteredNoise(torch.autograd.Function):
     def forward(ctx, magnitudes, noise):
         ctx.save_for_backward(noise)
         ctx.n_bands = magnitudes.shape[-1]
-        return _ops.noise_fwd(magnitudes, noise)
+        return _ops.noise_fwd(magnitudes, noise, None, False, 0.0)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
         (noise,) = ctx.saved_tensors
-        return _ops.noise_bwd(g, noise, ctx.n_bands), None   # the draw itself has no gradient
+        return _ops.noise_bwd(g, noise, None, ctx.n_bands, False, 0.0), None   # the draw has no gradient
+
+
+class FilteredNoiseFused(torch.autograd.Function):
+    """get_controls + forward + the mix of decoder.py:115-121 in one launch:
+    scale_function(raw + bias) -> IR -> FIR of the noise draw -> + ``add`` (the harmonic audio)."""
+
+    @staticmethod
+    def forward(ctx, magnitudes_raw, noise, add, bias):
+        ctx.save_for_backward(magnitudes_raw, noise)
+        ctx.bias = float(bias)
+        return _ops.noise_fwd(magnitudes_raw, noise, add, True, ctx.bias)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        raw, noise = ctx.saved_tensors
+        d_raw = _ops.noise_bwd(g, noise, raw, raw.shape[-1], True, ctx.bias)
+        return d_raw, None, (g if ctx.needs_input_grad[2] else None), None
 
 
 class FFTConvolve(torch.autograd.Function):

@@ -81,12 +81,10 @@ class SynthStep:
             leaves = [i["amp_raw"], i["dist_raw"], i["mag_raw"]]
             if self.reverb is not None:
                 leaves += [self.reverb.noise, self.reverb.decay, self.reverb.wet]
-        amps, dist = F_.HarmonicControls.apply(leaves[0], leaves[1], i["pitch"], float(s.sample_rate))
-        weights = dist * amps
+        _, _, weights = F_.HarmonicControlsWeights.apply(leaves[0], leaves[1], i["pitch"], float(s.sample_rate))
         harmonic, _ = core.harmonic_synth_frames(i["pitch"], weights, s.block_size, s.sample_rate)
-        mags = core.scale_function(leaves[2] + (-5.0))
-        noise = core.filtered_noise(mags, i["noise"])
-        signal = harmonic + noise
+        # FilteredNoise.get_controls + forward + "harmonic + noise" in one launch
+        signal = F_.FilteredNoiseFused.apply(leaves[2], i["noise"], harmonic, -5.0)
         if self.reverb is not None:
             impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
             taps = min(s.samples, s.reverb_length)
@@ -137,6 +135,53 @@ class SynthStep:
 
     def replay(self, forward_only: bool = False):
         (self._graph_fwd if forward_only else self._graph).replay()
+
+    # ---- host-fed execution: H2D of the next batch overlaps the current step -------------------
+    def _staging(self):
+        if getattr(self, "_stage", None) is None:
+            self._stage = [{k: torch.empty_like(v) for k, v in self.inputs.items()} for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream()
+            self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            self._slot = 0
+            self._primed = False
+        return self._stage
+
+    def prefetch(self, host: Dict[str, torch.Tensor]) -> int:
+        """Start the host->device copy of a batch (pinned tensors) on the copy stream into the idle
+        staging set; returns the bytes queued.  The copy runs while the current step computes."""
+        stage = self._staging()
+        slot = self._slot
+        n = 0
+        self._copy_stream.wait_event(self._consumed[slot])       # staging set free again
+        with torch.cuda.stream(self._copy_stream), torch.no_grad():
+            for k in INPUT_NAMES:
+                if k in host:
+                    stage[slot][k].copy_(host[k], non_blocking=True)
+                    n += host[k].numel() * host[k].element_size()
+            self._ready[slot].record(self._copy_stream)
+        self._primed = True
+        return n
+
+    def step_prefetched(self, forward_only: bool = False):
+        """Run one step on the batch most recently handed to ``prefetch``: wait for its copy, move it
+        into the graph's static inputs (device-to-device), replay."""
+        assert getattr(self, "_primed", False), "call prefetch() first"
+        slot = self._slot
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._ready[slot])
+        with torch.no_grad():
+            for k, v in self._stage[slot].items():
+                self.inputs[k].copy_(v, non_blocking=True)
+        self._consumed[slot].record(cur)
+        self._slot ^= 1
+        graph = self._graph_fwd if forward_only else self._graph
+        if graph is not None:
+            graph.replay()
+        elif forward_only:
+            self.run_forward()
+        else:
+            self.run()
 
     def load_inputs(self, host: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
         """Copy a batch from (pinned) host tensors into the static buffers; returns bytes copied."""

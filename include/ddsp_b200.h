@@ -50,14 +50,16 @@ int ddsp_b200_remove_above_nyquist(const float *amp, const float *f0, float *out
 
 /* ---- a3  HarmonicSynth.get_controls, fused          (ddsp/models/modules.py:44-67) ---------- */
 /* amp_raw[rows], dist_raw[rows,H], f0[rows]  ->  amps[rows] = scale(amp_raw),
- * dist[rows,H] = normalise(scale(dist_raw) * nyquist_mask).                                    */
+ * dist[rows,H] = normalise(scale(dist_raw) * nyquist_mask) and, if weights != NULL,
+ * weights[rows,H] = dist * amps (the in-place product of HarmonicSynth.forward, modules.py:73).
+ * Backward: any of d_amps / d_dist / d_weights may be NULL (= zero upstream gradient).          */
 int ddsp_b200_harmonic_controls_fwd(const float *amp_raw, const float *dist_raw, const float *f0,
-                                    float *amps, float *dist, int64_t rows, int H,
+                                    float *amps, float *dist, float *weights, int64_t rows, int H,
                                     float sample_rate, void *stream);
 int ddsp_b200_harmonic_controls_bwd(const float *amp_raw, const float *dist_raw, const float *f0,
-                                    const float *d_amps, const float *d_dist, float *d_amp_raw,
-                                    float *d_dist_raw, int64_t rows, int H, float sample_rate,
-                                    void *stream);
+                                    const float *d_amps, const float *d_dist, const float *d_weights,
+                                    float *d_amp_raw, float *d_dist_raw, int64_t rows, int H,
+                                    float sample_rate, void *stream);
 
 /* ---- a4+a5+a6  HarmonicSynth.forward, fused         (ddsp/models/modules.py:69-80,
  *                upsample ddsp/core.py:64-67, harmonic_synth ddsp/core.py:136-141) ------------ */
@@ -101,11 +103,17 @@ int ddsp_b200_amp_to_ir_bwd(const float *d_ir, float *d_amp, int64_t rows, int N
 
 /* ---- a7+a8+a9  FilteredNoise.forward, fused        (ddsp/models/modules.py:116-128) -------- */
 /* mags[rows,NB], noise[rows,bs] (the uniform(-1,1) draw, an INPUT) -> out[rows*bs]; rows = B*T;
- * requires bs >= 2(NB-1). */
-int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, float *out, int64_t rows,
-                                 int NB, int block_size, void *stream);
-int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise, float *d_mags,
-                                 int64_t rows, int NB, int block_size, void *stream);
+ * requires bs >= 2(NB-1), bs % 4 == 0, (NB-1) % 4 == 0.
+ * apply_scale != 0: `mags` are the raw noise_proj outputs and FilteredNoise.get_controls
+ *   (modules.py:111-114: scale_function(raw + bias)) is applied inside the kernel.
+ * add != NULL: out = filtered noise + add[rows*bs] (decoder.py:121: harmonic + noise).
+ * Backward: d_mags w.r.t. what `mags` was (raw when apply_scale, which then needs mags_raw).      */
+int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, const float *add, float *out,
+                                 int64_t rows, int NB, int block_size, int apply_scale, float bias,
+                                 void *stream);
+int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise, const float *mags_raw,
+                                 float *d_mags, int64_t rows, int NB, int block_size, int apply_scale,
+                                 float bias, void *stream);
 
 /* ---- FFT tables (caller-owned constant tables) --------------------------------------------- */
 /* table[m] = (cos, -sin)(2*pi*m/n), m in [0,n): n float2 = 2n floats; n a power of two.  One
