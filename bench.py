@@ -238,6 +238,9 @@ def run_b200(args, rank, world):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # keep stdout to the single JSON line: NCCL prints its version banner there at level VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
@@ -259,15 +262,15 @@ def run_b200(args, rank, world):
     h2d = step.load_inputs(host)
     torch.cuda.synchronize()
 
-    # parameter gradients (reverb.noise/decay/wet) are summed across ranks: the only collective
-    n_param = sum(p.numel() for p in step.reverb.parameters())
-    flat = torch.zeros(n_param, device=dev)
+    # parameter gradients (reverb.noise/decay/wet) are averaged across ranks: the only collective
+    from ddsp_pytorch_b200.distributed import GradBucket
+    params = list(step.reverb.parameters())
+    n_param = sum(p.numel() for p in params)
+    bucket = GradBucket([p.shape for p in params], dev)
 
     def allreduce_grads():
-        if dist is None:
-            return
-        torch.cat([g.reshape(-1) for g in step.grads[3:]], out=flat)
-        dist.all_reduce(flat)
+        if dist is not None:
+            bucket.all_reduce_mean(step.grads[3:])
 
     c0 = lib.ddsp_b200_launch_count()
     step.run()
