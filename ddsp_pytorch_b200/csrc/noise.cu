@@ -306,6 +306,222 @@ filtered_noise_bwd_kernel(const float *__restrict__ g_out, const float *__restri
     }
 }
 
+// =============================================================================================
+// Second generation of the fused kernels.  The IR design is linear in the magnitudes with a CONSTANT
+// matrix:  taps[j] = sum_k m[k] * D[k][j],  j < F  (j < half: causal tap j, window folded in;
+// j >= half: far tap e = j - half).  D (NB x F, 33 KB for 65 bands) comes from a caller-owned table
+// (ddsp_b200_noise_design_table) and sits in shared memory; a sweep of RPC frames is then
+//   A  stage magnitudes (+ scale_function) and noise          B  taps = M x D   (register-tiled matmul)
+//   C  64-tap FIRs (main + far) with a register sliding window   D  coalesced store (+ mix-in)
+// with every thread busy in every phase and 3 barriers per sweep.  Backward mirrors it:
+//   d taps = correlation (same sliding-window kernel), d m = d taps x D^T (table holds D^T too).
+// =============================================================================================
+constexpr int kN2Threads = 256;
+
+__global__ void noise_design_kernel(float *__restrict__ tab, int NB) {
+    // tab = D[NB][F] followed by Dt[F][NBq], NBq = NB rounded up to 4
+    const int half = NB - 1, F = 2 * half, NBq = (NB + 3) & ~3;
+    const int total = NB * F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int k = i / F, j = i - k * F;
+        const int n = j < half ? j : half - (j - half);          // h index feeding this tap
+        const int wi = j < half ? j + half : j - half;           // window index
+        const double ck = (k == 0 || k == half) ? 1.0 : 2.0;
+        const double c = ck * cospi(2.0 * (double)((k * n) % F) / F) / F;
+        const double w = 0.5 - 0.5 * cospi(2.0 * (double)wi / F);
+        const float v = (float)(c * w);
+        tab[i] = v;
+        tab[(size_t)total + (size_t)j * NBq + k] = v;
+    }
+    // zero the padding columns of Dt
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < F * (NBq - NB); i += gridDim.x * blockDim.x) {
+        const int j = i / (NBq - NB), k = NB + i % (NBq - NB);
+        tab[(size_t)total + (size_t)j * NBq + k] = 0.f;
+    }
+}
+
+// y[0..3] = sum_{d < ntaps} taps[d] * x[-d + 0..3]   (x points at sample i; x[-1..-ntaps] must be readable)
+__device__ __forceinline__ float4 fir4(const float4 *__restrict__ t4, const float *x, int ntaps) {
+    float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+    float4 hi = *reinterpret_cast<const float4 *>(x);
+    for (int d = 0; d < ntaps; d += 4) {
+        const float4 lo = *reinterpret_cast<const float4 *>(x - d - 4);
+        const float4 c = t4[d >> 2];
+        y0 = fmaf(c.x, hi.x, y0); y1 = fmaf(c.x, hi.y, y1); y2 = fmaf(c.x, hi.z, y2); y3 = fmaf(c.x, hi.w, y3);
+        y0 = fmaf(c.y, lo.w, y0); y1 = fmaf(c.y, hi.x, y1); y2 = fmaf(c.y, hi.y, y2); y3 = fmaf(c.y, hi.z, y3);
+        y0 = fmaf(c.z, lo.z, y0); y1 = fmaf(c.z, lo.w, y1); y2 = fmaf(c.z, hi.x, y2); y3 = fmaf(c.z, hi.y, y3);
+        y0 = fmaf(c.w, lo.y, y0); y1 = fmaf(c.w, lo.z, y1); y2 = fmaf(c.w, lo.w, y2); y3 = fmaf(c.w, hi.x, y3);
+        hi = lo;
+    }
+    return make_float4(y0, y1, y2, y3);
+}
+
+// a[0..3] = sum_{i < len, step 4} g[i..i+3] (x) x[i - d - 0..3]: gradient of taps d..d+3
+__device__ __forceinline__ float4 corr4(const float *g, const float *x, int d, int len) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    float4 lo = *reinterpret_cast<const float4 *>(x - d - 4);
+    for (int i = 0; i < len; i += 4) {
+        const float4 hi = *reinterpret_cast<const float4 *>(x + i - d);
+        const float4 gv = *reinterpret_cast<const float4 *>(g + i);
+        a0 = fmaf(gv.x, hi.x, a0); a0 = fmaf(gv.y, hi.y, a0); a0 = fmaf(gv.z, hi.z, a0); a0 = fmaf(gv.w, hi.w, a0);
+        a1 = fmaf(gv.x, lo.w, a1); a1 = fmaf(gv.y, hi.x, a1); a1 = fmaf(gv.z, hi.y, a1); a1 = fmaf(gv.w, hi.z, a1);
+        a2 = fmaf(gv.x, lo.z, a2); a2 = fmaf(gv.y, lo.w, a2); a2 = fmaf(gv.z, hi.x, a2); a2 = fmaf(gv.w, hi.y, a2);
+        a3 = fmaf(gv.x, lo.y, a3); a3 = fmaf(gv.y, lo.z, a3); a3 = fmaf(gv.z, lo.w, a3); a3 = fmaf(gv.w, hi.x, a3);
+        lo = hi;
+    }
+    return make_float4(a0, a1, a2, a3);
+}
+
+struct Noise2Layout {         // per-row shared areas of the second-generation kernels (floats)
+    int half, F, NBq, bs, xs_len, stride;
+    __host__ __device__ Noise2Layout(int NB, int bs_) {
+        half = NB - 1; F = 2 * half; NBq = (NB + 3) & ~3; bs = bs_;
+        xs_len = half + bs;                         // `half` zeros in front of the frame
+        stride = NBq + F + xs_len + bs + half;      // m | taps | xs | ys (fwd) or g (bwd) | yf
+    }
+    __host__ __device__ int m() const { return 0; }
+    __host__ __device__ int taps() const { return NBq; }
+    __host__ __device__ int xs() const { return NBq + F; }
+    __host__ __device__ int ys() const { return NBq + F + xs_len; }
+    __host__ __device__ int yf() const { return NBq + F + xs_len + bs; }
+};
+
+__global__ void __launch_bounds__(kN2Threads)
+filtered_noise2_fwd_kernel(const float *__restrict__ mags, const float *__restrict__ noise,
+                           const float *__restrict__ add, const float *__restrict__ design,
+                           float *__restrict__ out, int64_t rows, int NB, int bs, int RPC, int apply_scale,
+                           float bias) {
+    extern __shared__ __align__(16) float smem[];
+    const Noise2Layout L(NB, bs);
+    const int half = L.half, F = L.F;
+    float *D = smem;                                     // [NB][F]
+    float *rowbase = D + NB * F;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < NB * F / 4; i += kN2Threads)
+        reinterpret_cast<float4 *>(D)[i] = __ldg(reinterpret_cast<const float4 *>(design) + i);
+
+    const int QM = bs >> 2, QF = half >> 2;              // main / far output quads per row
+    for (int64_t r0 = (int64_t)blockIdx.x * RPC; r0 < rows; r0 += (int64_t)gridDim.x * RPC) {
+        const int nr = (int)min((int64_t)RPC, rows - r0);
+        __syncthreads();
+        // ---- A: stage
+        for (int i = tid; i < nr * NB; i += kN2Threads) {
+            const int r = i / NB, k = i - r * NB;
+            const float m = __ldg(mags + (r0 + r) * NB + k);
+            rowbase[r * L.stride + L.m() + k] = apply_scale ? ddsp_scale_fn(m + bias) : m;
+        }
+        for (int i = tid; i < nr * L.xs_len; i += kN2Threads) {
+            const int r = i / L.xs_len, j = i - r * L.xs_len;
+            rowbase[r * L.stride + L.xs() + j] = j < half ? 0.f : __ldg(noise + (r0 + r) * bs + (j - half));
+        }
+        __syncthreads();
+        // ---- B: taps[r][8cg..8cg+7] = sum_k m[r][k] * D[k][...]
+        for (int it = tid; it < nr * (F / 8); it += kN2Threads) {
+            const int r = it / (F / 8), cg = it - r * (F / 8);
+            const float *m = rowbase + r * L.stride + L.m();
+            const float4 *d4 = reinterpret_cast<const float4 *>(D) + cg * 2;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+            for (int k = 0; k < NB; ++k) {
+                const float mk = m[k];
+                const float4 u = d4[k * (F / 4)], v = d4[k * (F / 4) + 1];
+                a.x = fmaf(mk, u.x, a.x); a.y = fmaf(mk, u.y, a.y); a.z = fmaf(mk, u.z, a.z); a.w = fmaf(mk, u.w, a.w);
+                c.x = fmaf(mk, v.x, c.x); c.y = fmaf(mk, v.y, c.y); c.z = fmaf(mk, v.z, c.z); c.w = fmaf(mk, v.w, c.w);
+            }
+            float4 *t4 = reinterpret_cast<float4 *>(rowbase + r * L.stride + L.taps()) + cg * 2;
+            t4[0] = a;
+            t4[1] = c;
+        }
+        __syncthreads();
+        // ---- C: main FIR (causal taps) over the frame, far FIR over its first `half` samples
+        for (int it = tid; it < nr * (QM + QF); it += kN2Threads) {
+            const int r = it / (QM + QF), q = it - r * (QM + QF);
+            float *rb = rowbase + r * L.stride;
+            const float4 *t4 = reinterpret_cast<const float4 *>(rb + L.taps());
+            if (q < QM) {
+                const float4 y = fir4(t4, rb + L.xs() + half + 4 * q, half);
+                *reinterpret_cast<float4 *>(rb + L.ys() + 4 * q) = y;
+            } else {
+                const int qq = q - QM;
+                const float4 y = fir4(t4 + QF, rb + L.xs() + half + 4 * qq, half);
+                *reinterpret_cast<float4 *>(rb + L.yf() + 4 * qq) = y;
+            }
+        }
+        __syncthreads();
+        // ---- D: out = main + far (last `half` samples) (+ add)
+        for (int i = tid; i < nr * bs; i += kN2Threads) {
+            const int r = i / bs, j = i - r * bs;
+            const float *rb = rowbase + r * L.stride;
+            float y = rb[L.ys() + j];
+            if (j >= bs - half) y += rb[L.yf() + j - (bs - half)];
+            if (add) y += __ldg(add + (r0 + r) * bs + j);
+            out[(r0 + r) * bs + j] = y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kN2Threads)
+filtered_noise2_bwd_kernel(const float *__restrict__ g_out, const float *__restrict__ noise,
+                           const float *__restrict__ mags_raw, const float *__restrict__ design,
+                           float *__restrict__ d_mags, int64_t rows, int NB, int bs, int RPC,
+                           int apply_scale, float bias) {
+    extern __shared__ __align__(16) float smem[];
+    const Noise2Layout L(NB, bs);
+    const int half = L.half, F = L.F, NBq = L.NBq;
+    float *Dt = smem;                                    // [F][NBq]
+    float *rowbase = Dt + F * NBq;
+    const int tid = threadIdx.x;
+    const float *dt_src = design + (size_t)NB * F;
+    for (int i = tid; i < F * NBq / 4; i += kN2Threads)
+        reinterpret_cast<float4 *>(Dt)[i] = __ldg(reinterpret_cast<const float4 *>(dt_src) + i);
+
+    for (int64_t r0 = (int64_t)blockIdx.x * RPC; r0 < rows; r0 += (int64_t)gridDim.x * RPC) {
+        const int nr = (int)min((int64_t)RPC, rows - r0);
+        __syncthreads();
+        for (int i = tid; i < nr * L.xs_len; i += kN2Threads) {
+            const int r = i / L.xs_len, j = i - r * L.xs_len;
+            rowbase[r * L.stride + L.xs() + j] = j < half ? 0.f : __ldg(noise + (r0 + r) * bs + (j - half));
+        }
+        for (int i = tid; i < nr * bs; i += kN2Threads) {
+            const int r = i / bs, j = i - r * bs;
+            rowbase[r * L.stride + L.ys() + j] = __ldg(g_out + (r0 + r) * bs + j);
+        }
+        __syncthreads();
+        // ---- d taps: causal taps correlate the whole frame, far taps its last `half` outputs
+        for (int it = tid; it < nr * (F / 4); it += kN2Threads) {
+            const int r = it / (F / 4), tg = it - r * (F / 4);
+            float *rb = rowbase + r * L.stride;
+            const float *x = rb + L.xs() + half;
+            float4 a;
+            if (tg < half / 4) a = corr4(rb + L.ys(), x, 4 * tg, bs);
+            else a = corr4(rb + L.ys() + bs - half, x, 4 * (tg - half / 4), half);
+            *reinterpret_cast<float4 *>(rb + L.taps() + 4 * tg) = a;
+        }
+        __syncthreads();
+        // ---- d m[r][4kg..] = sum_j dtaps[r][j] * Dt[j][...]
+        for (int it = tid; it < nr * (NBq / 4); it += kN2Threads) {
+            const int r = it / (NBq / 4), kg = it - r * (NBq / 4);
+            const float *dt = rowbase + r * L.stride + L.taps();
+            const float4 *d4 = reinterpret_cast<const float4 *>(Dt) + kg;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < F; ++j) {
+                const float t = dt[j];
+                const float4 u = d4[j * (NBq / 4)];
+                a.x = fmaf(t, u.x, a.x); a.y = fmaf(t, u.y, a.y); a.z = fmaf(t, u.z, a.z); a.w = fmaf(t, u.w, a.w);
+            }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = 4 * kg + e;
+                if (k < NB) {
+                    float d = av[e];
+                    if (apply_scale) d *= ddsp_scale_grad(__ldg(mags_raw + (r0 + r) * NB + k) + bias);
+                    d_mags[(r0 + r) * NB + k] = d;
+                }
+            }
+        }
+    }
+}
+
 inline int noise_rows_per_cta(int bs) {
     int rpc = (kNoiseThreads * 4) / bs;
     if (rpc < 1) rpc = 1;
@@ -351,13 +567,49 @@ static int noise_launch_cfg(int64_t rows, int NB, int bs, int *rpc, size_t *smem
     return DDSP_B200_OK;
 }
 
+// second generation: needs the design table and (NB-1) % 4 == 0, bs % 4 == 0, bs >= F; rows per sweep
+// chosen so that two or three CTAs share an SM
+static bool noise2_cfg(int64_t rows, int NB, int bs, bool bwd, int *rpc, size_t *smem, int *grid) {
+    if (NB < 5 || (NB - 1) % 4 != 0 || bs % 4 != 0 || bs < 2 * (NB - 1)) return false;
+    const Noise2Layout L(NB, bs);
+    const size_t fixed = (bwd ? (size_t)L.F * L.NBq : (size_t)NB * L.F) * sizeof(float);
+    int r = 16;
+    while (r > 1 && fixed + (size_t)r * L.stride * sizeof(float) > 75 * 1024) r >>= 1;
+    *smem = fixed + (size_t)r * L.stride * sizeof(float);
+    if (*smem > 200 * 1024) return false;
+    *rpc = r;
+    const int64_t ctas = ddsp_ceil_div(rows, r);
+    *grid = (int)(ctas < DDSP_SM_COUNT * 3 ? ctas : DDSP_SM_COUNT * 3);
+    return true;
+}
+
+extern "C" int64_t ddsp_b200_noise_design_size(int NB) {
+    if (NB < 2) return 0;
+    const int F = 2 * (NB - 1), NBq = (NB + 3) & ~3;
+    return (int64_t)NB * F + (int64_t)F * NBq;
+}
+
+extern "C" int ddsp_b200_noise_design_table(float *table, int NB, void *stream) {
+    DDSP_REQUIRE(table && NB >= 2);
+    noise_design_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(table, NB);
+    return ddsp_launch_status();
+}
+
 extern "C" int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, const float *add,
-                                            float *out, int64_t rows, int NB, int block_size,
-                                            int apply_scale, float bias, void *stream) {
+                                            const float *design, float *out, int64_t rows, int NB,
+                                            int block_size, int apply_scale, float bias, void *stream) {
     DDSP_REQUIRE(mags && noise && out && rows >= 0);
     if (rows == 0) return DDSP_B200_OK;
     int rpc, grid;
     size_t smem;
+    if (design && noise2_cfg(rows, NB, block_size, false, &rpc, &smem, &grid)) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(filtered_noise2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        filtered_noise2_fwd_kernel<<<grid, kN2Threads, smem, (cudaStream_t)stream>>>(
+            mags, noise, add, design, out, rows, NB, block_size, rpc, apply_scale, bias);
+        return ddsp_launch_status();
+    }
     int s = noise_launch_cfg(rows, NB, block_size, &rpc, &smem, &grid);
     if (s) return s;
     if (smem > 48 * 1024)
@@ -369,12 +621,21 @@ extern "C" int ddsp_b200_filtered_noise_fwd(const float *mags, const float *nois
 }
 
 extern "C" int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise,
-                                            const float *mags_raw, float *d_mags, int64_t rows, int NB,
-                                            int block_size, int apply_scale, float bias, void *stream) {
+                                            const float *mags_raw, const float *design, float *d_mags,
+                                            int64_t rows, int NB, int block_size, int apply_scale,
+                                            float bias, void *stream) {
     DDSP_REQUIRE(g_out && noise && d_mags && rows >= 0 && (!apply_scale || mags_raw));
     if (rows == 0) return DDSP_B200_OK;
     int rpc, grid;
     size_t smem;
+    if (design && noise2_cfg(rows, NB, block_size, true, &rpc, &smem, &grid)) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(filtered_noise2_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem);
+        filtered_noise2_bwd_kernel<<<grid, kN2Threads, smem, (cudaStream_t)stream>>>(
+            g_out, noise, mags_raw, design, d_mags, rows, NB, block_size, rpc, apply_scale, bias);
+        return ddsp_launch_status();
+    }
     int s = noise_launch_cfg(rows, NB, block_size, &rpc, &smem, &grid);
     if (s) return s;
     if (smem > 48 * 1024)

@@ -558,6 +558,26 @@ __global__ void stft_fold_kernel(const float *__restrict__ edge, float *__restri
     }
 }
 
+// d_rec[b,m] = sum over scales of the per-scale gradients (fixed order) + the folded edges.  Lets the
+// per-scale launches run concurrently (own output buffers) and still be deterministic.
+__global__ void mss_combine_kernel(const float *__restrict__ per_scale, const float *__restrict__ edge,
+                                   float *__restrict__ d_sig, int B, int64_t N, FoldArgs fa) {
+    const int b = blockIdx.y;
+    const size_t plane = (size_t)B * N;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N;
+         m += (int64_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int k = 0; k < fa.n_scales; ++k) {
+            acc += per_scale[k * plane + (size_t)b * N + m];
+            const int hs = fa.s[k] >> 1;
+            const float *e = edge + fa.off[k] + (size_t)b * fa.s[k];
+            if (m >= 1 && m <= hs) acc += e[hs - m];
+            if (m <= N - 2 && m >= N - 1 - hs) acc += e[hs + (N - 2 - m)];
+        }
+        d_sig[(size_t)b * N + m] = acc;
+    }
+}
+
 struct FinArgs {
     int n_scales;
     int64_t off[8];          // pair offset of scale i's partials
@@ -770,15 +790,16 @@ extern "C" int ddsp_b200_mss_scale(const float *target, const float *rec, const 
     return ddsp_launch_status();
 }
 
-extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, float *d_rec, float *loss,
-                                    int B, int64_t N, const int *scales, const int *hops,
-                                    int n_scales, void *stream) {
+extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, const float *d_rec_scales,
+                                    float *d_rec, float *loss, int B, int64_t N, const int *scales,
+                                    const int *hops, int n_scales, void *stream) {
     DDSP_REQUIRE(partial && loss && scales && hops && n_scales > 0 && n_scales <= 8 && B > 0);
     DDSP_REQUIRE(!d_rec || edge);
     FinArgs fin;
     FoldArgs fold;
     fin.n_scales = fold.n_scales = n_scales;
     int64_t poff = 0, eoff = 0;
+    int hs_max = 0;
     for (int i = 0; i < n_scales; ++i) {
         HostGeom hg;
         int s = loss_geom(N, scales[i], hops[i], &hg);
@@ -790,13 +811,19 @@ extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, flo
         fold.s[i] = scales[i];
         fold.off[i] = eoff;
         eoff += (int64_t)B * scales[i];
+        hs_max = scales[i] / 2 > hs_max ? scales[i] / 2 : hs_max;
     }
     cudaStream_t st = (cudaStream_t)stream;
     mss_finalize_kernel<<<1, 256, 0, st>>>(partial, loss, fin);
     int s = ddsp_launch_status();
     if (s || !d_rec) return s;
-    int hs_max = 0;
-    for (int i = 0; i < n_scales; ++i) hs_max = scales[i] / 2 > hs_max ? scales[i] / 2 : hs_max;
+    if (d_rec_scales) {
+        // per-scale gradient buffers [n_scales][B][N] (scales launched concurrently): sum + fold
+        int gx = (int)ddsp_ceil_div(N, 256);
+        if (gx > 512) gx = 512;
+        mss_combine_kernel<<<dim3(gx, B), 256, 0, st>>>(d_rec_scales, edge, d_rec, B, N, fold);
+        return ddsp_launch_status();
+    }
     int gx = (int)ddsp_ceil_div(2 * (int64_t)hs_max + 2 >= N ? N : 2 * (int64_t)hs_max, 256);
     if (gx > 1024) gx = 1024;
     stft_fold_kernel<<<dim3(gx, B), 256, 0, st>>>(edge, d_rec, B, N, fold, hs_max);

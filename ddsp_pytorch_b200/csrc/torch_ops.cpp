@@ -9,6 +9,7 @@
 // torch::jit::load).
 #include <ATen/ATen.h>
 #include <ATen/cuda/CUDAContext.h>
+#include <ATen/cuda/CUDAEvent.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
 
@@ -66,6 +67,19 @@ Tensor stage_twiddle_table(const at::Device &dev, int64_t n_fft) {
         t = at::empty({n, 2}, at::TensorOptions().device(dev).dtype(at::kFloat));
         check(ddsp_b200_fft_stage_twiddles(fpm(t), (int)n_fft, cur_stream()), "stft_stage_twiddles");
     }
+    cache[key] = t;
+    return t;
+}
+
+Tensor noise_design_table(const at::Device &dev, int64_t NB) {
+    static std::mutex mu;
+    static std::map<std::pair<int, int64_t>, Tensor> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair((int)dev.index(), NB);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    Tensor t = at::empty({ddsp_b200_noise_design_size((int)NB)}, at::TensorOptions().device(dev).dtype(at::kFloat));
+    check(ddsp_b200_noise_design_table(fpm(t), (int)NB, cur_stream()), "noise_design_table");
     cache[key] = t;
     return t;
 }
@@ -281,8 +295,9 @@ Tensor noise_fwd(const Tensor &mags_, const Tensor &noise_, const c10::optional<
     TORCH_CHECK(!add.defined() || add.numel() == B * T * bs, "filtered noise: `add` must be (B,T*block,1)");
     c10::cuda::CUDAGuard guard(mags.device());
     Tensor out = at::empty({B, T * bs, 1}, mags.options());
-    check(ddsp_b200_filtered_noise_fwd(fp(mags), fp(noise), opt_fp(add), fpm(out), B * T, (int)NB, (int)bs,
-                                       apply_scale, (float)bias, cur_stream()),
+    Tensor design = noise_design_table(mags.device(), NB);
+    check(ddsp_b200_filtered_noise_fwd(fp(mags), fp(noise), opt_fp(add), fp(design), fpm(out), B * T, (int)NB,
+                                       (int)bs, apply_scale, (float)bias, cur_stream()),
           "filtered_noise_fwd");
     return out;
 }
@@ -296,8 +311,9 @@ Tensor noise_bwd(const Tensor &g_, const Tensor &noise_, const c10::optional<Ten
                 "filtered noise backward: raw magnitudes needed when the scale function is fused");
     c10::cuda::CUDAGuard guard(noise.device());
     Tensor d_mags = at::empty({B, T, NB}, noise.options());
-    check(ddsp_b200_filtered_noise_bwd(fp(g), fp(noise), opt_fp(raw), fpm(d_mags), B * T, (int)NB, (int)bs,
-                                       apply_scale, (float)bias, cur_stream()),
+    Tensor design = noise_design_table(noise.device(), NB);
+    check(ddsp_b200_filtered_noise_bwd(fp(g), fp(noise), opt_fp(raw), fp(design), fpm(d_mags), B * T, (int)NB,
+                                       (int)bs, apply_scale, (float)bias, cur_stream()),
           "filtered_noise_bwd");
     return d_mags;
 }
@@ -480,20 +496,37 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
     Tensor loss = at::empty({}, rec.options());
     Tensor d_rec = need_grad ? at::empty_like(rec) : at::empty({0}, rec.options());
     Tensor edge = need_grad ? at::empty({esum}, rec.options()) : Tensor();
-    void *st = cur_stream();
+    // The scales are independent (own partials, own gradient buffer): fork them over pool streams so
+    // these latency-bound launches overlap, join before the finish kernel.  Captured as graph branches.
+    Tensor d_scales = need_grad ? at::empty({ns, B, N}, rec.options()) : Tensor();
+    auto main_stream = at::cuda::getCurrentCUDAStream();
+    std::vector<at::cuda::CUDAStream> streams;
+    streams.push_back(main_stream);
+    for (int i = 1; i < ns; ++i) streams.push_back(at::cuda::getStreamFromPool(false, rec.device().index()));
+    at::cuda::CUDAEvent fork;
+    fork.record(main_stream);
+    for (int i = 1; i < ns; ++i) fork.block(streams[i]);
     int64_t woff = 0, poff = 0, eoff = 0;
     for (int i = 0; i < ns; ++i) {
         Tensor stw = stage_twiddle_table(rec.device(), sc[i]);
         check(ddsp_b200_mss_scale(fp(tgt), fp(rec), fp(win) + woff, fp(tw), (int)tw.size(0),
-                                  stw.defined() ? fp(stw) : nullptr, fpm(partial) + 2 * poff, need_grad ? fpm(d_rec) : nullptr,
-                                  need_grad ? fpm(edge) + eoff : nullptr, (int)B, N, sc[i], hp[i], i > 0, st),
+                                  stw.defined() ? fp(stw) : nullptr, fpm(partial) + 2 * poff,
+                                  need_grad ? fpm(d_scales) + (int64_t)i * B * N : nullptr,
+                                  need_grad ? fpm(edge) + eoff : nullptr, (int)B, N, sc[i], hp[i], 0,
+                                  (void *)streams[i].stream()),
               "mss_scale");
         woff += sc[i];
         poff += ddsp_b200_mss_tiles(N, sc[i], hp[i]) * B;
         eoff += B * sc[i];
     }
-    check(ddsp_b200_mss_finish(fp(partial), need_grad ? fp(edge) : nullptr, need_grad ? fpm(d_rec) : nullptr,
-                               fpm(loss), (int)B, N, sc.data(), hp.data(), ns, st),
+    for (int i = 1; i < ns; ++i) {
+        at::cuda::CUDAEvent join;
+        join.record(streams[i]);
+        join.block(main_stream);
+    }
+    check(ddsp_b200_mss_finish(fp(partial), need_grad ? fp(edge) : nullptr, need_grad ? fp(d_scales) : nullptr,
+                               need_grad ? fpm(d_rec) : nullptr, fpm(loss), (int)B, N, sc.data(), hp.data(), ns,
+                               (void *)main_stream.stream()),
           "mss_finish");
     return {loss, d_rec};
 }

@@ -108,12 +108,16 @@ int ddsp_b200_amp_to_ir_bwd(const float *d_ir, float *d_amp, int64_t rows, int N
  *   (modules.py:111-114: scale_function(raw + bias)) is applied inside the kernel.
  * add != NULL: out = filtered noise + add[rows*bs] (decoder.py:121: harmonic + noise).
  * Backward: d_mags w.r.t. what `mags` was (raw when apply_scale, which then needs mags_raw).      */
-int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, const float *add, float *out,
-                                 int64_t rows, int NB, int block_size, int apply_scale, float bias,
-                                 void *stream);
+/* design: the constant IR-design matrix of ddsp_b200_noise_design_table(NB) (caller-owned; NULL selects
+ * the first-generation kernels that rebuild the cosine sums per frame).                           */
+int64_t ddsp_b200_noise_design_size(int NB);                       /* floats */
+int ddsp_b200_noise_design_table(float *table, int NB, void *stream);
+int ddsp_b200_filtered_noise_fwd(const float *mags, const float *noise, const float *add,
+                                 const float *design, float *out, int64_t rows, int NB, int block_size,
+                                 int apply_scale, float bias, void *stream);
 int ddsp_b200_filtered_noise_bwd(const float *g_out, const float *noise, const float *mags_raw,
-                                 float *d_mags, int64_t rows, int NB, int block_size, int apply_scale,
-                                 float bias, void *stream);
+                                 const float *design, float *d_mags, int64_t rows, int NB,
+                                 int block_size, int apply_scale, float bias, void *stream);
 
 /* ---- FFT tables (caller-owned constant tables) --------------------------------------------- */
 /* table[m] = (cos, -sin)(2*pi*m/n), m in [0,n): n float2 = 2n floats; n a power of two.  One
@@ -186,15 +190,19 @@ int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int B, int64_t
  * |log(Sx+1e-7)-log(Sy+1e-7)|), ddsp_b200_mss_tiles(N,n_fft,hop)*B CTAs.  If d_rec != NULL the same
  * launch also produces d(loss)/d(rec) for unit upstream gradient (= or += into d_rec[B,N], reflect
  * padding part into edge[B,n_fft]).  ddsp_b200_mss_finish reduces the partials of all scales to
- * loss[0] (layout: scales back to back) and folds the edges.  scales/hops: HOST arrays.         */
+ * loss[0] (layout: scales back to back) and folds the edges.  scales/hops: HOST arrays.
+ * The per-scale launches are independent of each other when each gets its own d_rec buffer.      */
 int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop);
 /* stage_twiddle: the table above for n_fft (may be NULL outside 64..4096, where `twiddle` is used) */
 int ddsp_b200_mss_scale(const float *target, const float *rec, const float *window,
                         const float *twiddle, int n_tab, const float *stage_twiddle, float *partial,
                         float *d_rec, float *edge, int B, int64_t N, int n_fft, int hop, int accumulate,
                         void *stream);
-int ddsp_b200_mss_finish(const float *partial, const float *edge, float *d_rec, float *loss, int B,
-                         int64_t N, const int *scales, const int *hops, int n_scales, void *stream);
+/* d_rec_scales != NULL: the scales wrote their gradients to separate buffers [n_scales][B][N] (so
+ * their launches may overlap on different streams); finish sums them in scale order and folds.   */
+int ddsp_b200_mss_finish(const float *partial, const float *edge, const float *d_rec_scales,
+                         float *d_rec, float *loss, int B, int64_t N, const int *scales,
+                         const int *hops, int n_scales, void *stream);
 
 #ifdef __cplusplus
 }
