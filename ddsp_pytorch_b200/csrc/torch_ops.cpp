@@ -11,6 +11,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <ATen/cuda/CUDAEvent.h>
 #include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
 #include <torch/library.h>
 
 #include <map>
@@ -375,30 +376,57 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
     ConvPlan p = conv_plan(sig.device(), n + Lc - 1);
     const int pair = Rk == 1;
     const int64_t slots = pair ? (R + 1) / 2 : R;
-    void *st = cur_stream();
+    auto main_stream = at::cuda::getCurrentCUDAStream();
+    void *st = (void *)main_stream.stream();
     Tensor work_g = at::empty({slots, p.n, 2}, sig.options());
     check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(g)");
+    // d_kernel and d_signal are independent after the transform of g: the kernel-gradient chain runs on a
+    // pool stream (it only reads work_g), the signal-gradient chain (which filters work_g in place) waits
+    // for the correlation to have consumed work_g.
+    const bool fork = need_kernel && need_signal;
+    at::cuda::CUDAStream side = fork ? at::cuda::getStreamFromPool(false, sig.device().index()) : main_stream;
+    void *ss = (void *)side.stream();
+    Tensor hspec;
+    if (need_signal) {
+        hspec = at::empty({Rk, p.n, 2}, sig.options());
+        check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+        check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
+    }
+    at::cuda::CUDAEvent corr_done;
     if (need_kernel) {
+        if (fork) {
+            at::cuda::CUDAEvent g_ready;
+            g_ready.record(main_stream);
+            g_ready.block(side);
+        }
         Tensor work_x = at::empty({slots, p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), fp(p.st1), p.n1, p.n2, st),
+        check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), fp(p.st1), p.n1, p.n2, ss),
               "fft4_cols_fwd(x)");
         Tensor corr = at::empty({Rk, p.n, 2}, sig.options());
         Tensor scratch = at::empty({ddsp_b200_fft4_correlate_splits(slots, pair), p.n, 2}, sig.options());
         check(ddsp_b200_fft4_rows_correlate(fp(work_g), fp(work_x), slots, pair, fpm(scratch), fpm(corr),
-                                            fp(p.tw), fp(p.st2), p.n1, p.n2, st),
+                                            fp(p.tw), fp(p.st2), p.n1, p.n2, ss),
               "fft4_rows_correlate");
+        if (fork) corr_done.record(side);
         Tensor dk = Lc == Lk ? d_ker : at::empty({Rk, Lc}, sig.options());
-        check(ddsp_b200_fft4_cols_inv(fp(corr), fpm(dk), Rk, Lc, 0, fp(p.st1), p.n1, p.n2, st), "fft4_cols_inv(dh)");
-        if (Lc != Lk) d_ker.narrow(1, 0, Lc).copy_(dk);
+        check(ddsp_b200_fft4_cols_inv(fp(corr), fpm(dk), Rk, Lc, 0, fp(p.st1), p.n1, p.n2, ss), "fft4_cols_inv(dh)");
+        if (Lc != Lk) {
+            c10::cuda::CUDAStreamGuard sg(side);
+            d_ker.narrow(1, 0, Lc).copy_(dk);
+        }
+        // (temporaries are released after the join below, i.e. ordered after their last use)
     }
     if (need_signal) {
-        Tensor hspec = at::empty({Rk, p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
-        check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
+        if (fork) corr_done.block(main_stream);          // work_g is filtered in place below
         check(ddsp_b200_fft4_rows_filter(fpm(work_g), slots, fp(hspec), pair ? 0 : p.n, 1, fp(p.tw), fp(p.st2), p.n1, p.n2, st),
               "fft4_rows_filter(conj)");
         check(ddsp_b200_fft4_cols_inv(fp(work_g), fpm(d_sig), R, n, pair, fp(p.st1), p.n1, p.n2, st),
               "fft4_cols_inv(dx)");
+    }
+    if (fork) {
+        at::cuda::CUDAEvent join;
+        join.record(side);
+        join.block(main_stream);
     }
     return {d_sig, d_ker};
 }

@@ -58,6 +58,7 @@ class SynthStep:
             self.reverb = Reverb(s.reverb_length, s.sample_rate).to(dev)
             if reverb_state is not None:
                 self.reverb.load_state_dict(reverb_state)
+        self._side_stream = torch.cuda.Stream(device=dev)
         self.loss = torch.zeros((), **f32)
         self.signal = None
         self.grads = None
@@ -81,10 +82,20 @@ class SynthStep:
             leaves = [i["amp_raw"], i["dist_raw"], i["mag_raw"]]
             if self.reverb is not None:
                 leaves += [self.reverb.noise, self.reverb.decay, self.reverb.wet]
+        # The noise branch and the harmonic branch are independent until the mix (decoder.py:121): run the
+        # noise branch on a side stream.  Autograd replays each node's backward on its forward stream, so the
+        # two backward branches overlap as well; under capture both become parallel graph branches.
+        cur = torch.cuda.current_stream()
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            # FilteredNoise.get_controls + forward in one launch
+            noise = F_.FilteredNoiseFused.apply(leaves[2], i["noise"], None, -5.0)
         _, _, weights = F_.HarmonicControlsWeights.apply(leaves[0], leaves[1], i["pitch"], float(s.sample_rate))
         harmonic, _ = core.harmonic_synth_frames(i["pitch"], weights, s.block_size, s.sample_rate)
-        # FilteredNoise.get_controls + forward + "harmonic + noise" in one launch
-        signal = F_.FilteredNoiseFused.apply(leaves[2], i["noise"], harmonic, -5.0)
+        cur.wait_stream(side)
+        noise.record_stream(cur)
+        signal = harmonic + noise
         if self.reverb is not None:
             impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
             taps = min(s.samples, s.reverb_length)
