@@ -227,6 +227,18 @@ def kernel_table(step, shapes, flush, peaks):
     add("K4L mss_loss fwd+grad (6 scales + finish)",
         lambda: ops.mss_loss_fwd(i["target"], sig2, list(shapes.scales), shapes.overlap, windows, True),
         alg_bytes=4 * 3 * B * N, note="SURVEY 8d: read rec+target, write grad")
+    # the same kernel against the FP32 pipe: 5 n log2 n flops per complex FFT, one forward per frame
+    # (rec + i*target) and one inverse per frame pair
+    import math
+    fft_flops = 0.0
+    for s_ in shapes.scales:
+        hop = int(s_ * (1 - shapes.overlap))
+        fft_flops += 1.5 * (1 + N // hop) * 5.0 * s_ * math.log2(s_)
+    fft_flops *= B
+    k4 = rows[-1]
+    k4["fp32"] = {"achieved": fft_flops / (k4["ms"] * 1e-3) / 1e12, "peak": 2 * fma_peak / 1e12, "unit": "TFLOP/s",
+                  "frac": fft_flops / (k4["ms"] * 1e-3) / (2 * fma_peak),
+                  "note": "FFT butterflies only (7.0 GFLOP/step); the kernel is FP32/latency bound, not HBM bound"}
     add("K0 harmonic_controls_fwd", lambda: ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr, True),
         alg_bytes=4 * B * T * (2 * H + 3))
     return rows
@@ -378,6 +390,8 @@ def run_b200(args, rank, world):
                     "traffic": None, "ms": top["ms"], "peak_source": peaks["source"]}
             if top["bound"] != "hbm":
                 roof["bound_detail"] = "fp32 FMA pipe, not tensor cores (no GEMM on this path)"
+            if "fp32" in top:
+                roof["fp32"] = top["fp32"]
         cpu = None
         if world == 1 and not args.skip_cpu:
             cshapes, times, cores = time_cpu_port(args.cpu_batch, 3, 1)
