@@ -16,6 +16,8 @@
 //  * backward (d weights): one thread owns (frame, harmonic, chunk of samples) and walks TIME with
 //    the same recurrence (the frame's phase increment is constant), so the reduction over the
 //    frame's samples is a private accumulation; g is broadcast from shared memory.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -162,6 +164,124 @@ harmonic_frames_fwd_kernel(const float *__restrict__ weights, const uint64_t *__
 }
 
 // ------------------------------------------------------------------------------------------
+// Forward, packed-FP32 variant (sm_100 FFMA2 / FADD2: one instruction works on a register pair holding
+// two floats).  Thread = 4 consecutive samples = two pairs; the recurrence state (s, d, u) and the two
+// accumulators live in 64-bit registers, weights sit in shared memory already duplicated (A, A) so one
+// LDS.128 feeds two harmonics.  Per harmonic and 4 samples: 6 packed math instructions instead of 12.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+__global__ void __launch_bounds__(kFwdThreads)
+harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t *__restrict__ phi,
+                              const uint64_t *__restrict__ delta, float *__restrict__ audio, int T,
+                              int H, int Hp, int bs, int FR) {
+    extern __shared__ __align__(16) float smem[];
+    float2 *w2 = reinterpret_cast<float2 *>(smem);                         // [FR][Hp] of (A, A)
+    uint64_t *sphi = reinterpret_cast<uint64_t *>(w2 + (size_t)FR * Hp);   // [FR]
+    uint64_t *sdel = sphi + FR;
+
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FR;
+    const int nfr = min(FR, T - t0);
+    const int tid = threadIdx.x;
+    const float *wg = weights + ((size_t)b * T + t0) * H;
+    for (int i = tid; i < nfr * Hp; i += kFwdThreads) {
+        const int f = i / Hp, k = i - f * Hp;
+        const float a = k < H ? __ldg(wg + (size_t)f * H + k) : 0.f;
+        w2[i] = make_float2(a, a);
+    }
+    if (tid < nfr) {
+        sphi[tid] = phi[(size_t)b * T + t0 + tid];
+        sdel[tid] = delta[(size_t)b * T + t0 + tid];
+    }
+    __syncthreads();
+
+    const int S = nfr * bs;
+    float *out = audio + ((size_t)b * T + t0) * bs;
+    for (int i0 = tid * 4; i0 < S; i0 += kFwdThreads * 4) {
+        const int f = i0 / bs;
+        const int j0 = i0 - f * bs;
+        const uint64_t ph = sphi[f], dl = sdel[f];
+        const ulonglong2 *wr = reinterpret_cast<const ulonglong2 *>(w2 + (size_t)f * Hp);   // 2 harmonics each
+
+        float q[4], ch[4], s0[4], u0[4];
+        int flip[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const uint64_t p = ph + (uint64_t)(j0 + e + 1) * dl;
+            const float x = ddsp_fold_quarter(p, &flip[e]) * DDSP_PI_F;
+            const float sh = ddsp_sin_q(x);
+            ch[e] = ddsp_cos_q(x);
+            q[e] = 2.f * sh;
+            u0[e] = -q[e] * q[e];
+            s0[e] = q[e] * ch[e];
+        }
+        uint64_t sA = pk2(s0[0], s0[1]), sB = pk2(s0[2], s0[3]);
+        uint64_t dA = sA, dB = sB;
+        const uint64_t uA = pk2(u0[0], u0[1]), uB = pk2(u0[2], u0[3]);
+        uint64_t aeA = 0, aeB = 0, aoA = 0, aoB = 0;                       // (+0.f, +0.f)
+        for (int k0 = 0; k0 < Hp; k0 += kReseed) {
+            if (k0 > 0) {
+                float sn[4], dn[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint64_t p = ph + (uint64_t)(j0 + e + 1) * dl;
+                    const uint32_t r = (uint32_t)(((p >> 62) + 1) >> 1);
+                    const uint64_t psi = p - ((uint64_t)r << 63);
+                    const float a = ddsp_turns_signed((uint64_t)(k0 + 1) * psi) * DDSP_2PI_F;
+                    float sk, ck;
+                    __sincosf(a, &sk, &ck);
+                    sn[e] = sk;
+                    dn[e] = q[e] * fmaf(ck, ch[e], sk * (0.5f * q[e]));
+                }
+                sA = pk2(sn[0], sn[1]); sB = pk2(sn[2], sn[3]);
+                dA = pk2(dn[0], dn[1]); dB = pk2(dn[2], dn[3]);
+            }
+            const int kend = min(k0 + kReseed, Hp);
+            for (int k = k0; k < kend; k += 4) {
+                const ulonglong2 a01 = wr[k >> 1], a23 = wr[(k >> 1) + 1];
+                // harmonic k+1 (odd)
+                aoA = fma2(a01.x, sA, aoA); aoB = fma2(a01.x, sB, aoB);
+                dA = fma2(uA, sA, dA); dB = fma2(uB, sB, dB); sA = add2(sA, dA); sB = add2(sB, dB);
+                // harmonic k+2 (even)
+                aeA = fma2(a01.y, sA, aeA); aeB = fma2(a01.y, sB, aeB);
+                dA = fma2(uA, sA, dA); dB = fma2(uB, sB, dB); sA = add2(sA, dA); sB = add2(sB, dB);
+                aoA = fma2(a23.x, sA, aoA); aoB = fma2(a23.x, sB, aoB);
+                dA = fma2(uA, sA, dA); dB = fma2(uB, sB, dB); sA = add2(sA, dA); sB = add2(sB, dB);
+                aeA = fma2(a23.y, sA, aeA); aeB = fma2(a23.y, sB, aeB);
+                dA = fma2(uA, sA, dA); dB = fma2(uB, sB, dB); sA = add2(sA, dA); sB = add2(sB, dB);
+            }
+        }
+        float ae[4], ao[4];
+        unpk2(aeA, ae[0], ae[1]); unpk2(aeB, ae[2], ae[3]);
+        unpk2(aoA, ao[0], ao[1]); unpk2(aoB, ao[2], ao[3]);
+        float4 y;
+        y.x = flip[0] ? ae[0] - ao[0] : ae[0] + ao[0];
+        y.y = flip[1] ? ae[1] - ao[1] : ae[1] + ao[1];
+        y.z = flip[2] ? ae[2] - ao[2] : ae[2] + ao[2];
+        y.w = flip[3] ? ae[3] - ao[3] : ae[3] + ao[3];
+        *reinterpret_cast<float4 *>(out + i0) = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Backward w.r.t. weights.  CTA = FR frames of one voice; work item = (chunk, frame, harmonic).
 // ------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 256;
@@ -215,6 +335,79 @@ harmonic_frames_bwd_w_kernel(const float *__restrict__ g_audio, const uint64_t *
         }
         if (j < jhi) a0 = fmaf(gp[j], o.s, a0);
         part[((size_t)c * nfr + f) * H + k] = (r & 1u) ? a0 - a1 : a0 + a1;
+    }
+    __syncthreads();
+    float *dw = d_weights + ((size_t)b * T + t0) * H;
+    for (int i = tid; i < nfr * H; i += kBwdThreads) {
+        float acc = 0.f;
+        for (int c = 0; c < nchunk; ++c) acc += part[(size_t)c * nfr * H + i];
+        dw[i] = acc;
+    }
+}
+
+// Backward w.r.t. weights, packed-FP32 variant: one thread walks time for TWO harmonics (k, k+1) held in
+// a register pair; g is staged duplicated (g, g) so the packed FFMA2 needs no per-step packing.
+__global__ void __launch_bounds__(kBwdThreads)
+harmonic_frames_bwd_w_x2_kernel(const float *__restrict__ g_audio, const uint64_t *__restrict__ phi,
+                                const uint64_t *__restrict__ delta, float *__restrict__ d_weights,
+                                int T, int H, int bs, int FR, int nchunk, int clen) {
+    extern __shared__ __align__(16) float smem[];
+    float2 *g2 = reinterpret_cast<float2 *>(smem);                       // [FR*bs] of (g, g)
+    float *part = smem + 2 * (((size_t)FR * bs + 1) & ~(size_t)1);       // [nchunk][FR][H]
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * FR;
+    const int nfr = min(FR, T - t0);
+    const int tid = threadIdx.x;
+    const int HP2 = (H + 1) >> 1;                                        // harmonic pairs
+
+    const float *gg = g_audio + ((size_t)b * T + t0) * bs;
+    for (int i = tid; i < nfr * bs; i += kBwdThreads) {
+        const float v = __ldg(gg + i);
+        g2[i] = make_float2(v, v);
+    }
+    __syncthreads();
+
+    const int items = nchunk * nfr * HP2;
+    for (int it = tid; it < items; it += kBwdThreads) {
+        const int kp = it % HP2;
+        const int fc = it / HP2;
+        const int f = fc % nfr;
+        const int c = fc / nfr;
+        const int jlo = c * clen, jhi = min(jlo + clen, bs);
+        const uint64_t ph = phi[(size_t)b * T + t0 + f], dl = delta[(size_t)b * T + t0 + f];
+        float s0[2], d0[2], u0[2];
+        uint32_t rr[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const uint64_t kk = (uint64_t)(2 * kp + e + 1);
+            const uint64_t alpha = kk * dl;
+            const uint32_t r = (uint32_t)(((alpha >> 62) + 1) >> 1);
+            const uint64_t af = alpha - ((uint64_t)r << 63);
+            const float q = 2.f * ddsp_sin_q(ddsp_turns_signed(af) * DDSP_PI_F);
+            const uint64_t th = kk * (ph + (uint64_t)(jlo + 1) * dl);
+            rr[e] = r & 1u;
+            u0[e] = -q * q;
+            s0[e] = __sinf(ddsp_turns_signed(th) * DDSP_2PI_F);
+            d0[e] = q * __cosf(ddsp_turns_signed(th - (uint64_t)((int64_t)af >> 1)) * DDSP_2PI_F);
+        }
+        uint64_t sP = pk2(s0[0], s0[1]), dP = pk2(d0[0], d0[1]);
+        const uint64_t uP = pk2(u0[0], u0[1]);
+        uint64_t a0 = 0, a1 = 0;                        // even / odd sample offsets from jlo
+        const uint64_t *gp = reinterpret_cast<const uint64_t *>(g2 + (size_t)f * bs);
+        int j = jlo;
+        for (; j + 1 < jhi; j += 2) {
+            a0 = fma2(gp[j], sP, a0);
+            dP = fma2(uP, sP, dP); sP = add2(sP, dP);
+            a1 = fma2(gp[j + 1], sP, a1);
+            dP = fma2(uP, sP, dP); sP = add2(sP, dP);
+        }
+        if (j < jhi) a0 = fma2(gp[j], sP, a0);
+        float e0[2], e1[2];
+        unpk2(a0, e0[0], e0[1]);
+        unpk2(a1, e1[0], e1[1]);
+        float *dst = part + ((size_t)c * nfr + f) * H + 2 * kp;
+        dst[0] = rr[0] ? e0[0] - e1[0] : e0[0] + e1[0];
+        if (2 * kp + 1 < H) dst[1] = rr[1] ? e0[1] - e1[1] : e0[1] + e1[1];
     }
     __syncthreads();
     float *dw = d_weights + ((size_t)b * T + t0) * H;
@@ -463,7 +656,15 @@ extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_
         harmonic_frames_fwd_kernel<SPT><<<grid, kFwdThreads, smem, st>>>(weights, phi, delta,    \
                                                                          audio, T, H, Hp, bs, fr); \
     } while (0)
-    if (spt == 4) LAUNCH(4); else if (spt == 2) LAUNCH(2); else LAUNCH(1);
+    static const bool scalar_only = getenv("DDSP_B200_HARMONIC_SCALAR") != nullptr;   // A/B switch
+    const size_t smem2 = 2 * (size_t)fr * Hp * sizeof(float) + 2 * (size_t)fr * sizeof(uint64_t);
+    if (spt == 4 && !scalar_only && smem2 <= 200 * 1024) {
+        if (smem2 > 48 * 1024)
+            cudaFuncSetAttribute(harmonic_frames_fwd_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem2);
+        harmonic_frames_fwd_x2_kernel<<<grid, kFwdThreads, smem2, st>>>(weights, phi, delta, audio, T, H, Hp,
+                                                                       bs, fr);
+    } else if (spt == 4) LAUNCH(4); else if (spt == 2) LAUNCH(2); else LAUNCH(1);
 #undef LAUNCH
     return ddsp_launch_status();
 }
@@ -476,20 +677,32 @@ extern "C" int ddsp_b200_harmonic_frames_bwd_weights(const float *g_audio, const
     const int bs = block_size;
     const int nchunk = (bs + kChunk - 1) / kChunk;
     const int clen = (((bs + nchunk - 1) / nchunk) + 1) & ~1;   // even, so chunk parity is uniform
+    static const bool scalar_only = getenv("DDSP_B200_HARMONIC_SCALAR") != nullptr;   // A/B switch
+    const bool packed = !scalar_only;
+    const int per_frame = nchunk * (packed ? (H + 1) / 2 : H);          // work items per frame
     // enough (chunk, frame, harmonic) items for >= 4 sweeps of the CTA
-    int fr = (4 * kBwdThreads + nchunk * H - 1) / (nchunk * H);
+    int fr = (4 * kBwdThreads + per_frame - 1) / per_frame;
     if (fr > T) fr = T;
     if (fr < 1) fr = 1;
-    size_t smem = ((((size_t)fr * bs + 3) & ~(size_t)3) + (size_t)nchunk * fr * H) * sizeof(float);
-    while (smem > 200 * 1024 && fr > 1) {
-        fr = (fr + 1) / 2;
-        smem = ((((size_t)fr * bs + 3) & ~(size_t)3) + (size_t)nchunk * fr * H) * sizeof(float);
-    }
+    auto bytes = [&](int fr_) {
+        const size_t gsz = packed ? 2 * (((size_t)fr_ * bs + 1) & ~(size_t)1) : (((size_t)fr_ * bs + 3) & ~(size_t)3);
+        return (gsz + (size_t)nchunk * fr_ * H) * sizeof(float);
+    };
+    while (bytes(fr) > 200 * 1024 && fr > 1) fr = (fr + 1) / 2;
+    const size_t smem = bytes(fr);
     if (smem > 200 * 1024) return DDSP_B200_EUNSUPPORTED;
+    dim3 grid((T + fr - 1) / fr, B);
+    if (packed) {
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(harmonic_frames_bwd_w_x2_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        harmonic_frames_bwd_w_x2_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(
+            g_audio, phi, delta, d_weights, T, H, bs, fr, nchunk, clen);
+        return ddsp_launch_status();
+    }
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(harmonic_frames_bwd_w_kernel,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((T + fr - 1) / fr, B);
     harmonic_frames_bwd_w_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(
         g_audio, phi, delta, d_weights, T, H, bs, fr, nchunk, clen);
     return ddsp_launch_status();
