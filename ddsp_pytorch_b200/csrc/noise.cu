@@ -396,7 +396,8 @@ filtered_noise2_fwd_kernel(const float *__restrict__ mags, const float *__restri
     const int half = L.half, F = L.F;
     float *D = smem;                                     // [NB][F]
     float *rowbase = D + NB * F;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = kN2Threads / 32;
     for (int i = tid; i < NB * F / 4; i += kN2Threads)
         reinterpret_cast<float4 *>(D)[i] = __ldg(reinterpret_cast<const float4 *>(design) + i);
 
@@ -404,57 +405,77 @@ filtered_noise2_fwd_kernel(const float *__restrict__ mags, const float *__restri
     for (int64_t r0 = (int64_t)blockIdx.x * RPC; r0 < rows; r0 += (int64_t)gridDim.x * RPC) {
         const int nr = (int)min((int64_t)RPC, rows - r0);
         __syncthreads();
-        // ---- A: stage
-        for (int i = tid; i < nr * NB; i += kN2Threads) {
-            const int r = i / NB, k = i - r * NB;
-            const float m = __ldg(mags + (r0 + r) * NB + k);
-            rowbase[r * L.stride + L.m() + k] = apply_scale ? ddsp_scale_fn(m + bias) : m;
-        }
-        for (int i = tid; i < nr * L.xs_len; i += kN2Threads) {
-            const int r = i / L.xs_len, j = i - r * L.xs_len;
-            rowbase[r * L.stride + L.xs() + j] = j < half ? 0.f : __ldg(noise + (r0 + r) * bs + (j - half));
-        }
-        __syncthreads();
-        // ---- B: taps[r][8cg..8cg+7] = sum_k m[r][k] * D[k][...]
-        for (int it = tid; it < nr * (F / 8); it += kN2Threads) {
-            const int r = it / (F / 8), cg = it - r * (F / 8);
-            const float *m = rowbase + r * L.stride + L.m();
-            const float4 *d4 = reinterpret_cast<const float4 *>(D) + cg * 2;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-            for (int k = 0; k < NB; ++k) {
-                const float mk = m[k];
-                const float4 u = d4[k * (F / 4)], v = d4[k * (F / 4) + 1];
-                a.x = fmaf(mk, u.x, a.x); a.y = fmaf(mk, u.y, a.y); a.z = fmaf(mk, u.z, a.z); a.w = fmaf(mk, u.w, a.w);
-                c.x = fmaf(mk, v.x, c.x); c.y = fmaf(mk, v.y, c.y); c.z = fmaf(mk, v.z, c.z); c.w = fmaf(mk, v.w, c.w);
-            }
-            float4 *t4 = reinterpret_cast<float4 *>(rowbase + r * L.stride + L.taps()) + cg * 2;
-            t4[0] = a;
-            t4[1] = c;
-        }
-        __syncthreads();
-        // ---- C: main FIR (causal taps) over the frame, far FIR over its first `half` samples
-        for (int it = tid; it < nr * (QM + QF); it += kN2Threads) {
-            const int r = it / (QM + QF), q = it - r * (QM + QF);
+        // ---- A: stage (one warp per row, lanes along the row: coalesced, no index division)
+        for (int r = warp; r < nr; r += NW) {
             float *rb = rowbase + r * L.stride;
-            const float4 *t4 = reinterpret_cast<const float4 *>(rb + L.taps());
-            if (q < QM) {
-                const float4 y = fir4(t4, rb + L.xs() + half + 4 * q, half);
+            const float *mg = mags + (r0 + r) * NB;
+            for (int k = lane; k < NB; k += 32) {
+                const float m = __ldg(mg + k);
+                rb[L.m() + k] = apply_scale ? ddsp_scale_fn(m + bias) : m;
+            }
+            for (int j = lane; j < half; j += 32) rb[L.xs() + j] = 0.f;
+            const float4 *nz = reinterpret_cast<const float4 *>(noise + (r0 + r) * bs);
+            float4 *xs4 = reinterpret_cast<float4 *>(rb + L.xs() + half);
+            for (int j = lane; j < QM; j += 32) xs4[j] = __ldg(nz + j);
+        }
+        __syncthreads();
+        // ---- B: taps[r][4c..4c+3] for two rows at a time = sum_k m[r][k] * D[k][...]
+        //      (lanes take consecutive 16-byte columns of D: conflict-free)
+        for (int it = tid; it < ((nr + 1) >> 1) * (F / 4); it += kN2Threads) {
+            const int rp = it / (F / 4), c = it - rp * (F / 4);
+            const int ra = 2 * rp, rb_ = min(2 * rp + 1, nr - 1);
+            const float *ma = rowbase + ra * L.stride + L.m();
+            const float *mb = rowbase + rb_ * L.stride + L.m();
+            const float4 *d4 = reinterpret_cast<const float4 *>(D) + c;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), e = a;
+            for (int k = 0; k < NB; ++k) {
+                const float4 u = d4[k * (F / 4)];
+                const float x = ma[k], y = mb[k];
+                a.x = fmaf(x, u.x, a.x); a.y = fmaf(x, u.y, a.y); a.z = fmaf(x, u.z, a.z); a.w = fmaf(x, u.w, a.w);
+                e.x = fmaf(y, u.x, e.x); e.y = fmaf(y, u.y, e.y); e.z = fmaf(y, u.z, e.z); e.w = fmaf(y, u.w, e.w);
+            }
+            reinterpret_cast<float4 *>(rowbase + ra * L.stride + L.taps())[c] = a;
+            if (rb_ != ra) reinterpret_cast<float4 *>(rowbase + rb_ * L.stride + L.taps())[c] = e;
+        }
+        __syncthreads();
+        // ---- C: main FIR (causal taps) over the frame, then far FIR over its first `half` samples; the two
+        //      kinds of work item are laid out one after the other so that warps do not mix them
+        const int nmain = nr * QM;
+        for (int it = tid; it < nmain + nr * QF; it += kN2Threads) {
+            if (it < nmain) {
+                const int r = it / QM, q = it - r * QM;
+                float *rb = rowbase + r * L.stride;
+                const float4 y = fir4(reinterpret_cast<const float4 *>(rb + L.taps()), rb + L.xs() + half + 4 * q, half);
                 *reinterpret_cast<float4 *>(rb + L.ys() + 4 * q) = y;
             } else {
-                const int qq = q - QM;
-                const float4 y = fir4(t4 + QF, rb + L.xs() + half + 4 * qq, half);
+                const int i2 = it - nmain;
+                const int r = i2 / QF, qq = i2 - r * QF;
+                float *rb = rowbase + r * L.stride;
+                const float4 y = fir4(reinterpret_cast<const float4 *>(rb + L.taps()) + QF,
+                                      rb + L.xs() + half + 4 * qq, half);
                 *reinterpret_cast<float4 *>(rb + L.yf() + 4 * qq) = y;
             }
         }
         __syncthreads();
-        // ---- D: out = main + far (last `half` samples) (+ add)
-        for (int i = tid; i < nr * bs; i += kN2Threads) {
-            const int r = i / bs, j = i - r * bs;
+        // ---- D: out = main + far (last `half` samples) (+ add), one warp per row, float4
+        for (int r = warp; r < nr; r += NW) {
             const float *rb = rowbase + r * L.stride;
-            float y = rb[L.ys() + j];
-            if (j >= bs - half) y += rb[L.yf() + j - (bs - half)];
-            if (add) y += __ldg(add + (r0 + r) * bs + j);
-            out[(r0 + r) * bs + j] = y;
+            const float4 *ys4 = reinterpret_cast<const float4 *>(rb + L.ys());
+            const float4 *yf4 = reinterpret_cast<const float4 *>(rb + L.yf());
+            const float4 *ad4 = add ? reinterpret_cast<const float4 *>(add + (r0 + r) * bs) : nullptr;
+            float4 *o4 = reinterpret_cast<float4 *>(out + (r0 + r) * bs);
+            for (int j = lane; j < QM; j += 32) {
+                float4 y = ys4[j];
+                if (j >= QM - QF) {
+                    const float4 f = yf4[j - (QM - QF)];
+                    y.x += f.x; y.y += f.y; y.z += f.z; y.w += f.w;
+                }
+                if (ad4) {
+                    const float4 f = __ldg(ad4 + j);
+                    y.x += f.x; y.y += f.y; y.z += f.z; y.w += f.w;
+                }
+                o4[j] = y;
+            }
         }
     }
 }
@@ -469,32 +490,39 @@ filtered_noise2_bwd_kernel(const float *__restrict__ g_out, const float *__restr
     const int half = L.half, F = L.F, NBq = L.NBq;
     float *Dt = smem;                                    // [F][NBq]
     float *rowbase = Dt + F * NBq;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = kN2Threads / 32;
     const float *dt_src = design + (size_t)NB * F;
     for (int i = tid; i < F * NBq / 4; i += kN2Threads)
         reinterpret_cast<float4 *>(Dt)[i] = __ldg(reinterpret_cast<const float4 *>(dt_src) + i);
+    const int QM = bs >> 2;
 
     for (int64_t r0 = (int64_t)blockIdx.x * RPC; r0 < rows; r0 += (int64_t)gridDim.x * RPC) {
         const int nr = (int)min((int64_t)RPC, rows - r0);
         __syncthreads();
-        for (int i = tid; i < nr * L.xs_len; i += kN2Threads) {
-            const int r = i / L.xs_len, j = i - r * L.xs_len;
-            rowbase[r * L.stride + L.xs() + j] = j < half ? 0.f : __ldg(noise + (r0 + r) * bs + (j - half));
-        }
-        for (int i = tid; i < nr * bs; i += kN2Threads) {
-            const int r = i / bs, j = i - r * bs;
-            rowbase[r * L.stride + L.ys() + j] = __ldg(g_out + (r0 + r) * bs + j);
+        for (int r = warp; r < nr; r += NW) {
+            float *rb = rowbase + r * L.stride;
+            for (int j = lane; j < half; j += 32) rb[L.xs() + j] = 0.f;
+            const float4 *nz = reinterpret_cast<const float4 *>(noise + (r0 + r) * bs);
+            const float4 *gz = reinterpret_cast<const float4 *>(g_out + (r0 + r) * bs);
+            float4 *xs4 = reinterpret_cast<float4 *>(rb + L.xs() + half);
+            float4 *g4 = reinterpret_cast<float4 *>(rb + L.ys());
+            for (int j = lane; j < QM; j += 32) {
+                xs4[j] = __ldg(nz + j);
+                g4[j] = __ldg(gz + j);
+            }
         }
         __syncthreads();
-        // ---- d taps: causal taps correlate the whole frame, far taps its last `half` outputs
-        for (int it = tid; it < nr * (F / 4); it += kN2Threads) {
-            const int r = it / (F / 4), tg = it - r * (F / 4);
+        // ---- d taps: causal taps correlate the whole frame (long items first), far taps its last `half`
+        const int ncausal = nr * (half / 4);
+        for (int it = tid; it < 2 * ncausal; it += kN2Threads) {
+            const bool far = it >= ncausal;
+            const int i2 = far ? it - ncausal : it;
+            const int r = i2 / (half / 4), tg = i2 - r * (half / 4);
             float *rb = rowbase + r * L.stride;
             const float *x = rb + L.xs() + half;
-            float4 a;
-            if (tg < half / 4) a = corr4(rb + L.ys(), x, 4 * tg, bs);
-            else a = corr4(rb + L.ys() + bs - half, x, 4 * (tg - half / 4), half);
-            *reinterpret_cast<float4 *>(rb + L.taps() + 4 * tg) = a;
+            const float4 a = far ? corr4(rb + L.ys() + bs - half, x, 4 * tg, half) : corr4(rb + L.ys(), x, 4 * tg, bs);
+            *reinterpret_cast<float4 *>(rb + L.taps() + (far ? half : 0) + 4 * tg) = a;
         }
         __syncthreads();
         // ---- d m[r][4kg..] = sum_j dtaps[r][j] * Dt[j][...]
