@@ -42,12 +42,18 @@ def t64(a, grad=False):
     return t.requires_grad_(True) if grad else t
 
 
+def _ref64(ref):
+    if isinstance(ref, torch.Tensor):
+        return ref.detach().double().cpu()
+    return torch.as_tensor(np.asarray(ref)).double()
+
+
 def max_abs(got, ref):
-    return float((got.detach().double().cpu() - torch.as_tensor(np.asarray(ref)).double()).abs().max())
+    return float((got.detach().double().cpu() - _ref64(ref)).abs().max())
 
 
 def rel_err(got, ref):
-    ref = torch.as_tensor(np.asarray(ref)).double()
+    ref = _ref64(ref)
     return float((got.detach().double().cpu() - ref).norm() / ref.norm().clamp_min(1e-30))
 
 
@@ -484,3 +490,77 @@ def test_hotpath_step_against_oracle(ddsp, orc):
     step.step_prefetched()
     torch.cuda.synchronize()
     assert torch.equal(step.loss, eager_loss)
+
+
+# ------------------------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("B,T,bs,H,NB", [(1, 1, 128, 1, 65), (2, 3, 128, 7, 65), (1, 5, 256, 33, 33),
+                                           (3, 2, 64, 13, 9), (1, 2, 160, 101, 65)])
+def test_ragged_shapes_forward_backward(ddsp, orc, B, T, bs, H, NB):
+    """Single frame / single harmonic, harmonic counts that are not multiples of 4, block == filter size,
+    other band counts: module chain against the float64 oracle, forward and gradients."""
+    from ddsp_pytorch_b200.models.modules import FilteredNoise, HarmonicSynth
+    sr = 16000
+    gen = torch.Generator().manual_seed(B * 1000 + T * 100 + H)
+    amp = torch.randn(B, T, 1, generator=gen)
+    dist = torch.randn(B, T, H, generator=gen)
+    mag = torch.randn(B, T, NB, generator=gen)
+    f0 = torch.rand(B, T, 1, generator=gen) * 500 + 60
+    noise = torch.rand(B, T, bs, generator=gen) * 2 - 1
+    go = torch.randn(B, T * bs, 1, generator=gen)
+    # oracle
+    a64, d64, m64 = (t.double().requires_grad_(True) for t in (amp, dist, mag))
+    out = orc.synth_chain(a64, d64, m64, f0.double(), noise.double(), bs, sr, None)
+    (out["signal"] * go.double()).sum().backward()
+    # kernels
+    a, d, m = (t.cuda().requires_grad_(True) for t in (amp, dist, mag))
+    hs, fn = HarmonicSynth(bs, sr), FilteredNoise(bs, NB)
+    c = hs.get_controls(a, d, f0.cuda())
+    sig = hs(**c) + fn(fn.get_controls(m)["magnitudes"], noise=noise.cuda())
+    assert_audio(sig, out["signal"])
+    (sig * go.cuda()).sum().backward()
+    assert_grad(a.grad, a64.grad)
+    assert_grad(d.grad, d64.grad)
+    assert_grad(m.grad, m64.grad)
+
+
+def test_non_contiguous_and_strided_inputs(ddsp, orc):
+    """decoder.py:107-108 hands the synth strided slices of one projection (param[..., :1], param[..., 1:])."""
+    gen = torch.Generator().manual_seed(21)
+    B, T, H, bs, sr = 2, 6, 12, 160, 16000
+    param = torch.randn(B, T, H + 1, generator=gen)
+    f0 = torch.rand(B, T, 1, generator=gen) * 300 + 100
+    from ddsp_pytorch_b200.models.modules import HarmonicSynth
+    hs = HarmonicSynth(bs, sr)
+    p = param.cuda().requires_grad_(True)
+    c = hs.get_controls(p[..., :1], p[..., 1:], f0.cuda())
+    y = hs(**c)
+    p64 = param.double().requires_grad_(True)
+    c64 = orc.harmonic_controls(p64[..., :1], p64[..., 1:], f0.double(), sr)
+    y64 = orc.harmonic_synth_frames(c64["amplitudes"], c64["harmonic_distribution"], f0.double(), bs, sr)
+    assert_audio(y, y64)
+    go = torch.randn(y64.shape, generator=gen)
+    (y * go.cuda()).sum().backward()
+    (y64 * go.double()).sum().backward()
+    assert_grad(p.grad, p64.grad)
+
+
+def test_unsupported_shapes_fail_loudly(ddsp):
+    """Shapes outside what the kernels implement raise (no silent fallback)."""
+    with pytest.raises(RuntimeError):           # block smaller than the 128-tap noise filter
+        ddsp.filtered_noise(torch.rand(1, 2, 65).cuda(), torch.rand(1, 2, 64).cuda())
+    with pytest.raises(RuntimeError):           # reflect padding needs n_fft/2 < N, as torch.stft
+        ddsp.multiscale_fft(torch.rand(1, 100).cuda(), [512], 0.75)
+    with pytest.raises(RuntimeError):           # float64 is the oracle's job
+        ddsp.scale_function(torch.zeros(4, dtype=torch.float64).cuda())
+
+
+def test_large_amplitude_and_extreme_pitch(ddsp, orc):
+    """f0 near 0, near and above Nyquist, and loud controls: masks, folding and the recurrence hold."""
+    B, T, bs, H, sr = 1, 8, 160, 64, 16000
+    f0 = torch.tensor([0.5, 20.0, 7999.0, 8001.0, 15999.0, 3999.9, 125.0, 4000.0]).view(1, T, 1)
+    gen = torch.Generator().manual_seed(33)
+    w = torch.rand(B, T, H, generator=gen)
+    ref = orc.harmonic_synth(orc.upsample(f0.double(), bs), orc.upsample(w.double(), bs), sr)
+    got, _ = ddsp.harmonic_synth_frames(f0.cuda(), w.cuda(), bs, sr)
+    # sum of weights is ~32 here (not normalised): scale the 1e-4 bar accordingly
+    assert_audio(got, ref, 1e-4 * float(w.sum(-1).max()) / 2)
