@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "DDSP synth audio samples/sec (fwd+bwd)"
+K4L_DRAM_TRAFFIC = 197.2e6       # bytes per step, from the round-1 ncu --set full capture (profiles/)
 UNIT = "samples/s"
 WORKLOAD = dict(sample_rate=16000, block_size=160, n_harmonic=100, n_bands=65, frames=400, batch=64,
                 reverb_length=16000, scales=(4096, 2048, 1024, 512, 256, 128), overlap=0.75)
@@ -387,7 +388,12 @@ def run_b200(args, rank, world):
             top = max(kernels, key=lambda r: r["ms"])
             roof = {"kernel": top["kernel"], "bound": top["bound"] if top["bound"] == "hbm" else "tensor",
                     "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
-                    "traffic": None, "ms": top["ms"], "peak_source": peaks["source"]}
+                    "traffic": K4L_DRAM_TRAFFIC if top["kernel"].startswith("K4L") else None, "ms": top["ms"],
+                    "peak_source": peaks["source"]}
+            if top["kernel"].startswith("K4L"):
+                roof["traffic_note"] = ("dram__bytes_read+write summed over the 6 per-scale launches of one step, "
+                                        "profiles/r01_ncu_mss_scale_reg_full.csv (ncu flushes caches between "
+                                        "launches, so each scale re-reads rec+target = 32.8 MB; algorithmic 49 MB)")
             if top["bound"] != "hbm":
                 roof["bound_detail"] = "fp32 FMA pipe, not tensor cores (no GEMM on this path)"
             if "fp32" in top:

@@ -113,16 +113,16 @@ inline int ew_blocks(int64_t n) {
 }  // namespace
 
 extern "C" int ddsp_b200_scale_function_fwd(const float *x, float *y, int64_t n, void *stream) {
-    DDSP_REQUIRE(x && y && n >= 0);
     if (n == 0) return DDSP_B200_OK;
+    DDSP_REQUIRE(x && y && n > 0);
     scale_fwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, y, n);
     return ddsp_launch_status();
 }
 
 extern "C" int ddsp_b200_scale_function_bwd(const float *x, const float *dy, float *dx, int64_t n,
                                             void *stream) {
-    DDSP_REQUIRE(x && dy && dx && n >= 0);
     if (n == 0) return DDSP_B200_OK;
+    DDSP_REQUIRE(x && dy && dx && n > 0);
     scale_bwd_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, n);
     return ddsp_launch_status();
 }
@@ -130,8 +130,8 @@ extern "C" int ddsp_b200_scale_function_bwd(const float *x, const float *dy, flo
 extern "C" int ddsp_b200_remove_above_nyquist(const float *amp, const float *f0, float *out,
                                               int64_t rows, int H, float sample_rate,
                                               void *stream) {
-    DDSP_REQUIRE(amp && f0 && out && rows >= 0 && H > 0);
     if (rows == 0) return DDSP_B200_OK;
+    DDSP_REQUIRE(amp && f0 && out && rows > 0 && H > 0);
     nyquist_kernel<<<ew_blocks(rows * H), 256, 0, (cudaStream_t)stream>>>(amp, f0, out, rows, H,
                                                                            sample_rate * 0.5f);
     return ddsp_launch_status();
@@ -141,8 +141,8 @@ extern "C" int ddsp_b200_harmonic_controls_fwd(const float *amp_raw, const float
                                                const float *f0, float *amps, float *dist,
                                                float *weights, int64_t rows, int H, float sample_rate,
                                                void *stream) {
-    DDSP_REQUIRE(amp_raw && dist_raw && f0 && amps && dist && rows >= 0 && H > 0);
     if (rows == 0) return DDSP_B200_OK;
+    DDSP_REQUIRE(amp_raw && dist_raw && f0 && amps && dist && rows > 0 && H > 0);
     controls_fwd_kernel<<<(unsigned)ddsp_ceil_div(rows, kRowWarps), kRowWarps * 32, 0,
                           (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, amps, dist, weights, rows,
                                                   H, sample_rate * 0.5f);
@@ -154,9 +154,9 @@ extern "C" int ddsp_b200_harmonic_controls_bwd(const float *amp_raw, const float
                                                const float *d_dist, const float *d_weights,
                                                float *d_amp_raw, float *d_dist_raw, int64_t rows, int H,
                                                float sample_rate, void *stream) {
-    DDSP_REQUIRE(amp_raw && dist_raw && f0 && d_amp_raw && d_dist_raw);
-    DDSP_REQUIRE(rows >= 0 && H > 0);
     if (rows == 0) return DDSP_B200_OK;
+    DDSP_REQUIRE(amp_raw && dist_raw && f0 && d_amp_raw && d_dist_raw);
+    DDSP_REQUIRE(rows > 0 && H > 0);
     controls_bwd_kernel<<<(unsigned)ddsp_ceil_div(rows, kRowWarps), kRowWarps * 32, 0,
                           (cudaStream_t)stream>>>(amp_raw, dist_raw, f0, d_amps, d_dist, d_weights,
                                                   d_amp_raw, d_dist_raw, rows, H, sample_rate * 0.5f);

@@ -561,20 +561,38 @@ __global__ void stft_fold_kernel(const float *__restrict__ edge, float *__restri
 // d_rec[b,m] = sum over scales of the per-scale gradients (fixed order) + the folded edges.  Lets the
 // per-scale launches run concurrently (own output buffers) and still be deterministic.
 __global__ void mss_combine_kernel(const float *__restrict__ per_scale, const float *__restrict__ edge,
-                                   float *__restrict__ d_sig, int B, int64_t N, FoldArgs fa) {
+                                   float *__restrict__ d_sig, int B, int64_t N, FoldArgs fa, int hs_max) {
     const int b = blockIdx.y;
     const size_t plane = (size_t)B * N;
-    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N;
-         m += (int64_t)gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int k = 0; k < fa.n_scales; ++k) {
-            acc += per_scale[k * plane + (size_t)b * N + m];
-            const int hs = fa.s[k] >> 1;
-            const float *e = edge + fa.off[k] + (size_t)b * fa.s[k];
-            if (m >= 1 && m <= hs) acc += e[hs - m];
-            if (m <= N - 2 && m >= N - 1 - hs) acc += e[hs + (N - 2 - m)];
+    const bool vec = (N & 3) == 0;
+    const int64_t count = vec ? N / 4 : N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m0 = vec ? 4 * i : i;
+        const int width = vec ? 4 : 1;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec) {
+            for (int k = 0; k < fa.n_scales; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(per_scale + k * plane + (size_t)b * N + m0));
+                acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+            }
+        } else {
+            for (int k = 0; k < fa.n_scales; ++k) acc[0] += per_scale[k * plane + (size_t)b * N + m0];
         }
-        d_sig[(size_t)b * N + m] = acc;
+        // only samples 1..hs_max and N-1-hs_max..N-2 mirror into the reflect padding
+        if (m0 <= hs_max || m0 + width >= N - 1 - hs_max) {
+            for (int e = 0; e < width; ++e) {
+                const int64_t m = m0 + e;
+                for (int k = 0; k < fa.n_scales; ++k) {
+                    const int hs = fa.s[k] >> 1;
+                    const float *ed = edge + fa.off[k] + (size_t)b * fa.s[k];
+                    if (m >= 1 && m <= hs) acc[e] += ed[hs - m];
+                    if (m <= N - 2 && m >= N - 1 - hs) acc[e] += ed[hs + (N - 2 - m)];
+                }
+            }
+        }
+        if (vec) *reinterpret_cast<float4 *>(d_sig + (size_t)b * N + m0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else d_sig[(size_t)b * N + m0] = acc[0];
     }
 }
 
@@ -819,9 +837,9 @@ extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, con
     if (s || !d_rec) return s;
     if (d_rec_scales) {
         // per-scale gradient buffers [n_scales][B][N] (scales launched concurrently): sum + fold
-        int gx = (int)ddsp_ceil_div(N, 256);
+        int gx = (int)ddsp_ceil_div((N & 3) == 0 ? N / 4 : N, 256);
         if (gx > 512) gx = 512;
-        mss_combine_kernel<<<dim3(gx, B), 256, 0, st>>>(d_rec_scales, edge, d_rec, B, N, fold);
+        mss_combine_kernel<<<dim3(gx, B), 256, 0, st>>>(d_rec_scales, edge, d_rec, B, N, fold, hs_max);
         return ddsp_launch_status();
     }
     int gx = (int)ddsp_ceil_div(2 * (int64_t)hs_max + 2 >= N ? N : 2 * (int64_t)hs_max, 256);

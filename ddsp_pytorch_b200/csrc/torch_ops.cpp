@@ -175,6 +175,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> harmonic_fwd(const Tensor &f0_, const
     Tensor phi = at::empty({B, T}, opt64), delta = at::empty({B, T}, opt64);
     Tensor phase_end = at::empty({B}, w.options().dtype(at::kDouble));
     Tensor audio = at::empty({B, T * block_size, 1}, w.options());
+    if (B == 0 || T == 0) return {audio, phase_end.zero_(), phi, delta};      // empty batch: nothing to launch
     const double *p0 = nullptr;
     Tensor phase0;
     if (phase0_.has_value() && phase0_->defined()) {
@@ -206,6 +207,7 @@ std::tuple<Tensor, Tensor> harmonic_bwd(const Tensor &g_, const Tensor &weights_
                 "harmonic_bwd: bad phase workspace");
     c10::cuda::CUDAGuard guard(w.device());
     Tensor dw = at::empty_like(w);
+    if (B == 0 || T == 0) return {dw, at::empty({B, T, 1}, w.options())};
     const uint64_t *ph = (const uint64_t *)phi.data_ptr<int64_t>();
     const uint64_t *dl = (const uint64_t *)delta.data_ptr<int64_t>();
     check(ddsp_b200_harmonic_frames_bwd_weights(fp(g), ph, dl, fpm(dw), (int)B, (int)T, (int)H,
@@ -296,6 +298,7 @@ Tensor noise_fwd(const Tensor &mags_, const Tensor &noise_, const c10::optional<
     TORCH_CHECK(!add.defined() || add.numel() == B * T * bs, "filtered noise: `add` must be (B,T*block,1)");
     c10::cuda::CUDAGuard guard(mags.device());
     Tensor out = at::empty({B, T * bs, 1}, mags.options());
+    if (B * T == 0) return out;
     Tensor design = noise_design_table(mags.device(), NB);
     check(ddsp_b200_filtered_noise_fwd(fp(mags), fp(noise), opt_fp(add), fp(design), fpm(out), B * T, (int)NB,
                                        (int)bs, apply_scale, (float)bias, cur_stream()),
@@ -312,6 +315,7 @@ Tensor noise_bwd(const Tensor &g_, const Tensor &noise_, const c10::optional<Ten
                 "filtered noise backward: raw magnitudes needed when the scale function is fused");
     c10::cuda::CUDAGuard guard(noise.device());
     Tensor d_mags = at::empty({B, T, NB}, noise.options());
+    if (B * T == 0) return d_mags;
     Tensor design = noise_design_table(noise.device(), NB);
     check(ddsp_b200_filtered_noise_bwd(fp(g), fp(noise), opt_fp(raw), fp(design), fpm(d_mags), B * T, (int)NB,
                                        (int)bs, apply_scale, (float)bias, cur_stream()),

@@ -564,3 +564,18 @@ def test_large_amplitude_and_extreme_pitch(ddsp, orc):
     got, _ = ddsp.harmonic_synth_frames(f0.cuda(), w.cuda(), bs, sr)
     # sum of weights is ~32 here (not normalised): scale the 1e-4 bar accordingly
     assert_audio(got, ref, 1e-4 * float(w.sum(-1).max()) / 2)
+
+
+def test_empty_batch(ddsp):
+    """Zero voices / zero frames flow through the synth ops like any other shape (nothing is launched)."""
+    from ddsp_pytorch_b200.models.modules import FilteredNoise, HarmonicSynth
+    hs, fn = HarmonicSynth(160, 16000), FilteredNoise(160, 65)
+    for B, T in ((0, 4), (2, 0)):
+        a = torch.zeros(B, T, 1, device="cuda", requires_grad=True)
+        d = torch.zeros(B, T, 8, device="cuda", requires_grad=True)
+        m = torch.zeros(B, T, 65, device="cuda", requires_grad=True)
+        c = hs.get_controls(a, d, torch.zeros(B, T, 1, device="cuda"))
+        y = hs(**c) + fn(fn.get_controls(m)["magnitudes"])
+        assert y.shape == (B, T * 160, 1)
+        y.sum().backward()
+        assert d.grad.shape == d.shape and m.grad.shape == m.shape
