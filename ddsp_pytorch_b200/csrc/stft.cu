@@ -647,7 +647,7 @@ __global__ void stage_twiddle_kernel(float2 *__restrict__ tab, int n_fft, int to
 }
 
 // geometry of the register-FFT loss kernel: NF = 2G frame slots per batch, tiles of TF = FT + ov frames
-int make_geom_reg(int64_t N, int n_fft, int hop, HostGeom *out) {
+int make_geom_reg(int B, int64_t N, int n_fft, int hop, HostGeom *out) {
     if (n_fft & (n_fft - 1)) return DDSP_B200_EUNSUPPORTED;
     if (hop < 1 || hop > n_fft) return DDSP_B200_EUNSUPPORTED;
     if (N <= n_fft / 2 || N >= (1ll << 30)) return DDSP_B200_EUNSUPPORTED;
@@ -669,6 +669,10 @@ int make_geom_reg(int64_t N, int n_fft, int hop, HostGeom *out) {
     int tf = nf;
     while (tf - g.ov < 1) tf += nf;
     while (tf + nf <= 64 && total(tf + nf) <= 110 * 1024) tf += nf;
+    // small batches (strong scaling leaves 8 voices per GPU): prefer more, smaller tiles until there are
+    // about two CTAs per SM, at the price of recomputing the ov overlap frames more often
+    auto tiles_of = [&](int tf_) { return ddsp_ceil_div(N + n_fft, (int64_t)(tf_ - g.ov) * hop); };
+    while (tiles_of(tf) * B < 2 * DDSP_SM_COUNT && tf - nf - g.ov >= 1 && 2 * (tf - nf - g.ov) >= g.ov) tf -= nf;
     if (total(tf) > 220 * 1024) return DDSP_B200_EUNSUPPORTED;
     g.FT = tf - g.ov;
     out->g = g;
@@ -722,8 +726,8 @@ int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
-int loss_geom(int64_t N, int n_fft, int hop, HostGeom *hg) {
-    return reg_path(n_fft) ? make_geom_reg(N, n_fft, hop, hg) : make_geom(N, n_fft, hop, true, hg);
+int loss_geom(int B, int64_t N, int n_fft, int hop, HostGeom *hg) {
+    return reg_path(n_fft) ? make_geom_reg(B, N, n_fft, hop, hg) : make_geom(N, n_fft, hop, true, hg);
 }
 
 template <int LG>
@@ -760,9 +764,9 @@ extern "C" int ddsp_b200_fft_stage_twiddles(float *table, int n_fft, void *strea
     return ddsp_launch_status();
 }
 
-extern "C" int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop) {
+extern "C" int64_t ddsp_b200_mss_tiles(int B, int64_t N, int n_fft, int hop) {
     HostGeom hg;
-    if (loss_geom(N, n_fft, hop, &hg)) return -1;
+    if (B < 1 || loss_geom(B, N, n_fft, hop, &hg)) return -1;
     return hg.tiles;
 }
 
@@ -774,7 +778,7 @@ extern "C" int ddsp_b200_mss_scale(const float *target, const float *rec, const 
     DDSP_REQUIRE(!d_rec || edge);
     DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
     HostGeom hg;
-    int s = loss_geom(N, n_fft, hop, &hg);
+    int s = loss_geom(B, N, n_fft, hop, &hg);
     if (s) return s;
     const float inv_cnt = 1.0f / ((float)B * (float)(n_fft / 2 + 1) * (float)hg.g.frames);
     dim3 grid(hg.tiles, B);
@@ -820,7 +824,7 @@ extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, con
     int hs_max = 0;
     for (int i = 0; i < n_scales; ++i) {
         HostGeom hg;
-        int s = loss_geom(N, scales[i], hops[i], &hg);
+        int s = loss_geom(B, N, scales[i], hops[i], &hg);
         if (s) return s;
         fin.off[i] = poff;
         fin.cnt[i] = (int64_t)hg.tiles * B;

@@ -514,7 +514,7 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
     for (int i = 0; i < ns; ++i) {
         sc[i] = (int)scales[i];
         hp[i] = (int)((double)scales[i] * (1.0 - overlap));     // int(s * (1 - overlap)), core.py:33
-        const int64_t t = ddsp_b200_mss_tiles(N, sc[i], hp[i]);
+        const int64_t t = ddsp_b200_mss_tiles((int)B, N, sc[i], hp[i]);
         TORCH_CHECK(t > 0, "mss_loss: scale ", sc[i], " with hop ", hp[i], " unsupported for N=", N);
         tiles += t * B;
         wsum += sc[i];
@@ -548,7 +548,7 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
                                   (void *)streams[i].stream()),
               "mss_scale");
         woff += sc[i];
-        poff += ddsp_b200_mss_tiles(N, sc[i], hp[i]) * B;
+        poff += ddsp_b200_mss_tiles((int)B, N, sc[i], hp[i]) * B;
         eoff += B * sc[i];
     }
     for (int i = 1; i < ns; ++i) {

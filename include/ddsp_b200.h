@@ -187,12 +187,12 @@ int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int B, int64_t
 
 /* ---- a11+a12  multiscale spectral loss, fused                 (train.py:70-76,92-103) ------ */
 /* Per scale: CTA tiles of one voice; partial[] receives 2 floats per CTA (sum |Sx-Sy|, sum
- * |log(Sx+1e-7)-log(Sy+1e-7)|), ddsp_b200_mss_tiles(N,n_fft,hop)*B CTAs.  If d_rec != NULL the same
+ * |log(Sx+1e-7)-log(Sy+1e-7)|), ddsp_b200_mss_tiles(B,N,n_fft,hop)*B CTAs.  If d_rec != NULL the same
  * launch also produces d(loss)/d(rec) for unit upstream gradient (= or += into d_rec[B,N], reflect
  * padding part into edge[B,n_fft]).  ddsp_b200_mss_finish reduces the partials of all scales to
  * loss[0] (layout: scales back to back) and folds the edges.  scales/hops: HOST arrays.
  * The per-scale launches are independent of each other when each gets its own d_rec buffer.      */
-int64_t ddsp_b200_mss_tiles(int64_t N, int n_fft, int hop);
+int64_t ddsp_b200_mss_tiles(int B, int64_t N, int n_fft, int hop);   /* tiles per voice (depends on B) */
 /* stage_twiddle: the table above for n_fft (may be NULL outside 64..4096, where `twiddle` is used) */
 int ddsp_b200_mss_scale(const float *target, const float *rec, const float *window,
                         const float *twiddle, int n_tab, const float *stage_twiddle, float *partial,

@@ -59,9 +59,10 @@ def test_argument_errors_do_not_need_a_gpu(pkg):
     assert plan(192000 + 48000 - 1, n1, n2) == 0 and n1.value * n2.value == 1 << 18
     tiles = lib.ddsp_b200_mss_tiles
     tiles.restype = ctypes.c_int64
-    tiles.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int]
-    assert tiles(64000, 4096, 1024) > 0
-    assert tiles(1000, 4096, 1024) == -1          # reflect padding needs n_fft/2 < N, like torch.stft
+    tiles.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]
+    assert tiles(64, 64000, 4096, 1024) > 0
+    assert tiles(8, 64000, 4096, 1024) >= tiles(64, 64000, 4096, 1024)    # small batches get smaller tiles
+    assert tiles(64, 1000, 4096, 1024) == -1      # reflect padding needs n_fft/2 < N, like torch.stft
 
 
 def test_ops_registered_without_cpu_kernels(pkg):
