@@ -222,8 +222,9 @@ def kernel_table(step, shapes, flush, peaks):
     add("K1 harmonic_frames_bwd", lambda: ops.harmonic_bwd(g, w, phi, delta, bs, sr, False), fma_ops=2 * hs)
     add("K2 filtered_noise_fwd", lambda: ops.noise_fwd(i["mag_raw"], i["noise"], audio, True, -5.0), alg_bytes=4 * B * T * (NB + 3 * bs))
     add("K2 filtered_noise_bwd", lambda: ops.noise_bwd(g, i["noise"], i["mag_raw"], NB, True, -5.0), alg_bytes=4 * B * T * (NB + 2 * bs))
-    add("K3 reverb fftconv_fwd (5 launches)", lambda: ops.fftconv_fwd(sig2, imp), alg_bytes=4 * (2 * B * N + imp.numel()))
-    add("K3 reverb fftconv_bwd (8 launches)", lambda: ops.fftconv_bwd(sig2, sig2, imp, True, True),
+    kept = ops.fftconv_fwd(sig2, imp, True)
+    add("K3 reverb fftconv_fwd (5 launches)", lambda: ops.fftconv_fwd(sig2, imp, True), alg_bytes=4 * (2 * B * N + imp.numel()))
+    add("K3 reverb fftconv_bwd (5 launches, transforms kept by fwd)", lambda: ops.fftconv_bwd(sig2, sig2, imp, kept[1], kept[2], True, True),
         alg_bytes=4 * (3 * B * N + 2 * imp.numel()))
     add("K4L mss_loss fwd+grad (6 scales + finish)",
         lambda: ops.mss_loss_fwd(i["target"], sig2, list(shapes.scales), shapes.overlap, windows, True),

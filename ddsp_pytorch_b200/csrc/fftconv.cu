@@ -153,8 +153,8 @@ template <int LG2> struct RowCfg {
 // * W_n^(-i2 k1), write in place.
 template <int LG2, int MODE>
 __global__ void __launch_bounds__(kRowThreads)
-rows_kernel(float2 *__restrict__ work, const float2 *__restrict__ hspec, int64_t h_slot_stride, int conj_h,
-            const float2 *__restrict__ twn, const float2 *__restrict__ stw, int n1) {
+rows_kernel(const float2 *src_work, float2 *dst_work, const float2 *__restrict__ hspec, int64_t h_slot_stride,
+            int conj_h, const float2 *__restrict__ twn, const float2 *__restrict__ stw, int n1) {
     using P = Plan<LG2>;
     constexpr int n2 = P::N, T = P::T, PITCH = P::PITCH, ROWS = RowCfg<LG2>::ROWS;
     extern __shared__ __align__(16) float smem[];
@@ -164,12 +164,13 @@ rows_kernel(float2 *__restrict__ work, const float2 *__restrict__ hspec, int64_t
     const int tid = threadIdx.x, g = tid / T, t = tid - g * T;
     const int k1 = blockIdx.x * ROWS + g;
     const int64_t p = blockIdx.y;
-    float2 *row = work + ((size_t)p * n1 + k1) * n2;
+    const float2 *row_in = src_work + ((size_t)p * n1 + k1) * n2;
+    float2 *row = dst_work + ((size_t)p * n1 + k1) * n2;       // may alias row_in (in-place): read fully first
     float2 *buf = bufs + g * PITCH;
     if (MODE == 1) fill_step_twiddle(thi + g * (n2 / 16), tlo + g * 16, twn, k1, n2, t, T);
     float2 v[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = row[t + r * T];
+    for (int r = 0; r < 16; ++r) v[r] = row_in[t + r * T];
     stage_compute_store<LG2, 0, false>(v, buf, t, stw);
     mid_stages<LG2, false>(v, buf, t, stw, true);
     if (MODE == 0) {
@@ -442,24 +443,25 @@ extern "C" int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const fl
 #define CALL(LG)                                                                                        \
     if (!(s = set_smem(rows_kernel<LG, 0>, row_smem<LG>())))                                            \
         rows_kernel<LG, 0><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
-            reinterpret_cast<float2 *>(work), nullptr, 0, 0, reinterpret_cast<const float2 *>(twiddle),  \
-            reinterpret_cast<const float2 *>(stage2), n1)
+            reinterpret_cast<const float2 *>(work), reinterpret_cast<float2 *>(work), nullptr, 0, 0,     \
+            reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1)
     DDSP_LG_SWITCH_ROWS(ddsp_ilog2(n2), CALL)
 #undef CALL
     return s ? s : ddsp_launch_status();
 }
 
-extern "C" int ddsp_b200_fft4_rows_filter(float *work, int64_t slots, const float *hspec,
+extern "C" int ddsp_b200_fft4_rows_filter(const float *work, float *dst, int64_t slots, const float *hspec,
                                           int64_t h_slot_stride, int conj_h, const float *twiddle,
                                           const float *stage2, int n1, int n2, void *stream) {
-    DDSP_REQUIRE(work && hspec && twiddle && stage2 && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
+    DDSP_REQUIRE(work && dst && hspec && twiddle && stage2 && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
     int s = DDSP_B200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(LG)                                                                                        \
     if (!(s = set_smem(rows_kernel<LG, 1>, row_smem<LG>())))                                            \
         rows_kernel<LG, 1><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
-            reinterpret_cast<float2 *>(work), reinterpret_cast<const float2 *>(hspec), h_slot_stride,   \
-            conj_h, reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1)
+            reinterpret_cast<const float2 *>(work), reinterpret_cast<float2 *>(dst),                    \
+            reinterpret_cast<const float2 *>(hspec), h_slot_stride, conj_h,                             \
+            reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1)
     DDSP_LG_SWITCH_ROWS(ddsp_ilog2(n2), CALL)
 #undef CALL
     return s ? s : ddsp_launch_status();

@@ -341,14 +341,16 @@ ConvPlan conv_plan(const at::Device &dev, int64_t min_len) {
 }
 
 // signal (R,n), kernel (Rk,Lk) with Rk in {1,R}: out[r,i] = sum_{j<=i} signal[r,j] kernel[rk,i-j]
-Tensor fftconv_fwd(const Tensor &signal_, const Tensor &kernel_) {
+// keep != 0 also returns the column-transformed signal and the kernel spectrum for the backward pass
+std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tensor &kernel_, bool keep) {
     Tensor sig = prep(signal_, "signal"), ker = prep(kernel_, "kernel");
     TORCH_CHECK(sig.dim() == 2 && ker.dim() == 2, "fftconv: 2-D (rows, length) tensors expected");
     const int64_t R = sig.size(0), n = sig.size(1), Rk = ker.size(0), Lk = ker.size(1);
     TORCH_CHECK(Rk == 1 || Rk == R, "fftconv: kernel rows must be 1 or match the signal rows");
     c10::cuda::CUDAGuard guard(sig.device());
     Tensor out = at::empty_like(sig);
-    if (R == 0 || n == 0) return out;
+    Tensor none = at::empty({0}, sig.options());
+    if (R == 0 || n == 0) return {out, none, none};
     const int64_t Lc = std::min(Lk, n);                 // taps beyond the signal length never matter
     Tensor kc = Lc == Lk ? ker : ker.narrow(1, 0, Lc).contiguous();
     ConvPlan p = conv_plan(sig.device(), n + Lc - 1);
@@ -360,13 +362,17 @@ Tensor fftconv_fwd(const Tensor &signal_, const Tensor &kernel_) {
     check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
     Tensor work = at::empty({slots, p.n, 2}, sig.options());
     check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(x)");
-    check(ddsp_b200_fft4_rows_filter(fpm(work), slots, fp(hspec), pair ? 0 : p.n, 0, fp(p.tw), fp(p.st2), p.n1, p.n2, st),
+    Tensor filtered = keep ? at::empty_like(work) : work;
+    check(ddsp_b200_fft4_rows_filter(fp(work), fpm(filtered), slots, fp(hspec), pair ? 0 : p.n, 0, fp(p.tw), fp(p.st2),
+                                     p.n1, p.n2, st),
           "fft4_rows_filter");
-    check(ddsp_b200_fft4_cols_inv(fp(work), fpm(out), R, n, pair, fp(p.st1), p.n1, p.n2, st), "fft4_cols_inv");
-    return out;
+    check(ddsp_b200_fft4_cols_inv(fp(filtered), fpm(out), R, n, pair, fp(p.st1), p.n1, p.n2, st), "fft4_cols_inv");
+    if (keep) return {out, work, hspec};
+    return {out, none, none};
 }
 
 std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, const Tensor &kernel_,
+                                       const c10::optional<Tensor> &work_x_, const c10::optional<Tensor> &hspec_,
                                        bool need_signal, bool need_kernel) {
     Tensor g = prep(g_, "grad_out"), sig = prep(signal_, "signal"), ker = prep(kernel_, "kernel");
     const int64_t R = sig.size(0), n = sig.size(1), Rk = ker.size(0), Lk = ker.size(1);
@@ -390,8 +396,10 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
     const bool fork = need_kernel && need_signal;
     at::cuda::CUDAStream side = fork ? at::cuda::getStreamFromPool(false, sig.device().index()) : main_stream;
     void *ss = (void *)side.stream();
-    Tensor hspec;
-    if (need_signal) {
+    // transforms kept by the forward pass (FFTConvolve saves them) are reused instead of recomputed
+    Tensor hspec = (hspec_.has_value() && hspec_->defined() && hspec_->numel() == Rk * p.n * 2) ? *hspec_ : Tensor();
+    Tensor saved_x = (work_x_.has_value() && work_x_->defined() && work_x_->numel() == slots * p.n * 2) ? *work_x_ : Tensor();
+    if (need_signal && !hspec.defined()) {
         hspec = at::empty({Rk, p.n, 2}, sig.options());
         check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
         check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
@@ -403,9 +411,12 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
             g_ready.record(main_stream);
             g_ready.block(side);
         }
-        Tensor work_x = at::empty({slots, p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), fp(p.st1), p.n1, p.n2, ss),
-              "fft4_cols_fwd(x)");
+        Tensor work_x = saved_x;
+        if (!work_x.defined()) {
+            work_x = at::empty({slots, p.n, 2}, sig.options());
+            check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), fp(p.st1), p.n1, p.n2, ss),
+                  "fft4_cols_fwd(x)");
+        }
         Tensor corr = at::empty({Rk, p.n, 2}, sig.options());
         Tensor scratch = at::empty({ddsp_b200_fft4_correlate_splits(slots, pair), p.n, 2}, sig.options());
         check(ddsp_b200_fft4_rows_correlate(fp(work_g), fp(work_x), slots, pair, fpm(scratch), fpm(corr),
@@ -422,7 +433,8 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
     }
     if (need_signal) {
         if (fork) corr_done.block(main_stream);          // work_g is filtered in place below
-        check(ddsp_b200_fft4_rows_filter(fpm(work_g), slots, fp(hspec), pair ? 0 : p.n, 1, fp(p.tw), fp(p.st2), p.n1, p.n2, st),
+        check(ddsp_b200_fft4_rows_filter(fp(work_g), fpm(work_g), slots, fp(hspec), pair ? 0 : p.n, 1, fp(p.tw), fp(p.st2),
+                                         p.n1, p.n2, st),
               "fft4_rows_filter(conj)");
         check(ddsp_b200_fft4_cols_inv(fp(work_g), fpm(d_sig), R, n, pair, fp(p.st1), p.n1, p.n2, st),
               "fft4_cols_inv(dx)");
@@ -532,6 +544,10 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
     // these latency-bound launches overlap, join before the finish kernel.  Captured as graph branches.
     Tensor d_scales = need_grad ? at::empty({ns, B, N}, rec.options()) : Tensor();
     auto main_stream = at::cuda::getCurrentCUDAStream();
+    // constant tables are built (first use only) on the main stream BEFORE the fork, so that the side
+    // streams are ordered after their initialisation
+    std::vector<Tensor> stage_tables;
+    for (int i = 0; i < ns; ++i) stage_tables.push_back(stage_twiddle_table(rec.device(), sc[i]));
     std::vector<at::cuda::CUDAStream> streams;
     streams.push_back(main_stream);
     for (int i = 1; i < ns; ++i) streams.push_back(at::cuda::getStreamFromPool(false, rec.device().index()));
@@ -540,7 +556,7 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
     for (int i = 1; i < ns; ++i) fork.block(streams[i]);
     int64_t woff = 0, poff = 0, eoff = 0;
     for (int i = 0; i < ns; ++i) {
-        Tensor stw = stage_twiddle_table(rec.device(), sc[i]);
+        const Tensor &stw = stage_tables[i];
         check(ddsp_b200_mss_scale(fp(tgt), fp(rec), fp(win) + woff, fp(tw), (int)tw.size(0),
                                   stw.defined() ? fp(stw) : nullptr, fpm(partial) + 2 * poff,
                                   need_grad ? fpm(d_scales) + (int64_t)i * B * N : nullptr,
@@ -582,8 +598,8 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("amp_to_ir_bwd(Tensor d_ir, int n_bands) -> Tensor");
     m.def("noise_fwd(Tensor magnitudes, Tensor noise, Tensor? add, bool apply_scale, float bias) -> Tensor");
     m.def("noise_bwd(Tensor grad_out, Tensor noise, Tensor? magnitudes_raw, int n_bands, bool apply_scale, float bias) -> Tensor");
-    m.def("fftconv_fwd(Tensor signal, Tensor kernel) -> Tensor");
-    m.def("fftconv_bwd(Tensor grad_out, Tensor signal, Tensor kernel, bool need_signal, bool need_kernel) -> (Tensor, Tensor)");
+    m.def("fftconv_fwd(Tensor signal, Tensor kernel, bool keep_transforms) -> (Tensor, Tensor, Tensor)");
+    m.def("fftconv_bwd(Tensor grad_out, Tensor signal, Tensor kernel, Tensor? work_x, Tensor? hspec, bool need_signal, bool need_kernel) -> (Tensor, Tensor)");
     m.def("reverb_impulse_fwd(Tensor noise, Tensor decay, Tensor wet, Tensor t) -> Tensor");
     m.def("reverb_impulse_bwd(Tensor d_impulse, Tensor noise, Tensor decay, Tensor wet, Tensor t) -> (Tensor, Tensor, Tensor)");
     m.def("stft_mag_fwd(Tensor signal, Tensor window, int n_fft, int hop) -> Tensor");

@@ -91,7 +91,7 @@ class ScriptDDSP(nn.Module):
                                                              self.reverb_t)
             taps = min(signal.shape[1], self.reverb_length)
             kernel = impulse.reshape(1, self.reverb_length)[:, :taps]
-            signal = torch.ops.ddsp_b200.fftconv_fwd(signal.squeeze(-1), kernel).unsqueeze(-1)
+            signal = torch.ops.ddsp_b200.fftconv_fwd(signal.squeeze(-1), kernel, False)[0].unsqueeze(-1)
         return signal
 
     @torch.jit.export

@@ -182,18 +182,24 @@ class FilteredNoiseFused(torch.autograd.Function):
 
 
 class FFTConvolve(torch.autograd.Function):
-    """core.py:169-176 on 2-D (rows, n) operands; kernel rows 1 (shared) or equal to signal rows."""
+    """core.py:169-176 on 2-D (rows, n) operands; kernel rows 1 (shared) or equal to signal rows.
+    When a gradient will be needed the forward keeps the transform of the signal and the kernel spectrum
+    (32 MB + 1 MB at config 2) so the backward does not recompute them."""
 
     @staticmethod
     def forward(ctx, signal, kernel):
-        ctx.save_for_backward(signal, kernel)
-        return _ops.fftconv_fwd(signal, kernel)
+        keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        out, work_x, hspec = _ops.fftconv_fwd(signal, kernel, keep)
+        ctx.save_for_backward(signal, kernel, work_x, hspec)
+        return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, g):
-        signal, kernel = ctx.saved_tensors
-        ds, dk = _ops.fftconv_bwd(g, signal, kernel, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        signal, kernel, work_x, hspec = ctx.saved_tensors
+        ds, dk = _ops.fftconv_bwd(g, signal, kernel, work_x if work_x.numel() else None,
+                                  hspec if hspec.numel() else None, ctx.needs_input_grad[0],
+                                  ctx.needs_input_grad[1])
         return (ds if ctx.needs_input_grad[0] else None), (dk if ctx.needs_input_grad[1] else None)
 
 

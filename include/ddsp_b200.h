@@ -149,10 +149,12 @@ int ddsp_b200_fft4_cols_inv(const float *work, float *out /*[rows,len]*/, int64_
                             int pair, const float *stage1, int n1, int n2, void *stream);
 int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const float *twiddle, const float *stage2,
                                  int n1, int n2, void *stream);
-/* h_slot_stride in complex elements between the filter spectra of successive slots (0 = shared) */
-int ddsp_b200_fft4_rows_filter(float *work, int64_t slots, const float *hspec, int64_t h_slot_stride,
-                               int conj_h, const float *twiddle, const float *stage2, int n1, int n2,
-                               void *stream);
+/* h_slot_stride in complex elements between the filter spectra of successive slots (0 = shared);
+ * dst may be `work` itself (in place) or a second buffer (keeps `work` = the transform of x for the
+ * backward pass).                                                                                 */
+int ddsp_b200_fft4_rows_filter(const float *work, float *dst, int64_t slots, const float *hspec,
+                               int64_t h_slot_stride, int conj_h, const float *twiddle,
+                               const float *stage2, int n1, int n2, void *stream);
 /* out = rows of IFFT( FFT(g) * conj(FFT(x)) ), summed over slots into one slot when reduce != 0.
  * scratch: ddsp_b200_fft4_correlate_splits(slots, reduce) * n1*n2 complex (partial spectra).      */
 int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce);

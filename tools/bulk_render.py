@@ -32,7 +32,7 @@ def render(noise):
     amps, dist, w = ops.harmonic_controls_fwd(inp["amp_raw"], inp["dist_raw"], inp["pitch"], float(sr), True)
     audio, _, _, _ = ops.harmonic_fwd(inp["pitch"], w, bs, float(sr), None)
     sig = ops.noise_fwd(inp["mag_raw"], noise, audio, True, -5.0)
-    return ops.fftconv_fwd(sig.squeeze(-1), impulse)
+    return ops.fftconv_fwd(sig.squeeze(-1), impulse, False)[0]
 
 chunks = args.voices // args.chunk
 noise = torch.empty(args.chunk, T, bs, device=dev)
@@ -59,7 +59,7 @@ audio = ops.harmonic_fwd(inp["pitch"], w, bs, float(sr), None)[0]
 stage = {
     "harmonic_ms": t(lambda: ops.harmonic_fwd(inp["pitch"], w, bs, float(sr), None)),
     "noise_ms": t(lambda: ops.noise_fwd(inp["mag_raw"], noise, audio, True, -5.0)),
-    "reverb_ms": t(lambda: ops.fftconv_fwd(audio.squeeze(-1), impulse)),
+    "reverb_ms": t(lambda: ops.fftconv_fwd(audio.squeeze(-1), impulse, False)),
     "rng_ms": t(lambda: noise.uniform_(-1, 1)),
 }
 hs = args.chunk * N * H
