@@ -236,15 +236,23 @@ __device__ __forceinline__ void reg_stages_after0(float2 (&xa)[16], float2 (&xb)
     __syncthreads();
 }
 
-template <int LG, bool GRAD>
+// MODE: what the per-bin phase does with the spectra
+//   kLoss / kLossGrad : rec (re) + target (im) per frame; loss terms (+ gradient spectra)
+//   kMagFwd           : one signal; write |STFT| to mag_io[b][k][frame]               (multiscale_fft)
+//   kMagBwd           : one signal; gradient spectra from d_mag = mag_io[b][k][frame]  (its backward)
+enum { kLoss = 0, kLossGrad = 1, kMagFwd = 2, kMagBwd = 3 };
+
+template <int LG, int MODE>
 __global__ void __launch_bounds__(kStftThreads, 2)
 mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__ rec,
                      const float *__restrict__ window, const float2 *__restrict__ tw,
                      float *__restrict__ partial, float *__restrict__ d_rec, float *__restrict__ edge,
-                     TileGeom g, int accumulate, float inv_cnt) {
+                     float *__restrict__ mag_io, TileGeom g, int accumulate, float inv_cnt) {
     using namespace regfft;
     using P = Plan<LG>;
     using C = RegCfg<LG>;
+    constexpr bool GRAD = MODE == kLossGrad || MODE == kMagBwd;
+    constexpr bool MAG = MODE == kMagFwd || MODE == kMagBwd;
     constexpr int N = P::N, T = P::T, G = C::G, NF = C::NF, PITCH = P::PITCH;
     constexpr int HS = N / 2, BINS = HS + 1;
     extern __shared__ __align__(16) float smem[];
@@ -262,9 +270,10 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
     const int fs = GRAD ? max(0, f0 - g.ov) : min(f0, g.frames);
     const int fe = min(f0 + g.FT, g.frames);
     const float *xr = rec + (size_t)b * g.N;
-    const float *xt = target + (size_t)b * g.N;
+    const float *xt = MAG ? xr : target + (size_t)b * g.N;
     const float rs = rsqrtf((float)N);
     const int Ni = (int)g.N;
+    float *mg = MAG ? mag_io + (size_t)b * BINS * g.frames : nullptr;
 
     if (GRAD)
         for (int i = tid; i < owned; i += kStftThreads) ola[i] = 0.f;
@@ -286,7 +295,7 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
                             const float w = __ldg(window + t + r * T);
-                            x[r] = make_float2(__ldg(xr + base + r * T) * w, __ldg(xt + base + r * T) * w);
+                            x[r] = make_float2(__ldg(xr + base + r * T) * w, MAG ? 0.f : __ldg(xt + base + r * T) * w);
                         }
                     } else {
 #pragma unroll
@@ -295,7 +304,7 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
                             m = m < 0 ? -m : m;
                             m = m >= Ni ? 2 * (Ni - 1) - m : m;
                             const float w = __ldg(window + t + r * T);
-                            x[r] = make_float2(__ldg(xr + m) * w, __ldg(xt + m) * w);
+                            x[r] = make_float2(__ldg(xr + m) * w, MAG ? 0.f : __ldg(xt + m) * w);
                         }
                     }
                 } else {
@@ -307,6 +316,45 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
         }
         reg_stages_after0<LG, false>(xa, xb, bufa, bufb, act, act, t, tw);
 
+        if (MODE == kMagFwd) {
+            // ---- |STFT| out; lanes take consecutive frame slots so the (B, bins, frames) store coalesces
+            for (int idx = tid; idx < BINS * NF; idx += kStftThreads) {
+                const int q = idx & (NF - 1), k = idx / NF;
+                const int f = fb + q;
+                if (f < fe) {
+                    const float2 *Z = buf + (size_t)q * PITCH;
+                    const float2 Y = untangle_re(Z[pad16(k)], Z[pad16((N - k) & (N - 1))]);
+                    mg[(size_t)k * g.frames + f] = sqrtf(fmaf(Y.x, Y.x, Y.y * Y.y)) * rs;
+                }
+            }
+            continue;
+        }
+        if (MODE == kMagBwd) {
+            // ---- pass 1 (coalesced read of d_mag): U[q][k] = d_mag * X/|X| / sqrt(N), in place at index k
+            for (int idx = tid; idx < BINS * NF; idx += kStftThreads) {
+                const int q = idx & (NF - 1), k = idx / NF;
+                const int f = fb + q;
+                float2 *Z = buf + (size_t)q * PITCH;
+                const float2 Y = untangle_re(Z[pad16(k)], Z[pad16((N - k) & (N - 1))]);
+                const float yy = fmaf(Y.x, Y.x, Y.y * Y.y);
+                float c = 0.f;
+                if (f < fe && yy > 0.f) c = __ldg(mg + (size_t)k * g.frames + f) * rs * rsqrtf(yy);
+                Z[pad16(k)] = make_float2(c * Y.x, c * Y.y);
+            }
+            __syncthreads();
+            // ---- pass 2: Hermitian packing of the pair (slot p, slot p+G)
+            for (int idx = tid; idx < G * BINS; idx += kStftThreads) {
+                const int p = idx / BINS, k = idx - p * BINS;
+                const int km = (N - k) & (N - 1);
+                const float2 ua = buf[(size_t)p * PITCH + pad16(k)], ub = buf[(size_t)(p + G) * PITCH + pad16(k)];
+                float2 *dst = buf + (size_t)p * PITCH;
+                const bool edge_bin = (k == 0) | (k == HS);
+                dst[pad16(k)] = edge_bin ? make_float2(ua.x, ub.x)
+                                         : make_float2(0.5f * (ua.x - ub.y), 0.5f * (ua.y + ub.x));
+                if (!edge_bin) dst[pad16(km)] = make_float2(0.5f * (ua.x + ub.y), 0.5f * (-ua.y + ub.x));
+            }
+        }
+        if (!MAG)
         // ---- per bin: magnitudes, loss, gradient spectra of the pair (slot p, slot p+G)
         for (int idx = tid; idx < G * BINS; idx += kStftThreads) {
             const int p = idx / BINS, k = idx - p * BINS;
@@ -404,7 +452,7 @@ mss_scale_reg_kernel(const float *__restrict__ target, const float *__restrict__
     lgs = ddsp_warp_sum(lgs);
     if ((tid & 31) == 0) { red[0][tid >> 5] = lin; red[1][tid >> 5] = lgs; }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && !MAG) {
         float a = 0.f, c = 0.f;
         for (int i = 0; i < kStftThreads / 32; ++i) { a += red[0][i]; c += red[1][i]; }
         float *pp = partial + 2 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
@@ -603,24 +651,28 @@ struct FinArgs {
     float inv[8];            // 1 / (B * bins * frames)
 };
 
-__global__ void mss_finalize_kernel(const float *__restrict__ partial, float *__restrict__ loss,
-                                    FinArgs fa) {
-    __shared__ double red[256];
-    double total = 0.0;
+__global__ void __launch_bounds__(1024)
+mss_finalize_kernel(const float *__restrict__ partial, float *__restrict__ loss, FinArgs fa) {
+    // one pass: every thread adds its share of every scale's partials (already weighted by the scale's
+    // 1/count), then a single block reduction in double; fixed order -> deterministic
+    __shared__ double red[32];
+    double acc = 0.0;
     for (int i = 0; i < fa.n_scales; ++i) {
-        double acc = 0.0;
         const float *p = partial + 2 * fa.off[i];
-        for (int64_t j = threadIdx.x; j < fa.cnt[i]; j += blockDim.x) acc += (double)p[2 * j] + (double)p[2 * j + 1];
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-            __syncthreads();
-        }
-        total += red[0] * (double)fa.inv[i];
-        __syncthreads();
+        double a = 0.0;
+        for (int64_t j = threadIdx.x; j < fa.cnt[i]; j += blockDim.x) a += (double)p[2 * j] + (double)p[2 * j + 1];
+        acc += a * (double)fa.inv[i];
     }
-    if (threadIdx.x == 0) loss[0] = (float)total;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) loss[0] = (float)v;
+    }
 }
 
 // ---- host-side geometry ---------------------------------------------------------------------
@@ -730,22 +782,45 @@ int loss_geom(int B, int64_t N, int n_fft, int hop, HostGeom *hg) {
     return reg_path(n_fft) ? make_geom_reg(B, N, n_fft, hop, hg) : make_geom(N, n_fft, hop, true, hg);
 }
 
-template <int LG>
-int launch_reg(const float *target, const float *rec, const float *window, const float2 *tw,
-               float *partial, float *d_rec, float *edge, const HostGeom &hg, int B, int accumulate,
-               float inv_cnt, cudaStream_t st) {
-    dim3 grid(hg.tiles, B);
+template <int LG, int MODE>
+int launch_reg_mode(const float *target, const float *rec, const float *window, const float2 *tw,
+                    float *partial, float *d_rec, float *edge, float *mag_io, const HostGeom &hg, int B,
+                    int accumulate, float inv_cnt, cudaStream_t st) {
     int s;
-    if (d_rec) {
-        if ((s = set_smem(mss_scale_reg_kernel<LG, true>, hg.smem_loss))) return s;
-        mss_scale_reg_kernel<LG, true><<<grid, kStftThreads, hg.smem_loss, st>>>(
-            target, rec, window, tw, partial, d_rec, edge, hg.g, accumulate, inv_cnt);
-    } else {
-        if ((s = set_smem(mss_scale_reg_kernel<LG, false>, hg.smem_loss))) return s;
-        mss_scale_reg_kernel<LG, false><<<grid, kStftThreads, hg.smem_loss, st>>>(
-            target, rec, window, tw, partial, nullptr, nullptr, hg.g, accumulate, inv_cnt);
-    }
+    if ((s = set_smem(mss_scale_reg_kernel<LG, MODE>, hg.smem_loss))) return s;
+    mss_scale_reg_kernel<LG, MODE><<<dim3(hg.tiles, B), kStftThreads, hg.smem_loss, st>>>(
+        target, rec, window, tw, partial, d_rec, edge, mag_io, hg.g, accumulate, inv_cnt);
     return 0;
+}
+
+template <int LG>
+int launch_reg(int mode, const float *target, const float *rec, const float *window, const float2 *tw,
+               float *partial, float *d_rec, float *edge, float *mag_io, const HostGeom &hg, int B,
+               int accumulate, float inv_cnt, cudaStream_t st) {
+    switch (mode) {
+        case kLoss: return launch_reg_mode<LG, kLoss>(target, rec, window, tw, partial, d_rec, edge, mag_io, hg, B, accumulate, inv_cnt, st);
+        case kLossGrad: return launch_reg_mode<LG, kLossGrad>(target, rec, window, tw, partial, d_rec, edge, mag_io, hg, B, accumulate, inv_cnt, st);
+        case kMagFwd: return launch_reg_mode<LG, kMagFwd>(target, rec, window, tw, partial, d_rec, edge, mag_io, hg, B, accumulate, inv_cnt, st);
+        default: return launch_reg_mode<LG, kMagBwd>(target, rec, window, tw, partial, d_rec, edge, mag_io, hg, B, accumulate, inv_cnt, st);
+    }
+}
+
+int dispatch_reg(int mode, const float *target, const float *rec, const float *window, const float2 *stw,
+                 float *partial, float *d_rec, float *edge, float *mag_io, const HostGeom &hg, int B,
+                 int accumulate, float inv_cnt, cudaStream_t st) {
+    int s = DDSP_B200_EUNSUPPORTED;
+#define DDSP_REG_CASE(LG)                                                                            \
+    case LG:                                                                                         \
+        s = launch_reg<LG>(mode, target, rec, window, stw, partial, d_rec, edge, mag_io, hg, B,      \
+                           accumulate, inv_cnt, st);                                                 \
+        break;
+    switch (hg.g.lg) {
+        DDSP_REG_CASE(6) DDSP_REG_CASE(7) DDSP_REG_CASE(8) DDSP_REG_CASE(9) DDSP_REG_CASE(10)
+        DDSP_REG_CASE(11) DDSP_REG_CASE(12)
+        default: break;
+    }
+#undef DDSP_REG_CASE
+    return s ? s : ddsp_launch_status();
 }
 
 }  // namespace
@@ -786,19 +861,9 @@ extern "C" int ddsp_b200_mss_scale(const float *target, const float *rec, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (reg_path(n_fft)) {
         if (!stage_twiddle) return DDSP_B200_EINVAL;
-        const float2 *stw = reinterpret_cast<const float2 *>(stage_twiddle);
-#define DDSP_REG_CASE(LG)                                                                            \
-    case LG:                                                                                         \
-        s = launch_reg<LG>(target, rec, window, stw, partial, d_rec, edge, hg, B, accumulate,        \
-                           inv_cnt, st);                                                             \
-        break;
-        switch (hg.g.lg) {
-            DDSP_REG_CASE(6) DDSP_REG_CASE(7) DDSP_REG_CASE(8) DDSP_REG_CASE(9) DDSP_REG_CASE(10)
-            DDSP_REG_CASE(11) DDSP_REG_CASE(12)
-            default: return DDSP_B200_EUNSUPPORTED;
-        }
-#undef DDSP_REG_CASE
-        return s ? s : ddsp_launch_status();
+        return dispatch_reg(d_rec ? kLossGrad : kLoss, target, rec, window,
+                            reinterpret_cast<const float2 *>(stage_twiddle), partial, d_rec, edge, nullptr, hg, B,
+                            accumulate, inv_cnt, st);
     }
     if (d_rec) {
         if ((s = set_smem(mss_scale_kernel<true>, hg.smem_loss))) return s;
@@ -836,7 +901,7 @@ extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, con
         hs_max = scales[i] / 2 > hs_max ? scales[i] / 2 : hs_max;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    mss_finalize_kernel<<<1, 256, 0, st>>>(partial, loss, fin);
+    mss_finalize_kernel<<<1, 1024, 0, st>>>(partial, loss, fin);
     int s = ddsp_launch_status();
     if (s || !d_rec) return s;
     if (d_rec_scales) {
@@ -853,11 +918,17 @@ extern "C" int ddsp_b200_mss_finish(const float *partial, const float *edge, con
 }
 
 extern "C" int ddsp_b200_stft_mag_fwd(const float *signal, const float *window, const float *twiddle,
-                                      int n_tab, float *mag, int B, int64_t N, int n_fft, int hop,
-                                      void *stream) {
+                                      int n_tab, const float *stage_twiddle, float *mag, int B, int64_t N,
+                                      int n_fft, int hop, void *stream) {
     DDSP_REQUIRE(signal && window && twiddle && mag && B > 0 && B <= 65535);
     DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
     HostGeom hg;
+    if (reg_path(n_fft) && stage_twiddle) {
+        int s = loss_geom(B, N, n_fft, hop, &hg);
+        if (s) return s;
+        return dispatch_reg(kMagFwd, nullptr, signal, window, reinterpret_cast<const float2 *>(stage_twiddle),
+                            nullptr, nullptr, nullptr, mag, hg, B, 0, 0.f, (cudaStream_t)stream);
+    }
     int s = make_geom(N, n_fft, hop, false, &hg);
     if (s) return s;
     if ((s = set_smem(stft_mag_fwd_kernel, hg.smem_mag_fwd))) return s;
@@ -867,12 +938,19 @@ extern "C" int ddsp_b200_stft_mag_fwd(const float *signal, const float *window, 
 }
 
 extern "C" int ddsp_b200_stft_mag_bwd(const float *signal, const float *d_mag, const float *window,
-                                      const float *twiddle, int n_tab, float *d_signal, float *edge,
-                                      int B, int64_t N, int n_fft, int hop, int accumulate,
-                                      void *stream) {
+                                      const float *twiddle, int n_tab, const float *stage_twiddle,
+                                      float *d_signal, float *edge, int B, int64_t N, int n_fft, int hop,
+                                      int accumulate, void *stream) {
     DDSP_REQUIRE(signal && d_mag && window && twiddle && d_signal && edge && B > 0 && B <= 65535);
     DDSP_REQUIRE(n_tab >= n_fft && n_tab % n_fft == 0);
     HostGeom hg;
+    if (reg_path(n_fft) && stage_twiddle) {
+        int s = loss_geom(B, N, n_fft, hop, &hg);
+        if (s) return s;
+        return dispatch_reg(kMagBwd, nullptr, signal, window, reinterpret_cast<const float2 *>(stage_twiddle),
+                            nullptr, d_signal, edge, const_cast<float *>(d_mag), hg, B, accumulate, 0.f,
+                            (cudaStream_t)stream);
+    }
     int s = make_geom(N, n_fft, hop, true, &hg);
     if (s) return s;
     if ((s = set_smem(stft_mag_bwd_kernel, hg.smem_mag_bwd))) return s;

@@ -488,8 +488,9 @@ Tensor stft_mag_fwd(const Tensor &signal_, const Tensor &window_, int64_t n_fft,
     c10::cuda::CUDAGuard guard(sig.device());
     Tensor tw = twiddle_table(sig.device(), std::max<int64_t>(4096, n_fft));
     Tensor mag = at::empty({B, n_fft / 2 + 1, 1 + N / hop}, sig.options());
-    check(ddsp_b200_stft_mag_fwd(fp(sig), fp(win), fp(tw), (int)tw.size(0), fpm(mag), (int)B, N, (int)n_fft,
-                                 (int)hop, cur_stream()),
+    Tensor stw = stage_twiddle_table(sig.device(), n_fft);
+    check(ddsp_b200_stft_mag_fwd(fp(sig), fp(win), fp(tw), (int)tw.size(0), stw.defined() ? fp(stw) : nullptr, fpm(mag),
+                                 (int)B, N, (int)n_fft, (int)hop, cur_stream()),
           "stft_mag_fwd");
     return mag;
 }
@@ -504,8 +505,9 @@ Tensor stft_mag_bwd(const Tensor &signal_, const Tensor &d_mag_, const Tensor &w
     Tensor d_sig = at::empty_like(sig);
     Tensor edge = at::empty({B, n_fft}, sig.options());
     void *st = cur_stream();
-    check(ddsp_b200_stft_mag_bwd(fp(sig), fp(gm), fp(win), fp(tw), (int)tw.size(0), fpm(d_sig), fpm(edge), (int)B,
-                                 N, (int)n_fft, (int)hop, 0, st),
+    Tensor stw = stage_twiddle_table(sig.device(), n_fft);
+    check(ddsp_b200_stft_mag_bwd(fp(sig), fp(gm), fp(win), fp(tw), (int)tw.size(0), stw.defined() ? fp(stw) : nullptr,
+                                 fpm(d_sig), fpm(edge), (int)B, N, (int)n_fft, (int)hop, 0, st),
           "stft_mag_bwd");
     const int sc = (int)n_fft;
     check(ddsp_b200_stft_fold_edges(fp(edge), fpm(d_sig), (int)B, N, &sc, 1, st), "stft_fold_edges");

@@ -176,13 +176,17 @@ int ddsp_b200_reverb_impulse_bwd(const float *d_impulse, int Lvalid, const float
 /* signal[B,N] -> mag[B, n_fft/2+1, frames], frames = 1 + N/hop (centred, reflect padded, periodic
  * Hann, normalised).  window[n_fft] is the float32 torch.hann_window(n_fft) the reference builds on
  * the CPU; twiddle is a table of size n_tab (a multiple of n_fft).                              */
+/* stage_twiddle: ddsp_b200_fft_stage_twiddles(n_fft) selects the register-tiled FFT (64..4096);
+ * NULL falls back to the generic radix-4 kernels driven by `twiddle`.                             */
 int ddsp_b200_stft_mag_fwd(const float *signal, const float *window, const float *twiddle, int n_tab,
-                           float *mag, int B, int64_t N, int n_fft, int hop, void *stream);
+                           const float *stage_twiddle, float *mag, int B, int64_t N, int n_fft, int hop,
+                           void *stream);
 /* d_signal[B,N] (=, or += when accumulate) from d_mag; the gradient of the reflect padding goes to
  * edge[B, n_fft] and is folded in by ddsp_b200_stft_fold_edges.                                 */
 int ddsp_b200_stft_mag_bwd(const float *signal, const float *d_mag, const float *window,
-                           const float *twiddle, int n_tab, float *d_signal, float *edge, int B,
-                           int64_t N, int n_fft, int hop, int accumulate, void *stream);
+                           const float *twiddle, int n_tab, const float *stage_twiddle, float *d_signal,
+                           float *edge, int B, int64_t N, int n_fft, int hop, int accumulate,
+                           void *stream);
 /* edge holds the blocks of `n_scales` scales back to back: [scale][B][n_fft]; scales: HOST array */
 int ddsp_b200_stft_fold_edges(const float *edge, float *d_signal, int B, int64_t N,
                               const int *scales, int n_scales, void *stream);
