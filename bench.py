@@ -49,6 +49,8 @@ def parse():
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     p.add_argument("--cpu-batch", type=int, default=8, help="voices in the bounded CPU-baseline sample")
     p.add_argument("--skip-cpu", action="store_true")
+    p.add_argument("--global-batch", type=int, default=WORKLOAD["batch"],
+                   help="experiments only: the benchmark config is batch 64 (BASELINE.json configs[1])")
     p.add_argument("--skip-kernels", action="store_true")
     return p.parse_args()
 
@@ -267,7 +269,8 @@ def run_b200(args, rank, world):
     lib.ddsp_b200_launch_count.restype = ctypes.c_uint64
 
     w = dict(WORKLOAD)
-    assert w["batch"] % world == 0, "batch 64 must divide over the GPUs"
+    w["batch"] = args.global_batch
+    assert w["batch"] % world == 0, "the global batch must divide over the GPUs"
     w["batch"] //= world
     shapes = SynthShapes(**w)
     torch.manual_seed(0)
@@ -337,7 +340,7 @@ def run_b200(args, rank, world):
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt)
-    samples_per_step = WORKLOAD["batch"] * shapes.samples           # whole job, all ranks
+    samples_per_step = args.global_batch * shapes.samples           # whole job, all ranks
     value = samples_per_step * args.steps / (total_ms * 1e-3)
 
     # forward only (the "fwd" half of the metric)
@@ -410,7 +413,7 @@ def run_b200(args, rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "global_batch": WORKLOAD["batch"], "per_gpu_batch": shapes.batch,
+            "config": {"workload": WORKLOAD_NAME, "global_batch": args.global_batch, "per_gpu_batch": shapes.batch,
                        "samples_per_voice": shapes.samples, "parallelism": f"voices sharded x{world}, NCCL "
                        f"all-reduce of {n_param} reverb-parameter grads" if world > 1 else "single GPU",
                        "l2": "256 MiB memset between timed steps (outside the event pairs)",

@@ -7,7 +7,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ddsp_pytorch_b200 as ddsp
 from ddsp_pytorch_b200.models.decoder import DDSPDecoder
 
-ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=16); args = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=16); ap.add_argument("--tf32", action="store_true"); ap.add_argument("--graph", action="store_true"); args = ap.parse_args()
+if args.tf32:
+    torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
 torch.manual_seed(0)
 B, T, bs, sr = args.batch, 400, 160, 16000
 model = DDSPDecoder(hidden_size=512, n_harmonic=100, n_bands=65, sample_rate=sr, block_size=bs, has_reverb=True).cuda()
@@ -35,8 +37,20 @@ def timeit(fn, n=20):
     for _ in range(n): fn()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
 
+if args.graph:
+    # whole training step (control net, synth, fused loss, backward, Adam) captured once and replayed
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3): step(True)
+    torch.cuda.current_stream().wait_stream(side); torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        static_loss = step(True)
+    print(json.dumps({"config": f"batch {B}, tf32={args.tf32}", "ms_graph_replay_fused_loss": timeit(gr.replay), "loss": float(static_loss)}))
+    sys.exit(0)
 res = {"config": f"DDSPDecoder hidden 512, 16 kHz, block 160, H=100, 4 s, batch {B}: full train step incl. control net and Adam, eager",
-       "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
+       "tf32": args.tf32, "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
 with torch.no_grad():
     res["ms_forward_only"] = timeit(lambda: model(batch))
 t0 = time.perf_counter(); n = torch.rand(B, T, bs) * 2 - 1; res["ms_cpu_noise_draw"] = (time.perf_counter() - t0) * 1e3
