@@ -19,6 +19,7 @@ from typing import List, Optional, Sequence
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import functions as _F
 
@@ -121,9 +122,34 @@ def mlp(in_size, hidden_size, n_layers):
     return nn.Sequential(*layers)
 
 
+class ClusterGRU(nn.GRU):
+    """``nn.GRU`` (same parameters, state_dict keys and call signature) whose recurrence runs as one
+    cluster-persistent launch (csrc/gru.cu) instead of cuDNN's two launches per time step.  Used when the
+    layer has the shape the decoder builds (one layer, batch_first, hidden 512), the input is CUDA
+    float32 and the batch fits one pass of the resident clusters (70 voices on a B200; beyond that cuDNN's
+    batched SGEMM per step is faster); every other case takes the stock cuDNN path of the base class, as
+    the reference does."""
+
+    def _cluster_path(self, x, hx) -> bool:
+        return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3
+                and self.num_layers == 1 and not self.bidirectional and self.batch_first and self.bias
+                and self.proj_size == 0 and not torch.jit.is_scripting()
+                and 0 < x.shape[0] <= int(_F._ops.gru_supported(self.hidden_size)))
+
+    def forward(self, input, hx=None):      # noqa: A002 (nn.GRU's argument name)
+        if not self._cluster_path(input, hx):
+            return super().forward(input, hx)
+        gi = F.linear(input, self.weight_ih_l0, self.bias_ih_l0)
+        h0 = None
+        if hx is not None:
+            h0 = hx.expand(1, input.shape[0], self.hidden_size)[0].contiguous()
+        y = _F.GRURecurrence.apply(gi, self.weight_hh_l0, self.bias_hh_l0, h0)
+        return y, y[:, -1].unsqueeze(0)
+
+
 def gru(n_input, hidden_size):
     """ddsp/core.py:132-133."""
-    return nn.GRU(n_input * hidden_size, hidden_size, batch_first=True)
+    return ClusterGRU(n_input * hidden_size, hidden_size, batch_first=True)
 
 
 def harmonic_synth(f0, amplitudes, sample_rate):

@@ -581,12 +581,59 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
     return {loss, d_rec};
 }
 
+// ---------------------------------------------------------------------------------------- f3 GRU
+// voices one pass of the resident clusters covers (0: such clusters cannot run here, or hidden != 512);
+// above it the cluster kernel needs a second pass over time and the library recurrence wins
+int64_t gru_supported(int64_t hidden) {
+    if (hidden != 512) return 0;
+    const int clusters = ddsp_b200_gru_resident_clusters();
+    return clusters > 0 ? (int64_t)clusters * 10 : 0;
+}
+
+// gi (B,T,3H) = x W_ih^T + b_ih; returns (y (B,T,H), gates (B,T,4H) or empty)
+std::tuple<Tensor, Tensor> gru_fwd(const Tensor &gi_, const Tensor &w_hh_, const Tensor &b_hh_,
+                                   const c10::optional<Tensor> &h0_, bool save_gates) {
+    Tensor gi = prep(gi_, "gi"), w = prep(w_hh_, "weight_hh"), b = prep(b_hh_, "bias_hh"), h0 = opt_prep(h0_, "h0");
+    TORCH_CHECK(gi.dim() == 3 && gi.size(2) % 3 == 0, "gru_fwd: gi must be (B,T,3H)");
+    const int64_t B = gi.size(0), T = gi.size(1), H = gi.size(2) / 3;
+    TORCH_CHECK(w.numel() == 3 * H * H && b.numel() == 3 * H && (!h0.defined() || h0.numel() == B * H),
+                "gru_fwd: weight / bias / h0 shape mismatch");
+    c10::cuda::CUDAGuard guard(gi.device());
+    Tensor y = at::empty({B, T, H}, gi.options());
+    Tensor gates = save_gates ? at::empty({B, T, 4 * H}, gi.options()) : at::empty({0}, gi.options());
+    if (B == 0 || T == 0) return {y, gates};
+    check(ddsp_b200_gru_fwd(fp(gi), fp(w), fp(b), opt_fp(h0), fpm(y), save_gates ? fpm(gates) : nullptr, (int)B,
+                            (int)T, (int)H, cur_stream()),
+          "gru_fwd");
+    return {y, gates};
+}
+
+// returns (dgi, dgh, dh0)
+std::tuple<Tensor, Tensor, Tensor> gru_bwd(const Tensor &dy_, const c10::optional<Tensor> &dhT_, const Tensor &w_hh_,
+                                           const Tensor &y_, const c10::optional<Tensor> &h0_, const Tensor &gates_) {
+    Tensor dy = prep(dy_, "dy"), w = prep(w_hh_, "weight_hh"), y = prep(y_, "y"), gates = prep(gates_, "gates");
+    Tensor dhT = opt_prep(dhT_, "dhT"), h0 = opt_prep(h0_, "h0");
+    const int64_t B = y.size(0), T = y.size(1), H = y.size(2);
+    TORCH_CHECK(dy.numel() == y.numel() && gates.numel() == 4 * y.numel(), "gru_bwd: shape mismatch");
+    c10::cuda::CUDAGuard guard(y.device());
+    Tensor dgi = at::empty({B, T, 3 * H}, y.options()), dgh = at::empty({B, T, 3 * H}, y.options());
+    Tensor dh0 = at::empty({B, H}, y.options());
+    if (B == 0 || T == 0) return {dgi, dgh, dh0.zero_()};
+    check(ddsp_b200_gru_bwd(fp(dy), opt_fp(dhT), fp(w), fp(y), opt_fp(h0), fp(gates), fpm(dgi), fpm(dgh), fpm(dh0),
+                            (int)B, (int)T, (int)H, cur_stream()),
+          "gru_bwd");
+    return {dgi, dgh, dh0};
+}
+
 int64_t abi_version() { return ddsp_b200_abi_version(); }
 
 }  // namespace
 
 TORCH_LIBRARY(ddsp_b200, m) {
     m.def("abi_version() -> int", abi_version);
+    m.def("gru_supported(int hidden) -> int", gru_supported);
+    m.def("gru_fwd(Tensor gi, Tensor weight_hh, Tensor bias_hh, Tensor? h0, bool save_gates) -> (Tensor, Tensor)");
+    m.def("gru_bwd(Tensor dy, Tensor? dhT, Tensor weight_hh, Tensor y, Tensor? h0, Tensor gates) -> (Tensor, Tensor, Tensor)");
     m.def("scale_function_fwd(Tensor x) -> Tensor");
     m.def("scale_function_bwd(Tensor x, Tensor dy) -> Tensor");
     m.def("remove_above_nyquist(Tensor amplitudes, Tensor f0, float sample_rate) -> Tensor");
@@ -610,6 +657,8 @@ TORCH_LIBRARY(ddsp_b200, m) {
 }
 
 TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
+    m.impl("gru_fwd", gru_fwd);
+    m.impl("gru_bwd", gru_bwd);
     m.impl("scale_function_fwd", scale_function_fwd);
     m.impl("scale_function_bwd", scale_function_bwd);
     m.impl("remove_above_nyquist", remove_above_nyquist);

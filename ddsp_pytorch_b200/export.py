@@ -20,13 +20,14 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+from ._lib import get_ops
 from .models.decoder import DDSPDecoder
 
 
 class ScriptDDSP(nn.Module):
     # compile-time constants: the scripted graph only contains the branches that are taken
     __constants__ = ["block_size", "sample_rate", "reverb_length", "has_reverb", "realtime", "device_noise",
-                     "mean_loudness", "std_loudness", "noise_bias"]
+                     "mean_loudness", "std_loudness", "noise_bias", "cluster_gru"]
 
     def __init__(self, ddsp: DDSPDecoder, mean_loudness: float, std_loudness: float, realtime: bool = True,
                  device_noise: bool = True):
@@ -35,7 +36,12 @@ class ScriptDDSP(nn.Module):
         assert not dec.add_z, "export covers the f0 + loudness decoder (config.yaml's single-inst-decoder)"
         self.f0_mlp = dec.f0_mlp
         self.loudness_mlp = dec.loudness_mlp
-        self.gru = dec.gru
+        # a stock nn.GRU holds the weights in the scripted module (ClusterGRU's forward is Python-side
+        # dispatch); the graph calls ddsp_b200::gru_fwd on them when the kernel covers the layer
+        self.gru = nn.GRU(dec.gru.input_size, dec.gru.hidden_size, batch_first=True)
+        self.gru.load_state_dict(dec.gru.state_dict())
+        self.gru.to(dec.cache_gru.device)
+        self.cluster_gru: bool = bool(dec.cache_gru.is_cuda and get_ops().gru_supported(dec.gru.hidden_size) > 0)
         self.out_mlp = dec.out_mlp
         self.harmonic_proj = ddsp.harmonic_proj
         self.noise_proj = ddsp.noise_proj
@@ -61,7 +67,15 @@ class ScriptDDSP(nn.Module):
         f0 = pitch[:, ::self.block_size].contiguous()
         ld = loudness[:, ::self.block_size].contiguous()
         hidden = torch.cat([self.f0_mlp(f0), self.loudness_mlp(ld)], -1)
-        if self.realtime:
+        if self.cluster_gru:
+            gi = torch.nn.functional.linear(hidden, self.gru.weight_ih_l0, self.gru.bias_ih_l0)
+            h0: Optional[torch.Tensor] = None
+            if self.realtime:
+                h0 = self.cache_gru.expand(1, hidden.shape[0], hidden.shape[2] // 2)[0].contiguous()
+            gru_out = torch.ops.ddsp_b200.gru_fwd(gi, self.gru.weight_hh_l0, self.gru.bias_hh_l0, h0, False)[0]
+            if self.realtime:
+                self.cache_gru.copy_(gru_out[:1, -1:])
+        elif self.realtime:
             gru_out, cache = self.gru(hidden, self.cache_gru)
             self.cache_gru.copy_(cache)
         else:

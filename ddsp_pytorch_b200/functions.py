@@ -219,6 +219,42 @@ class ReverbImpulse(torch.autograd.Function):
         return dn.view_as(noise), dd.view_as(decay), dw.view_as(wet), None
 
 
+class GRURecurrence(torch.autograd.Function):
+    """The time loop of core.py:132-133's nn.GRU (one layer, batch_first) as one cluster-persistent launch.
+    gi (B,T,3H) = x W_ih^T + b_ih is computed by the caller (a cuBLAS GEMM autograd differentiates);
+    returns every hidden state (B,T,H).  Backward: one reverse-time launch for the gate gradients, then
+    dW_hh / db_hh as GEMM / reduction over them."""
+
+    @staticmethod
+    def forward(ctx, gi, weight_hh, bias_hh, h0):
+        need = any(ctx.needs_input_grad)
+        y, gates = _ops.gru_fwd(gi, weight_hh, bias_hh, h0, need)
+        ctx.save_for_backward(weight_hh, y, h0, gates)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        weight_hh, y, h0, gates = ctx.saved_tensors
+        B, T, H = y.shape
+        dgi, dgh, dh0 = _ops.gru_bwd(dy, None, weight_hh, y, h0, gates)
+        d_w = d_b = None
+        if ctx.needs_input_grad[1]:
+            h_prev = torch.empty_like(y)
+            h_prev[:, 1:] = y[:, :-1]
+            if h0 is None:
+                h_prev[:, 0].zero_()
+            else:
+                h_prev[:, 0] = h0.reshape(B, H)
+            d_w = dgh.reshape(B * T, 3 * H).t().mm(h_prev.reshape(B * T, H))
+        if ctx.needs_input_grad[2]:
+            d_b = dgh.sum((0, 1))
+        d_h0 = None
+        if h0 is not None and ctx.needs_input_grad[3]:
+            d_h0 = dh0.view_as(h0)
+        return (dgi if ctx.needs_input_grad[0] else None), d_w, d_b, d_h0
+
+
 class StftMag(torch.autograd.Function):
     """One scale of core.py:27-41: signal (B,N) -> |STFT| (B, s/2+1, 1+N//hop)."""
 

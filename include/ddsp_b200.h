@@ -210,6 +210,20 @@ int ddsp_b200_mss_finish(const float *partial, const float *edge, const float *d
                          float *d_rec, float *loss, int B, int64_t N, const int *scales,
                          const int *hops, int n_scales, void *stream);
 
+/* ---- f3 (next row)  GRU recurrence of the control net  (ddsp/core.py:132-133, decoder.py:40,59,65) --- */
+/* The cuDNN GRU the reference calls runs one SGEMM + one element-wise launch per time step.  Here the
+ * recurrence is one launch: 16-CTA clusters keep W_hh (3H x H fp32) in distributed shared memory.
+ * H must be 512; PyTorch gate order (r, z, n).  gi[B,T,3H] = x W_ih^T + b_ih (a library GEMM, caller).
+ * fwd: y[B,T,H] = h_1..h_T; gates[B,T,4H] = r, z, n, W_hn h + b_hn (NULL for inference); h0 may be NULL.
+ * bwd: dgi, dgh [B,T,3H] gradients of gi and of gh = W_hh h + b_hh; dh0[B,H]; dhT = gradient of the
+ * last hidden state (may be NULL).  Returns DDSP_B200_EUNSUPPORTED where such clusters cannot run.  */
+int ddsp_b200_gru_resident_clusters(void);
+int ddsp_b200_gru_fwd(const float *gi, const float *w_hh, const float *b_hh, const float *h0, float *y,
+                      float *gates, int B, int T, int H, void *stream);
+int ddsp_b200_gru_bwd(const float *dy, const float *dhT, const float *w_hh, const float *y, const float *h0,
+                      const float *gates, float *dgi, float *dgh, float *dh0, int B, int T, int H,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,12 +7,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ddsp_pytorch_b200 as ddsp
 from ddsp_pytorch_b200.models.decoder import DDSPDecoder
 
-ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=16); ap.add_argument("--tf32", action="store_true"); ap.add_argument("--graph", action="store_true"); args = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=16); ap.add_argument("--tf32", action="store_true"); ap.add_argument("--graph", action="store_true"); ap.add_argument("--stock-gru", action="store_true"); args = ap.parse_args()
 if args.tf32:
     torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
 torch.manual_seed(0)
 B, T, bs, sr = args.batch, 400, 160, 16000
 model = DDSPDecoder(hidden_size=512, n_harmonic=100, n_bands=65, sample_rate=sr, block_size=bs, has_reverb=True).cuda()
+if args.stock_gru:      # A/B: the cuDNN recurrence the reference runs
+    stock = torch.nn.GRU(1024, 512, batch_first=True).cuda(); stock.load_state_dict(model.decoder.gru.state_dict()); model.decoder.gru = stock
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 g = torch.Generator().manual_seed(1)
 batch = {"pitch": (torch.rand(B, T, 1, generator=g) * 400 + 100).cuda(), "loudness": torch.randn(B, T, 1, generator=g).cuda(),
@@ -47,10 +49,10 @@ if args.graph:
     gr = torch.cuda.CUDAGraph()
     with torch.cuda.graph(gr):
         static_loss = step(True)
-    print(json.dumps({"config": f"batch {B}, tf32={args.tf32}", "ms_graph_replay_fused_loss": timeit(gr.replay), "loss": float(static_loss)}))
+    print(json.dumps({"config": f"batch {B}, tf32={args.tf32}, gru={'cudnn' if args.stock_gru else 'cluster'}", "ms_graph_replay_fused_loss": timeit(gr.replay), "loss": float(static_loss)}))
     sys.exit(0)
 res = {"config": f"DDSPDecoder hidden 512, 16 kHz, block 160, H=100, 4 s, batch {B}: full train step incl. control net and Adam, eager",
-       "tf32": args.tf32, "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
+       "tf32": args.tf32, "gru": "cudnn" if args.stock_gru else "cluster", "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
 with torch.no_grad():
     res["ms_forward_only"] = timeit(lambda: model(batch))
 t0 = time.perf_counter(); n = torch.rand(B, T, bs) * 2 - 1; res["ms_cpu_noise_draw"] = (time.perf_counter() - t0) * 1e3
