@@ -1,0 +1,434 @@
+// FP32-accurate GEMM on the 5th-generation tensor cores (the control net's nn.Linear /
+// GRU input projections, ddsp/core.py:122-133, decoder.py:40-68,86-87).
+//
+// Reference path replaced: cuBLAS SIMT SGEMM (torch's default for float32 nn.Linear with TF32 off, the
+// reference's setting): ~50 TFLOP/s on a B200, half of a training step at batch 64
+// (profiles/r01_model_step_profile.txt).
+//
+// Method ("3xTF32"): every fp32 operand x is split once into hi = tf32_round(x) and lo = x - hi (exact).
+// C = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulated in fp32 in tensor memory: the dropped lo*lo term and the
+// truncation of lo to 11 significant bits are ~2^-22 relative per product, i.e. fp32-class accuracy at a
+// third of the TF32 tensor rate (several times the SIMT rate).
+//
+// Kernel: persistent, one CTA per SM walking 128 x 128 output tiles (x K splits), operands K-major.
+// Warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 3-stage mbarrier ring of 64 KB stages: A_hi,
+// A_lo, B_hi, B_lo), warp 1 = tcgen05.mma issuer (one thread, kind::tf32, M128 N128 K8, 12 MMAs per 32-wide
+// k block, two ping-pong pairs of 128-column TMEM accumulators), warps 2-5 = epilogue (tcgen05.ld 32x32b of
+// every finished 64-deep K chunk, accumulated in registers; + bias and global stores at the end of a tile).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;          // CTA tile; kBK fp32 = 128 B = one swizzle row
+constexpr int kStages = 3;
+constexpr int kChunk = 2;                                // k blocks accumulated in TMEM before promotion to registers
+constexpr int kTileBytes = kBM * kBK * 4;              // 16 KB per operand part
+constexpr int kStageBytes = 4 * kTileBytes;            // A_hi, A_lo, B_hi, B_lo
+constexpr int kGemmThreads = 192;
+constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr uint32_t kSpinLimit = 1u << 26;              // a lost barrier traps instead of hanging the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > kSpinLimit) __trap();
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1)
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
+struct GemmParams {
+    float *c;                  // output, or split-K partials [splits][M][N] (then ldc == N)
+    const float *bias;         // added in the epilogue when splits == 1
+    int M, N, ldc;
+    int a_lo_row, b_lo_row;    // row offset of the lo part inside the operand's tensor map
+    int k_blocks, k_blocks_per_split, splits;
+    int m_tiles, n_tiles;
+};
+
+// tile t -> (split z, m tile, n tile); consecutive tiles share the A rows (L2 reuse)
+__device__ __forceinline__ void tile_coords(const GemmParams &p, int t, int &z, int &m0, int &n0, int &kb0, int &nkb) {
+    const int per_split = p.m_tiles * p.n_tiles;
+    z = t / per_split;
+    const int r = t - z * per_split;
+    m0 = (r / p.n_tiles) * kBM;
+    n0 = (r % p.n_tiles) * kBN;
+    kb0 = z * p.k_blocks_per_split;
+    nkb = min(p.k_blocks, kb0 + p.k_blocks_per_split) - kb0;
+}
+
+// Persistent: CTA b works on tiles b, b + grid, ...  The tensor core's fp32 accumulation truncates, so the
+// error of a long K loop grows linearly with K; therefore K is accumulated in TMEM only over chunks of
+// kChunk k blocks (64 values of K) and the epilogue warps add every finished chunk into fp32 REGISTERS
+// (round-to-nearest) while the next chunk is being multiplied into the other TMEM buffer.  The two small
+// cross terms go to their own accumulator so that their rounding happens at their own (2^-11) scale.
+// TMEM columns: [main0 | small0 | main1 | small1], 128 each.
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + kStages * kStageBytes;
+    const uint32_t full0 = bars, empty0 = bars + 8 * kStages;
+    const uint32_t tfull0 = bars + 16 * kStages, tempty0 = tfull0 + 16;     // 2 TMEM buffers each
+    const uint32_t tmem_slot = tempty0 + 16;
+    uint32_t *tmem_slot_ptr = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles = p.m_tiles * p.n_tiles * p.splits;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull0 + 8 * b, 1);
+            mbar_init(tempty0 + 8 * b, 4);            // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0;                                                      // k blocks issued so far (ring position)
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int z, m0, n0, kb0, nkb;
+                tile_coords(p, t, z, m0, n0, kb0, nkb);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % kStages, round = it / kStages;
+                    mbar_wait(empty0 + 8 * s, (round & 1) ^ 1);
+                    const uint32_t st = base + s * kStageBytes, fb = full0 + 8 * s;
+                    mbar_expect_tx(fb, kStageBytes);
+                    const int k = (kb0 + i) * kBK;
+                    tma_load_2d(st, &map_a, fb, k, m0);
+                    tma_load_2d(st + kTileBytes, &map_a, fb, k, p.a_lo_row + m0);
+                    tma_load_2d(st + 2 * kTileBytes, &map_b, fb, k, n0);
+                    tma_load_2d(st + 3 * kTileBytes, &map_b, fb, k, p.b_lo_row + n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            int it = 0, chunk = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                int z, m0, n0, kb0, nkb;
+                tile_coords(p, t, z, m0, n0, kb0, nkb);
+                for (int i0 = 0; i0 < nkb; i0 += kChunk, ++chunk) {
+                    const int buf = chunk & 1, use = chunk >> 1;
+                    mbar_wait(tempty0 + 8 * buf, (use & 1) ^ 1);             // epilogue has drained this buffer
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_main = tmem_base + buf * 2 * kBN, d_small = d_main + kBN;
+                    const int i1 = min(nkb, i0 + kChunk);
+                    for (int i = i0; i < i1; ++i, ++it) {
+                        const int s = it % kStages, round = it / kStages;
+                        mbar_wait(full0 + 8 * s, round & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t st = base + s * kStageBytes;
+#pragma unroll
+                        for (int k = 0; k < kBK / 8; ++k) {
+                            const uint32_t off = k * 32;                           // 8 fp32 along K inside the 128 B row
+                            const uint64_t a_hi = umma_desc_k_sw128(st + off), a_lo = umma_desc_k_sw128(st + kTileBytes + off);
+                            const uint64_t b_hi = umma_desc_k_sw128(st + 2 * kTileBytes + off);
+                            const uint64_t b_lo = umma_desc_k_sw128(st + 3 * kTileBytes + off);
+                            const uint32_t acc = (i != i0 || k != 0) ? 1u : 0u;
+                            umma_tf32(d_main, a_hi, b_hi, idesc, acc);
+                            umma_tf32(d_small, a_lo, b_hi, idesc, acc);
+                            umma_tf32(d_small, a_hi, b_lo, idesc, 1u);
+                        }
+                        umma_commit(empty0 + 8 * s);                               // stage free when these MMAs retire
+                    }
+                    umma_commit(tfull0 + 8 * buf);                                 // chunk complete in TMEM
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 (its hardware quarter) = 32 output rows =====
+        const int quarter = warp & 3;
+        const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+        int chunk = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            int z, m0, n0, kb0, nkb;
+            tile_coords(p, t, z, m0, n0, kb0, nkb);
+            float acc[kBN];
+#pragma unroll
+            for (int j = 0; j < kBN; ++j) acc[j] = 0.f;
+            for (int i0 = 0; i0 < nkb; i0 += kChunk, ++chunk) {
+                const int buf = chunk & 1, use = chunk >> 1;
+                mbar_wait(tfull0 + 8 * buf, use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t t_main = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 2 * kBN;
+#pragma unroll
+                for (int cc = 0; cc < kBN / 32; ++cc) {
+                    uint32_t u[32];
+                    tmem_ld32(t_main + kBN + cc * 32, u);                     // cross terms first (small)
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(u[j]);
+                    tmem_ld32(t_main + cc * 32, u);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += __uint_as_float(u[j]);
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+            }
+            const int row = m0 + quarter * 32 + lane;
+            if (row < p.M) {
+                float *crow = p.c + (size_t)z * p.M * p.ldc + (size_t)row * p.ldc;
+#pragma unroll
+                for (int cc = 0; cc < kBN / 32; ++cc) {
+                    const int col0 = n0 + cc * 32;
+                    if (col0 >= p.N) break;
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) acc[cc * 32 + j] += __ldg(p.bias + col0 + j);
+                    }
+                    if (vec_ok && col0 + 32 <= p.N) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4 *>(crow + col0 + j) =
+                                make_float4(acc[cc * 32 + j], acc[cc * 32 + j + 1], acc[cc * 32 + j + 2], acc[cc * 32 + j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < p.N) crow[col0 + j] = acc[cc * 32 + j];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- split-K reduction: c[m][n] = bias[n] + sum_s partial[s][m][n]  (fixed order: deterministic)
+__global__ void gemm3x_reduce_kernel(const float *__restrict__ partial, const float *__restrict__ bias,
+                                     float *__restrict__ c, int M, int N, int ldc, int splits) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)M * N) return;
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    float acc = bias ? __ldg(bias + n) : 0.f;
+    for (int s = 0; s < splits; ++s) acc += __ldg(partial + (size_t)s * M * N + i);
+    c[(size_t)m * ldc + n] = acc;
+}
+
+// ---- operand split: out[r][c] = tf32_round(x), out[lo_row + r][c] = x - hi; columns cols..out_ld zeroed.
+// transpose == 0: logical operand = x (rows x cols, row pitch ld).  transpose == 1: operand = x^T.
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+__global__ void split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, float *__restrict__ out,
+                               int64_t lo_row, int out_ld) {
+    const int r = blockIdx.x;
+    float *hi_row = out + (size_t)r * out_ld, *lo_rowp = out + (size_t)(lo_row + r) * out_ld;
+    for (int c = (blockIdx.y * blockDim.x + threadIdx.x); c < out_ld; c += gridDim.y * blockDim.x) {
+        float hi = 0.f, lo = 0.f;
+        if (c < cols) split_tf32(__ldg(x + (size_t)r * ld + c), hi, lo);
+        hi_row[c] = hi;
+        lo_rowp[c] = lo;
+    }
+}
+
+// operand rows = x's columns, operand columns (K) = x's rows
+__global__ void split3x_transpose_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld,
+                                         float *__restrict__ out, int64_t lo_row, int out_ld) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;          // tile of x
+    const int tx = threadIdx.x, ty = threadIdx.y;                   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + tx;
+        tile[j][tx] = (r < rows && c < cols) ? __ldg(x + (size_t)r * ld + c) : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int orow = c0 + j, ocol = r0 + tx;                    // operand row = x column
+        if (orow < cols && ocol < out_ld) {
+            float hi, lo;
+            split_tf32(tile[tx][j], hi, lo);                        // zero beyond rows by construction
+            out[(size_t)orow * out_ld + ocol] = hi;
+            out[(size_t)(lo_row + orow) * out_ld + ocol] = lo;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// operand [total_rows][ld] fp32, box = 32 columns (128 B) x 128 rows, 128-byte swizzle
+int make_operand_map(CUtensorMap *map, const float *ptr, int64_t total_rows, int64_t ld) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return DDSP_B200_EUNSUPPORTED;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)total_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : DDSP_B200_EINVAL;
+}
+
+}  // namespace
+
+// Padded K extent (columns) of a split operand whose logical K is `k`
+extern "C" int64_t ddsp_b200_gemm3x_ld(int64_t k) { return (k + kBK - 1) / kBK * kBK; }
+
+// Number of K splits ddsp_b200_gemm3x uses for this shape (workspace = splits * M * N floats when > 1)
+extern "C" int ddsp_b200_gemm3x_splits(int M, int N, int K) {
+    const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+    const int kblocks = (int)(ddsp_b200_gemm3x_ld(K) / kBK);
+    if (tiles >= 96 || kblocks < 16) return 1;
+    int s = (148 + tiles - 1) / tiles;
+    if (s > kblocks / 4) s = kblocks / 4;
+    return s < 1 ? 1 : s;
+}
+
+// out: [2 * lo_row][out_ld] floats with out_ld = ddsp_b200_gemm3x_ld(K), lo_row >= operand rows.
+// transpose = 0: operand (rows x cols) = x; 1: operand (cols x rows) = x^T.  x has row pitch ld.
+extern "C" int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, float *out,
+                                      int64_t lo_row, void *stream) {
+    DDSP_REQUIRE(x && out && rows > 0 && cols > 0 && ld >= cols);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!transpose) {
+        DDSP_REQUIRE(lo_row >= rows);
+        const int out_ld = (int)ddsp_b200_gemm3x_ld(cols);
+        dim3 grid((unsigned)rows, (out_ld + 255) / 256);
+        split3x_kernel<<<grid, 256, 0, st>>>(x, (int)rows, (int)cols, ld, out, lo_row, out_ld);
+    } else {
+        DDSP_REQUIRE(lo_row >= cols);
+        const int out_ld = (int)ddsp_b200_gemm3x_ld(rows);
+        dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(out_ld / 32));
+        split3x_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(x, (int)rows, (int)cols, ld, out, lo_row, out_ld);
+    }
+    return ddsp_launch_status();
+}
+
+// C[M][N] (row pitch ldc) = A B^T + bias.  a, b: split operands (ddsp_b200_gemm3x_split) of logical shapes
+// M x K and N x K with lo-part row offsets a_lo_row / b_lo_row.  workspace: splits * M * N floats or NULL.
+extern "C" int ddsp_b200_gemm3x(const float *a, int64_t a_lo_row, const float *b, int64_t b_lo_row, const float *bias,
+                                float *c, int64_t ldc, int M, int N, int K, float *workspace, void *stream) {
+    DDSP_REQUIRE(a && b && c && M > 0 && N > 0 && K > 0 && ldc >= N && a_lo_row >= M && b_lo_row >= N);
+    const int64_t ld = ddsp_b200_gemm3x_ld(K);
+    const int kblocks = (int)(ld / kBK);
+    int splits = ddsp_b200_gemm3x_splits(M, N, K);
+    if (splits > 1 && !workspace) splits = 1;
+    alignas(64) CUtensorMap map_a, map_b;
+    int s = make_operand_map(&map_a, a, a_lo_row + M, ld);
+    if (s) return s;
+    s = make_operand_map(&map_b, b, b_lo_row + N, ld);
+    if (s) return s;
+    GemmParams p;
+    p.c = splits > 1 ? workspace : c;
+    p.bias = splits > 1 ? nullptr : bias;
+    p.M = M;
+    p.N = N;
+    p.ldc = splits > 1 ? N : (int)ldc;
+    p.a_lo_row = (int)a_lo_row;
+    p.b_lo_row = (int)b_lo_row;
+    p.k_blocks = kblocks;
+    p.k_blocks_per_split = (kblocks + splits - 1) / splits;
+    p.splits = splits;
+    p.m_tiles = (M + kBM - 1) / kBM;
+    p.n_tiles = (N + kBN - 1) / kBN;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaFuncSetAttribute(gemm3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    if (e != cudaSuccess) return (int)e;
+    const int tiles = p.m_tiles * p.n_tiles * splits;
+    gemm3x_kernel<<<tiles < DDSP_SM_COUNT ? tiles : DDSP_SM_COUNT, kGemmThreads, kGemmSmem, st>>>(map_a, map_b, p);
+    s = ddsp_launch_status();
+    if (s || splits == 1) return s;
+    const size_t total = (size_t)M * N;
+    gemm3x_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, bias, c, M, N, (int)ldc, splits);
+    return ddsp_launch_status();
+}

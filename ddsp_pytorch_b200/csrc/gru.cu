@@ -45,7 +45,7 @@ struct GruSmemFwd {
 struct GruSmemBwd {
     float w[kRows * kH];
     float partial[kV * kH];      // [v][512]: this CTA's rows' contribution to W_hh^T d
-    float down[kRows * 12];      // [row][12 (>= kV)] gate gradients of the own rows
+    float down[kRows * 24];      // [row][12 (>= kV)][2] gate gradients of the own rows, each stored twice (FFMA2 operand)
     float dhn[kV * kU];          // recurrent part of dh for the own units
 };
 
@@ -102,28 +102,38 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
                     gin[e] = __ldg(p + 2 * kH);
                 }
             }
-            // ---- gh[g][v] partial over this thread's eighth of k
+            // ---- gh[g][v] partial over this thread's eighth of k, packed FP32: each accumulator is a pair
+            //      (sum over even k, sum over odd k), one FFMA2 per W pair x h pair
+            uint64_t acc2[3][kV];
+#pragma unroll
+            for (int g = 0; g < 3; ++g)
+#pragma unroll
+                for (int v = 0; v < kV; ++v) acc2[g][v] = 0ull;
+            const ulonglong2 *w0 = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)(0 * kU + u) * kH);
+            const ulonglong2 *w1 = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)(1 * kU + u) * kH);
+            const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)(2 * kU + u) * kH);
+            const ulonglong2 *hf = reinterpret_cast<const ulonglong2 *>(s.hfull);
+#pragma unroll 4
+            for (int j = 0; j < 16; ++j) {
+                const int q = kq * 16 + (j ^ kq);                  // == swz(kq*16 + j)
+                const ulonglong2 a = w0[q], bq = w1[q], c = w2[q];
+#pragma unroll
+                for (int v = 0; v < kV; ++v) {
+                    const ulonglong2 h = hf[v * (kH / 4) + q];
+                    acc2[0][v] = fma2(a.y, h.y, fma2(a.x, h.x, acc2[0][v]));
+                    acc2[1][v] = fma2(bq.y, h.y, fma2(bq.x, h.x, acc2[1][v]));
+                    acc2[2][v] = fma2(c.y, h.y, fma2(c.x, h.x, acc2[2][v]));
+                }
+            }
             float acc[3][kV];
 #pragma unroll
             for (int g = 0; g < 3; ++g)
 #pragma unroll
-                for (int v = 0; v < kV; ++v) acc[g][v] = 0.f;
-            const float4 *w0 = reinterpret_cast<const float4 *>(s.w + (size_t)(0 * kU + u) * kH);
-            const float4 *w1 = reinterpret_cast<const float4 *>(s.w + (size_t)(1 * kU + u) * kH);
-            const float4 *w2 = reinterpret_cast<const float4 *>(s.w + (size_t)(2 * kU + u) * kH);
-            const float4 *hf = reinterpret_cast<const float4 *>(s.hfull);
-#pragma unroll 4
-            for (int j = 0; j < 16; ++j) {
-                const int q = kq * 16 + (j ^ kq);                  // == swz(kq*16 + j)
-                const float4 a = w0[q], bq = w1[q], c = w2[q];
-#pragma unroll
                 for (int v = 0; v < kV; ++v) {
-                    const float4 h = hf[v * (kH / 4) + q];
-                    acc[0][v] = fmaf(a.x, h.x, fmaf(a.y, h.y, fmaf(a.z, h.z, fmaf(a.w, h.w, acc[0][v]))));
-                    acc[1][v] = fmaf(bq.x, h.x, fmaf(bq.y, h.y, fmaf(bq.z, h.z, fmaf(bq.w, h.w, acc[1][v]))));
-                    acc[2][v] = fmaf(c.x, h.x, fmaf(c.y, h.y, fmaf(c.z, h.z, fmaf(c.w, h.w, acc[2][v]))));
+                    float lo, hi;
+                    unpk2(acc2[g][v], lo, hi);
+                    acc[g][v] = lo + hi;
                 }
-            }
             // ---- all-reduce over the 8 k-eighths (lane bits 0..2)
 #pragma unroll
             for (int g = 0; g < 3; ++g)
@@ -137,6 +147,7 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
                 }
             // ---- gates for voices kq and kq+8 of unit u
             const int colq = col >> 2;                              // float4 index of the own column in hfull
+            float rr[2], zz[2], nn[2], gg[2], hh[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int vi = kq + 8 * e;
@@ -152,15 +163,23 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
                     const float n = tanhf(fmaf(r, ghn, gin[e]));
                     const float hnew = fmaf(z, hprev - n, n);        // (1-z) n + z h
                     s.hown[((t & 1) * kV + vi) * kU + u] = hnew;
+                    rr[e] = r; zz[e] = z; nn[e] = n; gg[e] = ghn; hh[e] = hnew;
+                }
+            }
+            cluster.barrier_arrive();                               // own slice of h_t is published ...
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {                           // ... the global stores ride under the barrier
+                const int vi = kq + 8 * e;
+                if (vi < nv) {
                     const size_t o = (size_t)(b0 + vi) * T + t;
-                    y[o * kH + col] = hnew;
+                    y[o * kH + col] = hh[e];
                     if (gates) {
                         float *gp = gates + o * 4 * kH + col;
-                        gp[0] = r; gp[kH] = z; gp[2 * kH] = n; gp[3 * kH] = ghn;
+                        gp[0] = rr[e]; gp[kH] = zz[e]; gp[2 * kH] = nn[e]; gp[3 * kH] = gg[e];
                     }
                 }
             }
-            cluster.sync();                                         // every CTA's slice of h_t is published
+            cluster.barrier_wait();                                 // every CTA's slice is visible
             // ---- pull the 16 slices into the local full h (DSMEM), swizzled
             for (int i = tid; i < kV * (kH / 4); i += kGruThreads) {
                 const int v = i / (kH / 4), q = i - v * (kH / 4);
@@ -225,9 +244,9 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                     float *c = dgh + o * 3 * kH + col;
                     c[0] = dar; c[kH] = daz; c[2 * kH] = dghn;
                 }
-                s.down[(0 * kU + u) * 12 + v] = dar;
-                s.down[(1 * kU + u) * 12 + v] = daz;
-                s.down[(2 * kU + u) * 12 + v] = dghn;
+                reinterpret_cast<float2 *>(s.down)[(0 * kU + u) * 12 + v] = make_float2(dar, dar);
+                reinterpret_cast<float2 *>(s.down)[(1 * kU + u) * 12 + v] = make_float2(daz, daz);
+                reinterpret_cast<float2 *>(s.down)[(2 * kU + u) * 12 + v] = make_float2(dghn, dghn);
                 s.dhn[i] = direct;                       // the recurrent part is added after the reduce-scatter
             }
             __syncthreads();
@@ -236,25 +255,29 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                 const int half = lane >> 4;
                 const int q = warp * 16 + (lane & 15);               // logical float4 index of k
                 const int pq = swz(q);
-                float acc[kV][4];
+                uint64_t acc2[kV][2];                                // (k, k+1) and (k+2, k+3) of the quad
 #pragma unroll
-                for (int v = 0; v < kV; ++v) acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.f;
+                for (int v = 0; v < kV; ++v) acc2[v][0] = acc2[v][1] = 0ull;
                 const int r0 = half * (kRows / 2);
 #pragma unroll 2
                 for (int rr = 0; rr < kRows / 2; ++rr) {
                     const int row = r0 + rr;
-                    const float4 w = reinterpret_cast<const float4 *>(s.w + (size_t)row * kH)[pq];
-                    const float4 d0 = *reinterpret_cast<const float4 *>(s.down + row * 12);
-                    const float4 d1 = *reinterpret_cast<const float4 *>(s.down + row * 12 + 4);
-                    const float4 d2 = *reinterpret_cast<const float4 *>(s.down + row * 12 + 8);
-                    const float dv[12] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w};
+                    const ulonglong2 w = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)row * kH)[pq];
+                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + row * 24);
 #pragma unroll
-                    for (int v = 0; v < kV; ++v) {
-                        acc[v][0] = fmaf(dv[v], w.x, acc[v][0]);
-                        acc[v][1] = fmaf(dv[v], w.y, acc[v][1]);
-                        acc[v][2] = fmaf(dv[v], w.z, acc[v][2]);
-                        acc[v][3] = fmaf(dv[v], w.w, acc[v][3]);
+                    for (int vp = 0; vp < kV / 2; ++vp) {
+                        const ulonglong2 d = dp[vp];                 // (d_v, d_v), (d_v+1, d_v+1)
+                        acc2[2 * vp][0] = fma2(d.x, w.x, acc2[2 * vp][0]);
+                        acc2[2 * vp][1] = fma2(d.x, w.y, acc2[2 * vp][1]);
+                        acc2[2 * vp + 1][0] = fma2(d.y, w.x, acc2[2 * vp + 1][0]);
+                        acc2[2 * vp + 1][1] = fma2(d.y, w.y, acc2[2 * vp + 1][1]);
                     }
+                }
+                float acc[kV][4];
+#pragma unroll
+                for (int v = 0; v < kV; ++v) {
+                    unpk2(acc2[v][0], acc[v][0], acc[v][1]);
+                    unpk2(acc2[v][1], acc[v][2], acc[v][3]);
                 }
 #pragma unroll
                 for (int v = 0; v < kV; ++v)

@@ -625,6 +625,39 @@ std::tuple<Tensor, Tensor, Tensor> gru_bwd(const Tensor &dy_, const c10::optiona
     return {dgi, dgh, dh0};
 }
 
+// ---------------------------------------------------------------------------------------- f3 GEMM
+// x (rows, cols) contiguous -> split operand (2 * R, ld): hi rows [0, R), lo rows [R, 2R)
+Tensor gemm3x_split(const Tensor &x_, bool transpose) {
+    Tensor x = prep(x_, "x");
+    TORCH_CHECK(x.dim() == 2, "gemm3x_split: x must be 2-D");
+    const int64_t rows = x.size(0), cols = x.size(1);
+    const int64_t R = transpose ? cols : rows, K = transpose ? rows : cols;
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor out = at::empty({2 * R, ddsp_b200_gemm3x_ld(K)}, x.options());
+    if (rows == 0 || cols == 0) return out.zero_();
+    check(ddsp_b200_gemm3x_split(fp(x), rows, cols, cols, transpose ? 1 : 0, fpm(out), R, cur_stream()), "gemm3x_split");
+    return out;
+}
+
+// a (2M, ld), b (2N, ld) split operands -> a b^T + bias  (M, N)
+Tensor gemm3x_mm(const Tensor &a_, const Tensor &b_, int64_t K, const c10::optional<Tensor> &bias_) {
+    Tensor a = prep(a_, "a"), b = prep(b_, "b"), bias = opt_prep(bias_, "bias");
+    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1) && a.size(1) == ddsp_b200_gemm3x_ld(K),
+                "gemm3x_mm: operands must be gemm3x_split outputs of the same K");
+    const int64_t M = a.size(0) / 2, N = b.size(0) / 2;
+    TORCH_CHECK(!bias.defined() || bias.numel() == N, "gemm3x_mm: bias must have N entries");
+    c10::cuda::CUDAGuard guard(a.device());
+    Tensor c = at::empty({M, N}, a.options());
+    if (M == 0 || N == 0) return c;
+    if (K == 0) return bias.defined() ? c.copy_(bias.expand({M, N})) : c.zero_();
+    const int splits = ddsp_b200_gemm3x_splits((int)M, (int)N, (int)K);
+    Tensor ws = splits > 1 ? at::empty({splits, M, N}, a.options()) : Tensor();
+    check(ddsp_b200_gemm3x(fp(a), M, fp(b), N, opt_fp(bias), fpm(c), N, (int)M, (int)N, (int)K,
+                           splits > 1 ? fpm(ws) : nullptr, cur_stream()),
+          "gemm3x_mm");
+    return c;
+}
+
 int64_t abi_version() { return ddsp_b200_abi_version(); }
 
 }  // namespace
@@ -632,6 +665,8 @@ int64_t abi_version() { return ddsp_b200_abi_version(); }
 TORCH_LIBRARY(ddsp_b200, m) {
     m.def("abi_version() -> int", abi_version);
     m.def("gru_supported(int hidden) -> int", gru_supported);
+    m.def("gemm3x_split(Tensor x, bool transpose) -> Tensor");
+    m.def("gemm3x_mm(Tensor a, Tensor b, int K, Tensor? bias) -> Tensor");
     m.def("gru_fwd(Tensor gi, Tensor weight_hh, Tensor bias_hh, Tensor? h0, bool save_gates) -> (Tensor, Tensor)");
     m.def("gru_bwd(Tensor dy, Tensor? dhT, Tensor weight_hh, Tensor y, Tensor? h0, Tensor gates) -> (Tensor, Tensor, Tensor)");
     m.def("scale_function_fwd(Tensor x) -> Tensor");
@@ -657,6 +692,8 @@ TORCH_LIBRARY(ddsp_b200, m) {
 }
 
 TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
+    m.impl("gemm3x_split", gemm3x_split);
+    m.impl("gemm3x_mm", gemm3x_mm);
     m.impl("gru_fwd", gru_fwd);
     m.impl("gru_bwd", gru_bwd);
     m.impl("scale_function_fwd", scale_function_fwd);

@@ -224,6 +224,22 @@ int ddsp_b200_gru_bwd(const float *dy, const float *dhT, const float *w_hh, cons
                       const float *gates, float *dgi, float *dgh, float *dh0, int B, int T, int H,
                       void *stream);
 
+/* ---- f3 (next row)  fp32-accurate GEMM on the tcgen05 tensor cores for the control net's nn.Linear layers
+ * and the GRU projections (ddsp/core.py:122-133, decoder.py:40-68,86-87; torch runs them as SIMT SGEMM).
+ * "3xTF32": operands are split once into tf32 hi + fp32 residual lo; C = Ahi Bhi + Ahi Blo + Alo Bhi with
+ * fp32 accumulation in tensor memory.
+ * gemm3x_ld(K): padded column count of a split operand.  gemm3x_split: x (rows x cols, row pitch ld) ->
+ * out[2 * lo_row][gemm3x_ld(K)]: hi part in rows [0, R), lo part in rows [lo_row, lo_row + R), K padding
+ * zeroed; transpose = 0: operand = x (R = rows, K = cols); 1: operand = x^T (R = cols, K = rows).
+ * gemm3x: C[M][N] (row pitch ldc) = A B^T + bias (bias may be NULL), A, B split operands of M x K and
+ * N x K.  gemm3x_splits: K splits used for a shape; when > 1 pass workspace of splits * M * N floats.   */
+int64_t ddsp_b200_gemm3x_ld(int64_t k);
+int ddsp_b200_gemm3x_splits(int M, int N, int K);
+int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, float *out,
+                           int64_t lo_row, void *stream);
+int ddsp_b200_gemm3x(const float *a, int64_t a_lo_row, const float *b, int64_t b_lo_row, const float *bias,
+                     float *c, int64_t ldc, int M, int N, int K, float *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,55 @@
+"""The tcgen05 "3xTF32" GEMM (csrc/gemm3x.cu) against a float64 product.
+
+It stands in for the SIMT SGEMM torch runs for the reference's float32 nn.Linear layers
+(ddsp/core.py:122-129), so the bar is float32 accuracy: error relative to the largest output entry
+<= 2e-6 (a float32 dot product of length K accumulates ~sqrt(K) * 6e-8), and never worse than 4x torch's own
+float32 matmul on the same operands.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from ddsp_pytorch_b200._lib import get_ops
+    return get_ops()
+
+
+@pytest.mark.parametrize("M,N,K,bias", [(128, 128, 32, False), (128, 128, 512, True), (300, 200, 70, True),
+                                         (1, 65, 514, True), (2560, 512, 512, True), (512, 1024, 6400, False),
+                                         (101, 512, 3000, True)])
+def test_gemm3x_matches_float64(M, N, K, bias):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).cuda()
+    b = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bv = torch.randn(N, generator=g).cuda() if bias else None
+    ref = a.double() @ b.double().t() + (bv.double() if bias else 0)
+    got = ops.gemm3x_mm(ops.gemm3x_split(a, False), ops.gemm3x_split(b, False), K, bv)
+    assert got.shape == (M, N)
+    scale = float(ref.abs().max())
+    err = float((got.double() - ref).abs().max()) / scale
+    torch.backends.cuda.matmul.allow_tf32 = False
+    err_torch = float(((a @ b.t() + (bv if bias else 0)).double() - ref).abs().max()) / scale
+    assert err < 2e-6 and err < 4 * err_torch + 1e-7, (err, err_torch)
+
+
+def test_transposed_split_gives_the_transposed_product():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    dy = torch.randn(777, 130, generator=g).cuda()          # (M, N)
+    x = torch.randn(777, 90, generator=g).cuda()            # (M, K)
+    ref = dy.double().t() @ x.double()                      # dW = dy^T x  (N, K)
+    got = ops.gemm3x_mm(ops.gemm3x_split(dy, True), ops.gemm3x_split(x, True), 777, None)
+    assert float((got.double() - ref).abs().max()) / float(ref.abs().max()) < 2e-6
+
+
+def test_split_parts_are_exact():
+    ops = _ops()
+    x = torch.randn(50, 37, device="cuda") * 1e3
+    s = ops.gemm3x_split(x, False)
+    hi, lo = s[:50, :37], s[50:, :37]
+    assert torch.equal(hi + lo, x)                          # the residual is exact
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0      # hi has tf32's 10 mantissa bits
+    assert float(s[:, 37:].abs().max()) == 0.0              # K padding is zero
