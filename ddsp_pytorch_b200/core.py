@@ -112,13 +112,72 @@ def extract_pitch(signal, sample_rate, block_size):
     return f0
 
 
+LINEAR3X_MIN_ROWS = 512      # below this many rows a layer is launch-bound and stays on the library path
+
+
+class Linear(nn.Linear):
+    """``nn.Linear`` (same parameters, state_dict keys and call) whose three GEMMs run on the tcgen05
+    tensor cores with float32-class accuracy (csrc/gemm3x.cu, "3xTF32") instead of cuBLAS's SIMT SGEMM.
+    Small problems (fewer than ``LINEAR3X_MIN_ROWS`` rows, fan-in below 32) and non-CUDA / non-float32 inputs take
+    the stock path."""
+
+    __constants__ = ["in_features", "out_features", "min_rows"]
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True):
+        super().__init__(in_features, out_features, bias)
+        self.min_rows: int = LINEAR3X_MIN_ROWS
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:      # noqa: A002
+        rows = input.numel() // max(1, input.shape[-1])
+        fast = (input.is_cuda and input.dtype == torch.float32 and self.in_features >= 32
+                and rows >= self.min_rows)
+        if torch.jit.is_scripting():
+            if fast:
+                x2 = input.reshape(-1, self.in_features).contiguous()
+                y = torch.ops.ddsp_b200.gemm3x_mm(torch.ops.ddsp_b200.gemm3x_split(x2, False),
+                                                  torch.ops.ddsp_b200.gemm3x_split(self.weight, False),
+                                                  self.in_features, self.bias)
+                return y.view(input.shape[:-1] + [self.out_features])
+            return F.linear(input, self.weight, self.bias)
+        if fast:
+            return _F.Linear3x.apply(input, self.weight, self.bias)
+        return F.linear(input, self.weight, self.bias)
+
+
+class LayerNormLeakyReLU(nn.LayerNorm):
+    """``nn.LayerNorm`` (same parameters and state_dict keys) that also applies the LeakyReLU which follows it
+    in every MLP block, as one kernel each way (csrc/layernorm.cu).  Widths other than 128/256/384/512 and
+    non-CUDA inputs compose the two stock ops."""
+
+    __constants__ = ["normalized_shape", "eps", "elementwise_affine", "negative_slope", "fused"]
+
+    def __init__(self, normalized_shape: int, negative_slope: float = 0.01):
+        super().__init__(normalized_shape)
+        self.negative_slope: float = negative_slope
+        self.fused: bool = normalized_shape % 128 == 0 and 128 <= normalized_shape <= 512
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:      # noqa: A002
+        if self.fused and input.is_cuda and input.dtype == torch.float32:
+            if torch.jit.is_scripting():
+                return torch.ops.ddsp_b200.ln_lrelu_fwd(input, self.weight, self.bias, self.eps,
+                                                        self.negative_slope, False)[0]
+            return _F.LayerNormLeakyReLU.apply(input, self.weight, self.bias, self.eps, self.negative_slope)
+        return F.leaky_relu(F.layer_norm(input, self.normalized_shape, self.weight, self.bias, self.eps),
+                            self.negative_slope)
+
+
+class FusedIntoLayerNorm(nn.Identity):
+    """Placeholder at the Sequential index where the reference has ``nn.LeakyReLU`` (the activation is applied
+    by the preceding LayerNormLeakyReLU), so that state_dict keys keep the reference's numbering."""
+
+
 def mlp(in_size, hidden_size, n_layers):
     """ddsp/core.py:122-129: n_layers x (Linear, LayerNorm, LeakyReLU); same Sequential indices so
     state_dict keys match the reference's checkpoints."""
     sizes = [in_size] + [hidden_size] * n_layers
     layers = []
     for a, b in zip(sizes[:-1], sizes[1:]):
-        layers += [nn.Linear(a, b), nn.LayerNorm(b), nn.LeakyReLU()]
+        layers += [Linear(a, b), LayerNormLeakyReLU(b), FusedIntoLayerNorm()]
     return nn.Sequential(*layers)
 
 
@@ -139,7 +198,10 @@ class ClusterGRU(nn.GRU):
     def forward(self, input, hx=None):      # noqa: A002 (nn.GRU's argument name)
         if not self._cluster_path(input, hx):
             return super().forward(input, hx)
-        gi = F.linear(input, self.weight_ih_l0, self.bias_ih_l0)
+        if input.shape[0] * input.shape[1] >= LINEAR3X_MIN_ROWS:
+            gi = _F.Linear3x.apply(input, self.weight_ih_l0, self.bias_ih_l0)
+        else:
+            gi = F.linear(input, self.weight_ih_l0, self.bias_ih_l0)
         h0 = None
         if hx is not None:
             h0 = hx.expand(1, input.shape[0], self.hidden_size)[0].contiguous()

@@ -658,6 +658,41 @@ Tensor gemm3x_mm(const Tensor &a_, const Tensor &b_, int64_t K, const c10::optio
     return c;
 }
 
+// ---------------------------------------------------------------------------------------- f3 LayerNorm
+int64_t ln_lrelu_supported(int64_t n) { return n % 128 == 0 && n >= 128 && n <= 512; }
+
+// x (..., N) -> (y, stats (rows, 2) or empty)
+std::tuple<Tensor, Tensor> ln_lrelu_fwd(const Tensor &x_, const Tensor &gamma_, const Tensor &beta_, double eps,
+                                        double slope, bool save_stats) {
+    Tensor x = prep(x_, "x"), gamma = prep(gamma_, "weight"), beta = prep(beta_, "bias");
+    const int64_t N = x.size(-1), rows = N ? x.numel() / N : 0;
+    TORCH_CHECK(gamma.numel() == N && beta.numel() == N, "ln_lrelu_fwd: weight / bias must have N entries");
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor y = at::empty_like(x);
+    Tensor stats = save_stats ? at::empty({rows, 2}, x.options()) : at::empty({0}, x.options());
+    check(ddsp_b200_ln_lrelu_fwd(fp(x), fp(gamma), fp(beta), fpm(y), save_stats ? fpm(stats) : nullptr, rows, (int)N,
+                                 (float)eps, (float)slope, cur_stream()),
+          "ln_lrelu_fwd");
+    return {y, stats};
+}
+
+// -> (dx, d_gamma, d_beta)
+std::tuple<Tensor, Tensor, Tensor> ln_lrelu_bwd(const Tensor &dy_, const Tensor &x_, const Tensor &gamma_,
+                                                const Tensor &beta_, const Tensor &stats_, double slope) {
+    Tensor dy = prep(dy_, "dy"), x = prep(x_, "x"), gamma = prep(gamma_, "weight"), beta = prep(beta_, "bias");
+    Tensor stats = prep(stats_, "stats");
+    const int64_t N = x.size(-1), rows = N ? x.numel() / N : 0;
+    TORCH_CHECK(dy.numel() == x.numel() && stats.numel() == 2 * rows, "ln_lrelu_bwd: shape mismatch");
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor dx = at::empty_like(x), dg = at::empty({N}, x.options()), db = at::empty({N}, x.options());
+    if (rows == 0) return {dx, dg.zero_(), db.zero_()};
+    Tensor partial = at::empty({ddsp_b200_ln_lrelu_slots(rows), 2 * N}, x.options());
+    check(ddsp_b200_ln_lrelu_bwd(fp(dy), fp(x), fp(gamma), fp(beta), fp(stats), fpm(dx), fpm(dg), fpm(db), fpm(partial),
+                                 rows, (int)N, (float)slope, cur_stream()),
+          "ln_lrelu_bwd");
+    return {dx, dg, db};
+}
+
 int64_t abi_version() { return ddsp_b200_abi_version(); }
 
 }  // namespace
@@ -665,6 +700,9 @@ int64_t abi_version() { return ddsp_b200_abi_version(); }
 TORCH_LIBRARY(ddsp_b200, m) {
     m.def("abi_version() -> int", abi_version);
     m.def("gru_supported(int hidden) -> int", gru_supported);
+    m.def("ln_lrelu_supported(int n) -> int", ln_lrelu_supported);
+    m.def("ln_lrelu_fwd(Tensor x, Tensor weight, Tensor bias, float eps, float slope, bool save_stats) -> (Tensor, Tensor)");
+    m.def("ln_lrelu_bwd(Tensor dy, Tensor x, Tensor weight, Tensor bias, Tensor stats, float slope) -> (Tensor, Tensor, Tensor)");
     m.def("gemm3x_split(Tensor x, bool transpose) -> Tensor");
     m.def("gemm3x_mm(Tensor a, Tensor b, int K, Tensor? bias) -> Tensor");
     m.def("gru_fwd(Tensor gi, Tensor weight_hh, Tensor bias_hh, Tensor? h0, bool save_gates) -> (Tensor, Tensor)");
@@ -692,6 +730,8 @@ TORCH_LIBRARY(ddsp_b200, m) {
 }
 
 TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
+    m.impl("ln_lrelu_fwd", ln_lrelu_fwd);
+    m.impl("ln_lrelu_bwd", ln_lrelu_bwd);
     m.impl("gemm3x_split", gemm3x_split);
     m.impl("gemm3x_mm", gemm3x_mm);
     m.impl("gru_fwd", gru_fwd);

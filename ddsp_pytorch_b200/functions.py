@@ -219,6 +219,59 @@ class ReverbImpulse(torch.autograd.Function):
         return dn.view_as(noise), dd.view_as(decay), dw.view_as(wet), None
 
 
+def _mm3x(a: torch.Tensor, a_t: bool, b: torch.Tensor, b_t: bool, bias=None) -> torch.Tensor:
+    """(a or a^T) @ (b or b^T)^T + bias through the 3xTF32 tensor-core GEMM; a, b 2-D contiguous."""
+    k = a.shape[0] if a_t else a.shape[1]
+    return _ops.gemm3x_mm(_ops.gemm3x_split(a, a_t), _ops.gemm3x_split(b, b_t), k, bias)
+
+
+class Linear3x(torch.autograd.Function):
+    """``F.linear`` (core.py:122-129's nn.Linear layers, the GRU input projection, decoder.py:86-87's
+    projections) on the tcgen05 tensor cores with float32-class accuracy (csrc/gemm3x.cu); all three GEMMs
+    of a layer (y = x W^T + b, dx = dy W, dW = dy^T x) take the same kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        return _mm3x(x2, False, weight.contiguous(), False, bias).view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _mm3x(dy2, False, weight.contiguous(), True).view(*dy.shape[:-1], weight.shape[1])
+        if ctx.needs_input_grad[1]:
+            dw = _mm3x(dy2, True, x2, True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db
+
+
+class LayerNormLeakyReLU(torch.autograd.Function):
+    """leaky_relu(layer_norm(x)) over the last dimension in one pass each way (csrc/layernorm.cu):
+    core.py:122-129's LayerNorm -> LeakyReLU pair."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, slope):
+        x = x.contiguous()
+        y, stats = _ops.ln_lrelu_fwd(x, weight, bias, eps, slope, any(ctx.needs_input_grad[:3]))
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, weight, bias, stats = ctx.saved_tensors
+        dx, dg, db = _ops.ln_lrelu_bwd(dy.contiguous(), x, weight, bias, stats, ctx.slope)
+        return dx, dg, db, None, None
+
+
 class GRURecurrence(torch.autograd.Function):
     """The time loop of core.py:132-133's nn.GRU (one layer, batch_first) as one cluster-persistent launch.
     gi (B,T,3H) = x W_ih^T + b_ih is computed by the caller (a cuBLAS GEMM autograd differentiates);
@@ -246,7 +299,7 @@ class GRURecurrence(torch.autograd.Function):
                 h_prev[:, 0].zero_()
             else:
                 h_prev[:, 0] = h0.reshape(B, H)
-            d_w = dgh.reshape(B * T, 3 * H).t().mm(h_prev.reshape(B * T, H))
+            d_w = _mm3x(dgh.reshape(B * T, 3 * H), True, h_prev.reshape(B * T, H), True)
         if ctx.needs_input_grad[2]:
             d_b = dgh.sum((0, 1))
         d_h0 = None

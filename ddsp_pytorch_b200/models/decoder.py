@@ -49,8 +49,8 @@ class _SynthWiring(nn.Module):
     def _init_synth(self, hidden_size, n_harmonic, n_bands, sample_rate, block_size, has_reverb):
         self.register_buffer("sample_rate", torch.tensor(sample_rate))
         self.register_buffer("block_size", torch.tensor(block_size))
-        self.harmonic_proj = nn.Linear(hidden_size, n_harmonic + 1)
-        self.noise_proj = nn.Linear(hidden_size, n_bands)
+        self.harmonic_proj = core.Linear(hidden_size, n_harmonic + 1)
+        self.noise_proj = core.Linear(hidden_size, n_bands)
         self.harmonic_synth = HarmonicSynth(block_size=block_size, sample_rate=sample_rate)
         self.noise_synth = FilteredNoise(block_size=block_size, window_size=n_bands)
         self.has_reverb = has_reverb

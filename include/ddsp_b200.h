@@ -240,6 +240,17 @@ int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t l
 int ddsp_b200_gemm3x(const float *a, int64_t a_lo_row, const float *b, int64_t b_lo_row, const float *bias,
                      float *c, int64_t ldc, int M, int N, int K, float *workspace, void *stream);
 
+/* ---- f3 (next row)  LayerNorm + LeakyReLU of the MLP blocks in one pass (ddsp/core.py:122-129) ------
+ * y = leaky_relu(layer_norm(x; gamma, beta, eps), slope) over rows of N = 128, 256, 384 or 512 floats;
+ * stats[rows][2] = mean, rstd kept for the backward (NULL for inference).  bwd: dx, d_gamma, d_beta;
+ * partial = ln_lrelu_slots(rows) * 2 * N floats of scratch (deterministic two-level column sums).        */
+int ddsp_b200_ln_lrelu_slots(int64_t rows);
+int ddsp_b200_ln_lrelu_fwd(const float *x, const float *gamma, const float *beta, float *y, float *stats,
+                           int64_t rows, int N, float eps, float slope, void *stream);
+int ddsp_b200_ln_lrelu_bwd(const float *dy, const float *x, const float *gamma, const float *beta,
+                           const float *stats, float *dx, float *d_gamma, float *d_beta, float *partial,
+                           int64_t rows, int N, float slope, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

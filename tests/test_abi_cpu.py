@@ -113,7 +113,11 @@ def test_host_side_helpers_on_cpu(pkg):
     assert up.shape == (1, 20, 3) and torch.equal(up[0, 7], x[0, 1])
     assert torch.allclose(pkg.safe_log(torch.ones(2)), torch.log(torch.ones(2) + 1e-7))
     net = pkg.mlp(1, 8, 3)
-    assert [type(m).__name__ for m in net] == ["Linear", "LayerNorm", "LeakyReLU"] * 3
+    # core.py:122-129's (Linear, LayerNorm, LeakyReLU) x 3: same Sequential numbering, the activation fused
+    assert [type(m).__name__ for m in net] == ["Linear", "LayerNormLeakyReLU", "FusedIntoLayerNorm"] * 3
+    assert all(isinstance(m, (torch.nn.Linear, torch.nn.LayerNorm, torch.nn.Identity)) for m in net)
+    y = net(torch.randn(3, 5, 1))                  # CPU input: composes the stock ops
+    assert y.shape == (3, 5, 8) and bool((y > -0.2).all())
     assert pkg.gru(2, 8).input_size == 16
     m, s = pkg.mean_std_loudness([{"loudness": torch.tensor([1.0, 3.0])}, {"loudness": torch.tensor([2.0, 6.0])}])
     assert abs(m - 3.0) < 1e-6

@@ -53,3 +53,35 @@ def test_split_parts_are_exact():
     assert torch.equal(hi + lo, x)                          # the residual is exact
     assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0      # hi has tf32's 10 mantissa bits
     assert float(s[:, 37:].abs().max()) == 0.0              # K padding is zero
+
+
+@pytest.mark.parametrize("rows,fan_in,fan_out", [(4 * 400, 512, 512), (3 * 300, 514, 512), (2000, 512, 101)])
+def test_linear_module_matches_float64_forward_and_backward(rows, fan_in, fan_out):
+    """core.Linear = nn.Linear's parameters and call; y, dx, dW, db against float64 (grads 1e-3 relative bar
+    of the north star, met with three orders of margin)."""
+    from ddsp_pytorch_b200 import core
+    torch.manual_seed(rows + fan_in)
+    lin = core.Linear(fan_in, fan_out).cuda()
+    assert set(lin.state_dict()) == {"weight", "bias"}
+    x = torch.randn(rows // 100, 100, fan_in, device="cuda", requires_grad=True)
+    go = torch.randn(rows // 100, 100, fan_out, device="cuda")
+    y = lin(x)
+    y.backward(go)
+    xr = x.detach().double().requires_grad_(True)
+    w, b = lin.weight.detach().double().requires_grad_(True), lin.bias.detach().double().requires_grad_(True)
+    yr = torch.nn.functional.linear(xr, w, b)
+    yr.backward(go.double())
+
+    def rel(a, r):
+        return float((a.double() - r).abs().max() / r.abs().max())
+    assert rel(y.detach(), yr.detach()) < 2e-6
+    assert rel(x.grad, xr.grad) < 2e-6
+    assert rel(lin.weight.grad, w.grad) < 2e-6
+    assert rel(lin.bias.grad, b.grad) < 2e-6
+
+
+def test_small_inputs_take_the_library_path():
+    from ddsp_pytorch_b200 import core
+    lin = core.Linear(512, 512).cuda()
+    x = torch.randn(1, 8, 512, device="cuda")
+    assert torch.equal(lin(x), torch.nn.functional.linear(x, lin.weight, lin.bias))
