@@ -329,6 +329,35 @@ __global__ void split3x_transpose_kernel(const float *__restrict__ x, int rows, 
     }
 }
 
+// both operands of one matrix in one pass: out = split(x), out_t = split(x^T)
+__global__ void split3x_both_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, float *__restrict__ out,
+                                    int64_t lo_row, int out_ld, float *__restrict__ out_t, int64_t lo_row_t, int out_ld_t) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    for (int j = ty; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + tx;
+        const float v = (r < rows && c < cols) ? __ldg(x + (size_t)r * ld + c) : 0.f;
+        tile[j][tx] = v;
+        if (r < rows && c < out_ld) {
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            out[(size_t)r * out_ld + c] = hi;
+            out[(size_t)(lo_row + r) * out_ld + c] = lo;
+        }
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int orow = c0 + j, ocol = r0 + tx;
+        if (orow < cols && ocol < out_ld_t) {
+            float hi, lo;
+            split_tf32(tile[tx][j], hi, lo);
+            out_t[(size_t)orow * out_ld_t + ocol] = hi;
+            out_t[(size_t)(lo_row_t + orow) * out_ld_t + ocol] = lo;
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -391,6 +420,17 @@ extern "C" int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols
         dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(out_ld / 32));
         split3x_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(x, (int)rows, (int)cols, ld, out, lo_row, out_ld);
     }
+    return ddsp_launch_status();
+}
+
+// out = split operand of x (lo part at row lo_row), out_t = split operand of x^T (lo part at row lo_row_t)
+extern "C" int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t cols, int64_t ld, float *out,
+                                           int64_t lo_row, float *out_t, int64_t lo_row_t, void *stream) {
+    DDSP_REQUIRE(x && out && out_t && rows > 0 && cols > 0 && ld >= cols && lo_row >= rows && lo_row_t >= cols);
+    const int out_ld = (int)ddsp_b200_gemm3x_ld(cols), out_ld_t = (int)ddsp_b200_gemm3x_ld(rows);
+    dim3 grid((unsigned)(out_ld / 32), (unsigned)(out_ld_t / 32));
+    split3x_both_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (int)rows, (int)cols, ld, out, lo_row, out_ld,
+                                                                        out_t, lo_row_t, out_ld_t);
     return ddsp_launch_status();
 }
 

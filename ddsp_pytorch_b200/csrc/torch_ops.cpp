@@ -639,6 +639,20 @@ Tensor gemm3x_split(const Tensor &x_, bool transpose) {
     return out;
 }
 
+// x (rows, cols) -> (split operand of x, split operand of x^T) from one pass over x
+std::tuple<Tensor, Tensor> gemm3x_split_both(const Tensor &x_) {
+    Tensor x = prep(x_, "x");
+    TORCH_CHECK(x.dim() == 2, "gemm3x_split_both: x must be 2-D");
+    const int64_t rows = x.size(0), cols = x.size(1);
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor out = at::empty({2 * rows, ddsp_b200_gemm3x_ld(cols)}, x.options());
+    Tensor out_t = at::empty({2 * cols, ddsp_b200_gemm3x_ld(rows)}, x.options());
+    if (rows == 0 || cols == 0) return {out.zero_(), out_t.zero_()};
+    check(ddsp_b200_gemm3x_split_both(fp(x), rows, cols, cols, fpm(out), rows, fpm(out_t), cols, cur_stream()),
+          "gemm3x_split_both");
+    return {out, out_t};
+}
+
 // a (2M, ld), b (2N, ld) split operands -> a b^T + bias  (M, N)
 Tensor gemm3x_mm(const Tensor &a_, const Tensor &b_, int64_t K, const c10::optional<Tensor> &bias_) {
     Tensor a = prep(a_, "a"), b = prep(b_, "b"), bias = opt_prep(bias_, "bias");
@@ -704,6 +718,7 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("ln_lrelu_fwd(Tensor x, Tensor weight, Tensor bias, float eps, float slope, bool save_stats) -> (Tensor, Tensor)");
     m.def("ln_lrelu_bwd(Tensor dy, Tensor x, Tensor weight, Tensor bias, Tensor stats, float slope) -> (Tensor, Tensor, Tensor)");
     m.def("gemm3x_split(Tensor x, bool transpose) -> Tensor");
+    m.def("gemm3x_split_both(Tensor x) -> (Tensor, Tensor)");
     m.def("gemm3x_mm(Tensor a, Tensor b, int K, Tensor? bias) -> Tensor");
     m.def("gru_fwd(Tensor gi, Tensor weight_hh, Tensor bias_hh, Tensor? h0, bool save_gates) -> (Tensor, Tensor)");
     m.def("gru_bwd(Tensor dy, Tensor? dhT, Tensor weight_hh, Tensor y, Tensor? h0, Tensor gates) -> (Tensor, Tensor, Tensor)");
@@ -733,6 +748,7 @@ TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
     m.impl("ln_lrelu_fwd", ln_lrelu_fwd);
     m.impl("ln_lrelu_bwd", ln_lrelu_bwd);
     m.impl("gemm3x_split", gemm3x_split);
+    m.impl("gemm3x_split_both", gemm3x_split_both);
     m.impl("gemm3x_mm", gemm3x_mm);
     m.impl("gru_fwd", gru_fwd);
     m.impl("gru_bwd", gru_bwd);

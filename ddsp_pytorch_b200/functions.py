@@ -233,20 +233,34 @@ class Linear3x(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        ctx.save_for_backward(x2, weight)
+        w = weight.contiguous()
+        k = x2.shape[1]
+        if ctx.needs_input_grad[1]:          # the operand dW will need (x^T) comes from the same read of x
+            xs, xts = _ops.gemm3x_split_both(x2)
+        else:
+            xs, xts = _ops.gemm3x_split(x2, False), None
+        ctx.save_for_backward(xts, w)
         ctx.has_bias = bias is not None
-        return _mm3x(x2, False, weight.contiguous(), False, bias).view(*x.shape[:-1], weight.shape[0])
+        ctx.rows = x2.shape[0]
+        return _ops.gemm3x_mm(xs, _ops.gemm3x_split(w, False), k, bias).view(*x.shape[:-1], w.shape[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x2, weight = ctx.saved_tensors
+        xts, w = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        n = dy2.shape[1]
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_x and need_w:
+            dys, dyts = _ops.gemm3x_split_both(dy2)
+        else:
+            dys = _ops.gemm3x_split(dy2, False) if need_x else None
+            dyts = _ops.gemm3x_split(dy2, True) if need_w else None
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = _mm3x(dy2, False, weight.contiguous(), True).view(*dy.shape[:-1], weight.shape[1])
-        if ctx.needs_input_grad[1]:
-            dw = _mm3x(dy2, True, x2, True)
+        if need_x:
+            dx = _ops.gemm3x_mm(dys, _ops.gemm3x_split(w, True), n, None).view(*dy.shape[:-1], w.shape[1])
+        if need_w:
+            dw = _ops.gemm3x_mm(dyts, xts, ctx.rows, None)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.sum(0)
         return dx, dw, db
