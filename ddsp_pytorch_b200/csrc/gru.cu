@@ -5,17 +5,19 @@
 // STEP (400 + 400 launches of ~19 us and ~3 us forward, the same again backward; measured 16 ms of a
 // 23 ms training step at batch 64, profiles/r01_model_step_b64.json).
 //
-// Design.  The input projections gi = x W_ih^T + b_ih for all time steps stay one big library GEMM.  The
-// recurrence is ONE launch: a cluster of 16 CTAs (non-portable size; 7 such clusters are resident on a
-// B200) keeps the whole 1536x512 fp32 W_hh in its distributed shared memory (96 rows = 32 hidden units x
-// 3 gates = 192 KB per CTA, XOR-swizzled instead of padded) for all T steps and owns up to 10 voices.
-// Per step each CTA computes its 96 x V gate pre-activations (thread = (unit, eighth of k), all-reduce
-// over k with shuffles), applies the gates, publishes its 32 new hidden values per voice in a double
-// buffer, and after ONE cluster barrier every CTA pulls the other 15 slices through DSMEM.
-// Backward walks time in reverse with the same resident W_hh: per step each CTA turns dh of its units
-// into the gate gradients, multiplies them with its 96 rows (partial W_hh^T d for all 512 inputs), and
-// the 16 partials are reduce-scattered through DSMEM (two cluster barriers).  dW_hh, dW_ih, dx are
-// library GEMMs over the stored gate gradients afterwards.
+// Design.  The input projections gi = x W_ih^T + b_ih for all time steps stay one big GEMM (csrc/gemm3x.cu).
+// The recurrence is ONE launch: a cluster of 16 CTAs (non-portable size; 7 such clusters are resident on a
+// B200) keeps the whole 1536x512 fp32 W_hh on chip for all T steps -- 96 rows = 32 hidden units x 3 gates per
+// CTA, part in shared memory, part in registers -- and owns up to 10 voices.
+// Per step each CTA computes its 96 x V gate pre-activations with packed FP32 FMAs, applies the gates and
+// PUSHES its 32 new hidden values per voice to all 16 CTAs with bulk DSMEM copies that signal the receivers'
+// mbarriers (no cluster barrier on the critical path; h double buffered).
+// Backward walks time in reverse with the same resident W_hh: per step each CTA turns dh of its units into the
+// gate gradients, multiplies them with its 96 rows (partial W_hh^T d for all 512 inputs) and the 16 partials
+// are reduce-scattered with the same push protocol.  dW_hh, dW_ih, dx are GEMMs over the stored gate
+// gradients afterwards.
+// Measured (B200, T = 400, hidden 512): forward 4.9 us per step, backward 5.4 us per step at 64 voices,
+// against 11.8 / 15.8 us for cuDNN's per-step SGEMM + element-wise launches (profiles/r01_gru.json).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -31,37 +33,62 @@ constexpr int kV = 10;           // voices per cluster pass
 constexpr int kGruThreads = 256;
 constexpr int kRows = 3 * kU;    // W_hh rows resident per CTA
 
-// XOR swizzle of the float4 index inside a 512-float row: chunk = q/16 (eighth of k), j = q%16.
-// Lanes that differ in `chunk` (forward) or in `j` (backward) hit distinct bank groups.
-__device__ __forceinline__ int swz(int q) { return (q & ~15) | ((q ^ (q >> 4)) & 15); }
-
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
-
-struct GruSmemFwd {
-    float w[kRows * kH];         // [gate*32 + u][512] swizzled
-    float hfull[kV * kH];        // [v][512] swizzled
-    float hown[2 * kV * kU];     // [buf][v][u]
-};
-struct GruSmemBwd {
-    float w[kRows * kH];
-    float partial[kV * kH];      // [v][512]: this CTA's rows' contribution to W_hh^T d
-    float down[kRows * 24];      // [row][12 (>= kV)][2] gate gradients of the own rows, each stored twice (FFMA2 operand)
-    float dhn[kV * kU];          // recurrent part of dh for the own units
-};
-
-__device__ __forceinline__ void load_w_slice(float *w, const float *__restrict__ w_hh, int rank, int tid) {
-    // rows g*H + 32*rank + u  ->  w[(g*32+u)][swizzled]
-    for (int i = tid; i < kRows * (kH / 4); i += kGruThreads) {
-        const int row = i / (kH / 4), q = i - row * (kH / 4);
-        const int g = row / kU, u = row - g * kU;
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + q);
-        reinterpret_cast<float4 *>(w + (size_t)row * kH)[swz(q)] = v;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // forward
+//
+// Thread = (pair of hidden units up = tid/16, k slice ks = tid%16): 6 rows of W_hh x all voices, k quads
+// ks + 16 j.  The j = 0 quad of its rows lives in registers for the whole launch (that is what makes room for
+// a double-buffered h in shared memory), the other seven stream from shared memory.  Accumulators are packed
+// pairs (even k, odd k) so the inner loop is FFMA2 only.  The 16 k slices are combined by a recursive-halving
+// shuffle reduction (60 values -> 4 per lane), gates are applied with thread = (voice, unit).
+//
+// Exchange of h_t: no cluster barrier.  Every CTA writes its 32 x V slice into a staging buffer and 16 threads
+// push it with one bulk DSMEM copy each (cp.async.bulk.shared::cluster, 1280 B) into the SAME slot of every
+// CTA's next-h buffer; each copy signals the destination's mbarrier (complete_tx), and a CTA starts step t+1
+// as soon as its own barrier has seen all 16 slices.  h is double buffered: a slice of h_{t+1} can only be
+// sent by a CTA that has received all of h_t, i.e. after every CTA finished reading h_{t-1} (same buffer).
 // ---------------------------------------------------------------------------------------------
+constexpr int kWq = kH / 4 - 16;                 // W quads per row kept in shared memory (112 of 128)
+constexpr int kSliceBytes = kV * kU * 4;          // one CTA's slice of h for all voices (1280 B)
+
+struct GruSmemFwd {
+    float w[kRows * kWq * 4];                     // [g*32 + u][quads 16..127]
+    float hbuf[2][kC][kV][kU];                    // h, slice-major: [buffer][owner CTA][voice][unit]
+    float stage[2][kV][kU];                       // own slice of the step being published
+    float gh[3][kV][kU];                          // reduced W_hh h of the own units
+    unsigned long long bar[2];                    // one mbarrier per h buffer
+};
+
+__device__ __forceinline__ uint32_t gru_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t gru_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void gru_bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 24)) __trap();               // a lost slice traps instead of hanging the GPU
+    } while (!ok);
+}
+// push `bytes` of own shared memory into CTA `dst_rank`'s shared memory at the same offsets, signalling its barrier
+__device__ __forceinline__ void gru_push(uint32_t dst_local, uint32_t src, uint32_t bar_local, uint32_t dst_rank,
+                                         uint32_t bytes) {
+    const uint32_t dst = gru_mapa(dst_local, dst_rank), bar = gru_mapa(bar_local, dst_rank);
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "r"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(kGruThreads, 1)
 gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, const float *__restrict__ b_hh,
                const float *__restrict__ h0, float *__restrict__ y, float *__restrict__ gates, int B, int T,
@@ -71,132 +98,174 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = cluster.block_rank();
     const int cid = blockIdx.x / kC, ncl = gridDim.x / kC;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int u = warp * 4 + (lane >> 3), kq = lane & 7;
-    const int col = rank * kU + u;                                  // global hidden unit of this thread
+    const int tid = threadIdx.x;
+    const int up = tid >> 4, ks = tid & 15;                        // unit pair, k slice
 
-    load_w_slice(s.w, w_hh, rank, tid);
-    const float br = __ldg(b_hh + col), bz = __ldg(b_hh + kH + col), bn = __ldg(b_hh + 2 * kH + col);
+    // ---- W_hh slice: quad ks of the six own rows into registers, quads 16.. into shared memory
+    ulonglong2 wreg[6];
+#pragma unroll
+    for (int r6 = 0; r6 < 6; ++r6) {
+        const int g = r6 >> 1, u = 2 * up + (r6 & 1);
+        wreg[r6] = __ldg(reinterpret_cast<const ulonglong2 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + ks);
+    }
+    for (int i = tid; i < kRows * kWq; i += kGruThreads) {
+        const int row = i / kWq, q = i - row * kWq;
+        const int g = row / kU, u = row - g * kU;
+        reinterpret_cast<float4 *>(s.w)[i] =
+            __ldg(reinterpret_cast<const float4 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + 16 + q);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gru_smem_u32(&s.bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gru_smem_u32(&s.bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // gate-phase items of this thread: (voice, unit) = (tid/32, tid%32) and, for tid < 64, (8 + tid/32, tid%32)
+    const int gu = tid & 31, gcol = rank * kU + gu;
+    const float br = __ldg(b_hh + gcol), bz = __ldg(b_hh + kH + gcol), bn = __ldg(b_hh + 2 * kH + gcol);
 
-    for (int b0 = cid * vpc; b0 < B; b0 += ncl * vpc) {     // vpc <= kV voices per cluster pass
+    int it = 0;                                                     // steps done by this cluster (buffer / parity clock)
+    for (int b0 = cid * vpc; b0 < B; b0 += ncl * vpc) {             // vpc <= kV voices per cluster pass
         const int nv = min(vpc, B - b0);
-        __syncthreads();
-        for (int i = tid; i < kV * (kH / 4); i += kGruThreads) {
-            const int v = i / (kH / 4), q = i - v * (kH / 4);
-            float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (h0 && v < nv) hv = __ldg(reinterpret_cast<const float4 *>(h0 + (size_t)(b0 + v) * kH) + q);
-            reinterpret_cast<float4 *>(s.hfull + (size_t)v * kH)[swz(q)] = hv;
+        cluster.sync();                                             // previous pass fully drained everywhere
+        {   // h_{-1} = h0 into the buffer step `it` reads; staging zeroed (unused voices stay zero)
+            float *hb = &s.hbuf[(it + 1) & 1][0][0][0];
+            for (int i = tid; i < kC * kV * kU; i += kGruThreads) {
+                const int u = i % kU, v = (i / kU) % kV, r = i / (kU * kV);
+                hb[i] = (h0 && v < nv) ? __ldg(h0 + (size_t)(b0 + v) * kH + r * kU + u) : 0.f;
+            }
+            for (int i = tid; i < 2 * kV * kU; i += kGruThreads) (&s.stage[0][0][0])[i] = 0.f;
         }
         __syncthreads();
-        for (int t = 0; t < T; ++t) {
-            // prefetch the input projections of the (up to two) voices this lane finishes: kq and kq + 8
+        for (int t = 0; t < T; ++t, ++it) {
+            const int rb = (it + 1) & 1, wb = it & 1;               // h_{t-1} buffer, h_t buffer
+            // prefetch the input projections of this thread's gate items
             float gir[2], giz[2], gin[2];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int vi = kq + 8 * e;
+                const int v = (tid >> 5) + 8 * e;
                 gir[e] = giz[e] = gin[e] = 0.f;
-                if (vi < nv) {
-                    const float *p = gi + ((size_t)(b0 + vi) * T + t) * 3 * kH + col;
+                if ((e == 0 || tid < 64) && v < nv) {
+                    const float *p = gi + ((size_t)(b0 + v) * T + t) * 3 * kH + gcol;
                     gir[e] = __ldg(p);
                     giz[e] = __ldg(p + kH);
                     gin[e] = __ldg(p + 2 * kH);
                 }
             }
-            // ---- gh[g][v] partial over this thread's eighth of k, packed FP32: each accumulator is a pair
-            //      (sum over even k, sum over odd k), one FFMA2 per W pair x h pair
-            uint64_t acc2[3][kV];
-#pragma unroll
-            for (int g = 0; g < 3; ++g)
-#pragma unroll
-                for (int v = 0; v < kV; ++v) acc2[g][v] = 0ull;
-            const ulonglong2 *w0 = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)(0 * kU + u) * kH);
-            const ulonglong2 *w1 = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)(1 * kU + u) * kH);
-            const ulonglong2 *w2 = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)(2 * kU + u) * kH);
-            const ulonglong2 *hf = reinterpret_cast<const ulonglong2 *>(s.hfull);
-#pragma unroll 4
-            for (int j = 0; j < 16; ++j) {
-                const int q = kq * 16 + (j ^ kq);                  // == swz(kq*16 + j)
-                const ulonglong2 a = w0[q], bq = w1[q], c = w2[q];
+            // ---- partial W_hh h over this thread's k slice
+            uint64_t acc2[6][kV];
+            const ulonglong2 *hq = reinterpret_cast<const ulonglong2 *>(&s.hbuf[rb][0][0][0]);
+            {
+                const int hoff = (ks >> 3) * kV * 8 + (ks & 7);     // quad ks: owner ks/8, quad ks%8 inside its 32 units
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
-                    const ulonglong2 h = hf[v * (kH / 4) + q];
-                    acc2[0][v] = fma2(a.y, h.y, fma2(a.x, h.x, acc2[0][v]));
-                    acc2[1][v] = fma2(bq.y, h.y, fma2(bq.x, h.x, acc2[1][v]));
-                    acc2[2][v] = fma2(c.y, h.y, fma2(c.x, h.x, acc2[2][v]));
+                    const ulonglong2 h = hq[hoff + v * 8];
+#pragma unroll
+                    for (int r6 = 0; r6 < 6; ++r6) acc2[r6][v] = fma2(wreg[r6].y, h.y, fma2(wreg[r6].x, h.x, 0ull));
                 }
             }
-            float acc[3][kV];
+            const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w);
+#pragma unroll 1
+            for (int j = 1; j < 8; ++j) {
+                const int q = ks + 16 * j;
+                ulonglong2 w[6];
 #pragma unroll
-            for (int g = 0; g < 3; ++g)
+                for (int r6 = 0; r6 < 6; ++r6) w[r6] = wq[((r6 >> 1) * kU + 2 * up + (r6 & 1)) * kWq + (q - 16)];
+                const int hoff = (q >> 3) * kV * 8 + (q & 7);
+#pragma unroll
+                for (int v = 0; v < kV; ++v) {
+                    const ulonglong2 h = hq[hoff + v * 8];
+#pragma unroll
+                    for (int r6 = 0; r6 < 6; ++r6) acc2[r6][v] = fma2(w[r6].y, h.y, fma2(w[r6].x, h.x, acc2[r6][v]));
+                }
+            }
+            // ---- combine the 16 k slices: recursive halving, lane ks ends with entries 4 ks .. 4 ks + 3
+            float a[64];
+#pragma unroll
+            for (int r6 = 0; r6 < 6; ++r6)
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
                     float lo, hi;
-                    unpk2(acc2[g][v], lo, hi);
-                    acc[g][v] = lo + hi;
+                    unpk2(acc2[r6][v], lo, hi);
+                    a[r6 * kV + v] = lo + hi;
                 }
-            // ---- all-reduce over the 8 k-eighths (lane bits 0..2)
+            a[60] = a[61] = a[62] = a[63] = 0.f;
 #pragma unroll
-            for (int g = 0; g < 3; ++g)
+            for (int st = 0; st < 4; ++st) {
+                const int n = 32 >> st, m = 8 >> st;
+                const bool upper = (ks & m) != 0;
 #pragma unroll
-                for (int v = 0; v < kV; ++v) {
-                    float x = acc[g][v];
-                    x += __shfl_xor_sync(0xffffffffu, x, 1);
-                    x += __shfl_xor_sync(0xffffffffu, x, 2);
-                    x += __shfl_xor_sync(0xffffffffu, x, 4);
-                    acc[g][v] = x;
+                for (int i = 0; i < n; ++i) {
+                    const float keep = upper ? a[i + n] : a[i];
+                    const float send = upper ? a[i] : a[i + n];
+                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
                 }
-            // ---- gates for voices kq and kq+8 of unit u
-            const int colq = col >> 2;                              // float4 index of the own column in hfull
-            float rr[2], zz[2], nn[2], gg[2], hh[2];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int e = 4 * ks + i;                           // = r6 * kV + v
+                if (e < 6 * kV) {
+                    const int r6 = e / kV, v = e - r6 * kV;
+                    s.gh[r6 >> 1][v][2 * up + (r6 & 1)] = a[i];
+                }
+            }
+            __syncthreads();
+            // ---- gates: thread = (voice, unit)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int vi = kq + 8 * e;
-                if (vi < nv) {
-                    float ghr = 0.f, ghz = 0.f, ghn = 0.f;
-#pragma unroll
-                    for (int v = 0; v < kV; ++v)
-                        if (v == vi) { ghr = acc[0][v]; ghz = acc[1][v]; ghn = acc[2][v]; }
-                    ghr += br; ghz += bz; ghn += bn;
-                    const float hprev = s.hfull[(size_t)vi * kH + swz(colq) * 4 + (col & 3)];
+                const int v = (tid >> 5) + 8 * e;
+                if ((e == 0 || tid < 64) && v < nv) {
+                    const float ghr = s.gh[0][v][gu] + br, ghz = s.gh[1][v][gu] + bz, ghn = s.gh[2][v][gu] + bn;
+                    const float hprev = s.hbuf[rb][rank][v][gu];
                     const float r = sigmoid_acc(gir[e] + ghr);
                     const float z = sigmoid_acc(giz[e] + ghz);
                     const float n = tanhf(fmaf(r, ghn, gin[e]));
                     const float hnew = fmaf(z, hprev - n, n);        // (1-z) n + z h
-                    s.hown[((t & 1) * kV + vi) * kU + u] = hnew;
-                    rr[e] = r; zz[e] = z; nn[e] = n; gg[e] = ghn; hh[e] = hnew;
-                }
-            }
-            cluster.barrier_arrive();                               // own slice of h_t is published ...
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {                           // ... the global stores ride under the barrier
-                const int vi = kq + 8 * e;
-                if (vi < nv) {
-                    const size_t o = (size_t)(b0 + vi) * T + t;
-                    y[o * kH + col] = hh[e];
+                    s.stage[wb][v][gu] = hnew;
+                    const size_t o = (size_t)(b0 + v) * T + t;
+                    y[o * kH + gcol] = hnew;
                     if (gates) {
-                        float *gp = gates + o * 4 * kH + col;
-                        gp[0] = rr[e]; gp[kH] = zz[e]; gp[2 * kH] = nn[e]; gp[3 * kH] = gg[e];
+                        float *gp = gates + o * 4 * kH + gcol;
+                        gp[0] = r; gp[kH] = z; gp[2 * kH] = n; gp[3 * kH] = ghn;
                     }
                 }
             }
-            cluster.barrier_wait();                                 // every CTA's slice is visible
-            // ---- pull the 16 slices into the local full h (DSMEM), swizzled
-            for (int i = tid; i < kV * (kH / 4); i += kGruThreads) {
-                const int v = i / (kH / 4), q = i - v * (kH / 4);
-                const int src = q >> 3, qq = q & 7;                 // owner CTA, float4 inside its 32 units
-                const float *remote = cluster.map_shared_rank(s.hown, src);
-                const float4 hv = *reinterpret_cast<const float4 *>(remote + ((t & 1) * kV + v) * kU + qq * 4);
-                reinterpret_cast<float4 *>(s.hfull + (size_t)v * kH)[swz(q)] = hv;
-            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging visible to the bulk-copy engine
             __syncthreads();
+            // ---- publish: 16 bulk copies of the own slice, one per destination CTA; arm the own barrier
+            const uint32_t bar = gru_smem_u32(&s.bar[wb]);
+            if (tid < kC)
+                gru_push(gru_smem_u32(&s.hbuf[wb][rank][0][0]), gru_smem_u32(&s.stage[wb][0][0]), bar, tid, kSliceBytes);
+            if (tid == 32)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kC * kSliceBytes)
+                             : "memory");
+            gru_bar_wait(bar, (it >> 1) & 1);                        // all 16 slices of h_t have landed here
         }
     }
-    cluster.sync();        // nobody leaves while a neighbour may still read its shared memory
+    cluster.sync();        // nobody leaves while a neighbour may still write into its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward: dgi, dgh (B,T,3H), dh0 (B,H) from dy (B,T,H) (+ dhT (B,H) or NULL)
+//
+// Per step (time reversed): gate gradients of the own 32 units (thread = (voice, unit); their global inputs
+// are prefetched one step ahead), then partial[v][k] = sum over the own 96 rows of d[row][v] W_hh[row][k]
+// (thread = (k quad, half of the rows); 16 of its 48 rows of W_hh live in registers, 32 in shared memory),
+// stored slice-major by destination CTA.  Reduce-scatter without a cluster barrier: 16 bulk DSMEM copies push
+// slice d to CTA d's receive buffer and signal its mbarrier; each CTA then adds the 16 slices it received.
+// Receive and send buffers are double buffered (same argument as in the forward).
 // ---------------------------------------------------------------------------------------------
+constexpr int kRegRows = 16;                      // rows per thread (of its 48) whose W_hh quad stays in registers
+constexpr int kSmemRows = 2 * (kRows / 2 - kRegRows);
+
+struct GruSmemBwd {
+    float w[kSmemRows * kH];                      // [half*32 + (rr - 16)][512]
+    float partial[2][kC][kV][kU];                 // [buffer][destination CTA][voice][unit]
+    float recv[2][kC][kV][kU];                    // [buffer][source CTA][voice][unit]
+    float down[kRows * 24];                       // [row][12 (>= kV)][2] gate gradients, each stored twice (FFMA2 operand)
+    float dhn[kV * kU];                           // recurrent part of dh for the own units
+    unsigned long long bar[2];
+};
+
 __global__ void __launch_bounds__(kGruThreads, 1)
 gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, const float *__restrict__ w_hh,
                const float *__restrict__ y, const float *__restrict__ h0, const float *__restrict__ gates,
@@ -208,65 +277,114 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
     const int rank = cluster.block_rank();
     const int cid = blockIdx.x / kC, ncl = gridDim.x / kC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int half = lane >> 4, q = warp * 16 + (lane & 15);        // row half, float4 index of k
+    const int r0 = half * (kRows / 2);
 
-    load_w_slice(s.w, w_hh, rank, tid);
+    // ---- W_hh slice (slice row = g*32 + u  <->  global row g*H + 32*rank + u)
+    ulonglong2 wreg[kRegRows];
+#pragma unroll
+    for (int rr = 0; rr < kRegRows; ++rr) {
+        const int row = r0 + rr, g = row / kU, u = row - g * kU;
+        wreg[rr] = __ldg(reinterpret_cast<const ulonglong2 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + q);
+    }
+    for (int i = tid; i < kSmemRows * (kH / 4); i += kGruThreads) {
+        const int srow = i / (kH / 4), qq = i - srow * (kH / 4);
+        const int row = (srow >> 5) * (kRows / 2) + kRegRows + (srow & 31);
+        const int g = row / kU, u = row - g * kU;
+        reinterpret_cast<float4 *>(s.w)[i] =
+            __ldg(reinterpret_cast<const float4 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + qq);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gru_smem_u32(&s.bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gru_smem_u32(&s.bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int gu = tid & 31, gcol = rank * kU + gu;                  // gate items: (tid/32, gu) and, tid < 64, (8 + tid/32, gu)
 
-    for (int b0 = cid * vpc; b0 < B; b0 += ncl * vpc) {     // vpc <= kV voices per cluster pass
+    int it = 0;
+    for (int b0 = cid * vpc; b0 < B; b0 += ncl * vpc) {             // vpc <= kV voices per cluster pass
         const int nv = min(vpc, B - b0);
-        __syncthreads();
+        cluster.sync();
         for (int i = tid; i < kV * kU; i += kGruThreads) {
             const int v = i / kU, u = i - v * kU;
             s.dhn[i] = (dhT && v < nv) ? __ldg(dhT + (size_t)(b0 + v) * kH + rank * kU + u) : 0.f;
         }
-        __syncthreads();
-        for (int t = T - 1; t >= 0; --t) {
-            // ---- gate gradients of the own units: thread = (voice, unit)
-            for (int i = tid; i < kV * kU; i += kGruThreads) {
-                const int v = i / kU, u = i - v * kU;
-                const int col = rank * kU + u;
-                float dar = 0.f, daz = 0.f, dan = 0.f, dghn = 0.f, direct = 0.f;
-                if (v < nv) {
+        // inputs of the gate phase of step T-1
+        float p_dy[2], p_r[2], p_z[2], p_n[2], p_g[2], p_h[2];
+        auto prefetch = [&](int t) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int v = (tid >> 5) + 8 * e;
+                p_dy[e] = p_r[e] = p_z[e] = p_n[e] = p_g[e] = p_h[e] = 0.f;
+                if ((e == 0 || tid < 64) && v < nv) {
                     const size_t o = (size_t)(b0 + v) * T + t;
-                    const float dh = __ldg(dy + o * kH + col) + s.dhn[i];
-                    const float *gp = gates + o * 4 * kH + col;
-                    const float r = __ldg(gp), z = __ldg(gp + kH), n = __ldg(gp + 2 * kH), ghn = __ldg(gp + 3 * kH);
-                    const float hprev = t > 0 ? __ldg(y + (o - 1) * kH + col)
-                                              : (h0 ? __ldg(h0 + (size_t)(b0 + v) * kH + col) : 0.f);
-                    const float dn = dh * (1.f - z);
-                    const float dz = dh * (hprev - n);
-                    dan = dn * (1.f - n * n);
-                    dar = dan * ghn * r * (1.f - r);
-                    daz = dz * z * (1.f - z);
-                    dghn = dan * r;
-                    direct = dh * z;
-                    float *a = dgi + o * 3 * kH + col;
-                    a[0] = dar; a[kH] = daz; a[2 * kH] = dan;
-                    float *c = dgh + o * 3 * kH + col;
-                    c[0] = dar; c[kH] = daz; c[2 * kH] = dghn;
+                    p_dy[e] = __ldg(dy + o * kH + gcol);
+                    const float *gp = gates + o * 4 * kH + gcol;
+                    p_r[e] = __ldg(gp); p_z[e] = __ldg(gp + kH); p_n[e] = __ldg(gp + 2 * kH); p_g[e] = __ldg(gp + 3 * kH);
+                    p_h[e] = t > 0 ? __ldg(y + (o - 1) * kH + gcol) : (h0 ? __ldg(h0 + (size_t)(b0 + v) * kH + gcol) : 0.f);
                 }
-                reinterpret_cast<float2 *>(s.down)[(0 * kU + u) * 12 + v] = make_float2(dar, dar);
-                reinterpret_cast<float2 *>(s.down)[(1 * kU + u) * 12 + v] = make_float2(daz, daz);
-                reinterpret_cast<float2 *>(s.down)[(2 * kU + u) * 12 + v] = make_float2(dghn, dghn);
-                s.dhn[i] = direct;                       // the recurrent part is added after the reduce-scatter
+            }
+        };
+        prefetch(T - 1);
+        __syncthreads();
+        for (int t = T - 1; t >= 0; --t, ++it) {
+            const int pb = it & 1;
+            // ---- gate gradients of the own units: thread = (voice, unit)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int v = (tid >> 5) + 8 * e;
+                if (e == 0 || tid < 64) {
+                    const int i = v * kU + gu;
+                    float dar = 0.f, daz = 0.f, dghn = 0.f, direct = 0.f;
+                    if (v < nv) {
+                        const float r = p_r[e], z = p_z[e], n = p_n[e];
+                        const float dh = p_dy[e] + s.dhn[i];
+                        const float dn = dh * (1.f - z);
+                        const float dz = dh * (p_h[e] - n);
+                        const float dan = dn * (1.f - n * n);
+                        dar = dan * p_g[e] * r * (1.f - r);
+                        daz = dz * z * (1.f - z);
+                        dghn = dan * r;
+                        direct = dh * z;
+                        const size_t o = (size_t)(b0 + v) * T + t;
+                        float *a = dgi + o * 3 * kH + gcol;
+                        a[0] = dar; a[kH] = daz; a[2 * kH] = dan;
+                        float *c = dgh + o * 3 * kH + gcol;
+                        c[0] = dar; c[kH] = daz; c[2 * kH] = dghn;
+                    }
+                    reinterpret_cast<float2 *>(s.down)[(0 * kU + gu) * 12 + v] = make_float2(dar, dar);
+                    reinterpret_cast<float2 *>(s.down)[(1 * kU + gu) * 12 + v] = make_float2(daz, daz);
+                    reinterpret_cast<float2 *>(s.down)[(2 * kU + gu) * 12 + v] = make_float2(dghn, dghn);
+                    s.dhn[i] = direct;                   // the recurrent part is added after the reduce-scatter
+                }
             }
             __syncthreads();
-            // ---- partial[v][k] = sum over own 96 rows of d[row][v] * W[row][k]; thread = (k-quad, row half)
+            if (t > 0) prefetch(t - 1);                  // rides under the matrix product below
+            // ---- partial[v][k] over the own row half
             {
-                const int half = lane >> 4;
-                const int q = warp * 16 + (lane & 15);               // logical float4 index of k
-                const int pq = swz(q);
                 uint64_t acc2[kV][2];                                // (k, k+1) and (k+2, k+3) of the quad
 #pragma unroll
                 for (int v = 0; v < kV; ++v) acc2[v][0] = acc2[v][1] = 0ull;
-                const int r0 = half * (kRows / 2);
-#pragma unroll 2
-                for (int rr = 0; rr < kRows / 2; ++rr) {
-                    const int row = r0 + rr;
-                    const ulonglong2 w = reinterpret_cast<const ulonglong2 *>(s.w + (size_t)row * kH)[pq];
-                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + row * 24);
+#pragma unroll
+                for (int rr = 0; rr < kRegRows; ++rr) {
+                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
 #pragma unroll
                     for (int vp = 0; vp < kV / 2; ++vp) {
                         const ulonglong2 d = dp[vp];                 // (d_v, d_v), (d_v+1, d_v+1)
+                        acc2[2 * vp][0] = fma2(d.x, wreg[rr].x, acc2[2 * vp][0]);
+                        acc2[2 * vp][1] = fma2(d.x, wreg[rr].y, acc2[2 * vp][1]);
+                        acc2[2 * vp + 1][0] = fma2(d.y, wreg[rr].x, acc2[2 * vp + 1][0]);
+                        acc2[2 * vp + 1][1] = fma2(d.y, wreg[rr].y, acc2[2 * vp + 1][1]);
+                    }
+                }
+                const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w) + (size_t)half * 32 * (kH / 4) + q;
+#pragma unroll 2
+                for (int rr = kRegRows; rr < kRows / 2; ++rr) {
+                    const ulonglong2 w = wq[(size_t)(rr - kRegRows) * (kH / 4)];
+                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
+#pragma unroll
+                    for (int vp = 0; vp < kV / 2; ++vp) {
+                        const ulonglong2 d = dp[vp];
                         acc2[2 * vp][0] = fma2(d.x, w.x, acc2[2 * vp][0]);
                         acc2[2 * vp][1] = fma2(d.x, w.y, acc2[2 * vp][1]);
                         acc2[2 * vp + 1][0] = fma2(d.y, w.x, acc2[2 * vp + 1][0]);
@@ -286,24 +404,32 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                 if (half == 0) {
 #pragma unroll
                     for (int v = 0; v < kV; ++v)
-                        reinterpret_cast<float4 *>(s.partial + (size_t)v * kH)[q] =
+                        *reinterpret_cast<float4 *>(&s.partial[pb][q >> 3][v][(q & 7) * 4]) =
                             make_float4(acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
                 }
             }
-            cluster.sync();                                          // all 16 partials are complete
-            // ---- reduce-scatter: own 32 units of every voice summed over the 16 CTAs (fixed order)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            // ---- reduce-scatter: slice d goes to CTA d's receive slot `rank`
+            const uint32_t bar = gru_smem_u32(&s.bar[pb]);
+            if (tid < kC)
+                gru_push(gru_smem_u32(&s.recv[pb][rank][0][0]), gru_smem_u32(&s.partial[pb][tid][0][0]), bar, tid, kSliceBytes);
+            if (tid == 32)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kC * kSliceBytes)
+                             : "memory");
+            gru_bar_wait(bar, (it >> 1) & 1);
             for (int i = tid; i < kV * (kU / 4); i += kGruThreads) {
                 const int v = i / (kU / 4), uq = i - v * (kU / 4);
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int src = 0; src < kC; ++src) {
-                    const float *remote = cluster.map_shared_rank(s.partial, src);
-                    const float4 p = *reinterpret_cast<const float4 *>(remote + (size_t)v * kH + rank * kU + uq * 4);
-                    sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+#pragma unroll
+                for (int src = 0; src < kC; ++src) {                 // fixed order: deterministic
+                    const float4 pv = *reinterpret_cast<const float4 *>(&s.recv[pb][src][v][uq * 4]);
+                    sum.x += pv.x; sum.y += pv.y; sum.z += pv.z; sum.w += pv.w;
                 }
                 float *d = s.dhn + v * kU + uq * 4;
                 d[0] += sum.x; d[1] += sum.y; d[2] += sum.z; d[3] += sum.w;
             }
-            cluster.sync();                                          // partial buffers may be overwritten again
+            __syncthreads();
         }
         for (int i = tid; i < kV * kU; i += kGruThreads) {
             const int v = i / kU, u = i - v * kU;
