@@ -7,12 +7,29 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ddsp_pytorch_b200 as ddsp
 from ddsp_pytorch_b200.models.decoder import DDSPDecoder
 
-ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=16); ap.add_argument("--tf32", action="store_true"); ap.add_argument("--graph", action="store_true"); ap.add_argument("--stock-gru", action="store_true"); args = ap.parse_args()
+ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=16); ap.add_argument("--tf32", action="store_true"); ap.add_argument("--graph", action="store_true"); ap.add_argument("--stock-gru", action="store_true"); ap.add_argument("--stock-control-net", action="store_true", help="nn.Linear / nn.LayerNorm / nn.LeakyReLU / nn.GRU (cuBLAS, cuDNN) as in the reference"); args = ap.parse_args()
 if args.tf32:
     torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
 torch.manual_seed(0)
 B, T, bs, sr = args.batch, 400, 160, 16000
 model = DDSPDecoder(hidden_size=512, n_harmonic=100, n_bands=65, sample_rate=sr, block_size=bs, has_reverb=True).cuda()
+def to_stock(mod):
+    """Replace this repo's control-net layers by the stock torch.nn ones the reference builds (same weights)."""
+    from ddsp_pytorch_b200 import core
+    for name, child in list(mod.named_children()):
+        if isinstance(child, core.Linear):
+            new = torch.nn.Linear(child.in_features, child.out_features).cuda(); new.load_state_dict(child.state_dict())
+        elif isinstance(child, core.LayerNormLeakyReLU):
+            new = torch.nn.LayerNorm(child.normalized_shape).cuda(); new.load_state_dict(child.state_dict())
+        elif isinstance(child, core.FusedIntoLayerNorm):
+            new = torch.nn.LeakyReLU()
+        elif isinstance(child, core.ClusterGRU):
+            new = torch.nn.GRU(child.input_size, child.hidden_size, batch_first=True).cuda(); new.load_state_dict(child.state_dict())
+        else:
+            to_stock(child); continue
+        setattr(mod, name, new)
+if args.stock_control_net:
+    to_stock(model)
 if args.stock_gru:      # A/B: the cuDNN recurrence the reference runs
     stock = torch.nn.GRU(1024, 512, batch_first=True).cuda(); stock.load_state_dict(model.decoder.gru.state_dict()); model.decoder.gru = stock
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
@@ -52,7 +69,7 @@ if args.graph:
     print(json.dumps({"config": f"batch {B}, tf32={args.tf32}, gru={'cudnn' if args.stock_gru else 'cluster'}", "ms_graph_replay_fused_loss": timeit(gr.replay), "loss": float(static_loss)}))
     sys.exit(0)
 res = {"config": f"DDSPDecoder hidden 512, 16 kHz, block 160, H=100, 4 s, batch {B}: full train step incl. control net and Adam, eager",
-       "tf32": args.tf32, "gru": "cudnn" if args.stock_gru else "cluster", "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
+       "tf32": args.tf32, "gru": "cudnn" if (args.stock_gru or args.stock_control_net) else "cluster", "control_net": "torch.nn (cuBLAS SIMT SGEMM, cuDNN)" if args.stock_control_net else "this repo (3xTF32 tcgen05 GEMM, fused LayerNorm+LeakyReLU, cluster GRU)", "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
 with torch.no_grad():
     res["ms_forward_only"] = timeit(lambda: model(batch))
 t0 = time.perf_counter(); n = torch.rand(B, T, bs) * 2 - 1; res["ms_cpu_noise_draw"] = (time.perf_counter() - t0) * 1e3

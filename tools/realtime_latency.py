@@ -31,4 +31,4 @@ ts.sort()
 print(json.dumps({"config": "configs[2] realtime export: 48 kHz, block 512, 64 harmonics, batch 1, 1024-sample buffers",
                   "ms_per_buffer_median": ts[len(ts) // 2], "ms_per_buffer_p99": ts[int(len(ts) * 0.99)],
                   "budget_ms": 1024 / 48000 * 1e3, "realtime_factor": (1024 / 48000 * 1e3) / ts[len(ts) // 2],
-                  "includes": "H2D of 2x1024 floats, control net (cuDNN GRU), synth kernels, D2H of 1024 floats"}))
+                  "includes": "H2D of 2x1024 floats, control net (cluster GRU kernel, library GEMMs at this size), synth kernels, D2H of 1024 floats"}))
