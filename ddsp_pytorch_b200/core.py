@@ -117,7 +117,7 @@ LINEAR3X_MIN_ROWS = 512      # below this many rows a layer is launch-bound and 
 
 class Linear(nn.Linear):
     """``nn.Linear`` (same parameters, state_dict keys and call) whose three GEMMs run on the tcgen05
-    tensor cores with float32-class accuracy (csrc/gemm3x.cu, "3xTF32") instead of cuBLAS's SIMT SGEMM.
+    tensor cores with float32-class accuracy (csrc/gemm3x.cu, split-bf16) instead of cuBLAS's SIMT SGEMM.
     Small problems (fewer than ``LINEAR3X_MIN_ROWS`` rows, fan-in below 32) and non-CUDA / non-float32 inputs take
     the stock path."""
 

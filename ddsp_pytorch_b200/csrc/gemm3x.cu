@@ -5,27 +5,29 @@
 // reference's setting): ~50 TFLOP/s on a B200, half of a training step at batch 64
 // (profiles/r01_model_step_profile.txt).
 //
-// Method ("3xTF32"): every fp32 operand x is split once into hi = tf32_round(x) and lo = x - hi (exact).
-// C = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulated in fp32 in tensor memory: the dropped lo*lo term and the
-// truncation of lo to 11 significant bits are ~2^-22 relative per product, i.e. fp32-class accuracy at a
-// third of the TF32 tensor rate (several times the SIMT rate).
+// Method (bf16 x 3 split, 6 products): every fp32 operand x is split once into three bf16 parts
+// x = b0 + b1 + b2 (b0 = bf16(x), b1 = bf16(x - b0), b2 = bf16(x - b0 - b1): 3 x 8 mantissa bits, exact), and
+// C = A0 B0 + (A0 B1 + A1 B0) + (A1 B1 + A0 B2 + A2 B0) is accumulated in fp32 in tensor memory; the dropped
+// products are below 2^-24 relative.  Six bf16 MMAs cost half of three TF32 MMAs on this tensor core (the
+// first version of this kernel, "3xTF32", measured 128 cycles per M128 N128 K8 TF32 instruction).
 //
 // Kernel: persistent, one CTA per SM walking 128 x 128 output tiles (x K splits), operands K-major.
-// Warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 3-stage mbarrier ring of 64 KB stages: A_hi,
-// A_lo, B_hi, B_lo), warp 1 = tcgen05.mma issuer (one thread, kind::tf32, M128 N128 K8, 12 MMAs per 32-wide
-// k block, two ping-pong pairs of 128-column TMEM accumulators), warps 2-5 = epilogue (tcgen05.ld 32x32b of
-// every finished 64-deep K chunk, accumulated in registers; + bias and global stores at the end of a tile).
+// Warp 0 = TMA producer (cp.async.bulk.tensor, 128B swizzle, 2-stage mbarrier ring of 96 KB stages: three
+// parts of A and of B, 64 values of K), warp 1 = tcgen05.mma issuer (one thread, kind::f16, M128 N128 K16,
+// 24 MMAs per stage, two ping-pong pairs of 128-column TMEM accumulators), warps 2-5 = epilogue (tcgen05.ld
+// 32x32b of every finished 64-deep K chunk, accumulated in registers; + bias and global stores at tile end).
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32;          // CTA tile; kBK fp32 = 128 B = one swizzle row
-constexpr int kStages = 3;
-constexpr int kChunk = 2;                                // k blocks accumulated in TMEM before promotion to registers
-constexpr int kTileBytes = kBM * kBK * 4;              // 16 KB per operand part
-constexpr int kStageBytes = 4 * kTileBytes;            // A_hi, A_lo, B_hi, B_lo
+constexpr int kBM = 128, kBN = 128, kBK = 64;          // CTA tile; kBK bf16 = 128 B = one swizzle row
+constexpr int kStages = 2;
+constexpr int kChunk = 1;                                // k blocks accumulated in TMEM before promotion to registers
+constexpr int kTileBytes = kBM * kBK * 2;              // 16 KB per operand part
+constexpr int kStageBytes = 6 * kTileBytes;            // A0, A1, A2, B0, B1, B2
 constexpr int kGemmThreads = 192;
 constexpr int kGemmSmem = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr uint32_t kSpinLimit = 1u << 26;              // a lost barrier traps instead of hanging the GPU
@@ -67,11 +69,11 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
     return d;
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
@@ -98,7 +100,7 @@ struct GemmParams {
     float *c;                  // output, or split-K partials [splits][M][N] (then ldc == N)
     const float *bias;         // added in the epilogue when splits == 1
     int M, N, ldc;
-    int a_lo_row, b_lo_row;    // row offset of the lo part inside the operand's tensor map
+    int a_lo_row, b_lo_row;    // row distance between the three parts inside the operand's tensor map
     int k_blocks, k_blocks_per_split, splits;
     int m_tiles, n_tiles;
 };
@@ -116,7 +118,8 @@ __device__ __forceinline__ void tile_coords(const GemmParams &p, int t, int &z, 
 
 // Persistent: CTA b works on tiles b, b + grid, ...  The tensor core's fp32 accumulation truncates, so the
 // error of a long K loop grows linearly with K; therefore K is accumulated in TMEM only over chunks of
-// kChunk k blocks (64 values of K) and the epilogue warps add every finished chunk into fp32 REGISTERS
+// kChunk k blocks (64 values of K: 4 accumulations of the main term) and the epilogue warps add every
+// finished chunk into fp32 REGISTERS
 // (round-to-nearest) while the next chunk is being multiplied into the other TMEM buffer.  The two small
 // cross terms go to their own accumulator so that their rounding happens at their own (2^-11) scale.
 // TMEM columns: [main0 | small0 | main1 | small1], 128 each.
@@ -166,18 +169,19 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const uint32_t st = base + s * kStageBytes, fb = full0 + 8 * s;
                     mbar_expect_tx(fb, kStageBytes);
                     const int k = (kb0 + i) * kBK;
-                    tma_load_2d(st, &map_a, fb, k, m0);
-                    tma_load_2d(st + kTileBytes, &map_a, fb, k, p.a_lo_row + m0);
-                    tma_load_2d(st + 2 * kTileBytes, &map_b, fb, k, n0);
-                    tma_load_2d(st + 3 * kTileBytes, &map_b, fb, k, p.b_lo_row + n0);
+#pragma unroll
+                    for (int part = 0; part < 3; ++part) {
+                        tma_load_2d(st + part * kTileBytes, &map_a, fb, k, part * p.a_lo_row + m0);
+                        tma_load_2d(st + (3 + part) * kTileBytes, &map_b, fb, k, part * p.b_lo_row + n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            // instruction descriptor: D fp32, A/B tf32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
             int it = 0, chunk = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 int z, m0, n0, kb0, nkb;
@@ -194,15 +198,21 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t st = base + s * kStageBytes;
 #pragma unroll
-                        for (int k = 0; k < kBK / 8; ++k) {
-                            const uint32_t off = k * 32;                           // 8 fp32 along K inside the 128 B row
-                            const uint64_t a_hi = umma_desc_k_sw128(st + off), a_lo = umma_desc_k_sw128(st + kTileBytes + off);
-                            const uint64_t b_hi = umma_desc_k_sw128(st + 2 * kTileBytes + off);
-                            const uint64_t b_lo = umma_desc_k_sw128(st + 3 * kTileBytes + off);
+                        for (int k = 0; k < kBK / 16; ++k) {
+                            const uint32_t off = k * 32;                           // 16 bf16 along K inside the 128 B row
+                            uint64_t a[3], b[3];
+#pragma unroll
+                            for (int part = 0; part < 3; ++part) {
+                                a[part] = umma_desc_k_sw128(st + part * kTileBytes + off);
+                                b[part] = umma_desc_k_sw128(st + (3 + part) * kTileBytes + off);
+                            }
                             const uint32_t acc = (i != i0 || k != 0) ? 1u : 0u;
-                            umma_tf32(d_main, a_hi, b_hi, idesc, acc);
-                            umma_tf32(d_small, a_lo, b_hi, idesc, acc);
-                            umma_tf32(d_small, a_hi, b_lo, idesc, 1u);
+                            umma_bf16(d_main, a[0], b[0], idesc, acc);
+                            umma_bf16(d_small, a[1], b[1], idesc, acc);             // 2^-16 terms first
+                            umma_bf16(d_small, a[0], b[2], idesc, 1u);
+                            umma_bf16(d_small, a[2], b[0], idesc, 1u);
+                            umma_bf16(d_small, a[0], b[1], idesc, 1u);              // 2^-8 terms
+                            umma_bf16(d_small, a[1], b[0], idesc, 1u);
                         }
                         umma_commit(empty0 + 8 * s);                               // stage free when these MMAs retire
                     }
@@ -286,30 +296,32 @@ __global__ void gemm3x_reduce_kernel(const float *__restrict__ partial, const fl
     c[(size_t)m * ldc + n] = acc;
 }
 
-// ---- operand split: out[r][c] = tf32_round(x), out[lo_row + r][c] = x - hi; columns cols..out_ld zeroed.
-// transpose == 0: logical operand = x (rows x cols, row pitch ld).  transpose == 1: operand = x^T.
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    lo = x - hi;
+// ---- operand split: x = b0 + b1 + b2 in bf16; part p of row r at out[(p * part_rows + r)][c]; columns
+// cols..out_ld zeroed.  transpose == 0: logical operand = x (rows x cols, row pitch ld); 1: operand = x^T.
+__device__ __forceinline__ void split_bf16x3(float x, __nv_bfloat16 &b0, __nv_bfloat16 &b1, __nv_bfloat16 &b2) {
+    b0 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b0);          // exact
+    b1 = __float2bfloat16_rn(r1);
+    b2 = __float2bfloat16_rn(r1 - __bfloat162float(b1));  // exact residual, <= 8 significant bits
+}
+__device__ __forceinline__ void store_parts(__nv_bfloat16 *out, size_t idx, size_t part_stride, float x) {
+    __nv_bfloat16 b0, b1, b2;
+    split_bf16x3(x, b0, b1, b2);
+    out[idx] = b0;
+    out[idx + part_stride] = b1;
+    out[idx + 2 * part_stride] = b2;
 }
 
-__global__ void split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, float *__restrict__ out,
-                               int64_t lo_row, int out_ld) {
+__global__ void split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv_bfloat16 *__restrict__ out,
+                               int64_t part_rows, int out_ld) {
     const int r = blockIdx.x;
-    float *hi_row = out + (size_t)r * out_ld, *lo_rowp = out + (size_t)(lo_row + r) * out_ld;
-    for (int c = (blockIdx.y * blockDim.x + threadIdx.x); c < out_ld; c += gridDim.y * blockDim.x) {
-        float hi = 0.f, lo = 0.f;
-        if (c < cols) split_tf32(__ldg(x + (size_t)r * ld + c), hi, lo);
-        hi_row[c] = hi;
-        lo_rowp[c] = lo;
-    }
+    for (int c = (blockIdx.y * blockDim.x + threadIdx.x); c < out_ld; c += gridDim.y * blockDim.x)
+        store_parts(out, (size_t)r * out_ld + c, (size_t)part_rows * out_ld, c < cols ? __ldg(x + (size_t)r * ld + c) : 0.f);
 }
 
 // operand rows = x's columns, operand columns (K) = x's rows
 __global__ void split3x_transpose_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld,
-                                         float *__restrict__ out, int64_t lo_row, int out_ld) {
+                                         __nv_bfloat16 *__restrict__ out, int64_t part_rows, int out_ld) {
     __shared__ float tile[32][33];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;          // tile of x
     const int tx = threadIdx.x, ty = threadIdx.y;                   // 32 x 8
@@ -320,18 +332,15 @@ __global__ void split3x_transpose_kernel(const float *__restrict__ x, int rows, 
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int orow = c0 + j, ocol = r0 + tx;                    // operand row = x column
-        if (orow < cols && ocol < out_ld) {
-            float hi, lo;
-            split_tf32(tile[tx][j], hi, lo);                        // zero beyond rows by construction
-            out[(size_t)orow * out_ld + ocol] = hi;
-            out[(size_t)(lo_row + orow) * out_ld + ocol] = lo;
-        }
+        if (orow < cols && ocol < out_ld)
+            store_parts(out, (size_t)orow * out_ld + ocol, (size_t)part_rows * out_ld, tile[tx][j]);
     }
 }
 
 // both operands of one matrix in one pass: out = split(x), out_t = split(x^T)
-__global__ void split3x_both_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, float *__restrict__ out,
-                                    int64_t lo_row, int out_ld, float *__restrict__ out_t, int64_t lo_row_t, int out_ld_t) {
+__global__ void split3x_both_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv_bfloat16 *__restrict__ out,
+                                    int64_t part_rows, int out_ld, __nv_bfloat16 *__restrict__ out_t, int64_t part_rows_t,
+                                    int out_ld_t) {
     __shared__ float tile[32][33];
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -339,22 +348,13 @@ __global__ void split3x_both_kernel(const float *__restrict__ x, int rows, int c
         const int r = r0 + j, c = c0 + tx;
         const float v = (r < rows && c < cols) ? __ldg(x + (size_t)r * ld + c) : 0.f;
         tile[j][tx] = v;
-        if (r < rows && c < out_ld) {
-            float hi, lo;
-            split_tf32(v, hi, lo);
-            out[(size_t)r * out_ld + c] = hi;
-            out[(size_t)(lo_row + r) * out_ld + c] = lo;
-        }
+        if (r < rows && c < out_ld) store_parts(out, (size_t)r * out_ld + c, (size_t)part_rows * out_ld, v);
     }
     __syncthreads();
     for (int j = ty; j < 32; j += 8) {
         const int orow = c0 + j, ocol = r0 + tx;
-        if (orow < cols && ocol < out_ld_t) {
-            float hi, lo;
-            split_tf32(tile[tx][j], hi, lo);
-            out_t[(size_t)orow * out_ld_t + ocol] = hi;
-            out_t[(size_t)(lo_row_t + orow) * out_ld_t + ocol] = lo;
-        }
+        if (orow < cols && ocol < out_ld_t)
+            store_parts(out_t, (size_t)orow * out_ld_t + ocol, (size_t)part_rows_t * out_ld_t, tile[tx][j]);
     }
 }
 
@@ -374,15 +374,15 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// operand [total_rows][ld] fp32, box = 32 columns (128 B) x 128 rows, 128-byte swizzle
-int make_operand_map(CUtensorMap *map, const float *ptr, int64_t total_rows, int64_t ld) {
+// operand [total_rows][ld] bf16, box = 64 columns (128 B) x 128 rows, 128-byte swizzle
+int make_operand_map(CUtensorMap *map, const void *ptr, int64_t total_rows, int64_t ld) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return DDSP_B200_EUNSUPPORTED;
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)total_rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
     const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : DDSP_B200_EINVAL;
@@ -397,46 +397,49 @@ extern "C" int64_t ddsp_b200_gemm3x_ld(int64_t k) { return (k + kBK - 1) / kBK *
 extern "C" int ddsp_b200_gemm3x_splits(int M, int N, int K) {
     const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
     const int kblocks = (int)(ddsp_b200_gemm3x_ld(K) / kBK);
-    if (tiles >= 96 || kblocks < 16) return 1;
+    if (tiles >= 96 || kblocks < 8) return 1;
     int s = (148 + tiles - 1) / tiles;
-    if (s > kblocks / 4) s = kblocks / 4;
+    if (s > kblocks / 2) s = kblocks / 2;
     return s < 1 ? 1 : s;
 }
 
-// out: [2 * lo_row][out_ld] floats with out_ld = ddsp_b200_gemm3x_ld(K), lo_row >= operand rows.
-// transpose = 0: operand (rows x cols) = x; 1: operand (cols x rows) = x^T.  x has row pitch ld.
-extern "C" int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, float *out,
-                                      int64_t lo_row, void *stream) {
+// out: [3 * part_rows][out_ld] bf16 (uint16_t bits) with out_ld = ddsp_b200_gemm3x_ld(K), part_rows >= operand
+// rows.  transpose = 0: operand (rows x cols) = x; 1: operand (cols x rows) = x^T.  x has row pitch ld.
+extern "C" int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, void *out,
+                                      int64_t part_rows, void *stream) {
     DDSP_REQUIRE(x && out && rows > 0 && cols > 0 && ld >= cols);
     cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
     if (!transpose) {
-        DDSP_REQUIRE(lo_row >= rows);
+        DDSP_REQUIRE(part_rows >= rows);
         const int out_ld = (int)ddsp_b200_gemm3x_ld(cols);
         dim3 grid((unsigned)rows, (out_ld + 255) / 256);
-        split3x_kernel<<<grid, 256, 0, st>>>(x, (int)rows, (int)cols, ld, out, lo_row, out_ld);
+        split3x_kernel<<<grid, 256, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld);
     } else {
-        DDSP_REQUIRE(lo_row >= cols);
+        DDSP_REQUIRE(part_rows >= cols);
         const int out_ld = (int)ddsp_b200_gemm3x_ld(rows);
         dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(out_ld / 32));
-        split3x_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(x, (int)rows, (int)cols, ld, out, lo_row, out_ld);
+        split3x_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld);
     }
     return ddsp_launch_status();
 }
 
-// out = split operand of x (lo part at row lo_row), out_t = split operand of x^T (lo part at row lo_row_t)
-extern "C" int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t cols, int64_t ld, float *out,
-                                           int64_t lo_row, float *out_t, int64_t lo_row_t, void *stream) {
-    DDSP_REQUIRE(x && out && out_t && rows > 0 && cols > 0 && ld >= cols && lo_row >= rows && lo_row_t >= cols);
+// out = split operand of x (parts part_rows apart), out_t = split operand of x^T (parts part_rows_t apart)
+extern "C" int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t cols, int64_t ld, void *out,
+                                           int64_t part_rows, void *out_t, int64_t part_rows_t, void *stream) {
+    DDSP_REQUIRE(x && out && out_t && rows > 0 && cols > 0 && ld >= cols && part_rows >= rows && part_rows_t >= cols);
     const int out_ld = (int)ddsp_b200_gemm3x_ld(cols), out_ld_t = (int)ddsp_b200_gemm3x_ld(rows);
     dim3 grid((unsigned)(out_ld / 32), (unsigned)(out_ld_t / 32));
-    split3x_both_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (int)rows, (int)cols, ld, out, lo_row, out_ld,
-                                                                        out_t, lo_row_t, out_ld_t);
+    split3x_both_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        x, (int)rows, (int)cols, ld, static_cast<__nv_bfloat16 *>(out), part_rows, out_ld,
+        static_cast<__nv_bfloat16 *>(out_t), part_rows_t, out_ld_t);
     return ddsp_launch_status();
 }
 
 // C[M][N] (row pitch ldc) = A B^T + bias.  a, b: split operands (ddsp_b200_gemm3x_split) of logical shapes
-// M x K and N x K with lo-part row offsets a_lo_row / b_lo_row.  workspace: splits * M * N floats or NULL.
-extern "C" int ddsp_b200_gemm3x(const float *a, int64_t a_lo_row, const float *b, int64_t b_lo_row, const float *bias,
+// M x K and N x K whose three parts are a_part_rows / b_part_rows rows apart.  workspace: splits * M * N floats
+// or NULL.
+extern "C" int ddsp_b200_gemm3x(const void *a, int64_t a_lo_row, const void *b, int64_t b_lo_row, const float *bias,
                                 float *c, int64_t ldc, int M, int N, int K, float *workspace, void *stream) {
     DDSP_REQUIRE(a && b && c && M > 0 && N > 0 && K > 0 && ldc >= N && a_lo_row >= M && b_lo_row >= N);
     const int64_t ld = ddsp_b200_gemm3x_ld(K);
@@ -444,9 +447,9 @@ extern "C" int ddsp_b200_gemm3x(const float *a, int64_t a_lo_row, const float *b
     int splits = ddsp_b200_gemm3x_splits(M, N, K);
     if (splits > 1 && !workspace) splits = 1;
     alignas(64) CUtensorMap map_a, map_b;
-    int s = make_operand_map(&map_a, a, a_lo_row + M, ld);
+    int s = make_operand_map(&map_a, a, 2 * a_lo_row + M, ld);
     if (s) return s;
-    s = make_operand_map(&map_b, b, b_lo_row + N, ld);
+    s = make_operand_map(&map_b, b, 2 * b_lo_row + N, ld);
     if (s) return s;
     GemmParams p;
     p.c = splits > 1 ? workspace : c;

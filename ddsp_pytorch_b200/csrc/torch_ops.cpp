@@ -626,16 +626,16 @@ std::tuple<Tensor, Tensor, Tensor> gru_bwd(const Tensor &dy_, const c10::optiona
 }
 
 // ---------------------------------------------------------------------------------------- f3 GEMM
-// x (rows, cols) contiguous -> split operand (2 * R, ld): hi rows [0, R), lo rows [R, 2R)
+// x (rows, cols) contiguous -> split operand (3 * R, ld) bf16: part p in rows [p R, (p + 1) R)
 Tensor gemm3x_split(const Tensor &x_, bool transpose) {
     Tensor x = prep(x_, "x");
     TORCH_CHECK(x.dim() == 2, "gemm3x_split: x must be 2-D");
     const int64_t rows = x.size(0), cols = x.size(1);
     const int64_t R = transpose ? cols : rows, K = transpose ? rows : cols;
     c10::cuda::CUDAGuard guard(x.device());
-    Tensor out = at::empty({2 * R, ddsp_b200_gemm3x_ld(K)}, x.options());
+    Tensor out = at::empty({3 * R, ddsp_b200_gemm3x_ld(K)}, x.options().dtype(at::kBFloat16));
     if (rows == 0 || cols == 0) return out.zero_();
-    check(ddsp_b200_gemm3x_split(fp(x), rows, cols, cols, transpose ? 1 : 0, fpm(out), R, cur_stream()), "gemm3x_split");
+    check(ddsp_b200_gemm3x_split(fp(x), rows, cols, cols, transpose ? 1 : 0, out.data_ptr(), R, cur_stream()), "gemm3x_split");
     return out;
 }
 
@@ -645,28 +645,31 @@ std::tuple<Tensor, Tensor> gemm3x_split_both(const Tensor &x_) {
     TORCH_CHECK(x.dim() == 2, "gemm3x_split_both: x must be 2-D");
     const int64_t rows = x.size(0), cols = x.size(1);
     c10::cuda::CUDAGuard guard(x.device());
-    Tensor out = at::empty({2 * rows, ddsp_b200_gemm3x_ld(cols)}, x.options());
-    Tensor out_t = at::empty({2 * cols, ddsp_b200_gemm3x_ld(rows)}, x.options());
+    Tensor out = at::empty({3 * rows, ddsp_b200_gemm3x_ld(cols)}, x.options().dtype(at::kBFloat16));
+    Tensor out_t = at::empty({3 * cols, ddsp_b200_gemm3x_ld(rows)}, x.options().dtype(at::kBFloat16));
     if (rows == 0 || cols == 0) return {out.zero_(), out_t.zero_()};
-    check(ddsp_b200_gemm3x_split_both(fp(x), rows, cols, cols, fpm(out), rows, fpm(out_t), cols, cur_stream()),
+    check(ddsp_b200_gemm3x_split_both(fp(x), rows, cols, cols, out.data_ptr(), rows, out_t.data_ptr(), cols, cur_stream()),
           "gemm3x_split_both");
     return {out, out_t};
 }
 
-// a (2M, ld), b (2N, ld) split operands -> a b^T + bias  (M, N)
-Tensor gemm3x_mm(const Tensor &a_, const Tensor &b_, int64_t K, const c10::optional<Tensor> &bias_) {
-    Tensor a = prep(a_, "a"), b = prep(b_, "b"), bias = opt_prep(bias_, "bias");
-    TORCH_CHECK(a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1) && a.size(1) == ddsp_b200_gemm3x_ld(K),
+// a (3M, ld), b (3N, ld) split operands -> a b^T + bias  (M, N) float32
+Tensor gemm3x_mm(const Tensor &a, const Tensor &b, int64_t K, const c10::optional<Tensor> &bias_) {
+    Tensor bias = opt_prep(bias_, "bias");
+    TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 &&
+                    a.is_contiguous() && b.is_contiguous() && a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1) &&
+                    a.size(1) == ddsp_b200_gemm3x_ld(K) && a.size(0) % 3 == 0 && b.size(0) % 3 == 0,
                 "gemm3x_mm: operands must be gemm3x_split outputs of the same K");
-    const int64_t M = a.size(0) / 2, N = b.size(0) / 2;
+    const int64_t M = a.size(0) / 3, N = b.size(0) / 3;
     TORCH_CHECK(!bias.defined() || bias.numel() == N, "gemm3x_mm: bias must have N entries");
     c10::cuda::CUDAGuard guard(a.device());
-    Tensor c = at::empty({M, N}, a.options());
+    auto fopt = a.options().dtype(at::kFloat);
+    Tensor c = at::empty({M, N}, fopt);
     if (M == 0 || N == 0) return c;
     if (K == 0) return bias.defined() ? c.copy_(bias.expand({M, N})) : c.zero_();
     const int splits = ddsp_b200_gemm3x_splits((int)M, (int)N, (int)K);
-    Tensor ws = splits > 1 ? at::empty({splits, M, N}, a.options()) : Tensor();
-    check(ddsp_b200_gemm3x(fp(a), M, fp(b), N, opt_fp(bias), fpm(c), N, (int)M, (int)N, (int)K,
+    Tensor ws = splits > 1 ? at::empty({splits, M, N}, fopt) : Tensor();
+    check(ddsp_b200_gemm3x(a.data_ptr(), M, b.data_ptr(), N, opt_fp(bias), fpm(c), N, (int)M, (int)N, (int)K,
                            splits > 1 ? fpm(ws) : nullptr, cur_stream()),
           "gemm3x_mm");
     return c;

@@ -220,7 +220,7 @@ class ReverbImpulse(torch.autograd.Function):
 
 
 def _mm3x(a: torch.Tensor, a_t: bool, b: torch.Tensor, b_t: bool, bias=None) -> torch.Tensor:
-    """(a or a^T) @ (b or b^T)^T + bias through the 3xTF32 tensor-core GEMM; a, b 2-D contiguous."""
+    """(a or a^T) @ (b or b^T)^T + bias through the split-bf16 tensor-core GEMM; a, b 2-D contiguous."""
     k = a.shape[0] if a_t else a.shape[1]
     return _ops.gemm3x_mm(_ops.gemm3x_split(a, a_t), _ops.gemm3x_split(b, b_t), k, bias)
 

@@ -226,21 +226,21 @@ int ddsp_b200_gru_bwd(const float *dy, const float *dhT, const float *w_hh, cons
 
 /* ---- f3 (next row)  fp32-accurate GEMM on the tcgen05 tensor cores for the control net's nn.Linear layers
  * and the GRU projections (ddsp/core.py:122-133, decoder.py:40-68,86-87; torch runs them as SIMT SGEMM).
- * "3xTF32": operands are split once into tf32 hi + fp32 residual lo; C = Ahi Bhi + Ahi Blo + Alo Bhi with
- * fp32 accumulation in tensor memory.
+ * Operands are split once into three bf16 parts x = b0 + b1 + b2 (exact); C = sum of the six leading part
+ * products with fp32 accumulation (tensor memory, promoted to registers every 64 values of K).
  * gemm3x_ld(K): padded column count of a split operand.  gemm3x_split: x (rows x cols, row pitch ld) ->
- * out[2 * lo_row][gemm3x_ld(K)]: hi part in rows [0, R), lo part in rows [lo_row, lo_row + R), K padding
- * zeroed; transpose = 0: operand = x (R = rows, K = cols); 1: operand = x^T (R = cols, K = rows).
+ * out[3 * part_rows][gemm3x_ld(K)] bf16: part p in rows [p * part_rows, p * part_rows + R), K padding zeroed;
+ * transpose = 0: operand = x (R = rows, K = cols); 1: operand = x^T (R = cols, K = rows).
  * gemm3x_split_both: the operands of x and of x^T from one read of x.
  * gemm3x: C[M][N] (row pitch ldc) = A B^T + bias (bias may be NULL), A, B split operands of M x K and
  * N x K.  gemm3x_splits: K splits used for a shape; when > 1 pass workspace of splits * M * N floats.   */
 int64_t ddsp_b200_gemm3x_ld(int64_t k);
 int ddsp_b200_gemm3x_splits(int M, int N, int K);
-int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, float *out,
-                           int64_t lo_row, void *stream);
-int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t cols, int64_t ld, float *out,
-                                int64_t lo_row, float *out_t, int64_t lo_row_t, void *stream);
-int ddsp_b200_gemm3x(const float *a, int64_t a_lo_row, const float *b, int64_t b_lo_row, const float *bias,
+int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, void *out,
+                           int64_t part_rows, void *stream);
+int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t cols, int64_t ld, void *out,
+                                int64_t part_rows, void *out_t, int64_t part_rows_t, void *stream);
+int ddsp_b200_gemm3x(const void *a, int64_t a_part_rows, const void *b, int64_t b_part_rows, const float *bias,
                      float *c, int64_t ldc, int M, int N, int K, float *workspace, void *stream);
 
 /* ---- f3 (next row)  LayerNorm + LeakyReLU of the MLP blocks in one pass (ddsp/core.py:122-129) ------

@@ -1,4 +1,4 @@
-"""The tcgen05 "3xTF32" GEMM (csrc/gemm3x.cu) against a float64 product.
+"""The tcgen05 split-bf16 GEMM (csrc/gemm3x.cu) against a float64 product.
 
 It stands in for the SIMT SGEMM torch runs for the reference's float32 nn.Linear layers
 (ddsp/core.py:122-129), so the bar is float32 accuracy: error relative to the largest output entry
@@ -49,10 +49,12 @@ def test_split_parts_are_exact():
     ops = _ops()
     x = torch.randn(50, 37, device="cuda") * 1e3
     s = ops.gemm3x_split(x, False)
-    hi, lo = s[:50, :37], s[50:, :37]
-    assert torch.equal(hi + lo, x)                          # the residual is exact
-    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0      # hi has tf32's 10 mantissa bits
-    assert float(s[:, 37:].abs().max()) == 0.0              # K padding is zero
+    assert s.dtype == torch.bfloat16 and s.shape == (150, 64)
+    parts = s.view(3, 50, 64).float()
+    assert torch.equal(parts[0, :, :37] + parts[1, :, :37] + parts[2, :, :37], x)     # three bf16 parts carry all 24 bits
+    assert float(parts[:, :, 37:].abs().max()) == 0.0       # K padding is zero
+    both, both_t = ops.gemm3x_split_both(x)
+    assert torch.equal(both, s) and torch.equal(both_t, ops.gemm3x_split(x, True))
 
 
 @pytest.mark.parametrize("rows,fan_in,fan_out", [(4 * 400, 512, 512), (3 * 300, 514, 512), (2000, 512, 101)])

@@ -69,7 +69,7 @@ if args.graph:
     print(json.dumps({"config": f"batch {B}, tf32={args.tf32}, gru={'cudnn' if args.stock_gru else 'cluster'}", "ms_graph_replay_fused_loss": timeit(gr.replay), "loss": float(static_loss)}))
     sys.exit(0)
 res = {"config": f"DDSPDecoder hidden 512, 16 kHz, block 160, H=100, 4 s, batch {B}: full train step incl. control net and Adam, eager",
-       "tf32": args.tf32, "gru": "cudnn" if (args.stock_gru or args.stock_control_net) else "cluster", "control_net": "torch.nn (cuBLAS SIMT SGEMM, cuDNN)" if args.stock_control_net else "this repo (3xTF32 tcgen05 GEMM, fused LayerNorm+LeakyReLU, cluster GRU)", "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
+       "tf32": args.tf32, "gru": "cudnn" if (args.stock_gru or args.stock_control_net) else "cluster", "control_net": "torch.nn (cuBLAS SIMT SGEMM, cuDNN)" if args.stock_control_net else "this repo (split-bf16 tcgen05 GEMM, fused LayerNorm+LeakyReLU, cluster GRU)", "ms_fused_loss": timeit(lambda: step(True)), "ms_list_api_loss": timeit(lambda: step(False))}
 with torch.no_grad():
     res["ms_forward_only"] = timeit(lambda: model(batch))
 t0 = time.perf_counter(); n = torch.rand(B, T, bs) * 2 - 1; res["ms_cpu_noise_draw"] = (time.perf_counter() - t0) * 1e3

@@ -1,4 +1,4 @@
-"""Throughput of the 3xTF32 tcgen05 GEMM against torch's float32 matmul (SIMT SGEMM) and TF32 matmul on the
+"""Throughput of the split-bf16 tcgen05 GEMM against torch's float32 matmul (SIMT SGEMM) and TF32 matmul on the
 control net's shapes (rows = batch 64 x 400 frames)."""
 import json, os, sys
 import torch
