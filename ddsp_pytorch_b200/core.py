@@ -136,7 +136,8 @@ class Linear(nn.Linear):
                 x2 = input.reshape(-1, self.in_features).contiguous()
                 y = torch.ops.ddsp_b200.gemm3x_mm(torch.ops.ddsp_b200.gemm3x_split(x2, False),
                                                   torch.ops.ddsp_b200.gemm3x_split(self.weight, False),
-                                                  self.in_features, self.bias)
+                                                  x2.shape[0], self.out_features, self.in_features, self.bias,
+                                                  False, False)
                 return y.view(input.shape[:-1] + [self.out_features])
             return F.linear(input, self.weight, self.bias)
         if fast:

@@ -69,6 +69,17 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
     return d;
 }
+// MN-major operand tile (the matrix is stored K rows x MN columns), 128-byte swizzle: one 128 B row = 64
+// consecutive MN elements of one k; 8 consecutive k = 1024 B (SBO); the next 64 MN elements kBK rows later (LBO)
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((kBK * 128) >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -101,6 +112,7 @@ struct GemmParams {
     const float *bias;         // added in the epilogue when splits == 1
     int M, N, ldc;
     int a_lo_row, b_lo_row;    // row distance between the three parts inside the operand's tensor map
+    int a_mn, b_mn;            // operand stored K rows x MN columns (MN-major) instead of MN rows x K columns
     int k_blocks, k_blocks_per_split, splits;
     int m_tiles, n_tiles;
 };
@@ -171,8 +183,19 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                     const int k = (kb0 + i) * kBK;
 #pragma unroll
                     for (int part = 0; part < 3; ++part) {
-                        tma_load_2d(st + part * kTileBytes, &map_a, fb, k, part * p.a_lo_row + m0);
-                        tma_load_2d(st + (3 + part) * kTileBytes, &map_b, fb, k, part * p.b_lo_row + n0);
+                        const uint32_t ta = st + part * kTileBytes, tb = st + (3 + part) * kTileBytes;
+                        if (!p.a_mn) {
+                            tma_load_2d(ta, &map_a, fb, k, part * p.a_lo_row + m0);
+                        } else {                                   // two boxes of 64 MN x 64 k
+                            tma_load_2d(ta, &map_a, fb, m0, part * p.a_lo_row + k);
+                            tma_load_2d(ta + kTileBytes / 2, &map_a, fb, m0 + 64, part * p.a_lo_row + k);
+                        }
+                        if (!p.b_mn) {
+                            tma_load_2d(tb, &map_b, fb, k, part * p.b_lo_row + n0);
+                        } else {
+                            tma_load_2d(tb, &map_b, fb, n0, part * p.b_lo_row + k);
+                            tma_load_2d(tb + kTileBytes / 2, &map_b, fb, n0 + 64, part * p.b_lo_row + k);
+                        }
                     }
                 }
             }
@@ -181,7 +204,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         // ===== MMA issuer =====
         if (lane == 0) {
             // instruction descriptor: D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
+                                   ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
             int it = 0, chunk = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 int z, m0, n0, kb0, nkb;
@@ -199,12 +223,13 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         const uint32_t st = base + s * kStageBytes;
 #pragma unroll
                         for (int k = 0; k < kBK / 16; ++k) {
-                            const uint32_t off = k * 32;                           // 16 bf16 along K inside the 128 B row
+                            // 16 values of K further: 32 B inside the row (K-major) / 16 rows of 128 B (MN-major)
                             uint64_t a[3], b[3];
 #pragma unroll
                             for (int part = 0; part < 3; ++part) {
-                                a[part] = umma_desc_k_sw128(st + part * kTileBytes + off);
-                                b[part] = umma_desc_k_sw128(st + (3 + part) * kTileBytes + off);
+                                const uint32_t ta = st + part * kTileBytes, tb = st + (3 + part) * kTileBytes;
+                                a[part] = p.a_mn ? umma_desc_mn_sw128(ta + k * 2048) : umma_desc_k_sw128(ta + k * 32);
+                                b[part] = p.b_mn ? umma_desc_mn_sw128(tb + k * 2048) : umma_desc_k_sw128(tb + k * 32);
                             }
                             const uint32_t acc = (i != i0 || k != 0) ? 1u : 0u;
                             umma_bf16(d_main, a[0], b[0], idesc, acc);
@@ -314,9 +339,10 @@ __device__ __forceinline__ void store_parts(__nv_bfloat16 *out, size_t idx, size
 
 __global__ void split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv_bfloat16 *__restrict__ out,
                                int64_t part_rows, int out_ld) {
-    const int r = blockIdx.x;
+    const int r = blockIdx.x;                                       // < part_rows; rows beyond the matrix are zeroed
     for (int c = (blockIdx.y * blockDim.x + threadIdx.x); c < out_ld; c += gridDim.y * blockDim.x)
-        store_parts(out, (size_t)r * out_ld + c, (size_t)part_rows * out_ld, c < cols ? __ldg(x + (size_t)r * ld + c) : 0.f);
+        store_parts(out, (size_t)r * out_ld + c, (size_t)part_rows * out_ld,
+                    (r < rows && c < cols) ? __ldg(x + (size_t)r * ld + c) : 0.f);
 }
 
 // operand rows = x's columns, operand columns (K) = x's rows
@@ -374,13 +400,13 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 
-// operand [total_rows][ld] bf16, box = 64 columns (128 B) x 128 rows, 128-byte swizzle
-int make_operand_map(CUtensorMap *map, const void *ptr, int64_t total_rows, int64_t ld) {
+// operand [total_rows][ld] bf16, box = 64 columns (128 B) x box_rows rows, 128-byte swizzle
+int make_operand_map(CUtensorMap *map, const void *ptr, int64_t total_rows, int64_t ld, int box_rows) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return DDSP_B200_EUNSUPPORTED;
     const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)total_rows};
     const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -413,7 +439,7 @@ extern "C" int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols
     if (!transpose) {
         DDSP_REQUIRE(part_rows >= rows);
         const int out_ld = (int)ddsp_b200_gemm3x_ld(cols);
-        dim3 grid((unsigned)rows, (out_ld + 255) / 256);
+        dim3 grid((unsigned)part_rows, (out_ld + 255) / 256);
         split3x_kernel<<<grid, 256, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld);
     } else {
         DDSP_REQUIRE(part_rows >= cols);
@@ -436,20 +462,27 @@ extern "C" int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t
     return ddsp_launch_status();
 }
 
-// C[M][N] (row pitch ldc) = A B^T + bias.  a, b: split operands (ddsp_b200_gemm3x_split) of logical shapes
-// M x K and N x K whose three parts are a_part_rows / b_part_rows rows apart.  workspace: splits * M * N floats
-// or NULL.
-extern "C" int ddsp_b200_gemm3x(const void *a, int64_t a_lo_row, const void *b, int64_t b_lo_row, const float *bias,
-                                float *c, int64_t ldc, int M, int N, int K, float *workspace, void *stream) {
-    DDSP_REQUIRE(a && b && c && M > 0 && N > 0 && K > 0 && ldc >= N && a_lo_row >= M && b_lo_row >= N);
-    const int64_t ld = ddsp_b200_gemm3x_ld(K);
-    const int kblocks = (int)(ld / kBK);
+// C[M][N] (row pitch ldc) = A B^T + bias, A logically M x K, B logically N x K.  Each operand is a split
+// matrix (ddsp_b200_gemm3x_split, parts x_part_rows rows apart, row pitch x_ld elements) stored either
+//   K-major  (x_mn = 0): rows = M (or N), columns = K, x_ld = gemm3x_ld(K), or
+//   MN-major (x_mn = 1): rows = K, columns = M (or N), x_ld = gemm3x_ld(M or N); x_part_rows must then be a
+//   multiple of 64 with the rows K..x_part_rows zero (gemm3x_split does that when given such a part_rows),
+// so that a matrix split once serves as operand of y = x W^T, dx = dy W and dW = dy^T x without transposes.
+// workspace: splits * M * N floats or NULL.
+extern "C" int ddsp_b200_gemm3x(const void *a, int64_t a_lo_row, int64_t a_ld, int a_mn, const void *b, int64_t b_lo_row,
+                                int64_t b_ld, int b_mn, const float *bias, float *c, int64_t ldc, int M, int N, int K,
+                                float *workspace, void *stream) {
+    DDSP_REQUIRE(a && b && c && M > 0 && N > 0 && K > 0 && ldc >= N);
+    DDSP_REQUIRE(a_mn ? (a_lo_row >= K && a_lo_row % 64 == 0 && a_ld >= M) : (a_lo_row >= M && a_ld >= K));
+    DDSP_REQUIRE(b_mn ? (b_lo_row >= K && b_lo_row % 64 == 0 && b_ld >= N) : (b_lo_row >= N && b_ld >= K));
+    DDSP_REQUIRE(a_ld % 8 == 0 && b_ld % 8 == 0);
+    const int kblocks = (K + kBK - 1) / kBK;
     int splits = ddsp_b200_gemm3x_splits(M, N, K);
     if (splits > 1 && !workspace) splits = 1;
     alignas(64) CUtensorMap map_a, map_b;
-    int s = make_operand_map(&map_a, a, 2 * a_lo_row + M, ld);
+    int s = make_operand_map(&map_a, a, 3 * a_lo_row, a_ld, a_mn ? 64 : kBM);
     if (s) return s;
-    s = make_operand_map(&map_b, b, 2 * b_lo_row + N, ld);
+    s = make_operand_map(&map_b, b, 3 * b_lo_row, b_ld, b_mn ? 64 : kBN);
     if (s) return s;
     GemmParams p;
     p.c = splits > 1 ? workspace : c;
@@ -459,6 +492,8 @@ extern "C" int ddsp_b200_gemm3x(const void *a, int64_t a_lo_row, const void *b, 
     p.ldc = splits > 1 ? N : (int)ldc;
     p.a_lo_row = (int)a_lo_row;
     p.b_lo_row = (int)b_lo_row;
+    p.a_mn = a_mn;
+    p.b_mn = b_mn;
     p.k_blocks = kblocks;
     p.k_blocks_per_split = (kblocks + splits - 1) / splits;
     p.splits = splits;

@@ -626,16 +626,19 @@ std::tuple<Tensor, Tensor, Tensor> gru_bwd(const Tensor &dy_, const c10::optiona
 }
 
 // ---------------------------------------------------------------------------------------- f3 GEMM
-// x (rows, cols) contiguous -> split operand (3 * R, ld) bf16: part p in rows [p R, (p + 1) R)
+// x (rows, cols) contiguous -> split operand (3 * Rp, ld) bf16: part p in rows [p Rp, p Rp + R).
+// transpose = false: R = rows, Rp = R rounded up to 64 with zero rows (usable K-major and MN-major);
+// transpose = true: operand of x^T, R = cols, Rp = R (K-major use only).
 Tensor gemm3x_split(const Tensor &x_, bool transpose) {
     Tensor x = prep(x_, "x");
     TORCH_CHECK(x.dim() == 2, "gemm3x_split: x must be 2-D");
     const int64_t rows = x.size(0), cols = x.size(1);
     const int64_t R = transpose ? cols : rows, K = transpose ? rows : cols;
+    const int64_t Rp = transpose ? R : (R + 63) / 64 * 64;
     c10::cuda::CUDAGuard guard(x.device());
-    Tensor out = at::empty({3 * R, ddsp_b200_gemm3x_ld(K)}, x.options().dtype(at::kBFloat16));
+    Tensor out = at::empty({3 * Rp, ddsp_b200_gemm3x_ld(K)}, x.options().dtype(at::kBFloat16));
     if (rows == 0 || cols == 0) return out.zero_();
-    check(ddsp_b200_gemm3x_split(fp(x), rows, cols, cols, transpose ? 1 : 0, out.data_ptr(), R, cur_stream()), "gemm3x_split");
+    check(ddsp_b200_gemm3x_split(fp(x), rows, cols, cols, transpose ? 1 : 0, out.data_ptr(), Rp, cur_stream()), "gemm3x_split");
     return out;
 }
 
@@ -653,14 +656,20 @@ std::tuple<Tensor, Tensor> gemm3x_split_both(const Tensor &x_) {
     return {out, out_t};
 }
 
-// a (3M, ld), b (3N, ld) split operands -> a b^T + bias  (M, N) float32
-Tensor gemm3x_mm(const Tensor &a, const Tensor &b, int64_t K, const c10::optional<Tensor> &bias_) {
+// a, b split operands (gemm3x_split) -> A B^T + bias (M, N) float32 with A logically M x K, B logically N x K;
+// x_mn = false: the operand tensor is (rows = M or N) x K; true: K x (M or N) as split from a non-transposed matrix
+Tensor gemm3x_mm(const Tensor &a, const Tensor &b, int64_t M, int64_t N, int64_t K, const c10::optional<Tensor> &bias_,
+                 bool a_mn, bool b_mn) {
     Tensor bias = opt_prep(bias_, "bias");
     TORCH_CHECK(a.is_cuda() && b.is_cuda() && a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 &&
-                    a.is_contiguous() && b.is_contiguous() && a.dim() == 2 && b.dim() == 2 && a.size(1) == b.size(1) &&
-                    a.size(1) == ddsp_b200_gemm3x_ld(K) && a.size(0) % 3 == 0 && b.size(0) % 3 == 0,
-                "gemm3x_mm: operands must be gemm3x_split outputs of the same K");
-    const int64_t M = a.size(0) / 3, N = b.size(0) / 3;
+                    a.is_contiguous() && b.is_contiguous() && a.dim() == 2 && b.dim() == 2 && a.size(0) % 3 == 0 &&
+                    b.size(0) % 3 == 0,
+                "gemm3x_mm: operands must be gemm3x_split outputs");
+    const int64_t a_pr = a.size(0) / 3, b_pr = b.size(0) / 3;
+    TORCH_CHECK(a_mn ? (a_pr >= K && a_pr % 64 == 0 && a.size(1) >= M) : (a_pr >= M && a.size(1) >= K),
+                "gemm3x_mm: operand a does not hold an ", M, " x ", K, " matrix in the stated orientation");
+    TORCH_CHECK(b_mn ? (b_pr >= K && b_pr % 64 == 0 && b.size(1) >= N) : (b_pr >= N && b.size(1) >= K),
+                "gemm3x_mm: operand b does not hold an ", N, " x ", K, " matrix in the stated orientation");
     TORCH_CHECK(!bias.defined() || bias.numel() == N, "gemm3x_mm: bias must have N entries");
     c10::cuda::CUDAGuard guard(a.device());
     auto fopt = a.options().dtype(at::kFloat);
@@ -669,8 +678,8 @@ Tensor gemm3x_mm(const Tensor &a, const Tensor &b, int64_t K, const c10::optiona
     if (K == 0) return bias.defined() ? c.copy_(bias.expand({M, N})) : c.zero_();
     const int splits = ddsp_b200_gemm3x_splits((int)M, (int)N, (int)K);
     Tensor ws = splits > 1 ? at::empty({splits, M, N}, fopt) : Tensor();
-    check(ddsp_b200_gemm3x(a.data_ptr(), M, b.data_ptr(), N, opt_fp(bias), fpm(c), N, (int)M, (int)N, (int)K,
-                           splits > 1 ? fpm(ws) : nullptr, cur_stream()),
+    check(ddsp_b200_gemm3x(a.data_ptr(), a_pr, a.size(1), a_mn ? 1 : 0, b.data_ptr(), b_pr, b.size(1), b_mn ? 1 : 0,
+                           opt_fp(bias), fpm(c), N, (int)M, (int)N, (int)K, splits > 1 ? fpm(ws) : nullptr, cur_stream()),
           "gemm3x_mm");
     return c;
 }
@@ -722,7 +731,7 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("ln_lrelu_bwd(Tensor dy, Tensor x, Tensor weight, Tensor bias, Tensor stats, float slope) -> (Tensor, Tensor, Tensor)");
     m.def("gemm3x_split(Tensor x, bool transpose) -> Tensor");
     m.def("gemm3x_split_both(Tensor x) -> (Tensor, Tensor)");
-    m.def("gemm3x_mm(Tensor a, Tensor b, int K, Tensor? bias) -> Tensor");
+    m.def("gemm3x_mm(Tensor a, Tensor b, int M, int N, int K, Tensor? bias, bool a_mn, bool b_mn) -> Tensor");
     m.def("gru_fwd(Tensor gi, Tensor weight_hh, Tensor bias_hh, Tensor? h0, bool save_gates) -> (Tensor, Tensor)");
     m.def("gru_bwd(Tensor dy, Tensor? dhT, Tensor weight_hh, Tensor y, Tensor? h0, Tensor gates) -> (Tensor, Tensor, Tensor)");
     m.def("scale_function_fwd(Tensor x) -> Tensor");

@@ -219,48 +219,37 @@ class ReverbImpulse(torch.autograd.Function):
         return dn.view_as(noise), dd.view_as(decay), dw.view_as(wet), None
 
 
-def _mm3x(a: torch.Tensor, a_t: bool, b: torch.Tensor, b_t: bool, bias=None) -> torch.Tensor:
-    """(a or a^T) @ (b or b^T)^T + bias through the split-bf16 tensor-core GEMM; a, b 2-D contiguous."""
-    k = a.shape[0] if a_t else a.shape[1]
-    return _ops.gemm3x_mm(_ops.gemm3x_split(a, a_t), _ops.gemm3x_split(b, b_t), k, bias)
-
-
 class Linear3x(torch.autograd.Function):
     """``F.linear`` (core.py:122-129's nn.Linear layers, the GRU input projection, decoder.py:86-87's
-    projections) on the tcgen05 tensor cores with float32-class accuracy (csrc/gemm3x.cu); all three GEMMs
-    of a layer (y = x W^T + b, dx = dy W, dW = dy^T x) take the same kernel."""
+    projections) on the tcgen05 tensor cores with float32-class accuracy (csrc/gemm3x.cu).  All three GEMMs of a
+    layer take the same kernel, and every matrix is split into its bf16 parts exactly once: x and W in the
+    forward (kept for the backward), dy in the backward; y = x W^T reads them K-major, dx = dy W reads W
+    MN-major, dW = dy^T x reads dy and x MN-major -- no transposed copies."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        w = weight.contiguous()
-        k = x2.shape[1]
-        if ctx.needs_input_grad[1]:          # the operand dW will need (x^T) comes from the same read of x
-            xs, xts = _ops.gemm3x_split_both(x2)
-        else:
-            xs, xts = _ops.gemm3x_split(x2, False), None
-        ctx.save_for_backward(xts, w)
+        m, k = x2.shape
+        n = weight.shape[0]
+        xs = _ops.gemm3x_split(x2, False)
+        ws = _ops.gemm3x_split(weight.contiguous(), False)
+        ctx.save_for_backward(xs if ctx.needs_input_grad[1] else None, ws if ctx.needs_input_grad[0] else None)
         ctx.has_bias = bias is not None
-        ctx.rows = x2.shape[0]
-        return _ops.gemm3x_mm(xs, _ops.gemm3x_split(w, False), k, bias).view(*x.shape[:-1], w.shape[0])
+        ctx.mnk = (m, n, k)
+        return _ops.gemm3x_mm(xs, ws, m, n, k, bias, False, False).view(*x.shape[:-1], n)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        xts, w = ctx.saved_tensors
-        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
-        n = dy2.shape[1]
-        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if need_x and need_w:
-            dys, dyts = _ops.gemm3x_split_both(dy2)
-        else:
-            dys = _ops.gemm3x_split(dy2, False) if need_x else None
-            dyts = _ops.gemm3x_split(dy2, True) if need_w else None
+        xs, ws = ctx.saved_tensors
+        m, n, k = ctx.mnk
+        dy2 = dy.reshape(m, n).contiguous()
+        dys = _ops.gemm3x_split(dy2, False)
         dx = dw = db = None
-        if need_x:
-            dx = _ops.gemm3x_mm(dys, _ops.gemm3x_split(w, True), n, None).view(*dy.shape[:-1], w.shape[1])
-        if need_w:
-            dw = _ops.gemm3x_mm(dyts, xts, ctx.rows, None)
+        if ctx.needs_input_grad[0]:          # (m, n) x (n, k): dy K-major, W (n rows = contraction) MN-major
+            dx = _ops.gemm3x_mm(dys, ws, m, k, n, None, False, True).view(*dy.shape[:-1], k)
+        if ctx.needs_input_grad[1]:          # (n, m) x (m, k): both stored with the contraction (rows) outermost
+            dw = _ops.gemm3x_mm(dys, xs, n, k, m, None, True, True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy2.sum(0)
         return dx, dw, db
@@ -313,7 +302,8 @@ class GRURecurrence(torch.autograd.Function):
                 h_prev[:, 0].zero_()
             else:
                 h_prev[:, 0] = h0.reshape(B, H)
-            d_w = _mm3x(dgh.reshape(B * T, 3 * H), True, h_prev.reshape(B * T, H), True)
+            d_w = _ops.gemm3x_mm(_ops.gemm3x_split(dgh.reshape(B * T, 3 * H), False),
+                                 _ops.gemm3x_split(h_prev.reshape(B * T, H), False), 3 * H, H, B * T, None, True, True)
         if ctx.needs_input_grad[2]:
             d_b = dgh.sum((0, 1))
         d_h0 = None

@@ -232,16 +232,21 @@ int ddsp_b200_gru_bwd(const float *dy, const float *dhT, const float *w_hh, cons
  * out[3 * part_rows][gemm3x_ld(K)] bf16: part p in rows [p * part_rows, p * part_rows + R), K padding zeroed;
  * transpose = 0: operand = x (R = rows, K = cols); 1: operand = x^T (R = cols, K = rows).
  * gemm3x_split_both: the operands of x and of x^T from one read of x.
- * gemm3x: C[M][N] (row pitch ldc) = A B^T + bias (bias may be NULL), A, B split operands of M x K and
- * N x K.  gemm3x_splits: K splits used for a shape; when > 1 pass workspace of splits * M * N floats.   */
+ * gemm3x: C[M][N] (row pitch ldc) = A B^T + bias (bias may be NULL), A logically M x K, B logically N x K.
+ * Each operand is a split matrix (parts x_part_rows rows apart, row pitch x_ld elements) stored K-major
+ * (x_mn = 0: rows = M or N, columns = K) or MN-major (x_mn = 1: rows = K, columns = M or N; x_part_rows a
+ * multiple of 64 with rows K..x_part_rows zero, which gemm3x_split writes when given such a part_rows), so a
+ * matrix split once serves y = x W^T, dx = dy W and dW = dy^T x without transposed copies.
+ * gemm3x_splits: K splits used for a shape; when > 1 pass workspace of splits * M * N floats.             */
 int64_t ddsp_b200_gemm3x_ld(int64_t k);
 int ddsp_b200_gemm3x_splits(int M, int N, int K);
 int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, void *out,
                            int64_t part_rows, void *stream);
 int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t cols, int64_t ld, void *out,
                                 int64_t part_rows, void *out_t, int64_t part_rows_t, void *stream);
-int ddsp_b200_gemm3x(const void *a, int64_t a_part_rows, const void *b, int64_t b_part_rows, const float *bias,
-                     float *c, int64_t ldc, int M, int N, int K, float *workspace, void *stream);
+int ddsp_b200_gemm3x(const void *a, int64_t a_part_rows, int64_t a_ld, int a_mn, const void *b,
+                     int64_t b_part_rows, int64_t b_ld, int b_mn, const float *bias, float *c, int64_t ldc, int M,
+                     int N, int K, float *workspace, void *stream);
 
 /* ---- f3 (next row)  LayerNorm + LeakyReLU of the MLP blocks in one pass (ddsp/core.py:122-129) ------
  * y = leaky_relu(layer_norm(x; gamma, beta, eps), slope) over rows of N = 128, 256, 384 or 512 floats;

@@ -26,7 +26,7 @@ def test_gemm3x_matches_float64(M, N, K, bias):
     b = (torch.randn(N, K, generator=g) * 0.05).cuda()
     bv = torch.randn(N, generator=g).cuda() if bias else None
     ref = a.double() @ b.double().t() + (bv.double() if bias else 0)
-    got = ops.gemm3x_mm(ops.gemm3x_split(a, False), ops.gemm3x_split(b, False), K, bv)
+    got = ops.gemm3x_mm(ops.gemm3x_split(a, False), ops.gemm3x_split(b, False), M, N, K, bv, False, False)
     assert got.shape == (M, N)
     scale = float(ref.abs().max())
     err = float((got.double() - ref).abs().max()) / scale
@@ -41,20 +41,42 @@ def test_transposed_split_gives_the_transposed_product():
     dy = torch.randn(777, 130, generator=g).cuda()          # (M, N)
     x = torch.randn(777, 90, generator=g).cuda()            # (M, K)
     ref = dy.double().t() @ x.double()                      # dW = dy^T x  (N, K)
-    got = ops.gemm3x_mm(ops.gemm3x_split(dy, True), ops.gemm3x_split(x, True), 777, None)
+    got = ops.gemm3x_mm(ops.gemm3x_split(dy, True), ops.gemm3x_split(x, True), 130, 90, 777, None, False, False)
     assert float((got.double() - ref).abs().max()) / float(ref.abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("rows,n,k", [(777, 130, 90), (64, 64, 64), (3000, 512, 514), (130, 1536, 1024)])
+def test_mn_major_operands_need_no_transposed_copies(rows, n, k):
+    """One split per matrix serves all three GEMMs of a layer: dx = dy W reads W MN-major, dW = dy^T x reads dy
+    and x MN-major (the contraction index is the row index of the stored matrix)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows + n)
+    dy = torch.randn(rows, n, generator=g).cuda()
+    x = torch.randn(rows, k, generator=g).cuda()
+    w = (torch.randn(n, k, generator=g) * 0.05).cuda()
+    dys, xs, ws = ops.gemm3x_split(dy, False), ops.gemm3x_split(x, False), ops.gemm3x_split(w, False)
+    dw = ops.gemm3x_mm(dys, xs, n, k, rows, None, True, True)
+    ref = dy.double().t() @ x.double()
+    assert float((dw.double() - ref).abs().max()) / float(ref.abs().max()) < 2e-6
+    dx = ops.gemm3x_mm(dys, ws, rows, k, n, None, False, True)
+    ref = dy.double() @ w.double()
+    assert float((dx.double() - ref).abs().max()) / float(ref.abs().max()) < 2e-6
+    y = ops.gemm3x_mm(xs, ws, rows, n, k, None, False, False)
+    ref = x.double() @ w.double().t()
+    assert float((y.double() - ref).abs().max()) / float(ref.abs().max()) < 2e-6
 
 
 def test_split_parts_are_exact():
     ops = _ops()
     x = torch.randn(50, 37, device="cuda") * 1e3
     s = ops.gemm3x_split(x, False)
-    assert s.dtype == torch.bfloat16 and s.shape == (150, 64)
-    parts = s.view(3, 50, 64).float()
-    assert torch.equal(parts[0, :, :37] + parts[1, :, :37] + parts[2, :, :37], x)     # three bf16 parts carry all 24 bits
-    assert float(parts[:, :, 37:].abs().max()) == 0.0       # K padding is zero
+    assert s.dtype == torch.bfloat16 and s.shape == (192, 64)          # 3 parts x 64 rows (50 padded with zero rows)
+    parts = s.view(3, 64, 64).float()
+    assert torch.equal(parts[0, :50, :37] + parts[1, :50, :37] + parts[2, :50, :37], x)   # 3 x 8 mantissa bits: exact
+    assert float(parts[:, :, 37:].abs().max()) == 0.0 and float(parts[:, 50:].abs().max()) == 0.0     # padding is zero
     both, both_t = ops.gemm3x_split_both(x)
-    assert torch.equal(both, s) and torch.equal(both_t, ops.gemm3x_split(x, True))
+    st = ops.gemm3x_split(x, True)
+    assert torch.equal(both_t, st) and torch.equal(both.view(3, 50, 64), s.view(3, 64, 64)[:, :50])
 
 
 @pytest.mark.parametrize("rows,fan_in,fan_out", [(4 * 400, 512, 512), (3 * 300, 514, 512), (2000, 512, 101)])

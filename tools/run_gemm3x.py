@@ -21,7 +21,7 @@ for M, N, K in [(25600, 512, 512), (25600, 1536, 1024), (512, 512, 25600), (1536
     row = {"M": M, "N": N, "K": K, "gflop": 2e-9 * M * N * K}
     row["split_a_ms"] = timeit(lambda: ops.gemm3x_split(a, False))
     row["split_a_T_ms"] = timeit(lambda: ops.gemm3x_split(a, True))
-    row["gemm3x_ms"] = timeit(lambda: ops.gemm3x_mm(a_s, b_s, K, None))
+    row["gemm3x_ms"] = timeit(lambda: ops.gemm3x_mm(a_s, b_s, M, N, K, None, False, False))
     torch.backends.cuda.matmul.allow_tf32 = False
     row["torch_fp32_ms"] = timeit(lambda: a @ b.t())
     torch.backends.cuda.matmul.allow_tf32 = True
@@ -30,6 +30,6 @@ for M, N, K in [(25600, 512, 512), (25600, 1536, 1024), (512, 512, 25600), (1536
     row["gemm3x_tflops_fp32_equiv"] = row["gflop"] / row["gemm3x_ms"]
     row["torch_fp32_tflops"] = row["gflop"] / row["torch_fp32_ms"]
     ref = a.double() @ b.double().t()
-    row["err_gemm3x"] = float((ops.gemm3x_mm(a_s, b_s, K, None).double() - ref).abs().max() / ref.abs().max())
+    row["err_gemm3x"] = float((ops.gemm3x_mm(a_s, b_s, M, N, K, None, False, False).double() - ref).abs().max() / ref.abs().max())
     row["err_torch_fp32"] = float(((a @ b.t()).double() - ref).abs().max() / ref.abs().max())
     print(json.dumps({k: (round(v, 5) if isinstance(v, float) and v > 1e-3 else v) for k, v in row.items()}), flush=True)
