@@ -337,12 +337,70 @@ __device__ __forceinline__ void store_parts(__nv_bfloat16 *out, size_t idx, size
     out[idx + 2 * part_stride] = b2;
 }
 
-__global__ void split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv_bfloat16 *__restrict__ out,
-                               int64_t part_rows, int out_ld) {
-    const int r = blockIdx.x;                                       // < part_rows; rows beyond the matrix are zeroed
-    for (int c = (blockIdx.y * blockDim.x + threadIdx.x); c < out_ld; c += gridDim.y * blockDim.x)
-        store_parts(out, (size_t)r * out_ld + c, (size_t)part_rows * out_ld,
-                    (r < rows && c < cols) ? __ldg(x + (size_t)r * ld + c) : 0.f);
+// Non-transposed split, vectorised: a block owns 64 consecutive operand rows; thread = (column group of 8, row
+// lane); 2 x 16 B loads and 3 x 16 B stores per item.  COLSUM additionally produces the column sums of x (the
+// bias gradient of a Linear layer whose dy is being split) as per-block partials, reduced by a second launch in
+// a fixed order (deterministic).
+constexpr int kSplitRows = 64;
+
+template <bool COLSUM>
+__global__ void __launch_bounds__(256)
+split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv_bfloat16 *__restrict__ out,
+               int64_t part_rows, int out_ld, float *__restrict__ partial, int cgroups, int lanes) {
+    extern __shared__ float red[];                                  // [lanes][cgroups * 8] when COLSUM
+    const int cl = threadIdx.x % cgroups, rl = threadIdx.x / cgroups;
+    const int c0 = (blockIdx.y * cgroups + cl) * 8;                 // grid.y > 1 only beyond 2048 columns
+    const bool live = c0 < out_ld;
+    const int rbeg = blockIdx.x * kSplitRows;
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && c0 + 8 <= cols;
+    const size_t pstride = (size_t)part_rows * out_ld;
+    float sum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum[j] = 0.f;
+    for (int r = rbeg + rl; live && r < rbeg + kSplitRows && r < part_rows; r += lanes) {
+        float v[8];
+        if (r < rows && vec) {
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(x + (size_t)r * ld + c0));
+            const float4 hi = __ldg(reinterpret_cast<const float4 *>(x + (size_t)r * ld + c0 + 4));
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (r < rows && c0 + j < cols) ? __ldg(x + (size_t)r * ld + c0 + j) : 0.f;
+        }
+        __align__(16) __nv_bfloat16 b0[8], b1[8], b2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            split_bf16x3(v[j], b0[j], b1[j], b2[j]);
+            if (COLSUM) sum[j] += v[j];
+        }
+        const size_t o = (size_t)r * out_ld + c0;
+        *reinterpret_cast<uint4 *>(out + o) = *reinterpret_cast<const uint4 *>(b0);
+        *reinterpret_cast<uint4 *>(out + o + pstride) = *reinterpret_cast<const uint4 *>(b1);
+        *reinterpret_cast<uint4 *>(out + o + 2 * pstride) = *reinterpret_cast<const uint4 *>(b2);
+    }
+    if (COLSUM) {
+        const int w = cgroups * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[rl * w + cl * 8 + j] = sum[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < w; c += blockDim.x) {
+            const int cglob = blockIdx.y * w + c;
+            if (cglob < out_ld) {
+                float t = 0.f;
+                for (int l = 0; l < lanes; ++l) t += red[l * w + c];
+                partial[(size_t)blockIdx.x * out_ld + cglob] = t;
+            }
+        }
+    }
+}
+
+__global__ void colsum_finalize_kernel(const float *__restrict__ partial, float *__restrict__ colsum, int cols, int out_ld,
+                                       int blocks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    float t = 0.f;
+    for (int b = 0; b < blocks; ++b) t += __ldg(partial + (size_t)b * out_ld + c);
+    colsum[c] = t;
 }
 
 // operand rows = x's columns, operand columns (K) = x's rows
@@ -429,6 +487,38 @@ extern "C" int ddsp_b200_gemm3x_splits(int M, int N, int K) {
     return s < 1 ? 1 : s;
 }
 
+static int launch_split(const float *x, int64_t rows, int64_t cols, int64_t ld, __nv_bfloat16 *o, int64_t part_rows,
+                        float *colsum, float *partial, cudaStream_t st) {
+    const int out_ld = (int)ddsp_b200_gemm3x_ld(cols);
+    const int cgroups = out_ld / 8 < 256 ? out_ld / 8 : 256;
+    const int lanes = 256 / cgroups;
+    dim3 blocks((unsigned)((part_rows + kSplitRows - 1) / kSplitRows), (unsigned)((out_ld / 8 + cgroups - 1) / cgroups));
+    if (colsum) {
+        split3x_kernel<true><<<blocks, cgroups * lanes, (size_t)lanes * cgroups * 8 * 4, st>>>(
+            x, (int)rows, (int)cols, ld, o, part_rows, out_ld, partial, cgroups, lanes);
+        int s = ddsp_launch_status();
+        if (s) return s;
+        colsum_finalize_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(partial, colsum, (int)cols, out_ld, (int)blocks.x);
+    } else {
+        split3x_kernel<false><<<blocks, cgroups * lanes, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld, nullptr,
+                                                                 cgroups, lanes);
+    }
+    return ddsp_launch_status();
+}
+
+// Scratch floats ddsp_b200_gemm3x_split_colsum needs for a part_rows x cols operand
+extern "C" int64_t ddsp_b200_gemm3x_colsum_scratch(int64_t part_rows, int64_t cols) {
+    return (part_rows + kSplitRows - 1) / kSplitRows * ddsp_b200_gemm3x_ld(cols);
+}
+
+// gemm3x_split (non-transposed) that also returns colsum[c] = sum over rows of x[r][c] (a Linear layer's bias
+// gradient when x = dy); partial: ddsp_b200_gemm3x_colsum_scratch(part_rows, cols) floats
+extern "C" int ddsp_b200_gemm3x_split_colsum(const float *x, int64_t rows, int64_t cols, int64_t ld, void *out,
+                                             int64_t part_rows, float *colsum, float *partial, void *stream) {
+    DDSP_REQUIRE(x && out && colsum && partial && rows > 0 && cols > 0 && ld >= cols && part_rows >= rows);
+    return launch_split(x, rows, cols, ld, static_cast<__nv_bfloat16 *>(out), part_rows, colsum, partial, (cudaStream_t)stream);
+}
+
 // out: [3 * part_rows][out_ld] bf16 (uint16_t bits) with out_ld = ddsp_b200_gemm3x_ld(K), part_rows >= operand
 // rows.  transpose = 0: operand (rows x cols) = x; 1: operand (cols x rows) = x^T.  x has row pitch ld.
 extern "C" int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, void *out,
@@ -438,9 +528,7 @@ extern "C" int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols
     __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(out);
     if (!transpose) {
         DDSP_REQUIRE(part_rows >= rows);
-        const int out_ld = (int)ddsp_b200_gemm3x_ld(cols);
-        dim3 grid((unsigned)part_rows, (out_ld + 255) / 256);
-        split3x_kernel<<<grid, 256, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld);
+        return launch_split(x, rows, cols, ld, o, part_rows, nullptr, nullptr, st);
     } else {
         DDSP_REQUIRE(part_rows >= cols);
         const int out_ld = (int)ddsp_b200_gemm3x_ld(rows);

@@ -642,6 +642,21 @@ Tensor gemm3x_split(const Tensor &x_, bool transpose) {
     return out;
 }
 
+// non-transposed gemm3x_split that also returns the column sums of x: (operand, colsum (cols))
+std::tuple<Tensor, Tensor> gemm3x_split_colsum(const Tensor &x_) {
+    Tensor x = prep(x_, "x");
+    TORCH_CHECK(x.dim() == 2, "gemm3x_split_colsum: x must be 2-D");
+    const int64_t rows = x.size(0), cols = x.size(1), Rp = (rows + 63) / 64 * 64;
+    c10::cuda::CUDAGuard guard(x.device());
+    Tensor out = at::empty({3 * Rp, ddsp_b200_gemm3x_ld(cols)}, x.options().dtype(at::kBFloat16));
+    Tensor colsum = at::empty({cols}, x.options());
+    if (rows == 0 || cols == 0) return {out.zero_(), colsum.zero_()};
+    Tensor partial = at::empty({ddsp_b200_gemm3x_colsum_scratch(Rp, cols)}, x.options());
+    check(ddsp_b200_gemm3x_split_colsum(fp(x), rows, cols, cols, out.data_ptr(), Rp, fpm(colsum), fpm(partial), cur_stream()),
+          "gemm3x_split_colsum");
+    return {out, colsum};
+}
+
 // x (rows, cols) -> (split operand of x, split operand of x^T) from one pass over x
 std::tuple<Tensor, Tensor> gemm3x_split_both(const Tensor &x_) {
     Tensor x = prep(x_, "x");
@@ -731,6 +746,7 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("ln_lrelu_bwd(Tensor dy, Tensor x, Tensor weight, Tensor bias, Tensor stats, float slope) -> (Tensor, Tensor, Tensor)");
     m.def("gemm3x_split(Tensor x, bool transpose) -> Tensor");
     m.def("gemm3x_split_both(Tensor x) -> (Tensor, Tensor)");
+    m.def("gemm3x_split_colsum(Tensor x) -> (Tensor, Tensor)");
     m.def("gemm3x_mm(Tensor a, Tensor b, int M, int N, int K, Tensor? bias, bool a_mn, bool b_mn) -> Tensor");
     m.def("gru_fwd(Tensor gi, Tensor weight_hh, Tensor bias_hh, Tensor? h0, bool save_gates) -> (Tensor, Tensor)");
     m.def("gru_bwd(Tensor dy, Tensor? dhT, Tensor weight_hh, Tensor y, Tensor? h0, Tensor gates) -> (Tensor, Tensor, Tensor)");
@@ -761,6 +777,7 @@ TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
     m.impl("ln_lrelu_bwd", ln_lrelu_bwd);
     m.impl("gemm3x_split", gemm3x_split);
     m.impl("gemm3x_split_both", gemm3x_split_both);
+    m.impl("gemm3x_split_colsum", gemm3x_split_colsum);
     m.impl("gemm3x_mm", gemm3x_mm);
     m.impl("gru_fwd", gru_fwd);
     m.impl("gru_bwd", gru_bwd);

@@ -244,14 +244,15 @@ class Linear3x(torch.autograd.Function):
         xs, ws = ctx.saved_tensors
         m, n, k = ctx.mnk
         dy2 = dy.reshape(m, n).contiguous()
-        dys = _ops.gemm3x_split(dy2, False)
         dx = dw = db = None
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            dys, db = _ops.gemm3x_split_colsum(dy2)          # the bias gradient rides on the split of dy
+        else:
+            dys = _ops.gemm3x_split(dy2, False)
         if ctx.needs_input_grad[0]:          # (m, n) x (n, k): dy K-major, W (n rows = contraction) MN-major
             dx = _ops.gemm3x_mm(dys, ws, m, k, n, None, False, True).view(*dy.shape[:-1], k)
         if ctx.needs_input_grad[1]:          # (n, m) x (m, k): both stored with the contraction (rows) outermost
             dw = _ops.gemm3x_mm(dys, xs, n, k, m, None, True, True)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy2.sum(0)
         return dx, dw, db
 
 

@@ -231,7 +231,8 @@ int ddsp_b200_gru_bwd(const float *dy, const float *dhT, const float *w_hh, cons
  * gemm3x_ld(K): padded column count of a split operand.  gemm3x_split: x (rows x cols, row pitch ld) ->
  * out[3 * part_rows][gemm3x_ld(K)] bf16: part p in rows [p * part_rows, p * part_rows + R), K padding zeroed;
  * transpose = 0: operand = x (R = rows, K = cols); 1: operand = x^T (R = cols, K = rows).
- * gemm3x_split_both: the operands of x and of x^T from one read of x.
+ * gemm3x_split_both: the operands of x and of x^T from one read of x.  gemm3x_split_colsum: gemm3x_split
+ * (transpose = 0) that also returns the column sums of x (bias gradient when x = dy; deterministic).
  * gemm3x: C[M][N] (row pitch ldc) = A B^T + bias (bias may be NULL), A logically M x K, B logically N x K.
  * Each operand is a split matrix (parts x_part_rows rows apart, row pitch x_ld elements) stored K-major
  * (x_mn = 0: rows = M or N, columns = K) or MN-major (x_mn = 1: rows = K, columns = M or N; x_part_rows a
@@ -242,6 +243,9 @@ int64_t ddsp_b200_gemm3x_ld(int64_t k);
 int ddsp_b200_gemm3x_splits(int M, int N, int K);
 int ddsp_b200_gemm3x_split(const float *x, int64_t rows, int64_t cols, int64_t ld, int transpose, void *out,
                            int64_t part_rows, void *stream);
+int64_t ddsp_b200_gemm3x_colsum_scratch(int64_t part_rows, int64_t cols);
+int ddsp_b200_gemm3x_split_colsum(const float *x, int64_t rows, int64_t cols, int64_t ld, void *out,
+                                  int64_t part_rows, float *colsum, float *partial, void *stream);
 int ddsp_b200_gemm3x_split_both(const float *x, int64_t rows, int64_t cols, int64_t ld, void *out,
                                 int64_t part_rows, void *out_t, int64_t part_rows_t, void *stream);
 int ddsp_b200_gemm3x(const void *a, int64_t a_part_rows, int64_t a_ld, int a_mn, const void *b,

@@ -104,6 +104,17 @@ def test_linear_module_matches_float64_forward_and_backward(rows, fan_in, fan_ou
     assert rel(lin.bias.grad, b.grad) < 2e-6
 
 
+@pytest.mark.parametrize("rows,cols", [(1, 8), (100, 101), (25600, 512), (700, 1536), (130, 2500)])
+def test_split_with_column_sums(rows, cols):
+    ops = _ops()
+    x = torch.randn(rows, cols, device="cuda")
+    s, colsum = ops.gemm3x_split_colsum(x)
+    assert torch.equal(s, ops.gemm3x_split(x, False))
+    ref = x.double().sum(0)
+    assert float((colsum.double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+    assert torch.equal(colsum, ops.gemm3x_split_colsum(x)[1])        # fixed summation order
+
+
 def test_small_inputs_take_the_library_path():
     from ddsp_pytorch_b200 import core
     lin = core.Linear(512, 512).cuda()
