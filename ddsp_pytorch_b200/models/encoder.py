@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import core
 from .decoder import GRUDecoder, _SynthWiring
 
 
@@ -17,8 +18,8 @@ class MFCCEncoder(nn.Module):
         self.hidden_size = hidden_size
         self.z_dim = z_dim
         self.norm = nn.LayerNorm(n_mfccs)
-        self.gru = nn.GRU(n_mfccs, hidden_size, batch_first=True)
-        self.proj = nn.Linear(hidden_size, z_dim)
+        self.gru = core.ClusterGRU(n_mfccs, hidden_size, batch_first=True)     # nn.GRU's parameters and keys
+        self.proj = core.Linear(hidden_size, z_dim)
 
     def forward(self, mfccs: torch.Tensor):
         x, _ = self.gru(self.norm(mfccs))

@@ -103,3 +103,51 @@ def test_decoder_step_through_cluster_gru_matches_library_gru():
         model.decoder.gru = stock
         b = model({"pitch": pitch, "loudness": loud, "noise": noise})["signal"]
     assert float((a - b).abs().max()) < 1e-4
+
+
+def test_autoencoder_matches_stock_layers():
+    """encoder.py:10-103 (MFCC encoder GRU with fan-in 30, z projection, decoder GRU with fan-in 1536): the model
+    on this repo's control-net kernels against the same weights in stock torch.nn layers."""
+    from ddsp_pytorch_b200 import core
+    from ddsp_pytorch_b200.models.encoder import DDSPAutoencoder
+    torch.manual_seed(0)
+    kw = dict(hidden_size=512, n_harmonic=100, n_bands=65, sample_rate=16000, block_size=160, has_reverb=False)
+    model = DDSPAutoencoder(**kw).cuda()
+    B, T = 6, 100
+    batch = {"pitch": 100 + 300 * torch.rand(B, T, 1, device="cuda"), "loudness": torch.randn(B, T, 1, device="cuda"),
+             "mfcc": torch.randn(B, T, 30, device="cuda"), "noise": torch.rand(B, T, 160, device="cuda") * 2 - 1}
+    out = model(batch)
+    out["signal"].square().mean().backward()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    def to_stock(mod):
+        for name, child in list(mod.named_children()):
+            if isinstance(child, core.Linear):
+                new = nn.Linear(child.in_features, child.out_features)
+            elif isinstance(child, core.LayerNormLeakyReLU):
+                new = nn.LayerNorm(child.normalized_shape)
+            elif isinstance(child, core.FusedIntoLayerNorm):
+                setattr(mod, name, nn.LeakyReLU())
+                continue
+            elif isinstance(child, core.ClusterGRU):
+                new = nn.GRU(child.input_size, child.hidden_size, batch_first=True)
+            else:
+                to_stock(child)
+                continue
+            new = new.cuda()
+            new.load_state_dict(child.state_dict())
+            setattr(mod, name, new)
+
+    torch.backends.cudnn.allow_tf32 = False
+    sd = model.state_dict()
+    to_stock(model)
+    assert list(model.state_dict()) == list(sd)
+    model.zero_grad(set_to_none=True)
+    ref = model(batch)
+    ref["signal"].square().mean().backward()
+    assert float((out["signal"] - ref["signal"]).abs().max()) < 1e-4
+    assert float((out["z"] - ref["z"]).abs().max()) < 1e-4
+    for k, p in model.named_parameters():
+        if p.grad is not None and float(p.grad.abs().max()) > 0:
+            rel = float((grads[k] - p.grad).abs().max() / p.grad.abs().max())
+            assert rel < 5e-3, (k, rel)
