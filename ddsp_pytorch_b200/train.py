@@ -154,7 +154,8 @@ class Trainer:
     with identical initial parameters on every rank (same seed, or broadcast by ``sync_parameters``)."""
 
     def __init__(self, model: torch.nn.Module, scales: Sequence[int], overlap: float, lr: float,
-                 mean_loudness: float, std_loudness: float, device, group=None):
+                 mean_loudness: float, std_loudness: float, device, group=None, use_graph: bool = False,
+                 graph_after: int = 3):
         self.model, self.scales, self.overlap = model, [int(s) for s in scales], float(overlap)
         self.mean_loudness, self.std_loudness = float(mean_loudness), float(std_loudness)
         self.device, self.group = device, group
@@ -162,6 +163,9 @@ class Trainer:
         self.opt = torch.optim.Adam(self.params, lr=lr)
         self.bucket = GradBucket([p.shape for p in self.params], device, group=group)
         self.step_count = 0
+        self.use_graph, self.graph_after, self.graph = use_graph, graph_after, None
+        self.static_batch: Dict[str, torch.Tensor] = {}
+        self.static_loss: Optional[torch.Tensor] = None
 
     def sync_parameters(self) -> None:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -174,19 +178,50 @@ class Trainer:
         rec = self.model(batch)["signal"].squeeze(-1)
         return core.multiscale_spectral_loss(batch["sig"], rec, self.scales, self.overlap)
 
-    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """Forward, backward, gradient all-reduce (mean over ranks = gradient of the global-batch mean loss),
-        Adam.  Returns the global-batch loss (a device scalar, no host sync)."""
-        loss = self.loss_of(batch)
-        self.opt.zero_grad(set_to_none=True)
-        loss.backward()
+    def _all_reduce_grads(self) -> None:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
             for p, g in zip(self.params, self.bucket.all_reduce_mean(grads)):
                 p.grad = g.clone() if p.grad is None else p.grad.copy_(g)
-        self.opt.step()
+
+    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Forward, backward, gradient all-reduce (mean over ranks = gradient of the global-batch mean loss),
+        Adam.  Returns the global-batch loss (a device scalar, no host sync).
+
+        With ``use_graph`` the forward + backward of the whole model (~350 launches, host-bound in eager mode)
+        is captured once into a CUDA graph after ``graph_after`` eager steps and replayed on static input
+        buffers; the all-reduce and the optimizer stay outside the graph."""
         self.step_count += 1
+        if self.use_graph and self.graph is None and self.step_count > self.graph_after:
+            self._capture(batch)
+        if self.graph is not None and all(batch[k].shape == v.shape for k, v in self.static_batch.items()):
+            for k, v in self.static_batch.items():
+                v.copy_(batch[k], non_blocking=True)
+            self.graph.replay()
+            loss = self.static_loss
+        else:
+            loss = self.loss_of(batch)
+            self.opt.zero_grad(set_to_none=self.graph is None)
+            loss.backward()
+        self._all_reduce_grads()
+        self.opt.step()
         return global_mean(loss, self.group)
+
+    def _capture(self, batch: Dict[str, torch.Tensor]) -> None:
+        keys = [k for k in ("sig", "pitch", "loudness", "mfcc") if k in batch]
+        self.static_batch = {k: batch[k].clone() for k in keys}
+        self.opt.zero_grad(set_to_none=True)             # the graph owns the gradient buffers from here on
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):                    # one un-captured pass on the capture stream's allocator state
+            self.loss_of(self.static_batch).backward()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.opt.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.static_loss = self.loss_of(self.static_batch)
+            self.static_loss.backward()
+        self.graph = graph
 
     @torch.no_grad()
     def evaluate(self, loader) -> float:
@@ -228,7 +263,7 @@ def run(args) -> dict:
     # batch 64, more than the GPU step); the default here is to draw on the device, --cpu-noise restores it
     model.noise_synth.device_noise = not args.cpu_noise
     mean_l, std_l = loudness_stats(data, args.batch)
-    trainer = Trainer(model, args.scales, args.overlap, args.lr, mean_l, std_l, device)
+    trainer = Trainer(model, args.scales, args.overlap, args.lr, mean_l, std_l, device, use_graph=not (args.no_graph or args.cpu_noise))      # a CPU draw cannot be captured
     trainer.sync_parameters()
     loader = ShardedLoader(data, args.batch, rank, world, device, seed=args.seed)
     if len(loader) == 0:
@@ -287,7 +322,7 @@ def run(args) -> dict:
     seconds = n / args.sample_rate
     return {"model": args.model, "world_size": world, "global_batch": args.batch, "steps": done,
             "ms_per_step": float(t), "audio_seconds_per_s": args.batch * seconds / (float(t) * 1e-3),
-            "first_logged_loss": first, "last_logged_loss": last, "replica_param_spread": float(spread),
+            "cuda_graph": trainer.graph is not None, "first_logged_loss": first, "last_logged_loss": last, "replica_param_spread": float(spread),
             "out_dir": str(out_dir)}
 
 
@@ -309,6 +344,7 @@ def parser() -> argparse.ArgumentParser:
     ap.add_argument("--sample-rate", type=int, default=16000)
     ap.add_argument("--no-reverb", action="store_true")
     ap.add_argument("--cpu-noise", action="store_true", help="draw the filtered-noise excitation with the CPU generator as the reference does")
+    ap.add_argument("--no-graph", action="store_true", help="run forward + backward eagerly instead of replaying a CUDA graph")
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--make-synthetic", type=int, default=0, metavar="N",
