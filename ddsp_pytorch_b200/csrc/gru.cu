@@ -164,7 +164,7 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
                 }
             }
             const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w);
-#pragma unroll 1
+#pragma unroll 7
             for (int j = 1; j < 8; ++j) {
                 const int q = ks + 16 * j;
                 ulonglong2 w[6];
@@ -378,7 +378,7 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                     }
                 }
                 const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w) + (size_t)half * 32 * (kH / 4) + q;
-#pragma unroll 2
+#pragma unroll 8
                 for (int rr = kRegRows; rr < kRows / 2; ++rr) {
                     const ulonglong2 w = wq[(size_t)(rr - kRegRows) * (kH / 4)];
                     const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
