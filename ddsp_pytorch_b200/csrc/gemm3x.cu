@@ -394,13 +394,17 @@ split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv
     }
 }
 
+// 8 lanes per column walk the per-block partials with a fixed stride and are combined in a fixed order
 __global__ void colsum_finalize_kernel(const float *__restrict__ partial, float *__restrict__ colsum, int cols, int out_ld,
                                        int blocks) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
     float t = 0.f;
-    for (int b = 0; b < blocks; ++b) t += __ldg(partial + (size_t)b * out_ld + c);
-    colsum[c] = t;
+    if (c < cols)
+        for (int b = sub; b < blocks; b += 8) t += __ldg(partial + (size_t)b * out_ld + c);
+    t += __shfl_xor_sync(0xffffffffu, t, 1);
+    t += __shfl_xor_sync(0xffffffffu, t, 2);
+    t += __shfl_xor_sync(0xffffffffu, t, 4);
+    if (c < cols && sub == 0) colsum[c] = t;
 }
 
 // operand rows = x's columns, operand columns (K) = x's rows
@@ -498,7 +502,7 @@ static int launch_split(const float *x, int64_t rows, int64_t cols, int64_t ld, 
             x, (int)rows, (int)cols, ld, o, part_rows, out_ld, partial, cgroups, lanes);
         int s = ddsp_launch_status();
         if (s) return s;
-        colsum_finalize_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(partial, colsum, (int)cols, out_ld, (int)blocks.x);
+        colsum_finalize_kernel<<<(unsigned)((cols * 8 + 127) / 128), 128, 0, st>>>(partial, colsum, (int)cols, out_ld, (int)blocks.x);
     } else {
         split3x_kernel<false><<<blocks, cgroups * lanes, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld, nullptr,
                                                                  cgroups, lanes);

@@ -127,15 +127,20 @@ ln_lrelu_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ x, c
     }
 }
 
-// d_gamma, d_beta = sum over the CTAs' partials, fixed order
+// d_gamma, d_beta = sum over the CTAs' partials: 8 lanes per column, fixed stride and combination order
 __global__ void ln_param_grad_kernel(const float *__restrict__ partial, float *__restrict__ d_gamma,
                                      float *__restrict__ d_beta, int N, int slots) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 2 * N) return;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
     float s = 0.f;
-    for (int k = 0; k < slots; ++k) s += __ldg(partial + (size_t)k * 2 * N + c);
-    if (c < N) d_gamma[c] = s;
-    else d_beta[c - N] = s;
+    if (c < 2 * N)
+        for (int k = sub; k < slots; k += 8) s += __ldg(partial + (size_t)k * 2 * N + c);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (c < 2 * N && sub == 0) {
+        if (c < N) d_gamma[c] = s;
+        else d_beta[c - N] = s;
+    }
 }
 
 int ln_grid(int64_t rows) {
@@ -183,6 +188,6 @@ extern "C" int ddsp_b200_ln_lrelu_bwd(const float *dy, const float *x, const flo
     }
     int s = ddsp_launch_status();
     if (s) return s;
-    ln_param_grad_kernel<<<(2 * N + 127) / 128, 128, 0, st>>>(partial, d_gamma, d_beta, N, grid);
+    ln_param_grad_kernel<<<(2 * N * 8 + 127) / 128, 128, 0, st>>>(partial, d_gamma, d_beta, N, grid);
     return ddsp_launch_status();
 }
