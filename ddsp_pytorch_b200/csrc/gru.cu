@@ -89,6 +89,8 @@ __device__ __forceinline__ void gru_push(uint32_t dst_local, uint32_t src, uint3
                  : "memory");
 }
 
+// NV = voices the matrix product is computed for (>= vpc); shared-memory layouts keep kV slots
+template <int NV>
 __global__ void __launch_bounds__(kGruThreads, 1)
 gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, const float *__restrict__ b_hh,
                const float *__restrict__ h0, float *__restrict__ y, float *__restrict__ gates, int B, int T,
@@ -152,12 +154,12 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
                 }
             }
             // ---- partial W_hh h over this thread's k slice
-            uint64_t acc2[6][kV];
+            uint64_t acc2[6][NV];
             const ulonglong2 *hq = reinterpret_cast<const ulonglong2 *>(&s.hbuf[rb][0][0][0]);
             {
                 const int hoff = (ks >> 3) * kV * 8 + (ks & 7);     // quad ks: owner ks/8, quad ks%8 inside its 32 units
 #pragma unroll
-                for (int v = 0; v < kV; ++v) {
+                for (int v = 0; v < NV; ++v) {
                     const ulonglong2 h = hq[hoff + v * 8];
 #pragma unroll
                     for (int r6 = 0; r6 < 6; ++r6) acc2[r6][v] = fma2(wreg[r6].y, h.y, fma2(wreg[r6].x, h.x, 0ull));
@@ -172,26 +174,29 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
                 for (int r6 = 0; r6 < 6; ++r6) w[r6] = wq[((r6 >> 1) * kU + 2 * up + (r6 & 1)) * kWq + (q - 16)];
                 const int hoff = (q >> 3) * kV * 8 + (q & 7);
 #pragma unroll
-                for (int v = 0; v < kV; ++v) {
+                for (int v = 0; v < NV; ++v) {
                     const ulonglong2 h = hq[hoff + v * 8];
 #pragma unroll
                     for (int r6 = 0; r6 < 6; ++r6) acc2[r6][v] = fma2(w[r6].y, h.y, fma2(w[r6].x, h.x, acc2[r6][v]));
                 }
             }
-            // ---- combine the 16 k slices: recursive halving, lane ks ends with entries 4 ks .. 4 ks + 3
-            float a[64];
+            // ---- combine the 16 k slices: recursive halving over P >= 6 NV entries, lane ks ends with entries
+            //      (P/16) ks .. (P/16) ks + P/16 - 1
+            constexpr int P = 6 * NV > 32 ? 64 : (6 * NV > 16 ? 32 : 16);
+            float a[P];
+#pragma unroll
+            for (int i = 0; i < P; ++i) a[i] = 0.f;
 #pragma unroll
             for (int r6 = 0; r6 < 6; ++r6)
 #pragma unroll
-                for (int v = 0; v < kV; ++v) {
+                for (int v = 0; v < NV; ++v) {
                     float lo, hi;
                     unpk2(acc2[r6][v], lo, hi);
-                    a[r6 * kV + v] = lo + hi;
+                    a[r6 * NV + v] = lo + hi;
                 }
-            a[60] = a[61] = a[62] = a[63] = 0.f;
 #pragma unroll
             for (int st = 0; st < 4; ++st) {
-                const int n = 32 >> st, m = 8 >> st;
+                const int n = (P / 2) >> st, m = 8 >> st;
                 const bool upper = (ks & m) != 0;
 #pragma unroll
                 for (int i = 0; i < n; ++i) {
@@ -201,10 +206,10 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
                 }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int e = 4 * ks + i;                           // = r6 * kV + v
-                if (e < 6 * kV) {
-                    const int r6 = e / kV, v = e - r6 * kV;
+            for (int i = 0; i < P / 16; ++i) {
+                const int e = (P / 16) * ks + i;                    // = r6 * NV + v
+                if (e < 6 * NV) {
+                    const int r6 = e / NV, v = e - r6 * NV;
                     s.gh[r6 >> 1][v][2 * up + (r6 & 1)] = a[i];
                 }
             }
@@ -266,6 +271,7 @@ struct GruSmemBwd {
     unsigned long long bar[2];
 };
 
+template <int NV>
 __global__ void __launch_bounds__(kGruThreads, 1)
 gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, const float *__restrict__ w_hh,
                const float *__restrict__ y, const float *__restrict__ h0, const float *__restrict__ gates,
@@ -309,6 +315,7 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
             const int v = i / kU, u = i - v * kU;
             s.dhn[i] = (dhT && v < nv) ? __ldg(dhT + (size_t)(b0 + v) * kH + rank * kU + u) : 0.f;
         }
+        for (int i = tid; i < 2 * kC * kV * kU; i += kGruThreads) (&s.partial[0][0][0][0])[i] = 0.f;   // slots >= NV stay zero
         // inputs of the gate phase of step T-1
         float p_dy[2], p_r[2], p_z[2], p_n[2], p_g[2], p_h[2];
         auto prefetch = [&](int t) {
@@ -362,14 +369,15 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
             if (t > 0) prefetch(t - 1);                  // rides under the matrix product below
             // ---- partial[v][k] over the own row half
             {
-                uint64_t acc2[kV][2];                                // (k, k+1) and (k+2, k+3) of the quad
+                constexpr int NVP = (NV + 1) / 2;                    // voice pairs the product is computed for
+                uint64_t acc2[2 * NVP][2];                           // (k, k+1) and (k+2, k+3) of the quad
 #pragma unroll
-                for (int v = 0; v < kV; ++v) acc2[v][0] = acc2[v][1] = 0ull;
+                for (int v = 0; v < 2 * NVP; ++v) acc2[v][0] = acc2[v][1] = 0ull;
 #pragma unroll
                 for (int rr = 0; rr < kRegRows; ++rr) {
                     const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
 #pragma unroll
-                    for (int vp = 0; vp < kV / 2; ++vp) {
+                    for (int vp = 0; vp < NVP; ++vp) {
                         const ulonglong2 d = dp[vp];                 // (d_v, d_v), (d_v+1, d_v+1)
                         acc2[2 * vp][0] = fma2(d.x, wreg[rr].x, acc2[2 * vp][0]);
                         acc2[2 * vp][1] = fma2(d.x, wreg[rr].y, acc2[2 * vp][1]);
@@ -383,7 +391,7 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                     const ulonglong2 w = wq[(size_t)(rr - kRegRows) * (kH / 4)];
                     const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
 #pragma unroll
-                    for (int vp = 0; vp < kV / 2; ++vp) {
+                    for (int vp = 0; vp < NVP; ++vp) {
                         const ulonglong2 d = dp[vp];
                         acc2[2 * vp][0] = fma2(d.x, w.x, acc2[2 * vp][0]);
                         acc2[2 * vp][1] = fma2(d.x, w.y, acc2[2 * vp][1]);
@@ -391,19 +399,19 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                         acc2[2 * vp + 1][1] = fma2(d.y, w.y, acc2[2 * vp + 1][1]);
                     }
                 }
-                float acc[kV][4];
+                float acc[2 * NVP][4];
 #pragma unroll
-                for (int v = 0; v < kV; ++v) {
+                for (int v = 0; v < 2 * NVP; ++v) {
                     unpk2(acc2[v][0], acc[v][0], acc[v][1]);
                     unpk2(acc2[v][1], acc[v][2], acc[v][3]);
                 }
 #pragma unroll
-                for (int v = 0; v < kV; ++v)
+                for (int v = 0; v < 2 * NVP; ++v)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) acc[v][e] += __shfl_xor_sync(0xffffffffu, acc[v][e], 16);
                 if (half == 0) {
 #pragma unroll
-                    for (int v = 0; v < kV; ++v)
+                    for (int v = 0; v < NV; ++v)
                         *reinterpret_cast<float4 *>(&s.partial[pb][q >> 3][v][(q & 7) * 4]) =
                             make_float4(acc[v][0], acc[v][1], acc[v][2], acc[v][3]);
                 }
@@ -495,8 +503,8 @@ void pick_clusters(int B, int resident, int *clusters, int *vpc) {
 extern "C" int ddsp_b200_gru_resident_clusters(void) {
     static int cached = -1;
     if (cached < 0) {
-        const int a = max_clusters(gru_fwd_kernel, sizeof(GruSmemFwd));
-        const int b = max_clusters(gru_bwd_kernel, sizeof(GruSmemBwd));
+        const int a = max_clusters(gru_fwd_kernel<kV>, sizeof(GruSmemFwd));
+        const int b = max_clusters(gru_bwd_kernel<kV>, sizeof(GruSmemBwd));
         cached = a < b ? a : b;
     }
     return cached;
@@ -512,7 +520,14 @@ extern "C" int ddsp_b200_gru_fwd(const float *gi, const float *w_hh, const float
     pick_clusters(B, resident, &clusters, &vpc);
     void *args[] = {(void *)&gi, (void *)&w_hh, (void *)&b_hh, (void *)&h0, (void *)&y, (void *)&gates, (void *)&B, (void *)&T,
                     (void *)&vpc};
-    int s = launch_cluster(gru_fwd_kernel, sizeof(GruSmemFwd), clusters, (cudaStream_t)stream, args);
+    // the kernel variant computes the product for the smallest supported voice count >= vpc
+    cudaStream_t st = (cudaStream_t)stream;
+    int s;
+    if (vpc <= 1) s = launch_cluster(gru_fwd_kernel<1>, sizeof(GruSmemFwd), clusters, st, args);
+    else if (vpc <= 2) s = launch_cluster(gru_fwd_kernel<2>, sizeof(GruSmemFwd), clusters, st, args);
+    else if (vpc <= 3) s = launch_cluster(gru_fwd_kernel<3>, sizeof(GruSmemFwd), clusters, st, args);
+    else if (vpc <= 5) s = launch_cluster(gru_fwd_kernel<5>, sizeof(GruSmemFwd), clusters, st, args);
+    else s = launch_cluster(gru_fwd_kernel<kV>, sizeof(GruSmemFwd), clusters, st, args);
     return s ? s : ddsp_launch_status();
 }
 
@@ -527,6 +542,12 @@ extern "C" int ddsp_b200_gru_bwd(const float *dy, const float *dhT, const float 
     pick_clusters(B, resident, &clusters, &vpc);
     void *args[] = {(void *)&dy, (void *)&dhT, (void *)&w_hh, (void *)&y, (void *)&h0, (void *)&gates,
                     (void *)&dgi, (void *)&dgh, (void *)&dh0, (void *)&B, (void *)&T, (void *)&vpc};
-    int s = launch_cluster(gru_bwd_kernel, sizeof(GruSmemBwd), clusters, (cudaStream_t)stream, args);
+    cudaStream_t st = (cudaStream_t)stream;
+    int s;
+    if (vpc <= 1) s = launch_cluster(gru_bwd_kernel<1>, sizeof(GruSmemBwd), clusters, st, args);
+    else if (vpc <= 2) s = launch_cluster(gru_bwd_kernel<2>, sizeof(GruSmemBwd), clusters, st, args);
+    else if (vpc <= 3) s = launch_cluster(gru_bwd_kernel<3>, sizeof(GruSmemBwd), clusters, st, args);
+    else if (vpc <= 5) s = launch_cluster(gru_bwd_kernel<5>, sizeof(GruSmemBwd), clusters, st, args);
+    else s = launch_cluster(gru_bwd_kernel<kV>, sizeof(GruSmemBwd), clusters, st, args);
     return s ? s : ddsp_launch_status();
 }
