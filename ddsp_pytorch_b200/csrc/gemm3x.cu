@@ -80,12 +80,17 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+// descriptors are given as (low word, high word): the low word carries the 16-byte start address, so stepping
+// through a stage is one 32-bit add per operand and the issuing thread stays far below the 64-cycle MMA pace
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t acc) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -206,6 +211,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             // instruction descriptor: D fp32, A/B bf16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn ? 1 : 0) << 15) |
                                    ((uint32_t)(p.b_mn ? 1 : 0) << 16) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            // descriptor words of the six operand parts at stage 0, k step 0; a k step (16 values of K) is 32 B
+            // inside the 128 B row (K-major) or 16 rows of 128 B (MN-major) further, a stage kStageBytes
+            uint32_t a_lo[3], b_lo[3], a_hi = 0, b_hi = 0;
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                const uint32_t ta = base + part * kTileBytes, tb = base + (3 + part) * kTileBytes;
+                const uint64_t da = p.a_mn ? umma_desc_mn_sw128(ta) : umma_desc_k_sw128(ta);
+                const uint64_t db = p.b_mn ? umma_desc_mn_sw128(tb) : umma_desc_k_sw128(tb);
+                a_lo[part] = (uint32_t)da; a_hi = (uint32_t)(da >> 32);
+                b_lo[part] = (uint32_t)db; b_hi = (uint32_t)(db >> 32);
+            }
+            const uint32_t a_inc = p.a_mn ? (2048u >> 4) : (32u >> 4), b_inc = p.b_mn ? (2048u >> 4) : (32u >> 4);
             int it = 0, chunk = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 int z, m0, n0, kb0, nkb;
@@ -220,24 +237,18 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                         const int s = it % kStages, round = it / kStages;
                         mbar_wait(full0 + 8 * s, round & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t st = base + s * kStageBytes;
+                        uint32_t ao = s * (kStageBytes >> 4), bo = ao;
 #pragma unroll
-                        for (int k = 0; k < kBK / 16; ++k) {
-                            // 16 values of K further: 32 B inside the row (K-major) / 16 rows of 128 B (MN-major)
-                            uint64_t a[3], b[3];
-#pragma unroll
-                            for (int part = 0; part < 3; ++part) {
-                                const uint32_t ta = st + part * kTileBytes, tb = st + (3 + part) * kTileBytes;
-                                a[part] = p.a_mn ? umma_desc_mn_sw128(ta + k * 2048) : umma_desc_k_sw128(ta + k * 32);
-                                b[part] = p.b_mn ? umma_desc_mn_sw128(tb + k * 2048) : umma_desc_k_sw128(tb + k * 32);
-                            }
+                        for (int k = 0; k < kBK / 16; ++k, ao += a_inc, bo += b_inc) {
+                            const uint32_t a0 = a_lo[0] + ao, a1 = a_lo[1] + ao, a2 = a_lo[2] + ao;
+                            const uint32_t b0 = b_lo[0] + bo, b1 = b_lo[1] + bo, b2 = b_lo[2] + bo;
                             const uint32_t acc = (i != i0 || k != 0) ? 1u : 0u;
-                            umma_bf16(d_main, a[0], b[0], idesc, acc);
-                            umma_bf16(d_small, a[1], b[1], idesc, acc);             // 2^-16 terms first
-                            umma_bf16(d_small, a[0], b[2], idesc, 1u);
-                            umma_bf16(d_small, a[2], b[0], idesc, 1u);
-                            umma_bf16(d_small, a[0], b[1], idesc, 1u);              // 2^-8 terms
-                            umma_bf16(d_small, a[1], b[0], idesc, 1u);
+                            umma_bf16_w(d_main, a0, a_hi, b0, b_hi, idesc, acc);
+                            umma_bf16_w(d_small, a1, a_hi, b1, b_hi, idesc, acc);   // 2^-16 terms first
+                            umma_bf16_w(d_small, a0, a_hi, b2, b_hi, idesc, 1u);
+                            umma_bf16_w(d_small, a2, a_hi, b0, b_hi, idesc, 1u);
+                            umma_bf16_w(d_small, a0, a_hi, b1, b_hi, idesc, 1u);    // 2^-8 terms
+                            umma_bf16_w(d_small, a1, a_hi, b0, b_hi, idesc, 1u);
                         }
                         umma_commit(empty0 + 8 * s);                               // stage free when these MMAs retire
                     }

@@ -45,11 +45,19 @@ __global__ void __launch_bounds__(128, 1) probe(int mode, int N, int iters, long
     if (threadIdx.x == 0) {
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint64_t a = desc_k_sw128(base), b = desc_k_sw128(base + 32 * 1024);
+        uint64_t ak[4], bk[4];
+        for (int k = 0; k < 4; ++k) { ak[k] = a + 2 * k; bk[k] = b + 2 * k; }     // 32 B further per k step
         long long t0 = clock64();
-        for (int i = 0; i < iters; ++i) {
-            const uint32_t off = (i & 3) * 32;                       // walk the 4 k steps of a 64-wide stage
-            if (mode == 0) mma_ss(tm, a + (off >> 4), b + (off >> 4), idesc);
-            else mma_ts(tm, tm + 256 + (i & 3) * 8, b + (off >> 4), idesc);   // A: 8 columns (16 bf16) per k step
+        if (mode == 0) {
+            for (int i = 0; i < iters; i += 8) {                     // precomputed descriptors, 8 MMAs per trip
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mma_ss(tm, ak[j & 3], bk[j & 3], idesc);
+            }
+        } else {
+            for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mma_ts(tm, tm + 256 + (j & 3) * 8, bk[j & 3], idesc);   // A: 8 columns per k step
+            }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         uint32_t ok = 0;
