@@ -13,7 +13,7 @@ from oracle import ddsp_oracle as orc  # noqa: E402
 
 
 def mx(a, b):
-    return float((a.double().cpu() - b.double().cpu()).abs().max())
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
 
 
 def rel(a, b):
@@ -87,6 +87,45 @@ def main():
     mags = ddsp.multiscale_fft(rec.detach(), scales, ov)
     mags64 = orc.multiscale_fft(rec64.detach(), scales, ov)
     rep["stft_mag_max_abs"] = max(mx(a, b) for a, b in zip(mags, mags64))
+    # control net: float64 torch.nn layers are the oracle; torch's own float32 layers beside it
+    from ddsp_pytorch_b200 import core
+    torch.manual_seed(3)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, T, H = 16, 400, 512
+    x = torch.randn(B, T, H)
+    go2 = torch.randn(B, T, H)
+    blk = core.mlp(H, H, 1).cuda()
+    gru = core.gru(1, H).cuda()
+    ref_blk = torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.LayerNorm(H), torch.nn.LeakyReLU())
+    ref_blk.load_state_dict({k: v.detach().cpu() for k, v in blk.state_dict().items()})
+    ref_gru = torch.nn.GRU(H, H, batch_first=True)
+    ref_gru.load_state_dict({k: v.detach().cpu() for k, v in gru.state_dict().items()})
+
+    def run(b, g, xx, gg):
+        xx = xx.clone().requires_grad_(True)
+        b.zero_grad(set_to_none=True)
+        g.zero_grad(set_to_none=True)
+        mid = b(xx)
+        out = g(mid)[0]
+        (out * gg).sum().backward()
+        return mid.detach(), out.detach(), xx.grad, [p.grad.detach().double().cpu() for p in list(b.parameters()) + list(g.parameters())]
+
+    m64_, o64, gx64, gp64 = run(ref_blk.double(), ref_gru.double(), x.double(), go2.double())
+    mk, ok, gxk, gpk = run(blk, gru, x.cuda(), go2.cuda())
+    ref_blk.float().cuda(), ref_gru.float().cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    mt, ot, gxt, gpt = run(ref_blk, ref_gru, x.cuda(), go2.cuda())
+    torch.backends.cudnn.allow_tf32 = True
+    _, ot32, _, _ = run(ref_blk, ref_gru, x.cuda(), go2.cuda())
+    rep["linear_ln_lrelu_max_abs"] = mx(mk, m64_)
+    rep["linear_ln_lrelu_max_abs_torch_fp32"] = mx(mt, m64_)
+    rep["gru_output_max_abs"] = mx(ok, o64)
+    rep["gru_output_max_abs_cudnn_fp32"] = mx(ot, o64)
+    rep["gru_output_max_abs_cudnn_default_tf32"] = mx(ot32, o64)
+    rep["control_net_d_input_rel"] = rel(gxk, gx64)
+    rep["control_net_d_input_rel_torch_fp32"] = rel(gxt, gx64)
+    rep["control_net_d_params_rel_max"] = max(rel(a, b) for a, b in zip(gpk, gp64))
+    rep["control_net_d_params_rel_max_torch_fp32"] = max(rel(a, b) for a, b in zip(gpt, gp64))
     print(json.dumps(rep, indent=1))
 
 
