@@ -303,9 +303,10 @@ class GRURecurrence(torch.autograd.Function):
                 h_prev[:, 0].zero_()
             else:
                 h_prev[:, 0] = h0.reshape(B, H)
-            d_w = _ops.gemm3x_mm(_ops.gemm3x_split(dgh.reshape(B * T, 3 * H), False),
-                                 _ops.gemm3x_split(h_prev.reshape(B * T, H), False), 3 * H, H, B * T, None, True, True)
-        if ctx.needs_input_grad[2]:
+            dghs, d_b = _ops.gemm3x_split_colsum(dgh.reshape(B * T, 3 * H))     # db_hh rides on the split
+            d_w = _ops.gemm3x_mm(dghs, _ops.gemm3x_split(h_prev.reshape(B * T, H), False), 3 * H, H, B * T, None,
+                                 True, True)
+        elif ctx.needs_input_grad[2]:
             d_b = dgh.sum((0, 1))
         d_h0 = None
         if h0 is not None and ctx.needs_input_grad[3]:
