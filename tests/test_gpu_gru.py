@@ -151,3 +151,23 @@ def test_autoencoder_matches_stock_layers():
         if p.grad is not None and float(p.grad.abs().max()) > 0:
             rel = float((grads[k] - p.grad).abs().max() / p.grad.abs().max())
             assert rel < 5e-3, (k, rel)
+
+
+def test_control_net_layers_are_run_to_run_deterministic():
+    """Fixed-order reductions everywhere (split-K GEMM, column sums, DSMEM reduce-scatter): two runs of forward +
+    backward give bit-identical outputs and gradients."""
+    from ddsp_pytorch_b200 import core
+    torch.manual_seed(4)
+    blk, gru = core.mlp(512, 512, 1).cuda(), core.gru(1, 512).cuda()
+    x = torch.randn(16, 100, 512, device="cuda", requires_grad=True)
+    go = torch.randn(16, 100, 512, device="cuda")
+    runs = []
+    for _ in range(3):
+        blk.zero_grad(set_to_none=True)
+        gru.zero_grad(set_to_none=True)
+        x.grad = None
+        y = gru(blk(x))[0]
+        y.backward(go)
+        runs.append([y.detach().clone(), x.grad.clone()] + [p.grad.clone() for p in list(blk.parameters()) + list(gru.parameters())])
+    for other in runs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(runs[0], other))
