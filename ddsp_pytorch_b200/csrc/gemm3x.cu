@@ -357,18 +357,18 @@ constexpr int kSplitRows = 64;
 template <bool COLSUM>
 __global__ void __launch_bounds__(256)
 split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv_bfloat16 *__restrict__ out,
-               int64_t part_rows, int out_ld, float *__restrict__ partial, int cgroups, int lanes) {
+               int64_t part_rows, int out_ld, float *__restrict__ partial, int cgroups, int lanes, int rpb) {
     extern __shared__ float red[];                                  // [lanes][cgroups * 8] when COLSUM
     const int cl = threadIdx.x % cgroups, rl = threadIdx.x / cgroups;
     const int c0 = (blockIdx.y * cgroups + cl) * 8;                 // grid.y > 1 only beyond 2048 columns
     const bool live = c0 < out_ld;
-    const int rbeg = blockIdx.x * kSplitRows;
+    const int rbeg = blockIdx.x * rpb;                              // rpb rows per block (kSplitRows with COLSUM)
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && c0 + 8 <= cols;
     const size_t pstride = (size_t)part_rows * out_ld;
     float sum[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sum[j] = 0.f;
-    for (int r = rbeg + rl; live && r < rbeg + kSplitRows && r < part_rows; r += lanes) {
+    for (int r = rbeg + rl; live && r < rbeg + rpb && r < part_rows; r += lanes) {
         float v[8];
         if (r < rows && vec) {
             const float4 lo = __ldg(reinterpret_cast<const float4 *>(x + (size_t)r * ld + c0));
@@ -507,16 +507,23 @@ static int launch_split(const float *x, int64_t rows, int64_t cols, int64_t ld, 
     const int out_ld = (int)ddsp_b200_gemm3x_ld(cols);
     const int cgroups = out_ld / 8 < 256 ? out_ld / 8 : 256;
     const int lanes = 256 / cgroups;
-    dim3 blocks((unsigned)((part_rows + kSplitRows - 1) / kSplitRows), (unsigned)((out_ld / 8 + cgroups - 1) / cgroups));
+    // small matrices (the weights) get fewer rows per block so that the grid still covers the SMs
+    int rpb = kSplitRows;
+    if (!colsum) {
+        rpb = (int)((part_rows + 2 * DDSP_SM_COUNT - 1) / (2 * DDSP_SM_COUNT));
+        rpb = (rpb + lanes - 1) / lanes * lanes;
+        rpb = rpb < lanes ? lanes : (rpb > kSplitRows ? kSplitRows : rpb);
+    }
+    dim3 blocks((unsigned)((part_rows + rpb - 1) / rpb), (unsigned)((out_ld / 8 + cgroups - 1) / cgroups));
     if (colsum) {
         split3x_kernel<true><<<blocks, cgroups * lanes, (size_t)lanes * cgroups * 8 * 4, st>>>(
-            x, (int)rows, (int)cols, ld, o, part_rows, out_ld, partial, cgroups, lanes);
+            x, (int)rows, (int)cols, ld, o, part_rows, out_ld, partial, cgroups, lanes, rpb);
         int s = ddsp_launch_status();
         if (s) return s;
         colsum_finalize_kernel<<<(unsigned)((cols * 8 + 127) / 128), 128, 0, st>>>(partial, colsum, (int)cols, out_ld, (int)blocks.x);
     } else {
         split3x_kernel<false><<<blocks, cgroups * lanes, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld, nullptr,
-                                                                 cgroups, lanes);
+                                                                 cgroups, lanes, rpb);
     }
     return ddsp_launch_status();
 }
