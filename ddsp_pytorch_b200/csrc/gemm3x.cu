@@ -362,7 +362,7 @@ split3x_kernel(const float *__restrict__ x, int rows, int cols, int64_t ld, __nv
     const int cl = threadIdx.x % cgroups, rl = threadIdx.x / cgroups;
     const int c0 = (blockIdx.y * cgroups + cl) * 8;                 // grid.y > 1 only beyond 2048 columns
     const bool live = c0 < out_ld;
-    const int rbeg = blockIdx.x * rpb;                              // rpb rows per block (kSplitRows with COLSUM)
+    const int rbeg = blockIdx.x * rpb;                              // rpb rows per block (<= kSplitRows)
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && c0 + 8 <= cols;
     const size_t pstride = (size_t)part_rows * out_ld;
     float sum[8];
@@ -496,41 +496,51 @@ extern "C" int64_t ddsp_b200_gemm3x_ld(int64_t k) { return (k + kBK - 1) / kBK *
 extern "C" int ddsp_b200_gemm3x_splits(int M, int N, int K) {
     const int tiles = ((M + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
     const int kblocks = (int)(ddsp_b200_gemm3x_ld(K) / kBK);
+    // only skinny outputs (weight gradients) are split; splitting K to even out a ragged last wave (200 tiles
+    // on 148 SMs) was measured and lost to the extra reduction pass
     if (tiles >= 96 || kblocks < 8) return 1;
-    int s = (148 + tiles - 1) / tiles;
+    int s = (DDSP_SM_COUNT + tiles - 1) / tiles;
     if (s > kblocks / 2) s = kblocks / 2;
     return s < 1 ? 1 : s;
 }
 
+// launch geometry of the non-transposed split: column groups and row lanes per block, rows per block (small
+// matrices get fewer rows per block so that the grid still covers the SMs), blocks along the rows
+struct SplitGeom { int out_ld, cgroups, lanes, rpb, row_blocks, col_blocks; };
+static SplitGeom split_geometry(int64_t part_rows, int64_t cols) {
+    SplitGeom g;
+    g.out_ld = (int)ddsp_b200_gemm3x_ld(cols);
+    g.cgroups = g.out_ld / 8 < 256 ? g.out_ld / 8 : 256;
+    g.lanes = 256 / g.cgroups;
+    int rpb = (int)((part_rows + 2 * DDSP_SM_COUNT - 1) / (2 * DDSP_SM_COUNT));
+    rpb = (rpb + g.lanes - 1) / g.lanes * g.lanes;
+    g.rpb = rpb < g.lanes ? g.lanes : (rpb > kSplitRows ? kSplitRows : rpb);
+    g.row_blocks = (int)((part_rows + g.rpb - 1) / g.rpb);
+    g.col_blocks = (g.out_ld / 8 + g.cgroups - 1) / g.cgroups;
+    return g;
+}
+
 static int launch_split(const float *x, int64_t rows, int64_t cols, int64_t ld, __nv_bfloat16 *o, int64_t part_rows,
                         float *colsum, float *partial, cudaStream_t st) {
-    const int out_ld = (int)ddsp_b200_gemm3x_ld(cols);
-    const int cgroups = out_ld / 8 < 256 ? out_ld / 8 : 256;
-    const int lanes = 256 / cgroups;
-    // small matrices (the weights) get fewer rows per block so that the grid still covers the SMs
-    int rpb = kSplitRows;
-    if (!colsum) {
-        rpb = (int)((part_rows + 2 * DDSP_SM_COUNT - 1) / (2 * DDSP_SM_COUNT));
-        rpb = (rpb + lanes - 1) / lanes * lanes;
-        rpb = rpb < lanes ? lanes : (rpb > kSplitRows ? kSplitRows : rpb);
-    }
-    dim3 blocks((unsigned)((part_rows + rpb - 1) / rpb), (unsigned)((out_ld / 8 + cgroups - 1) / cgroups));
+    const SplitGeom g = split_geometry(part_rows, cols);
+    dim3 blocks((unsigned)g.row_blocks, (unsigned)g.col_blocks);
     if (colsum) {
-        split3x_kernel<true><<<blocks, cgroups * lanes, (size_t)lanes * cgroups * 8 * 4, st>>>(
-            x, (int)rows, (int)cols, ld, o, part_rows, out_ld, partial, cgroups, lanes, rpb);
+        split3x_kernel<true><<<blocks, g.cgroups * g.lanes, (size_t)g.lanes * g.cgroups * 8 * 4, st>>>(
+            x, (int)rows, (int)cols, ld, o, part_rows, g.out_ld, partial, g.cgroups, g.lanes, g.rpb);
         int s = ddsp_launch_status();
         if (s) return s;
-        colsum_finalize_kernel<<<(unsigned)((cols * 8 + 127) / 128), 128, 0, st>>>(partial, colsum, (int)cols, out_ld, (int)blocks.x);
+        colsum_finalize_kernel<<<(unsigned)((cols * 8 + 127) / 128), 128, 0, st>>>(partial, colsum, (int)cols, g.out_ld, g.row_blocks);
     } else {
-        split3x_kernel<false><<<blocks, cgroups * lanes, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, out_ld, nullptr,
-                                                                 cgroups, lanes, rpb);
+        split3x_kernel<false><<<blocks, g.cgroups * g.lanes, 0, st>>>(x, (int)rows, (int)cols, ld, o, part_rows, g.out_ld,
+                                                                     nullptr, g.cgroups, g.lanes, g.rpb);
     }
     return ddsp_launch_status();
 }
 
 // Scratch floats ddsp_b200_gemm3x_split_colsum needs for a part_rows x cols operand
 extern "C" int64_t ddsp_b200_gemm3x_colsum_scratch(int64_t part_rows, int64_t cols) {
-    return (part_rows + kSplitRows - 1) / kSplitRows * ddsp_b200_gemm3x_ld(cols);
+    const SplitGeom g = split_geometry(part_rows, cols);
+    return (int64_t)g.row_blocks * g.out_ld;
 }
 
 // gemm3x_split (non-transposed) that also returns colsum[c] = sum over rows of x[r][c] (a Linear layer's bias

@@ -6,7 +6,7 @@ from torch.profiler import profile, ProfilerActivity
 torch.backends.cuda.matmul.allow_tf32 = "--tf32" in sys.argv
 torch.backends.cudnn.allow_tf32 = "--tf32" in sys.argv
 torch.manual_seed(0)
-B, T, bs, sr = 64, 400, 160, 16000
+B, T, bs, sr = int(os.environ.get("BATCH", 64)), 400, 160, 16000
 model = DDSPDecoder(hidden_size=512, n_harmonic=100, n_bands=65, sample_rate=sr, block_size=bs, has_reverb=True).cuda()
 model.noise_synth.device_noise = True
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
