@@ -104,12 +104,17 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
     const int up = tid >> 4, ks = tid & 15;                        // unit pair, k slice
 
     // ---- W_hh slice: quad ks of the six own rows into registers, quads 16.. into shared memory
-    ulonglong2 wreg[6];
+    // few voices leave registers free: then four of the eight k quads of W_hh stay in registers instead of one
+    // and the per-step stream from shared memory (172 KB, 0.7 us) halves
+    constexpr int JR = NV <= 3 ? 4 : 1;
+    ulonglong2 wreg[JR][6];
 #pragma unroll
-    for (int r6 = 0; r6 < 6; ++r6) {
-        const int g = r6 >> 1, u = 2 * up + (r6 & 1);
-        wreg[r6] = __ldg(reinterpret_cast<const ulonglong2 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + ks);
-    }
+    for (int jr = 0; jr < JR; ++jr)
+#pragma unroll
+        for (int r6 = 0; r6 < 6; ++r6) {
+            const int g = r6 >> 1, u = 2 * up + (r6 & 1);
+            wreg[jr][r6] = __ldg(reinterpret_cast<const ulonglong2 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + ks + 16 * jr);
+        }
     for (int i = tid; i < kRows * kWq; i += kGruThreads) {
         const int row = i / kWq, q = i - row * kWq;
         const int g = row / kU, u = row - g * kU;
@@ -156,18 +161,25 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
             // ---- partial W_hh h over this thread's k slice
             uint64_t acc2[6][NV];
             const ulonglong2 *hq = reinterpret_cast<const ulonglong2 *>(&s.hbuf[rb][0][0][0]);
-            {
-                const int hoff = (ks >> 3) * kV * 8 + (ks & 7);     // quad ks: owner ks/8, quad ks%8 inside its 32 units
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int r6 = 0; r6 < 6; ++r6) acc2[r6][v] = 0ull;
+#pragma unroll
+            for (int jr = 0; jr < JR; ++jr) {
+                const int q = ks + 16 * jr;                         // quad q: owner q/8, quad q%8 inside its 32 units
+                const int hoff = (q >> 3) * kV * 8 + (q & 7);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const ulonglong2 h = hq[hoff + v * 8];
 #pragma unroll
-                    for (int r6 = 0; r6 < 6; ++r6) acc2[r6][v] = fma2(wreg[r6].y, h.y, fma2(wreg[r6].x, h.x, 0ull));
+                    for (int r6 = 0; r6 < 6; ++r6)
+                        acc2[r6][v] = fma2(wreg[jr][r6].y, h.y, fma2(wreg[jr][r6].x, h.x, acc2[r6][v]));
                 }
             }
             const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w);
-#pragma unroll 7
-            for (int j = 1; j < 8; ++j) {
+#pragma unroll
+            for (int j = JR; j < 8; ++j) {
                 const int q = ks + 16 * j;
                 ulonglong2 w[6];
 #pragma unroll
@@ -286,16 +298,20 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
     const int half = lane >> 4, q = warp * 16 + (lane & 15);        // row half, float4 index of k
     const int r0 = half * (kRows / 2);
 
-    // ---- W_hh slice (slice row = g*32 + u  <->  global row g*H + 32*rank + u)
-    ulonglong2 wreg[kRegRows];
+    // ---- W_hh slice (slice row = g*32 + u  <->  global row g*H + 32*rank + u).  KR of a thread's 48 rows stay
+    //      in registers: 16 with many voices, 40 when few voices leave the registers free (the shared-memory
+    //      buffer is sized for the first case)
+    constexpr int KR = NV <= 3 ? 40 : kRegRows;
+    constexpr int SR = kRows / 2 - KR;                               // rows per half streamed from shared memory
+    ulonglong2 wreg[KR];
 #pragma unroll
-    for (int rr = 0; rr < kRegRows; ++rr) {
+    for (int rr = 0; rr < KR; ++rr) {
         const int row = r0 + rr, g = row / kU, u = row - g * kU;
         wreg[rr] = __ldg(reinterpret_cast<const ulonglong2 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + q);
     }
-    for (int i = tid; i < kSmemRows * (kH / 4); i += kGruThreads) {
+    for (int i = tid; i < 2 * SR * (kH / 4); i += kGruThreads) {
         const int srow = i / (kH / 4), qq = i - srow * (kH / 4);
-        const int row = (srow >> 5) * (kRows / 2) + kRegRows + (srow & 31);
+        const int row = (srow / SR) * (kRows / 2) + KR + (srow % SR);
         const int g = row / kU, u = row - g * kU;
         reinterpret_cast<float4 *>(s.w)[i] =
             __ldg(reinterpret_cast<const float4 *>(w_hh + ((size_t)g * kH + rank * kU + u) * kH) + qq);
@@ -374,7 +390,7 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
 #pragma unroll
                 for (int v = 0; v < 2 * NVP; ++v) acc2[v][0] = acc2[v][1] = 0ull;
 #pragma unroll
-                for (int rr = 0; rr < kRegRows; ++rr) {
+                for (int rr = 0; rr < KR; ++rr) {
                     const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
 #pragma unroll
                     for (int vp = 0; vp < NVP; ++vp) {
@@ -385,10 +401,10 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                         acc2[2 * vp + 1][1] = fma2(d.y, wreg[rr].y, acc2[2 * vp + 1][1]);
                     }
                 }
-                const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w) + (size_t)half * 32 * (kH / 4) + q;
+                const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w) + (size_t)half * SR * (kH / 4) + q;
 #pragma unroll 8
-                for (int rr = kRegRows; rr < kRows / 2; ++rr) {
-                    const ulonglong2 w = wq[(size_t)(rr - kRegRows) * (kH / 4)];
+                for (int rr = KR; rr < kRows / 2; ++rr) {
+                    const ulonglong2 w = wq[(size_t)(rr - KR) * (kH / 4)];
                     const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
 #pragma unroll
                     for (int vp = 0; vp < NVP; ++vp) {
