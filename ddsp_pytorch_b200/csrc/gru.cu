@@ -106,7 +106,7 @@ gru_fwd_kernel(const float *__restrict__ gi, const float *__restrict__ w_hh, con
     // ---- W_hh slice: quad ks of the six own rows into registers, quads 16.. into shared memory
     // few voices leave registers free: then four of the eight k quads of W_hh stay in registers instead of one
     // and the per-step stream from shared memory (172 KB, 0.7 us) halves
-    constexpr int JR = NV <= 3 ? 4 : 1;
+    constexpr int JR = NV <= 3 ? 4 : (NV <= 5 ? 2 : 1);
     ulonglong2 wreg[JR][6];
 #pragma unroll
     for (int jr = 0; jr < JR; ++jr)
@@ -301,7 +301,7 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
     // ---- W_hh slice (slice row = g*32 + u  <->  global row g*H + 32*rank + u).  KR of a thread's 48 rows stay
     //      in registers: 16 with many voices, 40 when few voices leave the registers free (the shared-memory
     //      buffer is sized for the first case)
-    constexpr int KR = NV <= 3 ? 40 : kRegRows;
+    constexpr int KR = NV <= 3 ? 40 : (NV <= 5 ? 32 : kRegRows);
     constexpr int SR = kRows / 2 - KR;                               // rows per half streamed from shared memory
     ulonglong2 wreg[KR];
 #pragma unroll
