@@ -210,6 +210,29 @@ class ClusterGRU(nn.GRU):
         return y, y[:, -1].unsqueeze(0)
 
 
+def to_stock_layers(module: nn.Module) -> nn.Module:
+    """Replace, in place, this file's control-net layers by the stock ``torch.nn`` ones the reference builds
+    (same parameters, same state_dict keys): the A/B switch of the parity tests, ``tools/model_step.py`` and
+    ``train.py --stock-control-net``."""
+    for name, child in list(module.named_children()):
+        if isinstance(child, Linear):
+            new = nn.Linear(child.in_features, child.out_features, bias=child.bias is not None)
+        elif isinstance(child, LayerNormLeakyReLU):
+            new = nn.LayerNorm(child.normalized_shape, eps=child.eps)
+        elif isinstance(child, FusedIntoLayerNorm):
+            setattr(module, name, nn.LeakyReLU())
+            continue
+        elif isinstance(child, ClusterGRU):
+            new = nn.GRU(child.input_size, child.hidden_size, batch_first=True)
+        else:
+            to_stock_layers(child)
+            continue
+        new = new.to(next(child.parameters()).device)
+        new.load_state_dict(child.state_dict())
+        setattr(module, name, new)
+    return module
+
+
 def gru(n_input, hidden_size):
     """ddsp/core.py:132-133."""
     return ClusterGRU(n_input * hidden_size, hidden_size, batch_first=True)

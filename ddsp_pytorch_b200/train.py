@@ -262,6 +262,8 @@ def run(args) -> dict:
     # modules.py:119-123 draws the noise with the CPU generator and moves it (17 ms of host time per step at
     # batch 64, more than the GPU step); the default here is to draw on the device, --cpu-noise restores it
     model.noise_synth.device_noise = not args.cpu_noise
+    if args.stock_control_net:                                      # A/B: cuBLAS / cuDNN layers as in the reference
+        core.to_stock_layers(model)
     mean_l, std_l = loudness_stats(data, args.batch)
     trainer = Trainer(model, args.scales, args.overlap, args.lr, mean_l, std_l, device, use_graph=not (args.no_graph or args.cpu_noise))      # a CPU draw cannot be captured
     trainer.sync_parameters()
@@ -322,7 +324,7 @@ def run(args) -> dict:
     seconds = n / args.sample_rate
     return {"model": args.model, "world_size": world, "global_batch": args.batch, "steps": done,
             "ms_per_step": float(t), "audio_seconds_per_s": args.batch * seconds / (float(t) * 1e-3),
-            "cuda_graph": trainer.graph is not None, "first_logged_loss": first, "last_logged_loss": last, "replica_param_spread": float(spread),
+            "cuda_graph": trainer.graph is not None, "control_net": "torch.nn" if args.stock_control_net else "kernels", "first_logged_loss": first, "last_logged_loss": last, "replica_param_spread": float(spread),
             "out_dir": str(out_dir)}
 
 
@@ -344,6 +346,8 @@ def parser() -> argparse.ArgumentParser:
     ap.add_argument("--sample-rate", type=int, default=16000)
     ap.add_argument("--no-reverb", action="store_true")
     ap.add_argument("--cpu-noise", action="store_true", help="draw the filtered-noise excitation with the CPU generator as the reference does")
+    ap.add_argument("--stock-control-net", action="store_true",
+                    help="run the control net on stock torch.nn layers (cuBLAS, cuDNN) instead of this repo's kernels")
     ap.add_argument("--no-graph", action="store_true", help="run forward + backward eagerly instead of replaying a CUDA graph")
     ap.add_argument("--log-every", type=int, default=10)
     ap.add_argument("--seed", type=int, default=0)

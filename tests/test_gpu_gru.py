@@ -120,27 +120,9 @@ def test_autoencoder_matches_stock_layers():
     out["signal"].square().mean().backward()
     grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
 
-    def to_stock(mod):
-        for name, child in list(mod.named_children()):
-            if isinstance(child, core.Linear):
-                new = nn.Linear(child.in_features, child.out_features)
-            elif isinstance(child, core.LayerNormLeakyReLU):
-                new = nn.LayerNorm(child.normalized_shape)
-            elif isinstance(child, core.FusedIntoLayerNorm):
-                setattr(mod, name, nn.LeakyReLU())
-                continue
-            elif isinstance(child, core.ClusterGRU):
-                new = nn.GRU(child.input_size, child.hidden_size, batch_first=True)
-            else:
-                to_stock(child)
-                continue
-            new = new.cuda()
-            new.load_state_dict(child.state_dict())
-            setattr(mod, name, new)
-
     torch.backends.cudnn.allow_tf32 = False
     sd = model.state_dict()
-    to_stock(model)
+    core.to_stock_layers(model)
     assert list(model.state_dict()) == list(sd)
     model.zero_grad(set_to_none=True)
     ref = model(batch)

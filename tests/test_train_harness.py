@@ -57,3 +57,19 @@ def test_short_training_run_reduces_the_loss_and_saves_a_loadable_state(tmp_path
                                               block_size=160, has_reverb=True))
     model.load_state_dict(state)
     assert (tmp_path / "runs" / "t" / "config.yaml").exists()
+
+
+@pytest.mark.gpu
+def test_training_curve_matches_the_stock_control_net(tmp_path):
+    """Same data, seed and noise: 30 optimiser steps on this repo's control-net kernels and on the stock torch.nn
+    layers (cuBLAS / cuDNN fp32) end at the same loss to within rounding-driven drift."""
+    from ddsp_pytorch_b200 import train
+    torch.backends.cudnn.allow_tf32 = False
+    train.write_synthetic_dataset(tmp_path / "data" / "train", 16, seconds=1.0, seed=0)
+    common = ["--data", str(tmp_path / "data"), "--root", str(tmp_path / "runs"), "--steps", "30", "--batch", "8",
+              "--scales", "1024", "512", "256", "128", "--log-every", "5", "--warmup", "2", "--no-graph"]
+    ours = train.run(train.parser().parse_args(common + ["--name", "k"]))
+    stock = train.run(train.parser().parse_args(common + ["--name", "s", "--stock-control-net"]))
+    assert ours["control_net"] == "kernels" and stock["control_net"] == "torch.nn"
+    assert abs(ours["first_logged_loss"] - stock["first_logged_loss"]) < 1e-3 * stock["first_logged_loss"]
+    assert abs(ours["last_logged_loss"] - stock["last_logged_loss"]) < 2e-2 * stock["last_logged_loss"], (ours, stock)

@@ -13,23 +13,9 @@ if args.tf32:
 torch.manual_seed(0)
 B, T, bs, sr = args.batch, 400, 160, 16000
 model = DDSPDecoder(hidden_size=512, n_harmonic=100, n_bands=65, sample_rate=sr, block_size=bs, has_reverb=True).cuda()
-def to_stock(mod):
-    """Replace this repo's control-net layers by the stock torch.nn ones the reference builds (same weights)."""
-    from ddsp_pytorch_b200 import core
-    for name, child in list(mod.named_children()):
-        if isinstance(child, core.Linear):
-            new = torch.nn.Linear(child.in_features, child.out_features).cuda(); new.load_state_dict(child.state_dict())
-        elif isinstance(child, core.LayerNormLeakyReLU):
-            new = torch.nn.LayerNorm(child.normalized_shape).cuda(); new.load_state_dict(child.state_dict())
-        elif isinstance(child, core.FusedIntoLayerNorm):
-            new = torch.nn.LeakyReLU()
-        elif isinstance(child, core.ClusterGRU):
-            new = torch.nn.GRU(child.input_size, child.hidden_size, batch_first=True).cuda(); new.load_state_dict(child.state_dict())
-        else:
-            to_stock(child); continue
-        setattr(mod, name, new)
 if args.stock_control_net:
-    to_stock(model)
+    from ddsp_pytorch_b200 import core
+    core.to_stock_layers(model)
 if args.stock_gru:      # A/B: the cuDNN recurrence the reference runs
     stock = torch.nn.GRU(1024, 512, batch_first=True).cuda(); stock.load_state_dict(model.decoder.gru.state_dict()); model.decoder.gru = stock
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
