@@ -160,7 +160,7 @@ class Trainer:
         self.mean_loudness, self.std_loudness = float(mean_loudness), float(std_loudness)
         self.device, self.group = device, group
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.opt = torch.optim.Adam(self.params, lr=lr)
+        self.opt = torch.optim.Adam(self.params, lr=lr, fused=bool(self.params and self.params[0].is_cuda))
         self.bucket = GradBucket([p.shape for p in self.params], device, group=group)
         self.step_count = 0
         self.use_graph, self.graph_after, self.graph = use_graph, graph_after, None
