@@ -278,10 +278,25 @@ struct GruSmemBwd {
     float w[kSmemRows * kH];                      // [half*32 + (rr - 16)][512]
     float partial[2][kC][kV][kU];                 // [buffer][destination CTA][voice][unit]
     float recv[2][kC][kV][kU];                    // [buffer][source CTA][voice][unit]
-    float down[kRows * 24];                       // [row][12 (>= kV)][2] gate gradients, each stored twice (FFMA2 operand)
+    float down[kRows * 12];                       // [row][12 (>= kV)] gate gradients of the own rows
     float dhn[kV * kU];                           // recurrent part of dh for the own units
     unsigned long long bar[2];
 };
+
+// the gate gradients of one row for the voices the product covers: 1..3 LDS.128 (warp-uniform address)
+template <int NV>
+__device__ __forceinline__ void load_down(const float *p, float (&dv)[12]) {
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    dv[0] = a.x; dv[1] = a.y; dv[2] = a.z; dv[3] = a.w;
+    if (NV > 4) {
+        const float4 b = *reinterpret_cast<const float4 *>(p + 4);
+        dv[4] = b.x; dv[5] = b.y; dv[6] = b.z; dv[7] = b.w;
+    }
+    if (NV > 8) {
+        const float4 c = *reinterpret_cast<const float4 *>(p + 8);
+        dv[8] = c.x; dv[9] = c.y; dv[10] = c.z; dv[11] = c.w;
+    }
+}
 
 template <int NV>
 __global__ void __launch_bounds__(kGruThreads, 1)
@@ -375,9 +390,9 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                         float *c = dgh + o * 3 * kH + gcol;
                         c[0] = dar; c[kH] = daz; c[2 * kH] = dghn;
                     }
-                    reinterpret_cast<float2 *>(s.down)[(0 * kU + gu) * 12 + v] = make_float2(dar, dar);
-                    reinterpret_cast<float2 *>(s.down)[(1 * kU + gu) * 12 + v] = make_float2(daz, daz);
-                    reinterpret_cast<float2 *>(s.down)[(2 * kU + gu) * 12 + v] = make_float2(dghn, dghn);
+                    s.down[(0 * kU + gu) * 12 + v] = dar;
+                    s.down[(1 * kU + gu) * 12 + v] = daz;
+                    s.down[(2 * kU + gu) * 12 + v] = dghn;
                     s.dhn[i] = direct;                   // the recurrent part is added after the reduce-scatter
                 }
             }
@@ -391,28 +406,26 @@ gru_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ dhT, cons
                 for (int v = 0; v < 2 * NVP; ++v) acc2[v][0] = acc2[v][1] = 0ull;
 #pragma unroll
                 for (int rr = 0; rr < KR; ++rr) {
-                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
+                    float dv[12];
+                    load_down<NV>(s.down + (r0 + rr) * 12, dv);
 #pragma unroll
-                    for (int vp = 0; vp < NVP; ++vp) {
-                        const ulonglong2 d = dp[vp];                 // (d_v, d_v), (d_v+1, d_v+1)
-                        acc2[2 * vp][0] = fma2(d.x, wreg[rr].x, acc2[2 * vp][0]);
-                        acc2[2 * vp][1] = fma2(d.x, wreg[rr].y, acc2[2 * vp][1]);
-                        acc2[2 * vp + 1][0] = fma2(d.y, wreg[rr].x, acc2[2 * vp + 1][0]);
-                        acc2[2 * vp + 1][1] = fma2(d.y, wreg[rr].y, acc2[2 * vp + 1][1]);
+                    for (int v = 0; v < 2 * NVP; ++v) {
+                        const uint64_t d = pk2(dv[v], dv[v]);        // duplicated in registers (ALU pipe), not in shared memory
+                        acc2[v][0] = fma2(d, wreg[rr].x, acc2[v][0]);
+                        acc2[v][1] = fma2(d, wreg[rr].y, acc2[v][1]);
                     }
                 }
                 const ulonglong2 *wq = reinterpret_cast<const ulonglong2 *>(s.w) + (size_t)half * SR * (kH / 4) + q;
 #pragma unroll 8
                 for (int rr = KR; rr < kRows / 2; ++rr) {
                     const ulonglong2 w = wq[(size_t)(rr - KR) * (kH / 4)];
-                    const ulonglong2 *dp = reinterpret_cast<const ulonglong2 *>(s.down + (r0 + rr) * 24);
+                    float dv[12];
+                    load_down<NV>(s.down + (r0 + rr) * 12, dv);
 #pragma unroll
-                    for (int vp = 0; vp < NVP; ++vp) {
-                        const ulonglong2 d = dp[vp];
-                        acc2[2 * vp][0] = fma2(d.x, w.x, acc2[2 * vp][0]);
-                        acc2[2 * vp][1] = fma2(d.x, w.y, acc2[2 * vp][1]);
-                        acc2[2 * vp + 1][0] = fma2(d.y, w.x, acc2[2 * vp + 1][0]);
-                        acc2[2 * vp + 1][1] = fma2(d.y, w.y, acc2[2 * vp + 1][1]);
+                    for (int v = 0; v < 2 * NVP; ++v) {
+                        const uint64_t d = pk2(dv[v], dv[v]);
+                        acc2[v][0] = fma2(d, w.x, acc2[v][0]);
+                        acc2[v][1] = fma2(d, w.y, acc2[v][1]);
                     }
                 }
                 float acc[2 * NVP][4];
