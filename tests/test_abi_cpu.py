@@ -118,7 +118,15 @@ def test_host_side_helpers_on_cpu(pkg):
     assert all(isinstance(m, (torch.nn.Linear, torch.nn.LayerNorm, torch.nn.Identity)) for m in net)
     y = net(torch.randn(3, 5, 1))                  # CPU input: composes the stock ops
     assert y.shape == (3, 5, 8) and bool((y > -0.2).all())
-    assert pkg.gru(2, 8).input_size == 16
+    g = pkg.gru(2, 8)
+    assert g.input_size == 16 and isinstance(g, torch.nn.GRU)
+    ref = torch.nn.GRU(16, 8, batch_first=True)
+    ref.load_state_dict(g.state_dict())                      # same parameter names as nn.GRU
+    xg = torch.randn(2, 5, 16)
+    assert torch.equal(g(xg)[0], ref(xg)[0])                 # CPU / other widths: the stock path of the base class
+    from ddsp_pytorch_b200 import core as _core
+    lin = _core.Linear(40, 7)
+    assert torch.equal(lin(torch.ones(3, 40)), torch.nn.functional.linear(torch.ones(3, 40), lin.weight, lin.bias))
     m, s = pkg.mean_std_loudness([{"loudness": torch.tensor([1.0, 3.0])}, {"loudness": torch.tensor([2.0, 6.0])}])
     assert abs(m - 3.0) < 1e-6
     assert pkg.resample(torch.rand(2, 6, 3), 4).shape == (2, 24, 3)
