@@ -120,3 +120,36 @@ def test_small_inputs_take_the_library_path():
     lin = core.Linear(512, 512).cuda()
     x = torch.randn(1, 8, 512, device="cuda")
     assert torch.equal(lin(x), torch.nn.functional.linear(x, lin.weight, lin.bias))
+
+
+def test_c_abi_direct_call_of_the_gemm():
+    """split + GEMM through libddsp_b200.so with plain pointers (ctypes), no torch op."""
+    import ctypes
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    lib.ddsp_b200_gemm3x_ld.restype, lib.ddsp_b200_gemm3x_ld.argtypes = i64, [i64]
+    lib.ddsp_b200_gemm3x_split.restype = i32
+    lib.ddsp_b200_gemm3x_split.argtypes = [vp, i64, i64, i64, i32, vp, i64, vp]
+    lib.ddsp_b200_gemm3x.restype = i32
+    lib.ddsp_b200_gemm3x.argtypes = [vp, i64, i64, i32, vp, i64, i64, i32, vp, vp, i64, i32, i32, i32, vp, vp]
+    M, N, K = 300, 200, 70
+    g = torch.Generator().manual_seed(9)
+    x, w, b = torch.randn(M, K, generator=g).cuda(), torch.randn(N, K, generator=g).cuda(), torch.randn(N, generator=g).cuda()
+    y = torch.empty(M, N, device="cuda")
+    ld = lib.ddsp_b200_gemm3x_ld(K)
+    assert ld == 128
+
+    def rp(r):
+        return (r + 63) // 64 * 64
+    xs = torch.empty(3 * rp(M), ld, dtype=torch.bfloat16, device="cuda")
+    ws = torch.empty(3 * rp(N), ld, dtype=torch.bfloat16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.ddsp_b200_gemm3x_split(x.data_ptr(), M, K, K, 0, xs.data_ptr(), rp(M), st) == 0
+    assert lib.ddsp_b200_gemm3x_split(w.data_ptr(), N, K, K, 0, ws.data_ptr(), rp(N), st) == 0
+    assert lib.ddsp_b200_gemm3x(xs.data_ptr(), rp(M), ld, 0, ws.data_ptr(), rp(N), ld, 0, b.data_ptr(), y.data_ptr(), N,
+                                M, N, K, None, st) == 0
+    torch.cuda.synchronize()
+    ref = x.double() @ w.double().t() + b.double()
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < 2e-6
+    assert lib.ddsp_b200_gemm3x(None, rp(M), ld, 0, ws.data_ptr(), rp(N), ld, 0, None, y.data_ptr(), N, M, N, K, None, st) == -1
