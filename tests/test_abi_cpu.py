@@ -130,3 +130,19 @@ def test_host_side_helpers_on_cpu(pkg):
     m, s = pkg.mean_std_loudness([{"loudness": torch.tensor([1.0, 3.0])}, {"loudness": torch.tensor([2.0, 6.0])}])
     assert abs(m - 3.0) < 1e-6
     assert pkg.resample(torch.rand(2, 6, 3), 4).shape == (2, 24, 3)
+
+
+def test_control_net_wiring_reproduces_the_reference_golden_vectors_on_cpu():
+    """decoder.py:9-68: this repo's GRUDecoder (CPU float64: the stock path of every layer) against the float64
+    output of the UNMODIFIED reference GRUDecoder built from the same seed (oracle/make_golden_control_net.py)."""
+    import numpy as np
+    from conftest import load_golden
+    from ddsp_pytorch_b200.models.decoder import GRUDecoder
+    g = load_golden("control_net_gru_decoder")
+    torch.manual_seed(int(g["seed"]))
+    dec = GRUDecoder(hidden_size=512)
+    sums = torch.stack([p.detach().double().sum() for p in dec.state_dict().values()]).numpy()
+    if not np.allclose(sums, np.asarray(g["weight_sums"]), rtol=0, atol=1e-9):
+        pytest.skip("this torch build initialises the layers differently from the one that wrote the fixture")
+    out = dec.double()(torch.as_tensor(g["f0"]).double(), torch.as_tensor(g["loudness"]).double())
+    assert float((out.detach()[:, ::4, ::4] - torch.as_tensor(g["out"])).abs().max()) < 1e-10
