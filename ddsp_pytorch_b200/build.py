@@ -23,8 +23,8 @@ INCLUDE = os.path.join(ROOT, "include")
 LIB_CORE = os.path.join(PKG, "libddsp_b200.so")
 LIB_TORCH = os.path.join(PKG, "libddsp_b200_torch.so")
 
-CU_SOURCES = ["controls.cu", "harmonic.cu", "noise.cu", "stft.cu", "fftconv.cu", "gru.cu", "gemm3x.cu", "layernorm.cu"]
-CU_HEADERS = ["common.cuh", "fft.cuh", "regfft.cuh"]
+CU_SOURCES = ["controls.cu", "harmonic.cu", "noise.cu", "stft.cu", "mss_fused.cu", "fftconv.cu", "gru.cu", "gemm3x.cu", "layernorm.cu"]
+CU_HEADERS = ["common.cuh", "fft.cuh", "regfft.cuh", "pfft.cuh"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -92,8 +92,11 @@ __device__ __forceinline__ float ddsp_warp_sum(float v) {
     return v;
 }
 
-// ---- packed FP32 (sm_100 FFMA2 / FADD2): one instruction on a 64-bit register pair of two floats.  A plain
-// three-register FFMA issues every other cycle per scheduler; the packed form reaches the nominal FP32 rate.
+// ---- packed FP32 (sm_100 FFMA2 / FADD2 / FMUL2): one instruction on a 64-bit register pair of two floats.
+// Measured (tools/probes/fp32_pace_probe.cu, profiles/r02_fp32_pace_probe.txt): a scalar FFMA issues every cycle
+// per scheduler (128 lanes/clk/SM) and a packed one every other cycle, so the FP32 lane rate is the same; what the
+// packed forms save is issue slots (and, with two transforms in the two halves, index maths and LDS/STS count).
+// ptxas folds negation, a half swap (.LO_HI) and a scalar broadcast (R.F32) into the operand for free.
 __device__ __forceinline__ uint64_t pk2(float a, float b) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));

@@ -175,22 +175,50 @@ DDSP_HD void stage_compute_sink(float2 (&x)[16], int t, const float2 *tw, const 
         for (int r = 0; r < R; ++r) store(stage_out_index<LG, S>(t, m, r), x[m * R + r]);
 }
 
+// Padded shared-memory addresses as "base(t, m) + r * constant": the strides between a thread's R accesses of one
+// butterfly are multiples of 16 elements (or the accesses stay inside one run of 16), so the padding term splits
+// off exactly and the compiler addresses all R accesses from one register with immediate offsets.
+//   loads  (stage S >= 1): pad16(j + r*N/R)                  = pad16(j)            + r * (N/R) * 17/16
+//   stores stage 0       : pad16(16 j + r)                   = 17 j                + r
+//          stage 1       : pad16((j-k) R + k + 16 r), k<16   = pad16((j-k) R) + k  + r * 17
+//          stage 2       : pad16((j-k) R + k + 256 r), k<256 = pad16((j-k) R + k)  + r * 272
+template <int LG, int S> DDSP_HD int in_base_padded(int t, int m) { return pad16(t + m * Plan<LG>::T); }
+template <int LG, int S> DDSP_HD constexpr int in_stride_padded() {
+    return (Plan<LG>::N / Stage<LG, S>::R) / 16 * 17;
+}
+template <int LG, int S> DDSP_HD int out_base_padded(int t, int m) {
+    constexpr int R = Stage<LG, S>::R;
+    constexpr int NS = Stage<LG, S>::NS;
+    const int j = t + m * Plan<LG>::T;
+    const int k = j & (NS - 1);
+    return S == 0 ? 17 * j : pad16((j - k) * R + k);     // stage 1: (j-k) R is a multiple of 16, k < 16
+}
+template <int LG, int S> DDSP_HD constexpr int out_stride_padded() { return S == 0 ? 1 : (S == 1 ? 17 : 272); }
+static_assert(Plan<6>::N / Stage<6, 1>::R % 16 == 0 && Plan<9>::N / Stage<9, 2>::R % 16 == 0, "strides are multiples of 16");
+
 template <int LG, int S, bool INV>
 DDSP_HD void stage_compute_store(float2 (&x)[16], float2 *buf, int t, const float2 *tw) {
-    stage_compute_sink<LG, S, INV>(x, t, tw, SmemStore{buf});
+    constexpr int R = Stage<LG, S>::R;
+    constexpr int M = 16 / R;
+    stage_compute_regs<LG, S, INV>(x, t, tw);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        float2 *dst = buf + out_base_padded<LG, S>(t, m);
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst[r * out_stride_padded<LG, S>()] = x[m * R + r];
+    }
 }
 
 // Load the inputs of stage S (S >= 1) from buf into registers.
 template <int LG, int S>
 DDSP_HD void stage_load(float2 (&x)[16], const float2 *buf, int t) {
-    using P = Plan<LG>;
     constexpr int R = Stage<LG, S>::R;
     constexpr int M = 16 / R;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        const int j = t + m * P::T;
+        const float2 *src = buf + in_base_padded<LG, S>(t, m);
 #pragma unroll
-        for (int r = 0; r < R; ++r) x[m * R + r] = buf[pad16(j + r * (P::N / R))];
+        for (int r = 0; r < R; ++r) x[m * R + r] = src[r * in_stride_padded<LG, S>()];
     }
 }
 

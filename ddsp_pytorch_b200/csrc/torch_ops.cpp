@@ -41,6 +41,18 @@ void *cur_stream() { return (void *)at::cuda::getCurrentCUDAStream().stream(); }
 const float *fp(const Tensor &t) { return t.data_ptr<float>(); }
 float *fpm(Tensor &t) { return t.data_ptr<float>(); }
 
+// A constant table is built once per (device, size) by whichever thread and stream asks first, and is then
+// handed to every other thread and stream from the cache.  So the build must not be part of a CUDA graph capture
+// (the tensor would live in the graph's private pool) and must be complete before the cache publishes it.
+void finish_table_build(const char *what) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStream_t st = at::cuda::getCurrentCUDAStream().stream();
+    TORCH_CHECK(cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone,
+                "ddsp_b200: constant table '", what, "' would be built inside a CUDA graph capture; run the op "
+                "once eagerly (warm-up) before capturing");
+    TORCH_CHECK(cudaStreamSynchronize(st) == cudaSuccess, "ddsp_b200: building table '", what, "' failed");
+}
+
 // Caller-owned constant tables, created lazily per (device, size); safe from any thread.
 Tensor twiddle_table(const at::Device &dev, int64_t n) {
     static std::mutex mu;
@@ -51,6 +63,7 @@ Tensor twiddle_table(const at::Device &dev, int64_t n) {
     if (it != cache.end()) return it->second;
     Tensor t = at::empty({n, 2}, at::TensorOptions().device(dev).dtype(at::kFloat));
     check(ddsp_b200_twiddle_table(fpm(t), (int)n, cur_stream()), "twiddle_table");
+    finish_table_build("twiddle_table");
     cache[key] = t;
     return t;
 }
@@ -67,6 +80,7 @@ Tensor stage_twiddle_table(const at::Device &dev, int64_t n_fft) {
     if (n > 0) {
         t = at::empty({n, 2}, at::TensorOptions().device(dev).dtype(at::kFloat));
         check(ddsp_b200_fft_stage_twiddles(fpm(t), (int)n_fft, cur_stream()), "stft_stage_twiddles");
+        finish_table_build("fft_stage_twiddles");
     }
     cache[key] = t;
     return t;
@@ -81,6 +95,7 @@ Tensor noise_design_table(const at::Device &dev, int64_t NB) {
     if (it != cache.end()) return it->second;
     Tensor t = at::empty({ddsp_b200_noise_design_size((int)NB)}, at::TensorOptions().device(dev).dtype(at::kFloat));
     check(ddsp_b200_noise_design_table(fpm(t), (int)NB, cur_stream()), "noise_design_table");
+    finish_table_build("noise_design_table");
     cache[key] = t;
     return t;
 }
@@ -537,6 +552,25 @@ std::tuple<Tensor, Tensor> mss_loss_fwd(const Tensor &target_, const Tensor &rec
     }
     TORCH_CHECK(win.numel() == wsum, "mss_loss: windows must hold sum(scales) values");
     c10::cuda::CUDAGuard guard(rec.device());
+    if (ddsp_b200_mss_fused_supported(sc.data(), hp.data(), ns)) {
+        // the reference's setting (overlap 0.75): every scale in one launch
+        int64_t ws_floats = 0, part_floats = 0;
+        check(ddsp_b200_mss_fused_sizes((int)B, N, sc.data(), ns, &ws_floats, &part_floats), "mss_fused_sizes");
+        std::vector<Tensor> tables;
+        std::vector<const float *> tabs;
+        for (int i = 0; i < ns; ++i) {
+            tables.push_back(stage_twiddle_table(rec.device(), sc[i]));
+            tabs.push_back(fp(tables.back()));
+        }
+        Tensor partial = at::empty({part_floats}, rec.options());
+        Tensor loss = at::empty({}, rec.options());
+        Tensor d_rec = need_grad ? at::empty_like(rec) : at::empty({0}, rec.options());
+        Tensor ws = need_grad ? at::empty({ws_floats}, rec.options()) : Tensor();
+        check(ddsp_b200_mss_fused(fp(tgt), fp(rec), fp(win), tabs.data(), need_grad ? fpm(ws) : nullptr, fpm(partial),
+                                  need_grad ? fpm(d_rec) : nullptr, fpm(loss), (int)B, N, sc.data(), ns, cur_stream()),
+              "mss_fused");
+        return {loss, d_rec};
+    }
     Tensor tw = twiddle_table(rec.device(), std::max<int64_t>(4096, pow2_ge(smax)));
     Tensor partial = at::empty({tiles, 2}, rec.options());
     Tensor loss = at::empty({}, rec.options());

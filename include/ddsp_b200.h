@@ -210,6 +210,24 @@ int ddsp_b200_mss_finish(const float *partial, const float *edge, const float *d
                          float *d_rec, float *loss, int B, int64_t N, const int *scales,
                          const int *hops, int n_scales, void *stream);
 
+/* ---- a11+a12+a13, all scales in one launch  (ddsp/core.py:27-41 + train.py:70-76,92-103 + backward) ----
+ * The fused loss for the reference's setting hop = n_fft/4 (overlap 0.75), n_fft = 64..4096 powers of two
+ * (mss_fused_supported says whether a scale list qualifies; anything else goes through mss_scale/mss_finish).
+ * One launch covers every (scale, voice, tile of frames): each frame is transformed once, rec and target are
+ * read once per scale from L2, the per-scale gradients meet in `workspace` and a second small launch sums
+ * them in scale order and folds the reflect padding into d_rec (deterministic, no atomics).
+ *   windows        : the scales' windows back to back (sum(scales) floats), as for mss_scale
+ *   stage_twiddles : n_scales device pointers (host array), table i = ddsp_b200_fft_stage_twiddles(scales[i])
+ *   workspace / partial : caller-owned scratch of the sizes mss_fused_sizes returns (floats); partial is
+ *                    needed always, workspace only with d_rec
+ *   d_rec == NULL  : loss only.                                                                       */
+int ddsp_b200_mss_fused_supported(const int *scales, const int *hops, int n_scales);
+int ddsp_b200_mss_fused_sizes(int B, int64_t N, const int *scales, int n_scales, int64_t *workspace_floats,
+                              int64_t *partial_floats);
+int ddsp_b200_mss_fused(const float *target, const float *rec, const float *windows,
+                        const float *const *stage_twiddles, float *workspace, float *partial, float *d_rec,
+                        float *loss, int B, int64_t N, const int *scales, int n_scales, void *stream);
+
 /* ---- f3 (next row)  GRU recurrence of the control net  (ddsp/core.py:132-133, decoder.py:40,59,65) --- */
 /* The cuDNN GRU the reference calls runs one SGEMM + one element-wise launch per time step.  Here the
  * recurrence is one launch: 16-CTA clusters keep W_hh (3H x H fp32) in distributed shared memory.
