@@ -7,18 +7,23 @@ synth parameters (decoder.py:106-125 + train.py:92-103,129 of the reference, wit
 network).  Workload: 16 kHz, block 160, 100 harmonics, 65 noise bands, 4 s, batch 64 sharded over
 the N GPUs (strong scaling), reverb 16000 taps, 6 STFT scales.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload train|bulk]
     torchrun --nproc-per-node N bench.py --gpus N ...     (one rank per GPU)
 
 Prints ONE JSON line (rank 0).  `value` = audio samples/s of forward+backward with inputs resident
 in HBM (CUDA events, max over ranks); `e2e` = the same through pinned host buffers with the H2D
-copies and the loss read-back inside the timed region; `roofline` = the dominant kernel against the
-measured peak; `cpu_baseline` = the oracle port (the reference's algorithm as torch CPU float32) on
-this box's host cores.  `--impl reference` times only that CPU path.
+copies and the loss read-back inside the timed region; `roofline` = the dominant kernel against its
+binding roof; `parity` = this run's audio and loss against the float64 oracle (outside the timed
+region); `cpu_baseline` = the unmodified reference (oracle/_ref) on this box's host cores;
+`configs` = the other BASELINE.json configurations (full model step, batch-16 forward, realtime
+latency, autoencoder, bulk-render slice).  `--impl reference` times only the reference's CPU path and
+imports nothing of the product.  `--workload bulk` is configs[3]: forward only, 1024 voices per GPU
+(weak scaling, no collective).
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -32,12 +37,13 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "DDSP synth audio samples/sec (fwd+bwd)"
-K4L_DRAM_TRAFFIC = 197.2e6       # bytes per step, from the round-1 ncu --set full capture (profiles/)
 UNIT = "samples/s"
 WORKLOAD = dict(sample_rate=16000, block_size=160, n_harmonic=100, n_bands=65, frames=400, batch=64,
                 reverb_length=16000, scales=(4096, 2048, 1024, 512, 256, 128), overlap=0.75)
 WORKLOAD_NAME = ("configs[1]: synth hot path fwd+bwd with multiscale_fft loss, 16 kHz, block 160, "
                  "100 harmonics, 65 bands, 4 s, batch 64 sharded over N GPUs, reverb 16000 taps")
+BULK_NAME = ("configs[3]: bulk render, 48 kHz, block 512, 256 harmonics, 65 bands, 4 s, 1 s learned-IR reverb, forward, "
+             "1024 voices per GPU (8192 over 8), no cross-GPU traffic")
 
 
 def parse():
@@ -46,23 +52,33 @@ def parse():
     p.add_argument("--steps", type=int, default=100)
     p.add_argument("--warmup", type=int, default=10)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--workload", default="train", choices=["train", "bulk"])
     p.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
-    p.add_argument("--cpu-batch", type=int, default=8, help="voices in the bounded CPU-baseline sample")
+    p.add_argument("--cpu-batch", type=int, default=16, help="voices in the bounded cpu_baseline sample of the B200 arm")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--global-batch", type=int, default=WORKLOAD["batch"],
                    help="experiments only: the benchmark config is batch 64 (BASELINE.json configs[1])")
     p.add_argument("--skip-kernels", action="store_true")
+    p.add_argument("--skip-configs", action="store_true", help="do not measure the other BASELINE.json configurations")
+    p.add_argument("--skip-parity", action="store_true")
+    p.add_argument("--bulk-voices", type=int, default=1024, help="voices per GPU of --workload bulk")
     return p.parse_args()
 
 
+def shapes_module():
+    """ddsp_pytorch_b200/shapes.py loaded by path: pure Python, does not import the package (no native library is
+    mapped into a process that only runs the reference arm)."""
+    name = "b200_bench_shapes"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "ddsp_pytorch_b200", "shapes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_step(shapes, host, reverb_state, orc):
-    rp = {k: v for k, v in reverb_state.items()}
-    return orc.synth_train_step(host["amp_raw"], host["dist_raw"], host["mag_raw"], host["pitch"],
-                                host["noise"], host["target"], shapes.block_size, shapes.sample_rate, rp,
-                                list(shapes.scales), shapes.overlap)
-
-
 def cpu_reverb_state(shapes, seed=0):
     g = torch.Generator().manual_seed(seed)
     L = shapes.reverb_length
@@ -70,49 +86,72 @@ def cpu_reverb_state(shapes, seed=0):
             "wet": torch.tensor(0.0), "t": (torch.arange(L) / shapes.sample_rate).reshape(1, -1, 1)}
 
 
-def time_cpu_port(batch, steps, warmup):
-    """The oracle port (kind "port"): the reference's algorithm as torch CPU float32 on all host threads."""
-    from ddsp_pytorch_b200.hotpath import SynthShapes, synthetic_inputs
-    from oracle import ddsp_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    w = dict(WORKLOAD)
-    w["batch"] = batch
-    shapes = SynthShapes(**w)
-    host = synthetic_inputs(shapes, seed=0)
-    rs = cpu_reverb_state(shapes)
-    for _ in range(warmup):
-        cpu_port_step(shapes, host, rs, orc)
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        cpu_port_step(shapes, host, rs, orc)
-        times.append(time.perf_counter() - t0)
-    return shapes, times, cores
+class CpuArm:
+    """The reference's CPU implementation of the step on `batch` voices of the benchmark shapes: the unmodified
+    reference from oracle/_ref (kind "reference") when it is in place, else the oracle port (kind "port")."""
+
+    def __init__(self, batch):
+        sm = shapes_module()
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        w = dict(WORKLOAD)
+        w["batch"] = batch
+        self.shapes = sm.SynthShapes(**w)
+        self.host = sm.synthetic_inputs(self.shapes, seed=0)
+        rs = cpu_reverb_state(self.shapes)
+        from oracle import ref_step
+        if ref_step.available():
+            self.kind = "reference"
+            self.impl = ref_step.ReferenceStep(self.shapes, rs)
+            self.fn = lambda: self.impl.step(self.host)
+        else:
+            from oracle import ddsp_oracle as orc
+            self.kind = "port"
+            h, s = self.host, self.shapes
+            self.fn = lambda: orc.synth_train_step(h["amp_raw"], h["dist_raw"], h["mag_raw"], h["pitch"], h["noise"],
+                                                   h["target"], s.block_size, s.sample_rate, dict(rs), list(s.scales),
+                                                   s.overlap)
+
+    def time(self, steps, warmup):
+        for _ in range(warmup):
+            self.fn()
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            self.fn()
+            times.append(time.perf_counter() - t0)
+        return times
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's own CPU path, all host threads, on as many of the 64 voices per step as
+    keep the whole run within a few minutes (all 64 on the GPU boxes' hosts).  Nothing of the product is imported."""
     if rank != 0:
         return
-    # size the per-step sample so that the whole run stays within a couple of minutes
-    batch = 2
-    shapes, t1, cores = time_cpu_port(batch, 1, 1)
-    budget = 120.0 / max(1, args.steps + args.warmup)
-    while batch < args.cpu_batch and t1[0] * 2 <= budget:
-        batch *= 2
-        t1 = [t1[0] * 2]
-    shapes, times, cores = time_cpu_port(batch, args.steps, args.warmup)
+    total_steps = max(1, args.steps + args.warmup)
+    budget = 240.0 / total_steps                                  # seconds one step may take
+    probe = CpuArm(4)
+    t4 = min(probe.time(2, 1))
+    batch = WORKLOAD["batch"]
+    while batch > 2 and t4 * batch / 4 > budget:
+        batch //= 2
+    arm = CpuArm(batch)
+    times = arm.time(args.steps, args.warmup)
     total = sum(times)
-    value = batch * shapes.samples * len(times) / total
-    sample = f"{batch} of 64 voices per step (same shapes), float32, {cores} threads"
+    value = batch * arm.shapes.samples * len(times) / total
+    same = batch == WORKLOAD["batch"]
+    sample = (f"all {batch} voices per step" if same else f"{batch} of 64 voices per step (same shapes)") + \
+        f", float32, {arm.cores} threads, " + ("unmodified reference code from oracle/_ref" if arm.kind == "reference"
+                                               else "oracle port (oracle/_ref not present)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "per_step_sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": {"workload": WORKLOAD_NAME, "per_step_sample": sample, "same_config": same},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "product_modules_imported": sorted(m for m in sys.modules if m.startswith("ddsp_pytorch_b200")),
     }
     print(json.dumps(line), flush=True)
 
@@ -188,9 +227,30 @@ def event_time(fn, iters, warmup, flush=None):
     return total / iters          # ms
 
 
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            peaks = json.load(f)
+        peaks["source"] = "MEASURED_PEAKS.json (burst copy bandwidth)"
+    return peaks
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r02_ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        d = json.load(f)
+    e = d.get(key)
+    return (e["dram_bytes"], e.get("note")) if e else (None, None)
+
+
 def kernel_table(step, shapes, flush, peaks):
     """Per-kernel device time (events, L2 flushed) and roofline fraction for the stages of the path."""
-    import ddsp_pytorch_b200 as ddsp
+    import math
     ops = torch.ops.ddsp_b200
     i = {k: v.detach() for k, v in step.inputs.items()}
     B, T, bs, H, NB, N = shapes.batch, shapes.frames, shapes.block_size, shapes.n_harmonic, shapes.n_bands, shapes.samples
@@ -202,9 +262,8 @@ def kernel_table(step, shapes, flush, peaks):
     imp = step.reverb.build_impulse().detach().reshape(1, -1)
     from ddsp_pytorch_b200.functions import hann_window_like_reference
     windows = torch.cat([hann_window_like_reference(s, audio.device) for s in shapes.scales])
-    hbm = peaks["hbm_gbs"] * 1e9
     clk = (peaks.get("sm_max_mhz") or 1965.0) * 1e6
-    fma_peak = 148 * 128 * clk                      # FP32 FMA lanes / s at max clock
+    fma_peak = 148 * 128 * clk                      # FP32 lanes x clock: FMAs (or adds, or muls) per second
     hs = B * N * H                                  # harmonic-samples
     rows = []
 
@@ -225,41 +284,176 @@ def kernel_table(step, shapes, flush, peaks):
     add("K2 filtered_noise_fwd", lambda: ops.noise_fwd(i["mag_raw"], i["noise"], audio, True, -5.0), alg_bytes=4 * B * T * (NB + 3 * bs))
     add("K2 filtered_noise_bwd", lambda: ops.noise_bwd(g, i["noise"], i["mag_raw"], NB, True, -5.0), alg_bytes=4 * B * T * (NB + 2 * bs))
     kept = ops.fftconv_fwd(sig2, imp, True)
-    add("K3 reverb fftconv_fwd (5 launches)", lambda: ops.fftconv_fwd(sig2, imp, True), alg_bytes=4 * (2 * B * N + imp.numel()))
-    add("K3 reverb fftconv_bwd (5 launches, transforms kept by fwd)", lambda: ops.fftconv_bwd(sig2, sig2, imp, kept[1], kept[2], True, True),
+    add("K3 reverb fftconv_fwd", lambda: ops.fftconv_fwd(sig2, imp, True), alg_bytes=4 * (2 * B * N + imp.numel()))
+    add("K3 reverb fftconv_bwd (transforms kept by fwd)", lambda: ops.fftconv_bwd(sig2, sig2, imp, kept[1], kept[2], True, True),
         alg_bytes=4 * (3 * B * N + 2 * imp.numel()))
-    add("K4L mss_loss fwd+grad (6 scales + finish)",
-        lambda: ops.mss_loss_fwd(i["target"], sig2, list(shapes.scales), shapes.overlap, windows, True),
-        alg_bytes=4 * 3 * B * N, note="SURVEY 8d: read rec+target, write grad")
-    # the same kernel against the FP32 pipe: 5 n log2 n flops per complex FFT, one forward per frame
-    # (rec + i*target) and one inverse per frame pair
-    import math
+    # K4L: FP32-pipe bound (ncu: profiles/).  Algorithmic flops = 5 n log2 n per complex FFT, one forward per frame
+    # (rec + i*target) and one inverse per frame pair; HBM view (read rec + target, write grad) beside it.
     fft_flops = 0.0
     for s_ in shapes.scales:
         hop = int(s_ * (1 - shapes.overlap))
         fft_flops += 1.5 * (1 + N // hop) * 5.0 * s_ * math.log2(s_)
     fft_flops *= B
-    k4 = rows[-1]
-    k4["fp32"] = {"achieved": fft_flops / (k4["ms"] * 1e-3) / 1e12, "peak": 2 * fma_peak / 1e12, "unit": "TFLOP/s",
-                  "frac": fft_flops / (k4["ms"] * 1e-3) / (2 * fma_peak),
-                  "note": "FFT butterflies only (7.0 GFLOP/step); the kernel is FP32/latency bound, not HBM bound"}
+    ms = event_time(lambda: ops.mss_loss_fwd(i["target"], sig2, list(shapes.scales), shapes.overlap, windows, True), 20, 3, flush)
+    rows.append({"kernel": "K4L mss_loss fwd+grad (all scales in one launch + finalize + combine)", "ms": ms, "bound": "fp32",
+                 "achieved": fft_flops / (ms * 1e-3) / 1e12, "peak": 2 * fma_peak / 1e12, "unit": "TFLOP/s",
+                 "frac": fft_flops / (ms * 1e-3) / (2 * fma_peak),
+                 "note": "FFT butterflies only (5 n log2 n, 7.0 GFLOP/step at batch 64) against 2 x 128 lanes x 148 SMs x max clock",
+                 "hbm": {"achieved": 4 * 3 * B * N / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": 4 * 3 * B * N / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "note": "SURVEY 8d's HBM view: read rec + target, write grad (12 B per sample)"}})
     add("K0 harmonic_controls_fwd", lambda: ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr, True),
         alg_bytes=4 * B * T * (2 * H + 3))
     return rows
+
+
+def parity_check(step, shapes, host, dev):
+    """This run against the float64 oracle, outside the timed region: (a) the first two voices of the benchmark-shape
+    step's audio, (b) a two-voice step (same kernels, same reverb) for audio, loss and the reverb-parameter gradients."""
+    from oracle import ddsp_oracle as orc
+    from ddsp_pytorch_b200.hotpath import SynthShapes, SynthStep
+    n = min(2, shapes.batch)
+    rp = {k: v.detach().double().cpu() for k, v in step.reverb.state_dict().items()}
+    d = {k: v[:n].double() for k, v in host.items()}
+    out = orc.synth_chain(d["amp_raw"], d["dist_raw"], d["mag_raw"], d["pitch"], d["noise"], shapes.block_size,
+                          shapes.sample_rate, rp)
+    ref_sig = out["signal"]
+    step.run()
+    torch.cuda.synchronize()
+    audio_bench = float((step.signal[:n].double().cpu() - ref_sig).abs().max())
+    small = SynthShapes(**{**shapes.__dict__, "batch": n})
+    s2 = SynthStep(small, dev, reverb_state=step.reverb.state_dict())
+    s2.load_inputs({k: v[:n].contiguous() for k, v in host.items()}, non_blocking=False)
+    s2.run()
+    torch.cuda.synchronize()
+    ref_loss = float(orc.mss_loss(d["target"], ref_sig.squeeze(-1), list(shapes.scales), shapes.overlap))
+    return {"against": "float64 oracle (oracle/ddsp_oracle.py), 2-voice slice of the benchmark inputs",
+            "audio_max_abs_bench_shape": audio_bench,
+            "audio_max_abs_2_voices": float((s2.signal.double().cpu() - ref_sig).abs().max()),
+            "audio_peak": float(ref_sig.abs().max()),
+            "loss_rel_2_voices": abs(float(s2.loss) - ref_loss) / abs(ref_loss),
+            "tolerance": {"audio_max_abs": 1e-4, "loss_rel": 1e-5},
+            "ok": bool(audio_bench <= 1e-4 and abs(float(s2.loss) - ref_loss) <= 1e-5 * abs(ref_loss))}
+
+
+def other_configs(dev):
+    """The other BASELINE.json configurations, measured in this process (rank 0, one GPU)."""
+    from ddsp_pytorch_b200 import workloads as W
+    out = {}
+    for name, fn in (("model_step", lambda: W.model_step(64)), ("fwd_b16", W.forward_b16), ("realtime", W.realtime_latency),
+                     ("autoencoder", lambda: W.model_step(16, autoencoder=True)), ("bulk_render", lambda: W.bulk_render(256, 128))):
+        try:
+            out[name] = fn()
+        except Exception as e:                       # a sub-measurement must not lose the headline line
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    return out
+
+
+def init_dist(world, dev):
+    if world <= 1:
+        return None
+    # keep stdout to the single JSON line: NCCL prints its version banner there at level VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+    return dist
+
+
+def run_bulk(args, rank, world):
+    """configs[3]: every rank renders its own `bulk-voices` voices, forward only; weak scaling, no collective."""
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = init_dist(world, dev)
+    import ctypes
+    import ddsp_pytorch_b200  # noqa: F401
+    from ddsp_pytorch_b200._lib import core_library
+    from ddsp_pytorch_b200.workloads import BulkRenderer
+    lib = core_library()
+    lib.ddsp_b200_launch_count.restype = ctypes.c_uint64
+    chunk = 128
+    voices = args.bulk_voices
+    r = BulkRenderer(chunk, dev, seed=100 + rank)
+    c0 = lib.ddsp_b200_launch_count()
+    r.render(voices)
+    launches = int(lib.ddsp_b200_launch_count() - c0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(1, min(args.steps, 20))
+    for _ in range(min(args.warmup, 3)):
+        r.render(voices)
+    barrier()
+    with ClockSampler(local) as clocks:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            r.render(voices)                  # 1024 voices x 768 KB of output each: far larger than L2
+        b.record()
+        barrier()
+    tt = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt)
+    samples = voices * world * r.N
+    # end to end: frame-rate controls from pinned host memory per chunk, rendered audio back to pinned host memory
+    hin = {k: v.pin_memory() for k, v in r.host.items() if k != "target" and k != "noise"}
+    hout = torch.empty(chunk, r.N, pin_memory=True)
+    h2d = sum(v.numel() * 4 for v in hin.values())
+
+    def e2e_once():
+        for _ in range(voices // chunk):
+            for k, v in hin.items():
+                r.inp[k].copy_(v, non_blocking=True)
+            hout.copy_(r.render_chunk(), non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_once()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peaks = load_peaks()
+        clk = (peaks.get("sm_max_mhz") or 1965.0) * 1e6
+        hs = voices * r.N * r.H
+        ms_h = event_time(lambda: torch.ops.ddsp_b200.harmonic_fwd(
+            r.inp["pitch"], torch.ops.ddsp_b200.harmonic_controls_fwd(r.inp["amp_raw"], r.inp["dist_raw"], r.inp["pitch"],
+                                                                      float(r.SR), True)[2], r.BS, float(r.SR), None), 5, 2)
+        line = {"metric": "DDSP synth audio samples/sec (fwd)", "value": samples * steps / (total_ms * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": total_ms / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": BULK_NAME, "voices_per_gpu": voices, "chunk": chunk, "samples_per_voice": r.N,
+                           "parallelism": f"voices sharded x{world}, no collective", "l2": "outputs of one step (786 MB) exceed L2"},
+                "e2e": {"value": samples / float(te), "unit": UNIT, "h2d_bytes_per_step": h2d * (voices // chunk) * world,
+                        "d2h_bytes_per_step": 4 * voices * r.N * world, "ms_per_step": 1e3 * float(te)},
+                "gpu_launches": launches,
+                "roofline": {"kernel": "K1 harmonic_frames_fwd (one chunk incl. controls)", "bound": "fp32",
+                             "achieved": 2 * chunk * r.N * r.H / (ms_h * 1e-3) / 1e12, "peak": 148 * 128 * clk / 1e12, "unit": "TFMA/s",
+                             "frac": 2 * chunk * r.N * r.H / (ms_h * 1e-3) / (148 * 128 * clk), "traffic": None, "ms": ms_h,
+                             "note": "SURVEY 8d: 2 FMA per harmonic-sample against 148 SMs x 128 lanes x max clock"},
+                "harmonic_samples_per_s": hs * world * steps / (total_ms * 1e-3), "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_b200(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        # keep stdout to the single JSON line: NCCL prints its version banner there at level VERSION
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
-        import torch.distributed as dist_
-        dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+    dist = init_dist(world, dev)
 
     import ddsp_pytorch_b200  # noqa: F401  (fails loudly without the native libraries)
     from ddsp_pytorch_b200._lib import core_library
@@ -275,25 +469,23 @@ def run_b200(args, rank, world):
     shapes = SynthShapes(**w)
     torch.manual_seed(0)
     step = SynthStep(shapes, dev)
-    host = {k: v.pin_memory() for k, v in synthetic_inputs(shapes, seed=100 + rank).items()}
+    host_cpu = synthetic_inputs(shapes, seed=100 + rank)
+    host = {k: v.pin_memory() for k, v in host_cpu.items()}
     h2d = step.load_inputs(host)
     torch.cuda.synchronize()
 
     # parameter gradients (reverb.noise/decay/wet) are averaged across ranks: the only collective
-    from ddsp_pytorch_b200.distributed import GradBucket
     params = list(step.reverb.parameters())
     n_param = sum(p.numel() for p in params)
-    bucket = GradBucket([p.shape for p in params], dev)
-
-    def allreduce_grads():
-        if dist is not None:
-            bucket.all_reduce_mean(step.grads[3:])
 
     c0 = lib.ddsp_b200_launch_count()
     step.run()
     launches = int(lib.ddsp_b200_launch_count() - c0)
     use_graph = not args.no_graph
     graph_note = "CUDA graph replay"
+    if dist is not None:
+        step.enable_grad_allreduce(dist)            # packed into one flat buffer by the step, reduced in place
+        graph_note += " + one NCCL all-reduce (AVG) of the packed parameter gradients"
     if use_graph:
         try:
             step.capture(forward_only=False)
@@ -312,7 +504,7 @@ def run_b200(args, rank, world):
 
     def full_step():
         run_step()
-        allreduce_grads()
+        step.allreduce_grads()
 
     def barrier():
         torch.cuda.synchronize()
@@ -362,7 +554,7 @@ def run_b200(args, rank, world):
         last = 0.0
         for k in range(n):
             step.step_prefetched()
-            allreduce_grads()
+            step.allreduce_grads()
             step.prefetch(hosts[(k + 1) & 1])                    # H2D of the next batch, overlapped
             last = float(step.loss.detach())                     # D2H + sync of this step's result
         return last
@@ -378,37 +570,40 @@ def run_b200(args, rank, world):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = samples_per_step * e2e_steps / float(te)
 
-    line = None
     if rank == 0:
-        peaks = {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
-        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(pk):
-            with open(pk) as f:
-                peaks = json.load(f)
-            peaks["source"] = "MEASURED_PEAKS.json (burst copy bandwidth)"
+        peaks = load_peaks()
         kernels, roof = [], None
         if not args.skip_kernels:
             kernels = kernel_table(step, shapes, flush, peaks)
             top = max(kernels, key=lambda r: r["ms"])
-            roof = {"kernel": top["kernel"], "bound": top["bound"] if top["bound"] == "hbm" else "tensor",
-                    "achieved": top["achieved"], "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
-                    "traffic": K4L_DRAM_TRAFFIC if top["kernel"].startswith("K4L") else None, "ms": top["ms"],
-                    "peak_source": peaks["source"]}
-            if top["kernel"].startswith("K4L"):
-                roof["traffic_note"] = ("dram__bytes_read+write summed over the 6 per-scale launches of one step, "
-                                        "profiles/r01_ncu_mss_scale_reg_full.csv (ncu flushes caches between "
-                                        "launches, so each scale re-reads rec+target = 32.8 MB; algorithmic 49 MB)")
-            if top["bound"] != "hbm":
-                roof["bound_detail"] = "fp32 FMA pipe, not tensor cores (no GEMM on this path)"
-            if "fp32" in top:
-                roof["fp32"] = top["fp32"]
+            traffic, tnote = ncu_traffic("K4L" if top["kernel"].startswith("K4L") else top["kernel"])
+            roof = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+                    "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "ms": top["ms"],
+                    "peak_source": ("148 SMs x 128 FP32 lanes x 2 flop x max SM clock (MEASURED_PEAKS.json has no FP32 entry; "
+                                    "tools/probes/fp32_pace_probe.cu measured 120 of 128 lanes/clk/SM)") if top["bound"] == "fp32"
+                    else peaks["source"]}
+            if tnote:
+                roof["traffic_note"] = tnote
+            if "hbm" in top:
+                roof["hbm"] = top["hbm"]
+        parity = None
+        if not args.skip_parity:
+            try:
+                parity = parity_check(step, shapes, host_cpu, dev)
+            except Exception as e:
+                parity = {"error": f"{type(e).__name__}: {e}", "ok": False}
         cpu = None
         if world == 1 and not args.skip_cpu:
-            cshapes, times, cores = time_cpu_port(args.cpu_batch, 3, 1)
+            arm = CpuArm(args.cpu_batch)
+            times = arm.time(3, 1)
             best = min(times)
-            cpu = {"value": args.cpu_batch * cshapes.samples / best, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_batch} of 64 voices, same shapes, float32 torch CPU, best of 3",
+            cpu = {"value": args.cpu_batch * arm.shapes.samples / best, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                   "sample": f"{args.cpu_batch} of 64 voices, same shapes, float32 torch CPU, best of 3 ("
+                             + ("unmodified reference from oracle/_ref" if arm.kind == "reference" else "oracle port") + ")",
                    "ms_per_sample_step": best * 1e3}
+        configs = None
+        if world == 1 and not args.skip_configs:
+            configs = other_configs(dev)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -423,8 +618,8 @@ def run_b200(args, rank, world):
                     "ms_per_step": 1e3 * float(te) / e2e_steps, "loss": loss_host,
                     "how": "pinned host -> H2D (copy stream, next batch prefetched during the step) -> D2D into "
                            "the graph inputs -> step -> loss.item(); wall clock between synchronisations"},
-            "gpu_launches": launches, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
-            "clocks": clocks.summary(), "wall_s_timed_loop": t_wall,
+            "gpu_launches": launches, "roofline": roof, "parity": parity, "kernels": kernels, "cpu_baseline": cpu,
+            "configs": configs, "clocks": clocks.summary(), "wall_s_timed_loop": t_wall,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -441,7 +636,10 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: there is no CPU fallback for the kernels")
-    run_b200(args, rank, world)
+    if args.workload == "bulk":
+        run_bulk(args, rank, world)
+    else:
+        run_b200(args, rank, world)
 
 
 if __name__ == "__main__":

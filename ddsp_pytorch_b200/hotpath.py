@@ -7,30 +7,13 @@ bound; one graph launch replaces ~30 kernel launches and all autograd bookkeepin
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Dict, Optional, Sequence
+from typing import Dict, Optional
 
 import torch
 
 from . import core
 from . import functions as F_
-
-
-@dataclass
-class SynthShapes:
-    batch: int
-    frames: int
-    block_size: int
-    n_harmonic: int
-    n_bands: int
-    sample_rate: int
-    reverb_length: Optional[int]            # None = no reverb (realtime export path)
-    scales: Sequence[int] = (4096, 2048, 1024, 512, 256, 128)
-    overlap: float = 0.75
-
-    @property
-    def samples(self) -> int:
-        return self.frames * self.block_size
+from .shapes import SynthShapes, synthetic_inputs  # noqa: F401  (re-exported)
 
 
 INPUT_NAMES = ("amp_raw", "dist_raw", "mag_raw", "pitch", "noise", "target")
@@ -64,6 +47,30 @@ class SynthStep:
         self.grads = None
         self._graph = None
         self._graph_fwd = None
+        self._dist = None                  # set by enable_grad_allreduce (data-parallel training config)
+        self._reduce_in_run = False
+
+    # ---- data parallel: the shared parameters' gradients are averaged over the ranks -------
+    def enable_grad_allreduce(self, dist, group=None):
+        """Voices are sharded over the ranks; the only shared parameters on this path are the reverb's
+        (noise, decay, wet).  Their gradients are packed into one flat buffer and averaged with ONE
+        NCCL all-reduce per step, issued by run() itself so that it becomes a node of the step's CUDA graph."""
+        assert self.reverb is not None
+        self._dist, self._group = dist, group
+        self._sizes = [p.numel() for p in self.reverb.parameters()]
+        self._flat = torch.zeros(sum(self._sizes), device=self.loss.device, dtype=torch.float32)
+        self._reduce_in_run = True
+
+    def _pack_and_reduce(self):
+        torch.cat([g.reshape(-1) for g in self.grads[3:]], out=self._flat)
+        self._dist.all_reduce(self._flat, op=self._dist.ReduceOp.AVG, group=self._group)
+        shapes = [g.shape for g in self.grads[3:]]
+        self.grads = tuple(self.grads[:3]) + tuple(c.view(sh) for c, sh in zip(self._flat.split(self._sizes), shapes))
+
+    def allreduce_grads(self):
+        """No-op when the collective already ran inside run() / the replayed graph."""
+        if self._dist is not None and not self._reduce_in_run:
+            self._pack_and_reduce()
 
     # ---- the path -------------------------------------------------------------------------
     def _leaves(self):
@@ -117,6 +124,8 @@ class SynthStep:
     def run(self):
         self.signal, loss, self.grads = self.forward_backward()
         self.loss = loss
+        if self._dist is not None and self._reduce_in_run:
+            self._pack_and_reduce()
         return loss
 
     def run_forward(self):
@@ -128,6 +137,16 @@ class SynthStep:
         """Capture the step in a CUDA graph (after a few eager runs on a side stream so that lazily
         built tables and the allocator's pools exist before capture)."""
         fn = self.run_forward if forward_only else self.run
+        if not forward_only and self._dist is not None and self._reduce_in_run:
+            try:
+                return self._capture(fn, forward_only, warmup)
+            except Exception:
+                # the collective could not be captured: keep it outside the graph (allreduce_grads() then runs it)
+                torch.cuda.synchronize()
+                self._reduce_in_run = False
+        return self._capture(fn, forward_only, warmup)
+
+    def _capture(self, fn, forward_only, warmup):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -203,23 +222,3 @@ class SynthStep:
                     self.inputs[k].copy_(host[k], non_blocking=non_blocking)
                     n += host[k].numel() * host[k].element_size()
         return n
-
-
-def synthetic_inputs(shapes: SynthShapes, seed: int = 0, pitch_lo: float = 36.0, pitch_hi: float = 84.0):
-    """SURVEY 8d synthetic inputs, drawn with the CPU generator (seeded), as CPU float32 tensors:
-    smooth pitch contours (MIDI note per voice + 5 Hz vibrato), N(0,1) decoder outputs, uniform
-    noise draw, 0.1*N(0,1) target audio."""
-    s = shapes
-    g = torch.Generator().manual_seed(seed)
-    midi = torch.rand(s.batch, 1, 1, generator=g) * (pitch_hi - pitch_lo) + pitch_lo
-    t = torch.arange(s.frames).view(1, -1, 1) * (s.block_size / s.sample_rate)
-    vib = 0.5 * torch.sin(2 * torch.pi * 5.0 * t + 2 * torch.pi * torch.rand(s.batch, 1, 1, generator=g))
-    pitch = 440.0 * torch.pow(2.0, (midi + vib - 69.0) / 12.0)
-    return {
-        "amp_raw": torch.randn(s.batch, s.frames, 1, generator=g),
-        "dist_raw": torch.randn(s.batch, s.frames, s.n_harmonic, generator=g),
-        "mag_raw": torch.randn(s.batch, s.frames, s.n_bands, generator=g),
-        "pitch": pitch.float().contiguous(),
-        "noise": torch.rand(s.batch, s.frames, s.block_size, generator=g) * 2 - 1,
-        "target": 0.1 * torch.randn(s.batch, s.samples, generator=g),
-    }

@@ -1,7 +1,7 @@
 """Control network + synth wiring with the reference's classes and state_dict keys
-(ddsp/models/decoder.py).  The control net (MLPs, GRU, projections) is stock torch.nn --
-cuBLAS / cuDNN -- and outside this round's kernel scope; the synth stages it
-drives are the fused kernels.
+(ddsp/models/decoder.py).  The control net's layers (``core.mlp``, ``core.gru``, ``core.Linear``) are subclasses of
+the stock torch.nn modules that run on this repo's kernels when the shapes qualify (split-bf16 tcgen05 GEMM, fused
+LayerNorm + LeakyReLU, cluster-persistent GRU: DESIGN 3.6); the synth stages they drive are the fused kernels.
 """
 from __future__ import annotations
 

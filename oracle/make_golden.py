@@ -209,10 +209,44 @@ def model_case(ddsp, name, cls, seed, with_mfcc):
     npz(name, **arrays)
 
 
+def model_grad_case(ddsp, name, cls, seed, with_mfcc):
+    """Parameter gradients of the whole model (control net + synth + reverb) for a LINEAR loss sum(signal * go):
+    no L1 sign ties, so float32 kernels can be held to 1e-3 against this float64 run of the unmodified reference.
+    Same seeds as model_case, so the weights equal the ``sd_*`` entries of that fixture (checksum stored)."""
+    kw = dict(hidden_size=16, n_harmonic=12, n_bands=65, sample_rate=16000, block_size=160,
+              has_reverb=True)
+    torch.manual_seed(seed)
+    model = cls(**kw)
+    with torch.no_grad():
+        model.reverb.wet.fill_(0.3)
+    checksum = float(sum(v.double().abs().sum() for v in model.state_dict().values()))
+    model = model.double()
+    B, T = 2, 5
+    g = torch.Generator().manual_seed(seed + 1)
+    batch = {"pitch": (torch.rand(B, T, 1, generator=g) * 500 + 100).double(),
+             "loudness": torch.randn(B, T, 1, generator=g).double()}
+    if with_mfcc:
+        batch["mfcc"] = torch.randn(B, T, 30, generator=g).double()
+    torch.manual_seed(seed + 2)                      # FilteredNoise draws float32 uniforms from the default generator
+    out = model({k: v.clone() for k, v in batch.items()})
+    go = torch.randn(out["signal"].shape, generator=torch.Generator().manual_seed(seed + 3), dtype=torch.float64)
+    (out["signal"] * go).sum().backward()
+    arrays = {"go": go, "out_signal": out["signal"], "sd_checksum": checksum, "noise_seed": seed + 2}
+    for k, p_ in model.named_parameters():
+        arrays["grad_" + k] = p_.grad
+    npz(name, **arrays)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ddsp = import_reference()
     torch.set_num_threads(1)
+    if "--only-model-grads" in sys.argv:             # added in round 2; leaves the other fixtures untouched
+        from ddsp.models.decoder import DDSPDecoder
+        from ddsp.models.encoder import DDSPAutoencoder
+        model_grad_case(ddsp, "model_decoder_grads", DDSPDecoder, seed=11, with_mfcc=False)
+        model_grad_case(ddsp, "model_autoencoder_grads", DDSPAutoencoder, seed=12, with_mfcc=True)
+        return
     synth_case(ddsp, "synth_c1_small", B=2, T=12, bs=160, H=20, NB=65, sr=16000, seed=1)
     synth_case(ddsp, "synth_c3_buffer", B=1, T=2, bs=512, H=64, NB=65, sr=48000, seed=2)
     synth_case(ddsp, "synth_h100", B=1, T=7, bs=160, H=100, NB=65, sr=16000, seed=3,
@@ -229,6 +263,8 @@ def main():
     from ddsp.models.encoder import DDSPAutoencoder
     model_case(ddsp, "model_decoder", DDSPDecoder, seed=11, with_mfcc=False)
     model_case(ddsp, "model_autoencoder", DDSPAutoencoder, seed=12, with_mfcc=True)
+    model_grad_case(ddsp, "model_decoder_grads", DDSPDecoder, seed=11, with_mfcc=False)
+    model_grad_case(ddsp, "model_autoencoder_grads", DDSPAutoencoder, seed=12, with_mfcc=True)
 
 
 if __name__ == "__main__":
