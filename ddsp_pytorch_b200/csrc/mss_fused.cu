@@ -23,6 +23,8 @@
 //     gradient plane P, the last 3 hops are carried.  The carry of a tile's last batch goes to a small halo buffer
 //     that mss_combine2_kernel adds to the head of the next tile: no atomics, bit-reproducible.
 //   * mss_combine2_kernel sums the scales in order and folds the reflect padding back.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "pfft.cuh"
 
@@ -62,15 +64,18 @@ template <int T> __device__ __forceinline__ void gsync(int grp) {
     else asm volatile("bar.sync 4, %0;" ::"n"(T) : "memory");
 }
 
-// sign(d) in {-1, 0, +1}
-__device__ __forceinline__ float sgn3(float d) { return (d > 0.f) ? 1.f : (d < 0.f ? -1.f : 0.f); }
-
 // Loss terms and gradient spectra of bin k = t + Q*T (Q < 8; Q = 8 is k = n_fft/2, thread 0 only) for the two
 // frames in the lanes.  x = the thread's spectra after the last forward stage, gbuf = the parked mirror bins.
-// Q is a template parameter so that x[] and zi[] are indexed statically and stay in registers.
+// Q is a template parameter so that x[] and zi[] are indexed statically and stay in registers.  Everything except
+// the four special-function evaluations per lane runs on both frames at once (packed).
+//   Y2 = Z[k] + conj Z[-k] = 2 Y (rec), X2 = -i (Z[k] - conj Z[-k]) = 2 X (target): the halves are folded into rs2.
+//   loss terms  |sy - sx|, |log(sy + eps) - log(sx + eps)|   with sy = |Y| / sqrt(n_fft)
+//   dL/dY = (sgn(sy - sx) (1 + 1/(sy + eps)) inv_cnt / sqrt(n_fft)) Y / |Y|     (log is monotonic: one sign serves both)
+// A frame that does not exist has zero input, so Y = 0 and its gradient is 0 without a test; `own` only keeps its
+// log term (log(eps/eps), not exactly 0 in float) out of the sum.
 template <int LG, bool GRAD, int Q>
-__device__ __forceinline__ void bin_math(const pfft::C (&x)[16], float2 (&zi)[16], const pfft::E *gbuf, float2 *ex2,
-                                         int t, float mA, float mB, float rs2, float kc, float &lin, float &lgs) {
+__device__ __forceinline__ void bin_math(const pfft::C (&x)[16], pfft::V (&zi)[16], const pfft::E *gbuf, float2 *ex2,
+                                         int t, pfft::V own, float rs2, float kc, pfft::V &lin, pfft::V &lgs) {
     using namespace pfft;
     constexpr int T = Plan<LG>::T;
     constexpr int q = Q;
@@ -78,38 +83,80 @@ __device__ __forceinline__ void bin_math(const pfft::C (&x)[16], float2 (&zi)[16
     C zm = from_e(gbuf[q < 8 ? (8 - q) * T - t : 0]);     // Z[n_fft - k]
     const bool self = (q == 0 && t == 0) || q == 8;       // k = 0 and k = n_fft/2 mirror themselves
     if (q == 0 && t == 0) zm = zk;
-    // doubled spectra: rec Y2 = Z[k] + conj Z[-k], target X2 = -i (Z[k] - conj Z[-k])
     const V yr = zk.re + zm.re, yi = zk.im - zm.im;
     const V xre = zk.im + zm.im, xim = zm.re - zk.re;
     const V yy = fma(yr, yr, yi * yi), xx = fma(xre, xre, xim * xim);
-    float yyv[2], xxv[2], yrv[2], yiv[2], c[2];
-    get(yy, yyv[0], yyv[1]);
-    get(xx, xxv[0], xxv[1]);
-    get(yr, yrv[0], yrv[1]);
-    get(yi, yiv[0], yiv[1]);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        const float own = e ? mB : mA;
-        const float ry = rsqrtf(fmaxf(yyv[e], 1e-37f));                  // 1 / |Y2|
-        const float sy = yyv[e] * ry * rs2;                              // |Y| / sqrt(n_fft)
-        const float sx = xxv[e] * rsqrtf(fmaxf(xxv[e], 1e-37f)) * rs2;
-        const float d = sy - sx;
-        const float iy = __fdividef(1.0f, sy + 1e-7f);
-        lin = fmaf(own, fabsf(d), lin);
-        lgs = fmaf(own, fabsf(__log2f((sx + 1e-7f) * iy)), lgs);         // * ln 2 at the end
-        // log is monotonic: sign(log(sy+eps) - log(sx+eps)) == sign(sy - sx)
-        const float sg = sgn3(d);
-        float cc = fmaf(sg, iy, sg) * kc * ry;                           // dL/dY2 = cc * Y2
-        cc = (own != 0.f && yyv[e] > 0.f) ? cc : 0.f;
-        c[e] = self ? cc : 0.5f * cc;                                    // (U_A + i U_B) / 2 for interior bins
-    }
+    float a0, a1, b0, b1;
+    get(yy, a0, a1);
+    get(xx, b0, b1);
+    const V ry = mk(rsqrtf(fmaxf(a0, 1e-37f)), rsqrtf(fmaxf(a1, 1e-37f)));          // 1 / |Y2|
+    const V rx = mk(rsqrtf(fmaxf(b0, 1e-37f)), rsqrtf(fmaxf(b1, 1e-37f)));
+    const V sy = (yy * ry) * bc(rs2), sx = (xx * rx) * bc(rs2);
+    const V d = sy - sx;
+    const V sye = sy + bc(1e-7f);
+    get(sye, a0, a1);
+    const V iy = mk(__fdividef(1.0f, a0), __fdividef(1.0f, a1));
+    get((sx + bc(1e-7f)) * iy, b0, b1);
+    float d0, d1;
+    get(d, d0, d1);
+    lin = lin + mk(fabsf(d0), fabsf(d1));
+    lgs = fma(own, mk(fabsf(__log2f(b0)), fabsf(__log2f(b1))), lgs);               // * ln 2 at the end
     if (GRAD) {
-        const float pa = c[0] * yrv[0], qa = c[0] * yiv[0];              // U_A
-        const float2 own_bin = self ? make_float2(pa, c[1] * yrv[1])     // real bins: (U_A, U_B)
-                                    : make_float2(fmaf(-c[1], yiv[1], pa), fmaf(c[1], yrv[1], qa));
-        zi[q] = own_bin;
-        if (q == 8) ex2[0] = own_bin;                                    // keeps the read of the upper slots uniform
-        else if (!self) ex2[(8 - q) * T - t] = make_float2(fmaf(c[1], yiv[1], pa), fmaf(c[1], yrv[1], -qa));
+        // sign(d) * kc, 0 at an exact tie (torch.sign(0) = 0); interior bins carry the 1/2 of (U_A + i U_B) / 2
+        const float kq = self ? kc : 0.5f * kc;
+        const V sgk = mk(d0 == 0.f ? 0.f : copysignf(kq, d0), d1 == 0.f ? 0.f : copysignf(kq, d1));
+        const V c = fma(sgk, iy, sgk) * ry;                                        // dL/dY2 = c * Y2
+        const V ur = c * yr, ui = c * yi;                                          // U = (U_A, U_B) lanes
+        float ura, urb, uia, uib;
+        get(ur, ura, urb);
+        get(ui, uia, uib);
+        // (U_A + i U_B): real bins are (U_A, U_B); Zi[k] = (ura - uib, uia + urb), Zi[-k] = (ura + uib, urb - uia)
+        zi[q] = self ? mk(ura, urb) : mk(ura - uib, uia + urb);
+        if (q == 8) ex2[0] = make_float2(ura, urb);                                // keeps the read of the upper slots uniform
+        else if (!self) ex2[(8 - q) * T - t] = make_float2(ura + uib, urb - uia);
+    }
+}
+
+// Samples t + qT, q = 0..19, of rec and target from `start` on (reflect padding at the signal's ends): frame A uses
+// slots 0..15, frame B = A + 1 hop uses slots 4..19.
+__device__ __forceinline__ float ld_stream(const float *p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+template <int N, int T>
+__device__ __forceinline__ void load_frames(float (&r)[20], float (&g)[20], const float *__restrict__ xr,
+                                            const float *__restrict__ xt, int start, int t, int Ni) {
+    if (start >= 0 && start + N / 4 + N <= Ni) {
+#pragma unroll
+        for (int q = 0; q < 20; ++q) {
+            r[q] = ld_stream(xr + start + t + q * T);
+            g[q] = ld_stream(xt + start + t + q * T);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 20; ++q) {
+            int m = start + t + q * T;
+            m = m < 0 ? -m : m;
+            m = m >= Ni ? 2 * (Ni - 1) - m : m;
+            m = min(max(m, 0), Ni - 1);                      // only frames that do not exist reach this clamp
+            r[q] = ld_stream(xr + m);
+            g[q] = ld_stream(xt + m);
+        }
+    }
+}
+
+// The same lines, asked into L1 ahead of time (no registers held): issued before the gather, used after it.
+template <int N, int T>
+__device__ __forceinline__ void prefetch_frames(const float *__restrict__ xr, const float *__restrict__ xt, int start,
+                                                int t, int Ni) {
+    if (start >= 0 && start + N / 4 + N <= Ni) {
+#pragma unroll
+        for (int q = 0; q < 20; ++q) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(xr + start + t + q * T));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(xt + start + t + q * T));
+        }
     }
 }
 
@@ -136,6 +183,10 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
     float2 *ibuf = reinterpret_cast<float2 *>(gbase);
     float2 *ex2 = reinterpret_cast<float2 *>(gbase + EX2_OFF);
     float *plane = reinterpret_cast<float *>(gbase + PLANE_OFF);
+    // Groups narrower than a warp park their frames at the same bank offsets; XOR-ing the sample index with a
+    // per-group multiple of T (below 32) spreads the groups of a warp over the banks.  Multiples of 4: float4 reads
+    // of the gather stay intact.
+    const int swz = T < 32 ? ((grp * T) & 31) : 0;
 
     const float *xr = rec + (size_t)b * Ni;
     const float *xt = target + (size_t)b * Ni;
@@ -147,46 +198,27 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
     const float rs = rsqrtf((float)N);
     const float rs2 = 0.5f * rs;                                  // spectra are kept doubled (no 1/2 in the untangle)
     const float kc = sc.inv_cnt * rs;
-    float *Pb = ws + sc.p_off + (size_t)b * sc.rowlen;
-    float *Hb = ws + sc.h_off + ((size_t)b * sc.tiles + tile) * (3 * HOP);
 
     if (GRAD)
         for (int i = tid; i < 3 * HOP; i += kThreads) carry[i] = 0.f;
     int cb = 0;
-    float lin = 0.f, lgs = 0.f;
+    V lin = bc(0.f), lgs = bc(0.f);
+
+    // samples of frames A = fb + 2 grp (slots 0..15) and B = A + 1 (slots 4..19) of rec and target
+    float r[20], g[20];
 
     for (int fb = f0; fb < f1; fb += NFB) {
         const int fA = fb + 2 * grp;
         const float mA = fA < f1 ? 1.f : 0.f, mB = fA + 1 < f1 ? 1.f : 0.f;
+        load_frames<N, T>(r, g, xr, xt, fA * HOP - HS, t, Ni);
         C x[16];
-        {
-            // ---- windowed frames A (lane 0) and B = A + 1 (lane 1): sample slot q of B is slot q + 4 of A
-            float r[20], g[20];
-            const int start = fA * HOP - HS;
-            if (start >= 0 && start + HOP + N <= Ni) {
+        // ---- windowed frames A (lane 0) and B = A + 1 (lane 1): sample slot q of B is slot q + 4 of A
 #pragma unroll
-                for (int q = 0; q < 20; ++q) {
-                    r[q] = __ldg(xr + start + t + q * T);
-                    g[q] = __ldg(xt + start + t + q * T);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 20; ++q) {
-                    int m = start + t + q * T;
-                    m = m < 0 ? -m : m;
-                    m = m >= Ni ? 2 * (Ni - 1) - m : m;
-                    m = min(max(m, 0), Ni - 1);                  // only frames that do not exist reach this clamp
-                    r[q] = __ldg(xr + m);
-                    g[q] = __ldg(xt + m);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float w = __ldg(window + t + q * T);
-                const float wa = w * mA, wb = w * mB;
-                x[q].re = mk(r[q] * wa, r[q + 4] * wb);
-                x[q].im = mk(g[q] * wa, g[q + 4] * wb);
-            }
+        for (int q = 0; q < 16; ++q) {
+            const float w = __ldg(window + t + q * T);
+            const float wa = w * mA, wb = w * mB;
+            x[q].re = mk(r[q] * wa, r[q + 4] * wb);
+            x[q].im = mk(g[q] * wa, g[q + 4] * wb);
         }
         // ---- forward transform of both frames; the last stage stays in registers
         stage_compute_store<LG, 0, false>(x, gbuf, t, tw);
@@ -207,45 +239,53 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
         for (int q = 8; q < 16; ++q) gbuf[(q - 8) * T + t] = to_e(x[slot_of_q<LG>(q)]);
         gsync<T>(grp);
         // ---- per bin k = t + qT (q < 8; thread 0 also takes k = n_fft/2): loss terms and gradient spectra
-        float2 zi[16];
-        bin_math<LG, GRAD, 0>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        bin_math<LG, GRAD, 1>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        bin_math<LG, GRAD, 2>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        bin_math<LG, GRAD, 3>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        bin_math<LG, GRAD, 4>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        bin_math<LG, GRAD, 5>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        bin_math<LG, GRAD, 6>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        bin_math<LG, GRAD, 7>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
-        if (t == 0) bin_math<LG, GRAD, 8>(x, zi, gbuf, ex2, t, mA, mB, rs2, kc, lin, lgs);
+        V zi[16];
+        const V own = mk(mA, mB);
+        bin_math<LG, GRAD, 0>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        bin_math<LG, GRAD, 1>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        bin_math<LG, GRAD, 2>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        bin_math<LG, GRAD, 3>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        bin_math<LG, GRAD, 4>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        bin_math<LG, GRAD, 5>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        bin_math<LG, GRAD, 6>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        bin_math<LG, GRAD, 7>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        if (t == 0) bin_math<LG, GRAD, 8>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
         if (GRAD) {
             gsync<T>(grp);
 #pragma unroll
-            for (int q = 8; q < 16; ++q) zi[q] = ex2[(q - 8) * T + t];
-            // ---- inverse transform of U_A + i U_B (scalar registers: one transform per thread here)
-            regfft::stage_compute_store<LG, 0, true>(zi, ibuf, t, tw);
+            for (int q = 8; q < 16; ++q) zi[q] = zfft::from_f2(ex2[(q - 8) * T + t]);
+            // ---- inverse transform of U_A + i U_B, (re, im) in the lanes: one transform per thread here
+            zfft::stage_compute_store<LG, 0, true>(zi, ibuf, t, tw);
             gsync<T>(grp);
-            regfft::stage_load<LG, 1>(zi, ibuf, t);
+            zfft::stage_load<LG, 1>(zi, ibuf, t);
             if (P::STAGES == 3) {
                 gsync<T>(grp);
-                regfft::stage_compute_store<LG, 1, true>(zi, ibuf, t, tw);
+                zfft::stage_compute_store<LG, 1, true>(zi, ibuf, t, tw);
                 gsync<T>(grp);
-                regfft::stage_load<LG, 2>(zi, ibuf, t);
-                regfft::stage_compute_regs<LG, 2, true>(zi, t, tw);
+                zfft::stage_load<LG, 2>(zi, ibuf, t);
+                zfft::stage_compute_regs<LG, 2, true>(zi, t, tw);
             } else {
-                regfft::stage_compute_regs<LG, 1, true>(zi, t, tw);
+                zfft::stage_compute_regs<LG, 1, true>(zi, t, tw);
             }
+            // ---- the next batch's samples start their trip from L2 now; they land during the gather
             // ---- park the two real gradient frames (unwindowed) for the gather
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                const float2 v = zi[slot_of_q<LG>(q)];
-                plane[t + q * T] = v.x;
-                plane[N + t + q * T] = v.y;
+                const float2 v = zfft::to_f2(zi[slot_of_q<LG>(q)]);
+                plane[(t + q * T) ^ swz] = v.x;
+                plane[N + ((t + q * T) ^ swz)] = v.y;
             }
+            float4 wgat[4];                                       // window at the thread's four positions of every frame phase
+#pragma unroll
+            for (int dq = 0; dq < 4; ++dq)
+                wgat[dq] = __ldg(reinterpret_cast<const float4 *>(window + ((4 * tid) & (HOP - 1)) + dq * HOP));
             __syncthreads();
             // ---- ordered gather overlap-add over the batch's (NFB + 3) hops, four positions per thread
+            float *Pb = ws + sc.p_off + (size_t)b * sc.rowlen;
             const float *cold = carry + cb * (3 * HOP);
             float *cnew = carry + (cb ^ 1) * (3 * HOP);
             for (int v = tid; v < (NFB + 3) * (HOP / 4); v += kThreads) {
+                // rel = 4 tid + 1024 it and hop divides 1024: n0 (and so the window values) is the same every iteration
                 const int rel = v * 4, j = rel >> LH, n0 = rel & (HOP - 1);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (j < 3) acc = *reinterpret_cast<const float4 *>(cold + j * HOP + n0);
@@ -253,11 +293,12 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
                 for (int dq = 3; dq >= 0; --dq) {                 // frames j-3 .. j, oldest first
                     const int qf = j - dq;
                     if (qf >= 0 && qf < NFB) {
-                        const int n = n0 + dq * HOP;
-                        const float *pl = reinterpret_cast<const float *>(smem + (size_t)(qf >> 1) * GBYTES + PLANE_OFF) +
+                        const int gq = qf >> 1;
+                        const int n = (n0 + dq * HOP) ^ (T < 32 ? ((gq * T) & 31) : 0);
+                        const float *pl = reinterpret_cast<const float *>(smem + (size_t)gq * GBYTES + PLANE_OFF) +
                                           (qf & 1) * N;
                         const float4 xv = *reinterpret_cast<const float4 *>(pl + n);
-                        const float4 wv = __ldg(reinterpret_cast<const float4 *>(window + n));
+                        const float4 wv = wgat[dq];
                         acc.x = fmaf(wv.x, xv.x, acc.x);
                         acc.y = fmaf(wv.y, xv.y, acc.y);
                         acc.z = fmaf(wv.z, xv.z, acc.z);
@@ -275,13 +316,17 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
     }
     if (GRAD) {
         // tail of the tile: belongs to the head of the next tile (or to the end of the signal): halo buffer
+        float *Hb = ws + sc.h_off + ((size_t)b * sc.tiles + tile) * (3 * HOP);
         const float *cold = carry + cb * (3 * HOP);
         for (int i = tid; i < 3 * HOP / 4; i += kThreads)
             reinterpret_cast<float4 *>(Hb)[i] = reinterpret_cast<const float4 *>(cold)[i];
     }
-    lin = ddsp_warp_sum(lin);
-    lgs = ddsp_warp_sum(lgs * 0.69314718055994530942f);
-    if ((tid & 31) == 0) { red[0][tid >> 5] = lin; red[1][tid >> 5] = lgs; }
+    float l0, l1, g0, g1;
+    get(lin, l0, l1);
+    get(lgs, g0, g1);
+    const float lsum = ddsp_warp_sum(l0 + l1);
+    const float gsum = ddsp_warp_sum((g0 + g1) * 0.69314718055994530942f);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = lsum; red[1][tid >> 5] = gsum; }
     __syncthreads();
     if (tid == 0) {
         float a = 0.f, c = 0.f;
@@ -318,35 +363,73 @@ mss_fused_kernel(const float *__restrict__ target, const float *__restrict__ rec
     }
 }
 
-// value of scale s' padded gradient at padded position i (0 outside what the tiles produced)
-__device__ __forceinline__ float padded_grad(const ScaleDesc &sc, const float *__restrict__ ws, int b, int i) {
+// value of scale s' padded gradient at padded position i (0 outside what the tiles produced); W = 1 or 4 consecutive
+// positions (i % 4 == 0: they share the frame slot, so one decision serves all four)
+template <int W> struct Vec;
+template <> struct Vec<1> {
+    float v;
+    __device__ __forceinline__ static Vec zero() { return Vec{0.f}; }
+    __device__ __forceinline__ static Vec load(const float *p) { return Vec{__ldg(p)}; }
+    __device__ __forceinline__ void add(const Vec &o) { v += o.v; }
+};
+template <> struct Vec<4> {
+    float4 v;
+    __device__ __forceinline__ static Vec zero() { return Vec{make_float4(0.f, 0.f, 0.f, 0.f)}; }
+    __device__ __forceinline__ static Vec load(const float *p) { return Vec{__ldg(reinterpret_cast<const float4 *>(p))}; }
+    __device__ __forceinline__ void add(const Vec &o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+};
+
+template <int W>
+__device__ __forceinline__ Vec<W> padded_grad(const ScaleDesc &sc, const float *__restrict__ ws, int b, int i) {
     const int lh = sc.lg - 2;
     const int fi = i >> lh, n0 = i & (sc.hop - 1);
     const int tl = fi >> sc.ft_log, within = fi & ((1 << sc.ft_log) - 1);
-    float v = 0.f;
-    if (fi < sc.last_end) v = ws[sc.p_off + (size_t)b * sc.rowlen + i];
+    Vec<W> v = Vec<W>::zero();
+    if (fi < sc.last_end) v = Vec<W>::load(ws + sc.p_off + (size_t)b * sc.rowlen + i);
     if (tl >= 1 && tl < sc.tiles && within < 3)
-        v += ws[sc.h_off + ((size_t)b * sc.tiles + (tl - 1)) * (3 * sc.hop) + within * sc.hop + n0];
+        v.add(Vec<W>::load(ws + sc.h_off + ((size_t)b * sc.tiles + (tl - 1)) * (3 * sc.hop) + within * sc.hop + n0));
     if (fi >= sc.last_end && fi < sc.last_end + 3)
-        v += ws[sc.h_off + ((size_t)b * sc.tiles + (sc.tiles - 1)) * (3 * sc.hop) + (fi - sc.last_end) * sc.hop + n0];
+        v.add(Vec<W>::load(ws + sc.h_off + ((size_t)b * sc.tiles + (sc.tiles - 1)) * (3 * sc.hop) + (fi - sc.last_end) * sc.hop + n0));
     return v;
 }
 
-// d_rec[b, m] = sum over scales (fixed order) of the padded gradient at m + n_fft/2, plus the two reflections
+// reflect-padding contributions to sample m, all scales (only samples within n_fft/2 of either end have any)
+__device__ __forceinline__ float reflected_grad(const FusedArgs &a, const float *__restrict__ ws, int b, int m, int N) {
+    float acc = 0.f;
+    for (int k = 0; k < a.n_scales; ++k) {
+        const ScaleDesc &sc = a.sc[k];
+        const int hs = 2 * sc.hop;
+        if (m >= 1 && m <= hs) acc += padded_grad<1>(sc, ws, b, hs - m).v;                           // left pad
+        if (m <= N - 2 && m >= N - 1 - hs) acc += padded_grad<1>(sc, ws, b, 2 * (N - 1) - m + hs).v;  // right pad
+    }
+    return acc;
+}
+
+// d_rec[b, m] = sum over scales (fixed order) of the padded gradient at m + n_fft/2, then the reflections
+template <int W>
 __global__ void __launch_bounds__(256)
-mss_combine2_kernel(const float *__restrict__ ws, float *__restrict__ d_rec, const __grid_constant__ FusedArgs a) {
+mss_combine2_kernel(const float *__restrict__ ws, float *__restrict__ d_rec, const __grid_constant__ FusedArgs a,
+                    int hs_max) {
     const int b = blockIdx.y;
     const int N = (int)a.N;
-    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < N; m += gridDim.x * blockDim.x) {
-        float acc = 0.f;
-        for (int k = 0; k < a.n_scales; ++k) {
-            const ScaleDesc &sc = a.sc[k];
-            const int hs = 2 * sc.hop;
-            acc += padded_grad(sc, ws, b, m + hs);
-            if (m >= 1 && m <= hs) acc += padded_grad(sc, ws, b, hs - m);                    // left reflect pad
-            if (m <= N - 2 && m >= N - 1 - hs) acc += padded_grad(sc, ws, b, 2 * (N - 1) - m + hs);   // right
+    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) * W; m < N; m += gridDim.x * blockDim.x * W) {
+        Vec<W> acc = Vec<W>::zero();
+        for (int k = 0; k < a.n_scales; ++k) acc.add(padded_grad<W>(a.sc[k], ws, b, m + 2 * a.sc[k].hop));
+        const bool edge = m <= hs_max || m + W - 1 >= N - 1 - hs_max;
+        if (W == 1) {
+            float v = reinterpret_cast<float &>(acc);
+            if (edge) v += reflected_grad(a, ws, b, m, N);
+            d_rec[(size_t)b * N + m] = v;
+        } else {
+            float4 v = reinterpret_cast<float4 &>(acc);
+            if (edge) {
+                v.x += reflected_grad(a, ws, b, m, N);
+                v.y += reflected_grad(a, ws, b, m + 1, N);
+                v.z += reflected_grad(a, ws, b, m + 2, N);
+                v.w += reflected_grad(a, ws, b, m + 3, N);
+            }
+            *reinterpret_cast<float4 *>(d_rec + (size_t)b * N + m) = v;
         }
-        d_rec[(size_t)b * N + m] = acc;
     }
 }
 
@@ -397,8 +480,10 @@ int make_plan(int B, int64_t N, const int *scales, int n_scales, Plan2 *out) {
     out->fin.n_scales = n_scales;
     long long off = 0, pairs = 0;
     int item = 0, max_hop = 0;
-    // about 8 tiles per resident CTA slot in total, shared evenly by the scales (their work is about equal)
-    const long long want_tiles = ddsp_ceil_div(8ll * 2 * DDSP_SM_COUNT, (long long)n_scales * B);
+    // about 16 tiles per resident CTA slot in total, shared evenly by the scales (their work is about equal)
+    long long per_slot = 16;                 // measured: 4..32 are within 2 % of each other at batch 64
+    if (const char *e = getenv("DDSP_B200_MSS_TILES_PER_SLOT")) per_slot = atoi(e) > 0 ? atoi(e) : per_slot;   // tuning knob
+    const long long want_tiles = ddsp_ceil_div(per_slot * 2 * DDSP_SM_COUNT, (long long)n_scales * B);
     for (int i = 0; i < n_scales; ++i) {
         const int s = scales[i];
         if (s < 64 || s > 4096 || (s & (s - 1))) return DDSP_B200_EUNSUPPORTED;
@@ -495,8 +580,16 @@ extern "C" int ddsp_b200_mss_fused(const float *target, const float *rec, const 
     if ((s = ddsp_launch_status())) return s;
     mss_finalize2_kernel<<<1, 1024, 0, st>>>(partial, loss, p.fin);
     if ((s = ddsp_launch_status()) || !d_rec) return s;
-    int gx = (int)ddsp_ceil_div(N, 256);
-    if (gx > 64) gx = 64;
-    mss_combine2_kernel<<<dim3(gx, B), 256, 0, st>>>(workspace, d_rec, p.args);
+    int hs_max = 0;
+    for (int i = 0; i < n_scales; ++i) hs_max = scales[i] / 2 > hs_max ? scales[i] / 2 : hs_max;
+    if ((N & 3) == 0) {
+        int gx = (int)ddsp_ceil_div(N / 4, 256);
+        if (gx > 64) gx = 64;
+        mss_combine2_kernel<4><<<dim3(gx, B), 256, 0, st>>>(workspace, d_rec, p.args, hs_max);
+    } else {
+        int gx = (int)ddsp_ceil_div(N, 256);
+        if (gx > 64) gx = 64;
+        mss_combine2_kernel<1><<<dim3(gx, B), 256, 0, st>>>(workspace, d_rec, p.args, hs_max);
+    }
     return ddsp_launch_status();
 }

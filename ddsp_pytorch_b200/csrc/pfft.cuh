@@ -219,3 +219,145 @@ template <int LG> DDSP_HD constexpr int slot_of_q(int q) {
 }
 
 }  // namespace pfft
+
+// =====================================================================================================
+// One transform per thread with (re, im) in the two lanes ("zfft"): the inverse transform of the fused loss.
+// ptxas folds the half swap (.LO_HI), the negation of one half (.NP / .PN) and scalar broadcasts into the packed
+// operand, so a complex multiply is FMUL2 + FFMA2 and a multiplication by +-i rides in the butterfly's FFMA2:
+// half the instructions of the scalar float2 code in regfft.cuh for the same FP32 lane work.
+// =====================================================================================================
+namespace zfft {
+
+using pfft::V;
+using pfft::mk;
+using pfft::get;
+using pfft::bc;
+using pfft::fma;
+using regfft::Plan;
+using regfft::Stage;
+
+DDSP_HD V swp(V a) { float x, y; get(a, x, y); return mk(y, x); }
+DDSP_HD V from_f2(float2 a) { return mk(a.x, a.y); }
+DDSP_HD float2 to_f2(V a) { float2 r; get(a, r.x, r.y); return r; }
+// a * (wr + i wi)
+DDSP_HD V zmul(V a, float wr, float wi) { return fma(swp(a), mk(-wi, wi), a * bc(wr)); }
+DDSP_HD V add_i(V a, V b) { return fma(swp(b), mk(-1.f, 1.f), a); }     // a + i b
+DDSP_HD V sub_i(V a, V b) { return fma(swp(b), mk(1.f, -1.f), a); }     // a - i b
+// a + W4 b with W4 = -i (forward) / +i (inverse)
+template <bool INV> DDSP_HD V add_rot(V a, V b) { return INV ? add_i(a, b) : sub_i(a, b); }
+template <bool INV> DDSP_HD V sub_rot(V a, V b) { return INV ? sub_i(a, b) : add_i(a, b); }
+
+template <bool INV> DDSP_HD void dft2(V &a, V &b) {
+    const V t = a - b;
+    a = a + b;
+    b = t;
+}
+template <bool INV> DDSP_HD void dft4(V &v0, V &v1, V &v2, V &v3) {
+    const V a0 = v0 + v2, a1 = v0 - v2, a2 = v1 + v3, a3 = v1 - v3;
+    v0 = a0 + a2;
+    v2 = a0 - a2;
+    v1 = add_rot<INV>(a1, a3);
+    v3 = sub_rot<INV>(a1, a3);
+}
+// p = e + o W, m = e - o W for W = h (1 -+ i)   (forward: 1 - i)
+template <bool INV> DDSP_HD void bfly_w8_1(V e, V o, V &p, V &m) {
+    const float h = 0.70710678118654752440f;
+    const V s = INV ? add_i(o, o) : sub_i(o, o);        // o (1 +- i)
+    p = fma(s, bc(h), e);
+    m = fma(s, bc(-h), e);
+}
+// W = h (-1 -+ i) = -h (1 +- i)   (forward: -1 - i)
+template <bool INV> DDSP_HD void bfly_w8_3(V e, V o, V &p, V &m) {
+    const float h = 0.70710678118654752440f;
+    const V s = INV ? sub_i(o, o) : add_i(o, o);        // o (1 -+ i)
+    p = fma(s, bc(-h), e);
+    m = fma(s, bc(h), e);
+}
+DDSP_HD void bfly_w(V e, V o, float wr, float wi, V &p, V &m) {
+    p = fma(swp(o), mk(-wi, wi), fma(o, bc(wr), e));
+    m = fma(swp(o), mk(wi, -wi), fma(o, bc(-wr), e));
+}
+template <bool INV> DDSP_HD void dft8(V *v) {
+    V e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+    V o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4<INV>(e0, e1, e2, e3);
+    dft4<INV>(o0, o1, o2, o3);
+    v[0] = e0 + o0;                    v[4] = e0 - o0;
+    bfly_w8_1<INV>(e1, o1, v[1], v[5]);
+    v[2] = add_rot<INV>(e2, o2);       v[6] = sub_rot<INV>(e2, o2);
+    bfly_w8_3<INV>(e3, o3, v[3], v[7]);
+}
+template <bool INV> DDSP_HD void dft16(V *v) {
+    V e[8], o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    dft8<INV>(e);
+    dft8<INV>(o);
+    const float c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+    const float sg = INV ? 1.f : -1.f;
+    v[0] = e[0] + o[0];                          v[8] = e[0] - o[0];
+    bfly_w(e[1], o[1], c1, sg * s1, v[1], v[9]);
+    bfly_w8_1<INV>(e[2], o[2], v[2], v[10]);
+    bfly_w(e[3], o[3], s1, sg * c1, v[3], v[11]);
+    v[4] = add_rot<INV>(e[4], o[4]);             v[12] = sub_rot<INV>(e[4], o[4]);
+    bfly_w(e[5], o[5], -s1, sg * c1, v[5], v[13]);
+    bfly_w8_3<INV>(e[6], o[6], v[6], v[14]);
+    bfly_w(e[7], o[7], -c1, sg * s1, v[7], v[15]);
+}
+template <int R, bool INV> DDSP_HD void dft_r(V *v) {
+    if (R == 2) dft2<INV>(v[0], v[1]);
+    else if (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
+    else if (R == 8) dft8<INV>(v);
+    else if (R == 16) dft16<INV>(v);
+}
+
+template <int LG, int S, bool INV>
+DDSP_HD void stage_compute_regs(V (&x)[16], int t, const float2 *__restrict__ tw) {
+    using P = Plan<LG>;
+    constexpr int R = Stage<LG, S>::R;
+    constexpr int NS = Stage<LG, S>::NS;
+    constexpr int M = 16 / R;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int j = t + m * P::T;
+        const int k = j & (NS - 1);
+        if (S > 0) {
+            const float2 *tab = tw + (S == 1 ? 0 : regfft::stage_table_offset2<LG>());
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+#ifdef __CUDA_ARCH__
+                const float2 w = __ldg(tab + (r - 1) * NS + k);
+#else
+                const float2 w = tab[(r - 1) * NS + k];
+#endif
+                x[m * R + r] = zmul(x[m * R + r], w.x, INV ? -w.y : w.y);
+            }
+        }
+        dft_r<R, INV>(&x[m * R]);
+    }
+}
+template <int LG, int S, bool INV>
+DDSP_HD void stage_compute_store(V (&x)[16], float2 *buf, int t, const float2 *__restrict__ tw) {
+    constexpr int R = Stage<LG, S>::R;
+    constexpr int M = 16 / R;
+    stage_compute_regs<LG, S, INV>(x, t, tw);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        float2 *dst = buf + regfft::out_base_padded<LG, S>(t, m);
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst[r * regfft::out_stride_padded<LG, S>()] = to_f2(x[m * R + r]);
+    }
+}
+template <int LG, int S>
+DDSP_HD void stage_load(V (&x)[16], const float2 *buf, int t) {
+    constexpr int R = Stage<LG, S>::R;
+    constexpr int M = 16 / R;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const float2 *src = buf + regfft::in_base_padded<LG, S>(t, m);
+#pragma unroll
+        for (int r = 0; r < R; ++r) x[m * R + r] = from_f2(src[r * regfft::in_stride_padded<LG, S>()]);
+    }
+}
+
+}  // namespace zfft

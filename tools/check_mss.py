@@ -75,6 +75,30 @@ def main():
                 ts.append(a.elapsed_time(b))
             ts.sort()
             out["timing"].append({"B": B, "grad": need, "ms_median": ts[len(ts) // 2], "ms_min": ts[0]})
+    # one scale at a time (fused kernel + finalize + combine of that scale only)
+    B = args.batch
+    g = torch.Generator().manual_seed(0)
+    tgt = (0.1 * torch.randn(B, N, generator=g)).cuda()
+    rec = (0.1 * torch.randn(B, N, generator=g)).cuda()
+    out["per_scale_ms"] = {}
+    for s_ in SCALES:
+        win = hann_window_like_reference(s_, rec.device)
+        for need in (True, False):
+            fn = lambda: torch.ops.ddsp_b200.mss_loss_fwd(tgt, rec, [s_], 0.75, win, need)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(10):
+                flush_buf.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b))
+            ts.sort()
+            out["per_scale_ms"][f"{s_}{'_grad' if need else ''}"] = ts[len(ts) // 2]
     print(json.dumps(out, indent=1))
 
 
