@@ -354,9 +354,9 @@ def other_configs(dev):
 def init_dist(world, dev):
     if world <= 1:
         return None
-    # keep stdout to the single JSON line: NCCL prints its version banner there at level VERSION
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # keep stdout to the single JSON line: NCCL writes its version banner (and, at INFO, its topology lines) to
+    # stdout unless it is given a file; whoever asked for NCCL_DEBUG output still gets it, on stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
     return dist
@@ -484,8 +484,8 @@ def run_b200(args, rank, world):
     use_graph = not args.no_graph
     graph_note = "CUDA graph replay"
     if dist is not None:
-        step.enable_grad_allreduce(dist)            # packed into one flat buffer by the step, reduced in place
-        graph_note += " + one NCCL all-reduce (AVG) of the packed parameter gradients"
+        step.enable_grad_allreduce(dist)            # packed into one flat buffer inside the graph, reduced in place
+        graph_note += " + one NCCL all-reduce (AVG) launch on the packed parameter gradients"
     if use_graph:
         try:
             step.capture(forward_only=False)

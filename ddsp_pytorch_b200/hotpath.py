@@ -48,29 +48,27 @@ class SynthStep:
         self._graph = None
         self._graph_fwd = None
         self._dist = None                  # set by enable_grad_allreduce (data-parallel training config)
-        self._reduce_in_run = False
 
     # ---- data parallel: the shared parameters' gradients are averaged over the ranks -------
     def enable_grad_allreduce(self, dist, group=None):
         """Voices are sharded over the ranks; the only shared parameters on this path are the reverb's
-        (noise, decay, wet).  Their gradients are packed into one flat buffer and averaged with ONE
-        NCCL all-reduce per step, issued by run() itself so that it becomes a node of the step's CUDA graph."""
+        (noise, decay, wet).  run() packs their gradients into one flat buffer (a node of the step's CUDA
+        graph); allreduce_grads() averages that buffer with ONE NCCL all-reduce (op AVG) per step.  The collective
+        itself stays outside the graph: every rank must take the same decision about capturing it, and a capture
+        that fails on one rank only would leave the ranks waiting for each other."""
         assert self.reverb is not None
         self._dist, self._group = dist, group
         self._sizes = [p.numel() for p in self.reverb.parameters()]
         self._flat = torch.zeros(sum(self._sizes), device=self.loss.device, dtype=torch.float32)
-        self._reduce_in_run = True
 
-    def _pack_and_reduce(self):
+    def _pack(self):
         torch.cat([g.reshape(-1) for g in self.grads[3:]], out=self._flat)
-        self._dist.all_reduce(self._flat, op=self._dist.ReduceOp.AVG, group=self._group)
         shapes = [g.shape for g in self.grads[3:]]
         self.grads = tuple(self.grads[:3]) + tuple(c.view(sh) for c, sh in zip(self._flat.split(self._sizes), shapes))
 
     def allreduce_grads(self):
-        """No-op when the collective already ran inside run() / the replayed graph."""
-        if self._dist is not None and not self._reduce_in_run:
-            self._pack_and_reduce()
+        if self._dist is not None:
+            self._dist.all_reduce(self._flat, op=self._dist.ReduceOp.AVG, group=self._group)
 
     # ---- the path -------------------------------------------------------------------------
     def _leaves(self):
@@ -124,8 +122,8 @@ class SynthStep:
     def run(self):
         self.signal, loss, self.grads = self.forward_backward()
         self.loss = loss
-        if self._dist is not None and self._reduce_in_run:
-            self._pack_and_reduce()
+        if self._dist is not None:
+            self._pack()
         return loss
 
     def run_forward(self):
@@ -137,16 +135,6 @@ class SynthStep:
         """Capture the step in a CUDA graph (after a few eager runs on a side stream so that lazily
         built tables and the allocator's pools exist before capture)."""
         fn = self.run_forward if forward_only else self.run
-        if not forward_only and self._dist is not None and self._reduce_in_run:
-            try:
-                return self._capture(fn, forward_only, warmup)
-            except Exception:
-                # the collective could not be captured: keep it outside the graph (allreduce_grads() then runs it)
-                torch.cuda.synchronize()
-                self._reduce_in_run = False
-        return self._capture(fn, forward_only, warmup)
-
-    def _capture(self, fn, forward_only, warmup):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
