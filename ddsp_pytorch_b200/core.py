@@ -112,14 +112,14 @@ def extract_pitch(signal, sample_rate, block_size):
     return f0
 
 
-LINEAR3X_MIN_ROWS = 512      # below this many rows a layer is launch-bound and stays on the library path
+LINEAR3X_MIN_ROWS = 1        # every CUDA float32 call runs on the kernel (the realtime path's 2-row calls included)
 
 
 class Linear(nn.Linear):
     """``nn.Linear`` (same parameters, state_dict keys and call) whose three GEMMs run on the tcgen05
     tensor cores with float32-class accuracy (csrc/gemm3x.cu, split-bf16) instead of cuBLAS's SIMT SGEMM.
-    Small problems (fewer than ``LINEAR3X_MIN_ROWS`` rows, fan-in below 32) and non-CUDA / non-float32 inputs take
-    the stock path."""
+    Every CUDA float32 call takes the kernel, whatever the row count and fan-in (the decoder's first layers have fan-in 1,
+    the realtime path 2 rows); only non-CUDA / non-float32 inputs (the CPU tests) take the stock path."""
 
     __constants__ = ["in_features", "out_features", "min_rows"]
 
@@ -129,8 +129,7 @@ class Linear(nn.Linear):
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:      # noqa: A002
         rows = input.numel() // max(1, input.shape[-1])
-        fast = (input.is_cuda and input.dtype == torch.float32 and self.in_features >= 32
-                and rows >= self.min_rows)
+        fast = input.is_cuda and input.dtype == torch.float32 and rows >= self.min_rows
         if torch.jit.is_scripting():
             if fast:
                 x2 = input.reshape(-1, self.in_features).contiguous()
@@ -185,16 +184,16 @@ def mlp(in_size, hidden_size, n_layers):
 class ClusterGRU(nn.GRU):
     """``nn.GRU`` (same parameters, state_dict keys and call signature) whose recurrence runs as one
     cluster-persistent launch (csrc/gru.cu) instead of cuDNN's two launches per time step.  Used when the
-    layer has the shape the decoder builds (one layer, batch_first, hidden 512), the input is CUDA
-    float32 and the batch fits one pass of the resident clusters (70 voices on a B200; beyond that cuDNN's
-    batched SGEMM per step is faster); every other case takes the stock cuDNN path of the base class, as
-    the reference does."""
+    layer has the shape the reference's decoder and encoder build (one layer, batch_first, hidden 512) and the
+    input is CUDA float32.  Any batch: above one pass of the resident clusters (70 voices on a B200) the kernel
+    itself loops over groups of voices.  Other hidden sizes (the reference never builds one) and non-CUDA inputs
+    take the stock path of the base class."""
 
     def _cluster_path(self, x, hx) -> bool:
         return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 3
                 and self.num_layers == 1 and not self.bidirectional and self.batch_first and self.bias
                 and self.proj_size == 0 and not torch.jit.is_scripting()
-                and 0 < x.shape[0] <= int(_F._ops.gru_supported(self.hidden_size)))
+                and x.shape[0] > 0 and int(_F._ops.gru_supported(self.hidden_size)) > 0)
 
     def forward(self, input, hx=None):      # noqa: A002 (nn.GRU's argument name)
         if not self._cluster_path(input, hx):

@@ -115,13 +115,6 @@ def test_split_with_column_sums(rows, cols):
     assert torch.equal(colsum, ops.gemm3x_split_colsum(x)[1])        # fixed summation order
 
 
-def test_small_inputs_take_the_library_path():
-    from ddsp_pytorch_b200 import core
-    lin = core.Linear(512, 512).cuda()
-    x = torch.randn(1, 8, 512, device="cuda")
-    assert torch.equal(lin(x), torch.nn.functional.linear(x, lin.weight, lin.bias))
-
-
 def test_c_abi_direct_call_of_the_gemm():
     """split + GEMM through libddsp_b200.so with plain pointers (ctypes), no torch op."""
     import ctypes
@@ -153,3 +146,27 @@ def test_c_abi_direct_call_of_the_gemm():
     ref = x.double() @ w.double().t() + b.double()
     assert float((y.double() - ref).abs().max() / ref.abs().max()) < 2e-6
     assert lib.ddsp_b200_gemm3x(None, rp(M), ld, 0, ws.data_ptr(), rp(N), ld, 0, None, y.data_ptr(), N, M, N, K, None, st) == -1
+
+
+@pytest.mark.parametrize("rows,fan_in,fan_out", [(2, 1, 512), (2, 512, 101), (25600, 1, 512), (3, 514, 65), (1, 16, 512)])
+def test_small_and_narrow_layers_run_on_the_kernel(rows, fan_in, fan_out):
+    """No library fallback for CUDA float32 inputs: 2-row calls of the realtime path, the decoder's fan-in-1 first
+    layers (decoder.py:18-19) and odd widths all take the split-bf16 GEMM, forward and backward, against float64."""
+    from ddsp_pytorch_b200 import core
+    torch.manual_seed(rows + fan_in)
+    lin = core.Linear(fan_in, fan_out).cuda()
+    ref = torch.nn.Linear(fan_in, fan_out).double()
+    ref.load_state_dict({k: v.detach().cpu().double() for k, v in lin.state_dict().items()})
+    x = torch.randn(rows, fan_in)
+    xd = x.cuda().requires_grad_(True)
+    y = lin(xd)
+    x64 = x.double().requires_grad_(True)
+    y64 = ref(x64)
+    go = torch.randn(rows, fan_out)
+    (y * go.cuda()).sum().backward()
+    (y64 * go.double()).sum().backward()
+    scale = float(y64.abs().max())
+    assert float((y.detach().cpu().double() - y64.detach()).abs().max()) <= 2e-6 * max(1.0, scale)
+    for got, want in ((xd.grad, x64.grad), (lin.weight.grad, ref.weight.grad), (lin.bias.grad, ref.bias.grad)):
+        assert float((got.cpu().double() - want).norm()) <= 1e-5 * max(1e-30, float(want.norm()))
+    assert isinstance(y.grad_fn, torch.autograd.function.BackwardCFunction) and "Linear3x" in type(y.grad_fn).__name__

@@ -67,15 +67,24 @@ def test_cluster_gru_inference_has_no_saved_gates_and_is_deterministic():
     assert torch.equal(a, b)
 
 
-def test_multi_pass_batches_through_the_c_abi():
-    """B above one pass of the resident clusters: the module routes to cuDNN, the kernel itself loops."""
-    from ddsp_pytorch_b200._lib import get_ops
-    fast, ref = _pair(512, 7)
-    x = torch.randn(75, 6, 1024)
-    yr = ref(x.double())[0]
-    gi = torch.nn.functional.linear(x.cuda(), fast.weight_ih_l0, fast.bias_ih_l0)
-    y = get_ops().gru_fwd(gi, fast.weight_hh_l0, fast.bias_hh_l0, None, False)[0]
-    assert float((y.cpu().double() - yr).abs().max()) < 2e-5
+def test_multi_pass_batches_stay_on_the_kernel():
+    """B above one pass of the resident clusters (70 voices): no cuDNN fallback, the kernel loops over voice groups.
+    Module forward + backward against float64 torch.nn at B = 75 and B = 150."""
+    for B in (75, 150):
+        fast, ref = _pair(512, 7)
+        x = torch.randn(B, 6, 1024)
+        xr = x.double().requires_grad_(True)
+        yr = ref(xr)[0]
+        go = torch.randn(B, 6, 512)
+        (yr * go.double()).sum().backward()
+        xd = x.cuda().requires_grad_(True)
+        y = fast(xd)[0]
+        assert "GRURecurrence" in type(y.grad_fn).__name__, "the cluster kernel must run, not cuDNN"
+        (y * go.cuda()).sum().backward()
+        assert float((y.detach().cpu().double() - yr.detach()).abs().max()) < 2e-5
+        assert float((xd.grad.cpu().double() - xr.grad).norm() / xr.grad.norm()) < 1e-3
+        for (n, p), (_, pr) in zip(fast.named_parameters(), ref.named_parameters()):
+            assert float((p.grad.cpu().double() - pr.grad).norm() / pr.grad.norm()) < 1e-3, n
 
 
 def test_other_hidden_sizes_take_the_library_path():
