@@ -161,7 +161,7 @@ __device__ __forceinline__ void prefetch_frames(const float *__restrict__ xr, co
 }
 
 template <int LG, bool GRAD>
-__device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, int B, int Ni,
+__device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, int B, int Ni, int abl,
                                           const float *__restrict__ target, const float *__restrict__ rec,
                                           float *__restrict__ ws, float *__restrict__ partial,
                                           unsigned char *smem) {
@@ -255,6 +255,7 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
 #pragma unroll
             for (int q = 8; q < 16; ++q) zi[q] = zfft::from_f2(ex2[(q - 8) * T + t]);
             // ---- inverse transform of U_A + i U_B, (re, im) in the lanes: one transform per thread here
+            if (!(abl & 2)) {
             zfft::stage_compute_store<LG, 0, true>(zi, ibuf, t, tw);
             gsync<T>(grp);
             zfft::stage_load<LG, 1>(zi, ibuf, t);
@@ -266,6 +267,7 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
                 zfft::stage_compute_regs<LG, 2, true>(zi, t, tw);
             } else {
                 zfft::stage_compute_regs<LG, 1, true>(zi, t, tw);
+            }
             }
             // ---- the next batch's samples start their trip from L2 now; they land during the gather
             // ---- park the two real gradient frames (unwindowed) for the gather
@@ -284,7 +286,7 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
             float *Pb = ws + sc.p_off + (size_t)b * sc.rowlen;
             const float *cold = carry + cb * (3 * HOP);
             float *cnew = carry + (cb ^ 1) * (3 * HOP);
-            for (int v = tid; v < (NFB + 3) * (HOP / 4); v += kThreads) {
+            for (int v = tid; v < ((abl & 1) ? 0 : (NFB + 3) * (HOP / 4)); v += kThreads) {
                 // rel = 4 tid + 1024 it and hop divides 1024: n0 (and so the window values) is the same every iteration
                 const int rel = v * 4, j = rel >> LH, n0 = rel & (HOP - 1);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -353,13 +355,13 @@ mss_fused_kernel(const float *__restrict__ target, const float *__restrict__ rec
     const int tile = local / a.B, b = local - tile * a.B;
     const int Ni = (int)a.N;
     switch (sc.lg) {
-        case 6: tile_body<6, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
-        case 7: tile_body<7, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
-        case 8: tile_body<8, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
-        case 9: tile_body<9, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
-        case 10: tile_body<10, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
-        case 11: tile_body<11, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
-        default: tile_body<12, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
+        case 6: tile_body<6, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
+        case 7: tile_body<7, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
+        case 8: tile_body<8, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
+        case 9: tile_body<9, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
+        case 10: tile_body<10, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
+        case 11: tile_body<11, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
+        default: tile_body<12, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
     }
 }
 
@@ -522,7 +524,7 @@ int make_plan(int B, int64_t N, const int *scales, int n_scales, Plan2 *out) {
         if (d.hop > max_hop) max_hop = d.hop;
     }
     a.n_items = item;
-    a.pad_ = 0;
+    a.pad_ = getenv("DDSP_B200_MSS_ABLATE") ? atoi(getenv("DDSP_B200_MSS_ABLATE")) : 0;   // timing experiments only
     out->ws_floats = off;
     out->partial_pairs = pairs;
     out->smem = (size_t)kWorkBytes + 2 * 3 * (size_t)max_hop * sizeof(float);

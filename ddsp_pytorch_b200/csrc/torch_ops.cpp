@@ -357,7 +357,26 @@ ConvPlan conv_plan(const at::Device &dev, int64_t min_len) {
 
 // signal (R,n), kernel (Rk,Lk) with Rk in {1,R}: out[r,i] = sum_{j<=i} signal[r,j] kernel[rk,i-j]
 // keep != 0 also returns the column-transformed signal and the kernel spectrum for the backward pass
-std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tensor &kernel_, bool keep) {
+// spectrum of the convolution kernel in the layout the row passes multiply with (four-step [k1][k2]); depends on the
+// signal length only through the transform size.  Separate op so that a caller can compute it early / on another stream
+// (hotpath.py: the reverb's spectrum only depends on the reverb parameters, not on the audio).
+Tensor fftconv_spectrum(const Tensor &kernel_, int64_t n_signal) {
+    Tensor ker = prep(kernel_, "kernel");
+    TORCH_CHECK(ker.dim() == 2 && n_signal > 0, "fftconv_spectrum: 2-D (rows, length) kernel expected");
+    const int64_t Rk = ker.size(0), Lk = ker.size(1);
+    c10::cuda::CUDAGuard guard(ker.device());
+    const int64_t Lc = std::min(Lk, n_signal);          // taps beyond the signal length never matter
+    Tensor kc = Lc == Lk ? ker : ker.narrow(1, 0, Lc).contiguous();
+    ConvPlan p = conv_plan(ker.device(), n_signal + Lc - 1);
+    void *st = cur_stream();
+    Tensor hspec = at::empty({Rk, p.n, 2}, ker.options());
+    check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+    check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
+    return hspec;
+}
+
+std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tensor &kernel_, bool keep,
+                                               const c10::optional<Tensor> &hspec_) {
     Tensor sig = prep(signal_, "signal"), ker = prep(kernel_, "kernel");
     TORCH_CHECK(sig.dim() == 2 && ker.dim() == 2, "fftconv: 2-D (rows, length) tensors expected");
     const int64_t R = sig.size(0), n = sig.size(1), Rk = ker.size(0), Lk = ker.size(1);
@@ -367,14 +386,17 @@ std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tens
     Tensor none = at::empty({0}, sig.options());
     if (R == 0 || n == 0) return {out, none, none};
     const int64_t Lc = std::min(Lk, n);                 // taps beyond the signal length never matter
-    Tensor kc = Lc == Lk ? ker : ker.narrow(1, 0, Lc).contiguous();
     ConvPlan p = conv_plan(sig.device(), n + Lc - 1);
     const int pair = Rk == 1;
     const int64_t slots = pair ? (R + 1) / 2 : R;
     void *st = cur_stream();
-    Tensor hspec = at::empty({Rk, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
-    check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
+    Tensor hspec;
+    if (hspec_.has_value() && hspec_->defined()) {
+        hspec = prep(*hspec_, "hspec");
+        TORCH_CHECK(hspec.numel() == Rk * p.n * 2, "fftconv: hspec does not belong to this kernel / signal length");
+    } else {
+        hspec = fftconv_spectrum(ker, n);
+    }
     Tensor work = at::empty({slots, p.n, 2}, sig.options());
     check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(x)");
     Tensor filtered = keep ? at::empty_like(work) : work;
@@ -797,7 +819,8 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("amp_to_ir_bwd(Tensor d_ir, int n_bands) -> Tensor");
     m.def("noise_fwd(Tensor magnitudes, Tensor noise, Tensor? add, bool apply_scale, float bias) -> Tensor");
     m.def("noise_bwd(Tensor grad_out, Tensor noise, Tensor? magnitudes_raw, int n_bands, bool apply_scale, float bias) -> Tensor");
-    m.def("fftconv_fwd(Tensor signal, Tensor kernel, bool keep_transforms) -> (Tensor, Tensor, Tensor)");
+    m.def("fftconv_spectrum(Tensor kernel, int n_signal) -> Tensor");
+    m.def("fftconv_fwd(Tensor signal, Tensor kernel, bool keep_transforms, Tensor? hspec=None) -> (Tensor, Tensor, Tensor)");
     m.def("fftconv_bwd(Tensor grad_out, Tensor signal, Tensor kernel, Tensor? work_x, Tensor? hspec, bool need_signal, bool need_kernel) -> (Tensor, Tensor)");
     m.def("reverb_impulse_fwd(Tensor noise, Tensor decay, Tensor wet, Tensor t) -> Tensor");
     m.def("reverb_impulse_bwd(Tensor d_impulse, Tensor noise, Tensor decay, Tensor wet, Tensor t) -> (Tensor, Tensor, Tensor)");
@@ -828,6 +851,7 @@ TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
     m.impl("amp_to_ir_bwd", amp_to_ir_bwd);
     m.impl("noise_fwd", noise_fwd);
     m.impl("noise_bwd", noise_bwd);
+    m.impl("fftconv_spectrum", fftconv_spectrum);
     m.impl("fftconv_fwd", fftconv_fwd);
     m.impl("fftconv_bwd", fftconv_bwd);
     m.impl("reverb_impulse_fwd", reverb_impulse_fwd);

@@ -184,12 +184,13 @@ class FilteredNoiseFused(torch.autograd.Function):
 class FFTConvolve(torch.autograd.Function):
     """core.py:169-176 on 2-D (rows, n) operands; kernel rows 1 (shared) or equal to signal rows.
     When a gradient will be needed the forward keeps the transform of the signal and the kernel spectrum
-    (32 MB + 1 MB at config 2) so the backward does not recompute them."""
+    (32 MB + 1 MB at config 2) so the backward does not recompute them.  ``hspec`` = the kernel's spectrum from
+    ``fftconv_spectrum`` when the caller computed it ahead of time (hotpath.py does, on a side stream)."""
 
     @staticmethod
-    def forward(ctx, signal, kernel):
+    def forward(ctx, signal, kernel, hspec=None):
         keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        out, work_x, hspec = _ops.fftconv_fwd(signal, kernel, keep)
+        out, work_x, hspec = _ops.fftconv_fwd(signal, kernel, keep, hspec)
         ctx.save_for_backward(signal, kernel, work_x, hspec)
         return out
 
@@ -200,7 +201,7 @@ class FFTConvolve(torch.autograd.Function):
         ds, dk = _ops.fftconv_bwd(g, signal, kernel, work_x if work_x.numel() else None,
                                   hspec if hspec.numel() else None, ctx.needs_input_grad[0],
                                   ctx.needs_input_grad[1])
-        return (ds if ctx.needs_input_grad[0] else None), (dk if ctx.needs_input_grad[1] else None)
+        return (ds if ctx.needs_input_grad[0] else None), (dk if ctx.needs_input_grad[1] else None), None
 
 
 class ReverbImpulse(torch.autograd.Function):

@@ -164,6 +164,8 @@ class BulkRenderer:
         torch.manual_seed(0)
         self.impulse = Reverb(self.L, self.SR).to(self.dev).build_impulse().detach().reshape(1, self.L)
         self.noise = torch.empty(chunk, self.T, self.BS, device=self.dev)
+        # the learned IR is the same for every voice and chunk: its spectrum is computed once
+        self.hspec = torch.ops.ddsp_b200.fftconv_spectrum(self.impulse, self.N)
 
     def render_chunk(self, draw: bool = True):
         ops, i = torch.ops.ddsp_b200, self.inp
@@ -172,7 +174,7 @@ class BulkRenderer:
         _, _, w = ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], float(self.SR), True)
         audio = ops.harmonic_fwd(i["pitch"], w, self.BS, float(self.SR), None)[0]
         sig = ops.noise_fwd(i["mag_raw"], self.noise, audio, True, -5.0)
-        return ops.fftconv_fwd(sig.squeeze(-1), self.impulse, False)[0]
+        return ops.fftconv_fwd(sig.squeeze(-1), self.impulse, False, self.hspec)[0]
 
     def render(self, voices: int):
         out = None
