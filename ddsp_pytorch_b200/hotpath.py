@@ -201,6 +201,63 @@ class SynthStep:
         else:
             self.run()
 
+    # ---- host-fed execution without device-side copies: two input sets, one captured graph each -------
+    def capture_pair(self, warmup: int = 3):
+        """Capture the forward+backward step TWICE, over two sets of static input buffers.  ``feed`` copies a host
+        batch straight into the idle set on the copy stream while the other set's graph runs; ``step_fed`` replays the
+        graph of the set that was fed.  No staging buffers and no device-to-device copy: per step the GPU sees one
+        H2D transfer (copy engine) and one graph launch."""
+        first = self.inputs
+        second = {k: v.clone() for k, v in first.items()}
+        self._pair = []
+        for inputs in (first, second):
+            self.inputs = inputs
+            graph = self.capture(forward_only=False, warmup=warmup)
+            self._pair.append({"inputs": inputs, "graph": graph, "signal": self.signal, "loss": self.loss, "grads": self.grads})
+        self.inputs = first
+        self._graph = self._pair[0]["graph"]
+        self._copy_stream2 = torch.cuda.Stream()
+        self._fed = [torch.cuda.Event(), torch.cuda.Event()]
+        self._used = [torch.cuda.Event(), torch.cuda.Event()]
+        self._fill = 0
+        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        return self._pair
+
+    def feed(self, host: Dict[str, torch.Tensor]) -> int:
+        """Host batch (pinned tensors) -> the idle input set, on the copy stream; returns the bytes queued."""
+        k = self._fill
+        self._copy_stream2.wait_event(self._used[k])             # the graph that last read this set has finished
+        n = 0
+        with torch.cuda.stream(self._copy_stream2), torch.no_grad():
+            for name in INPUT_NAMES:
+                if name in host:
+                    self._pair[k]["inputs"][name].copy_(host[name], non_blocking=True)
+                    n += host[name].numel() * host[name].element_size()
+            self._fed[k].record(self._copy_stream2)
+        return n
+
+    def step_fed(self) -> int:
+        """Run the step on the set most recently fed; returns its index (for ``loss_to_host`` / ``read_loss``)."""
+        k = self._fill
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._fed[k])
+        e = self._pair[k]
+        e["graph"].replay()
+        self._used[k].record(cur)
+        self.inputs, self.signal, self.loss, self.grads = e["inputs"], e["signal"], e["loss"], e["grads"]
+        self._fill ^= 1
+        return k
+
+    def loss_to_host(self, k: int):
+        """Queue the device->host read of set k's loss (after the step, and after the gradient all-reduce if any)."""
+        self._loss_host[k:k + 1].copy_(self._pair[k]["loss"].detach().reshape(1), non_blocking=True)
+        self._loss_ready[k].record(torch.cuda.current_stream())
+
+    def read_loss(self, k: int) -> float:
+        self._loss_ready[k].synchronize()
+        return float(self._loss_host[k])
+
     def load_inputs(self, host: Dict[str, torch.Tensor], non_blocking: bool = True) -> int:
         """Copy a batch from (pinned) host tensors into the static buffers; returns bytes copied."""
         n = 0

@@ -490,6 +490,15 @@ def test_hotpath_step_against_oracle(ddsp, orc):
     step.step_prefetched()
     torch.cuda.synchronize()
     assert torch.equal(step.loss, eager_loss)
+    # double-buffered host feeding (two input sets, one graph each, no device-side copies): both sets reproduce it
+    step.capture_pair()
+    for _ in range(3):
+        step.feed(pinned)
+        k = step.step_fed()
+        step.loss_to_host(k)
+        assert step.read_loss(k) == float(eager_loss)
+        for a, b in zip(step.grads, eager):
+            assert torch.equal(a, b)
 
 
 # ------------------------------------------------------------------------------- edge cases
