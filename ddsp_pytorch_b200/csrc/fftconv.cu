@@ -76,7 +76,8 @@ __device__ __forceinline__ void mid_stages(float2 (&x)[16], float2 *buf, int t, 
 // ---- A: real rows -> column FFT over i1 -> * W_n^(i2 k1) -> work[slot][k1][i2] -------------------
 template <int LG1>
 __global__ void __launch_bounds__((1 << LG1))
-cols_fwd_kernel(const float *__restrict__ x, int64_t rows, int64_t len, int pair, float2 *__restrict__ work,
+cols_fwd_kernel(const float *__restrict__ x, const float *__restrict__ x2, int64_t rows, int64_t len, int pair,
+                float2 *__restrict__ work,
                 const float2 *__restrict__ twn, const float2 *__restrict__ stw, int n2) {
     using P = Plan<LG1>;
     constexpr int n1 = P::N, T = P::T, PITCH = P::PITCH + 1;     // odd pitch: the 16 columns hit 16 banks
@@ -99,6 +100,10 @@ cols_fwd_kernel(const float *__restrict__ x, int64_t rows, int64_t len, int pair
         if (pos < len) {
             v[r].x = __ldg(xr + pos);
             if (xi) v[r].y = __ldg(xi + pos);
+            if (x2) {                                   // transform of x + x2 (decoder.py:121: harmonic + noise)
+                v[r].x += __ldg(x2 + rre * len + pos);
+                if (xi) v[r].y += __ldg(x2 + rim * len + pos);
+            }
         }
     }
     float2 *buf = bufs + c * PITCH;
@@ -396,9 +401,9 @@ extern "C" int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2) {
     return plan_ok(*n1, *n2) ? DDSP_B200_OK : DDSP_B200_EUNSUPPORTED;
 }
 
-extern "C" int ddsp_b200_fft4_cols_fwd(const float *x, int64_t rows, int64_t len, int pair, float *work,
-                                       const float *twiddle, const float *stage1, int n1, int n2,
-                                       void *stream) {
+extern "C" int ddsp_b200_fft4_cols_fwd_sum(const float *x, const float *x2, int64_t rows, int64_t len, int pair,
+                                           float *work, const float *twiddle, const float *stage1, int n1, int n2,
+                                           void *stream) {
     DDSP_REQUIRE(x && work && twiddle && stage1 && rows > 0 && len > 0 && plan_ok(n1, n2));
     DDSP_REQUIRE(len <= (int64_t)n1 * n2);
     const int64_t slots = pair ? (rows + 1) / 2 : rows;
@@ -409,11 +414,17 @@ extern "C" int ddsp_b200_fft4_cols_fwd(const float *x, int64_t rows, int64_t len
 #define CALL(LG)                                                                                        \
     if (!(s = set_smem(cols_fwd_kernel<LG>, col_smem<LG>())))                                           \
         cols_fwd_kernel<LG><<<grid, 1 << LG, col_smem<LG>(), st>>>(                                      \
-            x, rows, len, pair, reinterpret_cast<float2 *>(work), reinterpret_cast<const float2 *>(twiddle), \
+            x, x2, rows, len, pair, reinterpret_cast<float2 *>(work), reinterpret_cast<const float2 *>(twiddle), \
             reinterpret_cast<const float2 *>(stage1), n2)
     DDSP_LG_SWITCH_COLS(ddsp_ilog2(n1), CALL)
 #undef CALL
     return s ? s : ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_fft4_cols_fwd(const float *x, int64_t rows, int64_t len, int pair, float *work,
+                                       const float *twiddle, const float *stage1, int n1, int n2,
+                                       void *stream) {
+    return ddsp_b200_fft4_cols_fwd_sum(x, nullptr, rows, len, pair, work, twiddle, stage1, n1, n2, stream);
 }
 
 extern "C" int ddsp_b200_fft4_cols_inv(const float *work, float *out, int64_t rows, int64_t len, int pair,

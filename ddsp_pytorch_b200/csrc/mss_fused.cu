@@ -407,44 +407,15 @@ __device__ __forceinline__ float reflected_grad(const FusedArgs &a, const float 
     return acc;
 }
 
-// d_rec[b, m] = sum over scales (fixed order) of the padded gradient at m + n_fft/2, then the reflections
-template <int W>
-__global__ void __launch_bounds__(256)
-mss_combine2_kernel(const float *__restrict__ ws, float *__restrict__ d_rec, const __grid_constant__ FusedArgs a,
-                    int hs_max) {
-    const int b = blockIdx.y;
-    const int N = (int)a.N;
-    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) * W; m < N; m += gridDim.x * blockDim.x * W) {
-        Vec<W> acc = Vec<W>::zero();
-        for (int k = 0; k < a.n_scales; ++k) acc.add(padded_grad<W>(a.sc[k], ws, b, m + 2 * a.sc[k].hop));
-        const bool edge = m <= hs_max || m + W - 1 >= N - 1 - hs_max;
-        if (W == 1) {
-            float v = reinterpret_cast<float &>(acc);
-            if (edge) v += reflected_grad(a, ws, b, m, N);
-            d_rec[(size_t)b * N + m] = v;
-        } else {
-            float4 v = reinterpret_cast<float4 &>(acc);
-            if (edge) {
-                v.x += reflected_grad(a, ws, b, m, N);
-                v.y += reflected_grad(a, ws, b, m + 1, N);
-                v.z += reflected_grad(a, ws, b, m + 2, N);
-                v.w += reflected_grad(a, ws, b, m + 3, N);
-            }
-            *reinterpret_cast<float4 *>(d_rec + (size_t)b * N + m) = v;
-        }
-    }
-}
-
 struct FinArgs2 {
     int n_scales;
     long long off[kMaxScales], cnt[kMaxScales];
     float inv[kMaxScales];
 };
 
-__global__ void __launch_bounds__(1024)
-mss_finalize2_kernel(const float *__restrict__ partial, float *__restrict__ loss, const __grid_constant__ FinArgs2 fa) {
-    // every thread adds its share of every scale's partials (weighted by the scale's 1/count), then one block
-    // reduction in double; fixed order -> deterministic
+// loss = sum over scales of inv[scale] * (sum of that scale's partial pairs), by ONE block in double, fixed order
+__device__ __forceinline__ void finalize_loss(const float *__restrict__ partial, float *__restrict__ loss,
+                                              const FinArgs2 &fa) {
     __shared__ double red[32];
     double acc = 0.0;
     for (int i = 0; i < fa.n_scales; ++i) {
@@ -462,6 +433,45 @@ mss_finalize2_kernel(const float *__restrict__ partial, float *__restrict__ loss
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (threadIdx.x == 0) loss[0] = (float)v;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+mss_finalize2_kernel(const float *__restrict__ partial, float *__restrict__ loss, const __grid_constant__ FinArgs2 fa) {
+    finalize_loss(partial, loss, fa);
+}
+
+// d_rec[b, m] = sum over scales (fixed order) of the padded gradient at m + n_fft/2, then the reflections; one extra
+// block reduces the loss partials (saves a launch on the critical path of the training step)
+template <int W>
+__global__ void __launch_bounds__(256)
+mss_combine2_kernel(const float *__restrict__ ws, float *__restrict__ d_rec, const __grid_constant__ FusedArgs a,
+                    int hs_max, const float *__restrict__ partial, float *__restrict__ loss,
+                    const __grid_constant__ FinArgs2 fa) {
+    if (blockIdx.x == gridDim.x - 1) {                  // the extra block (uniform branch)
+        if (blockIdx.y == 0) finalize_loss(partial, loss, fa);
+        return;
+    }
+    const int b = blockIdx.y;
+    const int N = (int)a.N;
+    for (int m = (blockIdx.x * blockDim.x + threadIdx.x) * W; m < N; m += (gridDim.x - 1) * blockDim.x * W) {
+        Vec<W> acc = Vec<W>::zero();
+        for (int k = 0; k < a.n_scales; ++k) acc.add(padded_grad<W>(a.sc[k], ws, b, m + 2 * a.sc[k].hop));
+        const bool edge = m <= hs_max || m + W - 1 >= N - 1 - hs_max;
+        if (W == 1) {
+            float v = reinterpret_cast<float &>(acc);
+            if (edge) v += reflected_grad(a, ws, b, m, N);
+            d_rec[(size_t)b * N + m] = v;
+        } else {
+            float4 v = reinterpret_cast<float4 &>(acc);
+            if (edge) {
+                v.x += reflected_grad(a, ws, b, m, N);
+                v.y += reflected_grad(a, ws, b, m + 1, N);
+                v.z += reflected_grad(a, ws, b, m + 2, N);
+                v.w += reflected_grad(a, ws, b, m + 3, N);
+            }
+            *reinterpret_cast<float4 *>(d_rec + (size_t)b * N + m) = v;
+        }
     }
 }
 
@@ -580,18 +590,21 @@ extern "C" int ddsp_b200_mss_fused(const float *target, const float *rec, const 
         mss_fused_kernel<false><<<p.args.n_items, kThreads, p.smem, st>>>(target, rec, workspace, partial, p.args);
     }
     if ((s = ddsp_launch_status())) return s;
-    mss_finalize2_kernel<<<1, 1024, 0, st>>>(partial, loss, p.fin);
-    if ((s = ddsp_launch_status()) || !d_rec) return s;
+    if (!d_rec) {
+        mss_finalize2_kernel<<<1, 1024, 0, st>>>(partial, loss, p.fin);
+        return ddsp_launch_status();
+    }
     int hs_max = 0;
     for (int i = 0; i < n_scales; ++i) hs_max = scales[i] / 2 > hs_max ? scales[i] / 2 : hs_max;
+    // grid.x - 1 blocks of samples per voice + one block column whose first block reduces the loss
     if ((N & 3) == 0) {
         int gx = (int)ddsp_ceil_div(N / 4, 256);
         if (gx > 64) gx = 64;
-        mss_combine2_kernel<4><<<dim3(gx, B), 256, 0, st>>>(workspace, d_rec, p.args, hs_max);
+        mss_combine2_kernel<4><<<dim3(gx + 1, B), 256, 0, st>>>(workspace, d_rec, p.args, hs_max, partial, loss, p.fin);
     } else {
         int gx = (int)ddsp_ceil_div(N, 256);
         if (gx > 64) gx = 64;
-        mss_combine2_kernel<1><<<dim3(gx, B), 256, 0, st>>>(workspace, d_rec, p.args, hs_max);
+        mss_combine2_kernel<1><<<dim3(gx + 1, B), 256, 0, st>>>(workspace, d_rec, p.args, hs_max, partial, loss, p.fin);
     }
     return ddsp_launch_status();
 }

@@ -376,8 +376,11 @@ Tensor fftconv_spectrum(const Tensor &kernel_, int64_t n_signal) {
 }
 
 std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tensor &kernel_, bool keep,
-                                               const c10::optional<Tensor> &hspec_) {
+                                               const c10::optional<Tensor> &hspec_,
+                                               const c10::optional<Tensor> &signal2_) {
     Tensor sig = prep(signal_, "signal"), ker = prep(kernel_, "kernel");
+    Tensor sig2 = opt_prep(signal2_, "signal2");                  // convolve signal + signal2
+    TORCH_CHECK(!sig2.defined() || sig2.sizes() == sig.sizes(), "fftconv: signal2 must have the signal's shape");
     TORCH_CHECK(sig.dim() == 2 && ker.dim() == 2, "fftconv: 2-D (rows, length) tensors expected");
     const int64_t R = sig.size(0), n = sig.size(1), Rk = ker.size(0), Lk = ker.size(1);
     TORCH_CHECK(Rk == 1 || Rk == R, "fftconv: kernel rows must be 1 or match the signal rows");
@@ -398,7 +401,8 @@ std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tens
         hspec = fftconv_spectrum(ker, n);
     }
     Tensor work = at::empty({slots, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(x)");
+    check(ddsp_b200_fft4_cols_fwd_sum(fp(sig), opt_fp(sig2), R, n, pair, fpm(work), fp(p.tw), fp(p.st1), p.n1, p.n2, st),
+          "fft4_cols_fwd(x)");
     Tensor filtered = keep ? at::empty_like(work) : work;
     check(ddsp_b200_fft4_rows_filter(fp(work), fpm(filtered), slots, fp(hspec), pair ? 0 : p.n, 0, fp(p.tw), fp(p.st2),
                                      p.n1, p.n2, st),
@@ -820,7 +824,7 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("noise_fwd(Tensor magnitudes, Tensor noise, Tensor? add, bool apply_scale, float bias) -> Tensor");
     m.def("noise_bwd(Tensor grad_out, Tensor noise, Tensor? magnitudes_raw, int n_bands, bool apply_scale, float bias) -> Tensor");
     m.def("fftconv_spectrum(Tensor kernel, int n_signal) -> Tensor");
-    m.def("fftconv_fwd(Tensor signal, Tensor kernel, bool keep_transforms, Tensor? hspec=None) -> (Tensor, Tensor, Tensor)");
+    m.def("fftconv_fwd(Tensor signal, Tensor kernel, bool keep_transforms, Tensor? hspec=None, Tensor? signal2=None) -> (Tensor, Tensor, Tensor)");
     m.def("fftconv_bwd(Tensor grad_out, Tensor signal, Tensor kernel, Tensor? work_x, Tensor? hspec, bool need_signal, bool need_kernel) -> (Tensor, Tensor)");
     m.def("reverb_impulse_fwd(Tensor noise, Tensor decay, Tensor wet, Tensor t) -> Tensor");
     m.def("reverb_impulse_bwd(Tensor d_impulse, Tensor noise, Tensor decay, Tensor wet, Tensor t) -> (Tensor, Tensor, Tensor)");

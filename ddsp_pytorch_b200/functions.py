@@ -185,12 +185,15 @@ class FFTConvolve(torch.autograd.Function):
     """core.py:169-176 on 2-D (rows, n) operands; kernel rows 1 (shared) or equal to signal rows.
     When a gradient will be needed the forward keeps the transform of the signal and the kernel spectrum
     (32 MB + 1 MB at config 2) so the backward does not recompute them.  ``hspec`` = the kernel's spectrum from
-    ``fftconv_spectrum`` when the caller computed it ahead of time (hotpath.py does, on a side stream)."""
+    ``fftconv_spectrum`` when the caller computed it ahead of time.  ``signal2``: convolve ``signal + signal2`` (the sum
+    is formed while the first pass loads its input: decoder.py:121's ``harmonic + noise`` without its own launch);
+    both summands receive the same gradient."""
 
     @staticmethod
-    def forward(ctx, signal, kernel, hspec=None):
-        keep = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
-        out, work_x, hspec = _ops.fftconv_fwd(signal, kernel, keep, hspec)
+    def forward(ctx, signal, kernel, hspec=None, signal2=None):
+        need = list(ctx.needs_input_grad) + [False] * 4           # apply() may be called with 2, 3 or 4 arguments
+        keep = bool(need[0] or need[1] or (signal2 is not None and need[3]))
+        out, work_x, hspec = _ops.fftconv_fwd(signal, kernel, keep, hspec, signal2)
         ctx.save_for_backward(signal, kernel, work_x, hspec)
         return out
 
@@ -198,10 +201,12 @@ class FFTConvolve(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, g):
         signal, kernel, work_x, hspec = ctx.saved_tensors
+        n = len(ctx.needs_input_grad)
+        need = list(ctx.needs_input_grad) + [False] * 4
         ds, dk = _ops.fftconv_bwd(g, signal, kernel, work_x if work_x.numel() else None,
-                                  hspec if hspec.numel() else None, ctx.needs_input_grad[0],
-                                  ctx.needs_input_grad[1])
-        return (ds if ctx.needs_input_grad[0] else None), (dk if ctx.needs_input_grad[1] else None), None
+                                  hspec if hspec.numel() else None, need[0] or need[3], need[1])
+        grads = ((ds if need[0] else None), (dk if need[1] else None), None, (ds if need[3] else None))
+        return grads[:n]
 
 
 class ReverbImpulse(torch.autograd.Function):

@@ -100,12 +100,14 @@ class SynthStep:
         harmonic, _ = core.harmonic_synth_frames(i["pitch"], weights, s.block_size, s.sample_rate)
         cur.wait_stream(side)
         noise.record_stream(cur)
-        signal = harmonic + noise
         if self.reverb is not None:
             impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
             taps = min(s.samples, s.reverb_length)
             kernel = impulse.reshape(1, s.reverb_length)[:, :taps]
-            signal = F_.FFTConvolve.apply(signal.squeeze(-1), kernel).unsqueeze(-1)
+            # decoder.py:121's `harmonic + noise` is formed by the reverb's first pass while it loads its input
+            signal = F_.FFTConvolve.apply(harmonic.squeeze(-1), kernel, None, noise.squeeze(-1)).unsqueeze(-1)
+        else:
+            signal = harmonic + noise
         return signal
 
     def forward_backward(self):
@@ -114,8 +116,14 @@ class SynthStep:
         s = self.shapes
         leaves = self._leaves()
         signal = self.forward(leaves)
-        loss = core.multiscale_spectral_loss(self.inputs["target"], signal.squeeze(-1), list(s.scales), s.overlap)
-        grads = torch.autograd.grad(loss, leaves)
+        # train.py:129 is loss.backward(): the loss node's upstream gradient is exactly 1, so the gradient w.r.t. the
+        # reconstruction that the fused loss launch already produced goes straight into the synth chain's backward
+        # (core.multiscale_spectral_loss would multiply it by that 1 in a separate elementwise launch)
+        scales = [int(x) for x in s.scales]
+        windows = torch.cat([F_.hann_window_like_reference(x, signal.device) for x in scales])
+        loss, d_rec = F_._ops.mss_loss_fwd(self.inputs["target"], signal.detach().squeeze(-1), scales, float(s.overlap),
+                                           windows, True)
+        grads = torch.autograd.grad(signal, leaves, grad_outputs=d_rec.view_as(signal))
         return signal, loss, grads
 
     # ---- eager / graph execution ---------------------------------------------------------

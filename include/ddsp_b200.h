@@ -145,6 +145,9 @@ int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2);          /* host onl
 int ddsp_b200_fft4_cols_fwd(const float *x /*[rows,len]*/, int64_t rows, int64_t len, int pair,
                             float *work, const float *twiddle, const float *stage1, int n1, int n2,
                             void *stream);
+/* the same for x + x2 (x2 may be NULL): the mix `harmonic + noise` of decoder.py:121 rides in the reverb's first pass */
+int ddsp_b200_fft4_cols_fwd_sum(const float *x, const float *x2, int64_t rows, int64_t len, int pair, float *work,
+                                const float *twiddle, const float *stage1, int n1, int n2, void *stream);
 int ddsp_b200_fft4_cols_inv(const float *work, float *out /*[rows,len]*/, int64_t rows, int64_t len,
                             int pair, const float *stage1, int n1, int n2, void *stream);
 int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const float *twiddle, const float *stage2,
