@@ -17,6 +17,7 @@
 // on both parts independently, so no Hermitian untangling is ever needed.  For the gradient of the
 // filter, sum_pairs G_p * conj(X_p) has the wanted cross-correlation in its real part.
 #include <atomic>
+#include <cstdlib>
 
 #include "fft.cuh"
 #include "regfft.cuh"
@@ -156,7 +157,9 @@ template <int LG2> struct RowCfg {
 
 // MODE 0 spectrum: row FFT, write.   MODE 1 filter: row FFT, * H (or conj H), inverse row FFT,
 // * W_n^(-i2 k1), write in place.
-template <int LG2, int MODE>
+// TWIN: the inter-step twiddle W_n^(i2 k1) of the FORWARD direction is applied here, while the row is loaded (the
+// direct column pass of the 5-smooth lengths writes plain DFT outputs); otherwise the column pass already applied it.
+template <int LG2, int MODE, bool TWIN>
 __global__ void __launch_bounds__(kRowThreads)
 rows_kernel(const float2 *src_work, float2 *dst_work, const float2 *__restrict__ hspec, int64_t h_slot_stride,
             int conj_h, const float2 *__restrict__ twn, const float2 *__restrict__ stw, int n1) {
@@ -172,10 +175,16 @@ rows_kernel(const float2 *src_work, float2 *dst_work, const float2 *__restrict__
     const float2 *row_in = src_work + ((size_t)p * n1 + k1) * n2;
     float2 *row = dst_work + ((size_t)p * n1 + k1) * n2;       // may alias row_in (in-place): read fully first
     float2 *buf = bufs + g * PITCH;
-    if (MODE == 1) fill_step_twiddle(thi + g * (n2 / 16), tlo + g * 16, twn, k1, n2, t, T);
+    if (MODE == 1 || TWIN) fill_step_twiddle(thi + g * (n2 / 16), tlo + g * 16, twn, k1, n2, t, T);
     float2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = row_in[t + r * T];
+    if (TWIN) {
+        __syncthreads();                                   // the row's twiddle tables are filled
+        const StepTwiddle sti{thi + g * (n2 / 16), tlo + g * 16};
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = c_mul(v[r], sti.at(t + r * T, false));
+    }
     stage_compute_store<LG2, 0, false>(v, buf, t, stw);
     mid_stages<LG2, false>(v, buf, t, stw, true);
     if (MODE == 0) {
@@ -203,10 +212,11 @@ rows_kernel(const float2 *src_work, float2 *dst_work, const float2 *__restrict__
 // Correlation, phase 1: partial[split][k1][k2] = sum over the slots of this split of
 // FFT_row(G)[k2] * conj(FFT_row(X)[k2]).  The accumulator lives in registers (same positions as the
 // last stage's outputs).
-template <int LG2>
+template <int LG2, bool TWIN>
 __global__ void __launch_bounds__(kRowThreads)
 rows_corr_kernel(const float2 *__restrict__ work_g, const float2 *__restrict__ work_x, int64_t slots,
-                 int nsplit, float2 *__restrict__ partial, const float2 *__restrict__ stw, int n1) {
+                 int nsplit, float2 *__restrict__ partial, const float2 *__restrict__ twn,
+                 const float2 *__restrict__ stw, int n1) {
     using P = Plan<LG2>;
     constexpr int n2 = P::N, T = P::T, PITCH = P::PITCH, ROWS = RowCfg<LG2>::ROWS;
     constexpr int R = Stage<LG2, P::STAGES - 1>::R, M = 16 / R;
@@ -216,16 +226,25 @@ rows_corr_kernel(const float2 *__restrict__ work_g, const float2 *__restrict__ w
     const int k1 = blockIdx.x * ROWS + g;
     const int split = blockIdx.y;
     float2 *buf = bufs + g * PITCH;
+    float2 *thi = bufs + ROWS * PITCH;                            // [ROWS][n2/16]   (TWIN only)
+    float2 *tlo = thi + ROWS * (n2 / 16);                         // [ROWS][16]
     float2 acc[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
-    float2 v[16];
+    float2 v[16], win[16];
+    if (TWIN) {
+        fill_step_twiddle(thi + g * (n2 / 16), tlo + g * 16, twn, k1, n2, t, T);
+        __syncthreads();
+        const StepTwiddle sti{thi + g * (n2 / 16), tlo + g * 16};
+#pragma unroll
+        for (int r = 0; r < 16; ++r) win[r] = sti.at(t + r * T, false);
+    }
     for (int64_t p = split; p < slots; p += nsplit) {
         const float2 *rg = work_g + ((size_t)p * n1 + k1) * n2;
         const float2 *rx = work_x + ((size_t)p * n1 + k1) * n2;
         // spectrum of the G row into shared memory
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = rg[t + r * T];
+        for (int r = 0; r < 16; ++r) v[r] = TWIN ? c_mul(rg[t + r * T], win[r]) : rg[t + r * T];
         __syncthreads();                                  // previous slot's spectrum fully consumed
         stage_compute_store<LG2, 0, false>(v, buf, t, stw);
         mid_stages<LG2, false>(v, buf, t, stw, true);
@@ -240,7 +259,7 @@ rows_corr_kernel(const float2 *__restrict__ work_g, const float2 *__restrict__ w
                 gs[m * R + r] = buf[pad16(stage_out_index<LG2, P::STAGES - 1>(t, m, r))];
         // spectrum of the X row, consumed straight from the last stage's registers
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = rx[t + r * T];
+        for (int r = 0; r < 16; ++r) v[r] = TWIN ? c_mul(rx[t + r * T], win[r]) : rx[t + r * T];
         __syncthreads();
         stage_compute_store<LG2, 0, false>(v, buf, t, stw);
         mid_stages<LG2, false>(v, buf, t, stw, true);
@@ -289,6 +308,96 @@ rows_corr_finish_kernel(const float2 *__restrict__ partial, int nsum, float2 *__
     stage_compute_sink<LG2, P::STAGES - 1, true>(v, t, stw, [&](int i2, float2 val) {
         row[i2] = c_mul(val, st.at(i2, true));
     });
+}
+
+
+// ---- Column passes of the 5-smooth transform lengths n = N1 * n2, N1 = 20 or 24 (n2 = 4096) -------------------
+// fft_convolve only needs n >= N + L - 1.  The power of two above 79 999 (config 2: N = 64000, L = 16000) is 131 072;
+// 20 * 4096 = 81 920 does the same job with 0.625x the data in every pass.  The N1-point column DFT is small enough to
+// be done directly in registers, one thread per column: fully coalesced rows in, rows out, no shared memory, no
+// barriers; the inter-step twiddle moves to the row pass (TWIN above).  Only the first ceil(len / n2) input rows of the
+// forward pass are non-zero and only that many output rows of the inverse pass are kept.
+template <int N1> struct DirectTw;
+template <> struct DirectTw<20> {
+    static __host__ __device__ constexpr float c(int j) { constexpr float t[20] = {1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f, 6.123234e-17f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, -1.8369702e-16f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f}; return t[j]; }
+    static __host__ __device__ constexpr float s(int j) { constexpr float t[20] = {0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f, 1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f, 1.2246468e-16f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f}; return t[j]; }
+};
+template <> struct DirectTw<24> {
+    static __host__ __device__ constexpr float c(int j) { constexpr float t[24] = {1.0f, 0.965925826f, 0.866025404f, 0.707106781f, 0.5f, 0.258819045f, 6.123234e-17f, -0.258819045f, -0.5f, -0.707106781f, -0.866025404f, -0.965925826f, -1.0f, -0.965925826f, -0.866025404f, -0.707106781f, -0.5f, -0.258819045f, -1.8369702e-16f, 0.258819045f, 0.5f, 0.707106781f, 0.866025404f, 0.965925826f}; return t[j]; }
+    static __host__ __device__ constexpr float s(int j) { constexpr float t[24] = {0.0f, 0.258819045f, 0.5f, 0.707106781f, 0.866025404f, 0.965925826f, 1.0f, 0.965925826f, 0.866025404f, 0.707106781f, 0.5f, 0.258819045f, 1.2246468e-16f, -0.258819045f, -0.5f, -0.707106781f, -0.866025404f, -0.965925826f, -1.0f, -0.965925826f, -0.866025404f, -0.707106781f, -0.5f, -0.258819045f}; return t[j]; }
+};
+
+constexpr int kDirectThreads = 128;
+
+template <int N1>
+__global__ void __launch_bounds__(2 * kDirectThreads)
+dcols_fwd_kernel(const float *__restrict__ x, const float *__restrict__ x2, int64_t rows, int64_t len, int pair,
+                 float2 *__restrict__ work, int n2) {
+    const int i2 = blockIdx.x * kDirectThreads + threadIdx.x;
+    const int half = threadIdx.y;                          // outputs k1 = half, half + 2, ...
+    const int64_t p = blockIdx.y;
+    const int64_t rre = pair ? 2 * p : p, rim = pair ? 2 * p + 1 : rows;
+    const float *xr = x + rre * len;
+    const float *xi = rim < rows ? x + rim * len : nullptr;
+    float2 z[N1];
+#pragma unroll
+    for (int i1 = 0; i1 < N1; ++i1) {
+        const int64_t pos = (int64_t)i1 * n2 + i2;
+        z[i1] = make_float2(0.f, 0.f);
+        if (pos < len) {
+            z[i1].x = __ldg(xr + pos);
+            if (xi) z[i1].y = __ldg(xi + pos);
+            if (x2) {
+                z[i1].x += __ldg(x2 + rre * len + pos);
+                if (xi) z[i1].y += __ldg(x2 + rim * len + pos);
+            }
+        }
+    }
+    float2 *w = work + (size_t)p * N1 * n2 + i2;
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) {
+        if ((k1 & 1) != half) continue;                    // uniform per warp (threadIdx.y)
+        float re = z[0].x, im = z[0].y;
+#pragma unroll
+        for (int i1 = 1; i1 < N1; ++i1) {
+            const float c = DirectTw<N1>::c((i1 * k1) % N1), sn = DirectTw<N1>::s((i1 * k1) % N1);   // W = c - i sn
+            re = fmaf(z[i1].x, c, re);  re = fmaf(z[i1].y, sn, re);
+            im = fmaf(z[i1].y, c, im);  im = fmaf(-z[i1].x, sn, im);
+        }
+        w[(size_t)k1 * n2] = make_float2(re, im);
+    }
+}
+
+template <int N1>
+__global__ void __launch_bounds__(2 * kDirectThreads)
+dcols_inv_kernel(const float2 *__restrict__ work, float *__restrict__ out, int64_t rows, int64_t len, int pair,
+                 int n2) {
+    const int i2 = blockIdx.x * kDirectThreads + threadIdx.x;
+    const int half = threadIdx.y;                          // output rows i1 = half, half + 2, ...
+    const int64_t p = blockIdx.y;
+    const float2 *w = work + (size_t)p * N1 * n2 + i2;
+    float2 v[N1];
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) v[k1] = w[(size_t)k1 * n2];
+    const float sc = 1.0f / ((float)N1 * (float)n2);
+    const int64_t rre = pair ? 2 * p : p, rim = pair ? 2 * p + 1 : rows;
+    float *yr = out + rre * len;
+    float *yi = rim < rows ? out + rim * len : nullptr;
+#pragma unroll
+    for (int i1 = 0; i1 < N1; ++i1) {
+        const int64_t pos = (int64_t)i1 * n2 + i2;
+        if ((i1 & 1) == half && pos < len) {               // uniform per warp except in the last row
+            float re = v[0].x, im = v[0].y;
+#pragma unroll
+            for (int k1 = 1; k1 < N1; ++k1) {
+                const float c = DirectTw<N1>::c((i1 * k1) % N1), sn = DirectTw<N1>::s((i1 * k1) % N1);   // W = c + i sn
+                re = fmaf(v[k1].x, c, re);  re = fmaf(-v[k1].y, sn, re);
+                im = fmaf(v[k1].y, c, im);  im = fmaf(v[k1].x, sn, im);
+            }
+            yr[pos] = re * sc;
+            if (yi) yi[pos] = im * sc;
+        }
+    }
 }
 
 // ---- Reverb impulse (modules.py:21-26) -------------------------------------------------------
@@ -350,7 +459,11 @@ int set_smem(K kernel, size_t bytes) {
 
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 // n1 (column transform, one CTA of n1 threads per 16 columns): 64..512; n2 (row transform): 64..4096
-bool plan_ok(int n1, int n2) { return pow2(n1) && pow2(n2) && n1 >= 64 && n1 <= 512 && n2 >= 64 && n2 <= 4096; }
+bool direct_n1(int n1) { return n1 == 20 || n1 == 24; }          // column DFT done directly in registers
+bool plan_ok(int n1, int n2) {
+    if (direct_n1(n1)) return n2 == 4096;
+    return pow2(n1) && pow2(n2) && n1 >= 64 && n1 <= 512 && n2 >= 64 && n2 <= 4096;
+}
 
 template <int LG> size_t col_smem() {
     return (size_t)kCols * (Plan<LG>::PITCH + 1 + Plan<LG>::N / 16 + 16) * sizeof(float2);
@@ -383,17 +496,27 @@ template <int LG> size_t row_smem() {
 }  // namespace
 
 extern "C" int ddsp_b200_twiddle_table(float *table, int n, void *stream) {
-    DDSP_REQUIRE(table && n > 0 && (n & (n - 1)) == 0);
+    DDSP_REQUIRE(table && n > 0);
     twiddle_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2 *>(table), n);
     return ddsp_launch_status();
 }
 
 extern "C" int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2) {
     DDSP_REQUIRE(n1 && n2 && min_len >= 1);
+    // 5-smooth lengths between 2^16 and 2^17: 20 * 4096 and 24 * 4096 (0.625x / 0.75x the work of 2^17)
+    if (!getenv("DDSP_B200_CONV_POW2") && min_len > 65536 && min_len <= 24 * 4096) {
+        *n1 = min_len <= 20 * 4096 ? 20 : 24;
+        *n2 = 4096;
+        return DDSP_B200_OK;
+    }
     int lg = ddsp_ilog2(min_len);
     if (lg < 12) lg = 12;
     int lg1 = lg / 2;
     if (lg1 > 9) lg1 = 9;
+    if (const char *e = getenv("DDSP_B200_CONV_LG1")) {          // tuning knob: split of the four-step transform
+        const int v = atoi(e);
+        if (v >= 6 && v <= 9 && lg - v >= 6 && lg - v <= 12) lg1 = v;
+    }
     const int lg2 = lg - lg1;
     if (lg2 > 12) return DDSP_B200_EUNSUPPORTED;
     *n1 = 1 << lg1;
@@ -404,12 +527,19 @@ extern "C" int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2) {
 extern "C" int ddsp_b200_fft4_cols_fwd_sum(const float *x, const float *x2, int64_t rows, int64_t len, int pair,
                                            float *work, const float *twiddle, const float *stage1, int n1, int n2,
                                            void *stream) {
-    DDSP_REQUIRE(x && work && twiddle && stage1 && rows > 0 && len > 0 && plan_ok(n1, n2));
+    DDSP_REQUIRE(x && work && rows > 0 && len > 0 && plan_ok(n1, n2));
     DDSP_REQUIRE(len <= (int64_t)n1 * n2);
     const int64_t slots = pair ? (rows + 1) / 2 : rows;
     DDSP_REQUIRE(slots <= 65535);
-    int s = DDSP_B200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    if (direct_n1(n1)) {                                 // plain column DFT in registers; twiddle applied by the row pass
+        const dim3 dgrid(n2 / kDirectThreads, (unsigned)slots);
+        if (n1 == 20) dcols_fwd_kernel<20><<<dgrid, dim3(kDirectThreads, 2), 0, st>>>(x, x2, rows, len, pair, reinterpret_cast<float2 *>(work), n2);
+        else dcols_fwd_kernel<24><<<dgrid, dim3(kDirectThreads, 2), 0, st>>>(x, x2, rows, len, pair, reinterpret_cast<float2 *>(work), n2);
+        return ddsp_launch_status();
+    }
+    DDSP_REQUIRE(twiddle && stage1);
+    int s = DDSP_B200_EUNSUPPORTED;
     const dim3 grid(n2 / kCols, (unsigned)slots);
 #define CALL(LG)                                                                                        \
     if (!(s = set_smem(cols_fwd_kernel<LG>, col_smem<LG>())))                                           \
@@ -429,12 +559,19 @@ extern "C" int ddsp_b200_fft4_cols_fwd(const float *x, int64_t rows, int64_t len
 
 extern "C" int ddsp_b200_fft4_cols_inv(const float *work, float *out, int64_t rows, int64_t len, int pair,
                                        const float *stage1, int n1, int n2, void *stream) {
-    DDSP_REQUIRE(work && out && stage1 && rows > 0 && len > 0 && plan_ok(n1, n2));
+    DDSP_REQUIRE(work && out && rows > 0 && len > 0 && plan_ok(n1, n2));
     DDSP_REQUIRE(len <= (int64_t)n1 * n2);
     const int64_t slots = pair ? (rows + 1) / 2 : rows;
     DDSP_REQUIRE(slots <= 65535);
-    int s = DDSP_B200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    if (direct_n1(n1)) {
+        const dim3 dgrid(n2 / kDirectThreads, (unsigned)slots);
+        if (n1 == 20) dcols_inv_kernel<20><<<dgrid, dim3(kDirectThreads, 2), 0, st>>>(reinterpret_cast<const float2 *>(work), out, rows, len, pair, n2);
+        else dcols_inv_kernel<24><<<dgrid, dim3(kDirectThreads, 2), 0, st>>>(reinterpret_cast<const float2 *>(work), out, rows, len, pair, n2);
+        return ddsp_launch_status();
+    }
+    DDSP_REQUIRE(stage1);
+    int s = DDSP_B200_EUNSUPPORTED;
     const dim3 grid(n2 / kCols, (unsigned)slots);
 #define CALL(LG)                                                                                        \
     if (!(s = set_smem(cols_inv_kernel<LG>, col_smem<LG>())))                                           \
@@ -451,9 +588,16 @@ extern "C" int ddsp_b200_fft4_rows_spectrum(float *work, int64_t slots, const fl
     DDSP_REQUIRE(work && twiddle && stage2 && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
     int s = DDSP_B200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    if (direct_n1(n1)) {                                 // n2 = 4096, forward twiddle applied on load
+        if ((s = set_smem(rows_kernel<12, 0, true>, row_smem<12>()))) return s;
+        rows_kernel<12, 0, true><<<dim3(n1, (unsigned)slots), kRowThreads, row_smem<12>(), st>>>(
+            reinterpret_cast<const float2 *>(work), reinterpret_cast<float2 *>(work), nullptr, 0, 0,
+            reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1);
+        return ddsp_launch_status();
+    }
 #define CALL(LG)                                                                                        \
-    if (!(s = set_smem(rows_kernel<LG, 0>, row_smem<LG>())))                                            \
-        rows_kernel<LG, 0><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
+    if (!(s = set_smem(rows_kernel<LG, 0, false>, row_smem<LG>())))                                     \
+        rows_kernel<LG, 0, false><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
             reinterpret_cast<const float2 *>(work), reinterpret_cast<float2 *>(work), nullptr, 0, 0,     \
             reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1)
     DDSP_LG_SWITCH_ROWS(ddsp_ilog2(n2), CALL)
@@ -467,9 +611,17 @@ extern "C" int ddsp_b200_fft4_rows_filter(const float *work, float *dst, int64_t
     DDSP_REQUIRE(work && dst && hspec && twiddle && stage2 && slots > 0 && slots <= 65535 && plan_ok(n1, n2));
     int s = DDSP_B200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    if (direct_n1(n1)) {
+        if ((s = set_smem(rows_kernel<12, 1, true>, row_smem<12>()))) return s;
+        rows_kernel<12, 1, true><<<dim3(n1, (unsigned)slots), kRowThreads, row_smem<12>(), st>>>(
+            reinterpret_cast<const float2 *>(work), reinterpret_cast<float2 *>(dst),
+            reinterpret_cast<const float2 *>(hspec), h_slot_stride, conj_h,
+            reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1);
+        return ddsp_launch_status();
+    }
 #define CALL(LG)                                                                                        \
-    if (!(s = set_smem(rows_kernel<LG, 1>, row_smem<LG>())))                                            \
-        rows_kernel<LG, 1><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
+    if (!(s = set_smem(rows_kernel<LG, 1, false>, row_smem<LG>())))                                     \
+        rows_kernel<LG, 1, false><<<dim3(n1 / RowCfg<LG>::ROWS, (unsigned)slots), kRowThreads, row_smem<LG>(), st>>>( \
             reinterpret_cast<const float2 *>(work), reinterpret_cast<float2 *>(dst),                    \
             reinterpret_cast<const float2 *>(hspec), h_slot_stride, conj_h,                             \
             reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1)
@@ -483,22 +635,47 @@ extern "C" int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce) {
     return slots < 8 ? slots : 8;
 }
 
+// splits for a given plan: the correlate kernel runs one CTA per SM, so (row blocks) x splits should not spill into a
+// second, nearly empty wave (20 rows x 8 splits = 160 CTAs on 148 SMs did)
+extern "C" int64_t ddsp_b200_fft4_correlate_splits_plan(int64_t slots, int reduce, int n1, int n2) {
+    if (!reduce) return slots;
+    int64_t s = slots < 8 ? slots : 8;
+    if (direct_n1(n1) && n2 == 4096)
+        while (s > 1 && (int64_t)n1 * s > DDSP_SM_COUNT) --s;
+    return s;
+}
+
 extern "C" int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots,
                                              int reduce, float *scratch, float *out, const float *twiddle,
                                              const float *stage2, int n1, int n2, void *stream) {
     DDSP_REQUIRE(work_g && work_x && scratch && out && twiddle && stage2 && slots > 0 && slots <= 65535);
     DDSP_REQUIRE(plan_ok(n1, n2));
-    const int nsplit = (int)ddsp_b200_fft4_correlate_splits(slots, reduce);
+    const int nsplit = (int)ddsp_b200_fft4_correlate_splits_plan(slots, reduce, n1, n2);
     const int nsum = reduce ? nsplit : 1;
     const int nout = reduce ? 1 : (int)slots;
     int s = DDSP_B200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    if (direct_n1(n1)) {
+        if ((s = set_smem(rows_corr_kernel<12, true>, row_smem<12>())) ||
+            (s = set_smem(rows_corr_finish_kernel<12>, row_smem<12>())))
+            return s;
+        rows_corr_kernel<12, true><<<dim3(n1, nsplit), kRowThreads, row_smem<12>(), st>>>(
+            reinterpret_cast<const float2 *>(work_g), reinterpret_cast<const float2 *>(work_x), slots, nsplit,
+            reinterpret_cast<float2 *>(scratch), reinterpret_cast<const float2 *>(twiddle),
+            reinterpret_cast<const float2 *>(stage2), n1);
+        if ((s = ddsp_launch_status())) return s;
+        rows_corr_finish_kernel<12><<<dim3(n1, nout), kRowThreads, row_smem<12>(), st>>>(
+            reinterpret_cast<const float2 *>(scratch), nsum, reinterpret_cast<float2 *>(out),
+            reinterpret_cast<const float2 *>(twiddle), reinterpret_cast<const float2 *>(stage2), n1);
+        return ddsp_launch_status();
+    }
 #define CALL(LG)                                                                                        \
-    if (!(s = set_smem(rows_corr_kernel<LG>, row_smem<LG>())) &&                                        \
+    if (!(s = set_smem(rows_corr_kernel<LG, false>, row_smem<LG>())) &&                                 \
         !(s = set_smem(rows_corr_finish_kernel<LG>, row_smem<LG>()))) {                                 \
-        rows_corr_kernel<LG><<<dim3(n1 / RowCfg<LG>::ROWS, nsplit), kRowThreads, row_smem<LG>(), st>>>(  \
+        rows_corr_kernel<LG, false><<<dim3(n1 / RowCfg<LG>::ROWS, nsplit), kRowThreads, row_smem<LG>(), st>>>(  \
             reinterpret_cast<const float2 *>(work_g), reinterpret_cast<const float2 *>(work_x), slots,  \
-            nsplit, reinterpret_cast<float2 *>(scratch), reinterpret_cast<const float2 *>(stage2), n1); \
+            nsplit, reinterpret_cast<float2 *>(scratch), reinterpret_cast<const float2 *>(twiddle),     \
+            reinterpret_cast<const float2 *>(stage2), n1);                                              \
         if (!(s = ddsp_launch_status()))                                                                \
             rows_corr_finish_kernel<LG><<<dim3(n1 / RowCfg<LG>::ROWS, nout), kRowThreads, row_smem<LG>(), st>>>( \
                 reinterpret_cast<const float2 *>(scratch), nsum, reinterpret_cast<float2 *>(out),       \

@@ -370,7 +370,7 @@ Tensor fftconv_spectrum(const Tensor &kernel_, int64_t n_signal) {
     ConvPlan p = conv_plan(ker.device(), n_signal + Lc - 1);
     void *st = cur_stream();
     Tensor hspec = at::empty({Rk, p.n, 2}, ker.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+    check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
     check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
     return hspec;
 }
@@ -401,13 +401,13 @@ std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tens
         hspec = fftconv_spectrum(ker, n);
     }
     Tensor work = at::empty({slots, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd_sum(fp(sig), opt_fp(sig2), R, n, pair, fpm(work), fp(p.tw), fp(p.st1), p.n1, p.n2, st),
+    check(ddsp_b200_fft4_cols_fwd_sum(fp(sig), opt_fp(sig2), R, n, pair, fpm(work), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, st),
           "fft4_cols_fwd(x)");
     Tensor filtered = keep ? at::empty_like(work) : work;
     check(ddsp_b200_fft4_rows_filter(fp(work), fpm(filtered), slots, fp(hspec), pair ? 0 : p.n, 0, fp(p.tw), fp(p.st2),
                                      p.n1, p.n2, st),
           "fft4_rows_filter");
-    check(ddsp_b200_fft4_cols_inv(fp(filtered), fpm(out), R, n, pair, fp(p.st1), p.n1, p.n2, st), "fft4_cols_inv");
+    check(ddsp_b200_fft4_cols_inv(fp(filtered), fpm(out), R, n, pair, opt_fp(p.st1), p.n1, p.n2, st), "fft4_cols_inv");
     if (keep) return {out, work, hspec};
     return {out, none, none};
 }
@@ -430,7 +430,7 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
     auto main_stream = at::cuda::getCurrentCUDAStream();
     void *st = (void *)main_stream.stream();
     Tensor work_g = at::empty({slots, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(g)");
+    check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(g)");
     // d_kernel and d_signal are independent after the transform of g: the kernel-gradient chain runs on a
     // pool stream (it only reads work_g), the signal-gradient chain (which filters work_g in place) waits
     // for the correlation to have consumed work_g.
@@ -442,7 +442,7 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
     Tensor saved_x = (work_x_.has_value() && work_x_->defined() && work_x_->numel() == slots * p.n * 2) ? *work_x_ : Tensor();
     if (need_signal && !hspec.defined()) {
         hspec = at::empty({Rk, p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
+        check(ddsp_b200_fft4_cols_fwd(fp(kc), Rk, Lc, 0, fpm(hspec), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(h)");
         check(ddsp_b200_fft4_rows_spectrum(fpm(hspec), Rk, fp(p.tw), fp(p.st2), p.n1, p.n2, st), "fft4_rows_spectrum");
     }
     at::cuda::CUDAEvent corr_done;
@@ -455,17 +455,17 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
         Tensor work_x = saved_x;
         if (!work_x.defined()) {
             work_x = at::empty({slots, p.n, 2}, sig.options());
-            check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), fp(p.st1), p.n1, p.n2, ss),
+            check(ddsp_b200_fft4_cols_fwd(fp(sig), R, n, pair, fpm(work_x), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, ss),
                   "fft4_cols_fwd(x)");
         }
         Tensor corr = at::empty({Rk, p.n, 2}, sig.options());
-        Tensor scratch = at::empty({ddsp_b200_fft4_correlate_splits(slots, pair), p.n, 2}, sig.options());
+        Tensor scratch = at::empty({ddsp_b200_fft4_correlate_splits_plan(slots, pair, p.n1, p.n2), p.n, 2}, sig.options());
         check(ddsp_b200_fft4_rows_correlate(fp(work_g), fp(work_x), slots, pair, fpm(scratch), fpm(corr),
                                             fp(p.tw), fp(p.st2), p.n1, p.n2, ss),
               "fft4_rows_correlate");
         if (fork) corr_done.record(side);
         Tensor dk = Lc == Lk ? d_ker : at::empty({Rk, Lc}, sig.options());
-        check(ddsp_b200_fft4_cols_inv(fp(corr), fpm(dk), Rk, Lc, 0, fp(p.st1), p.n1, p.n2, ss), "fft4_cols_inv(dh)");
+        check(ddsp_b200_fft4_cols_inv(fp(corr), fpm(dk), Rk, Lc, 0, opt_fp(p.st1), p.n1, p.n2, ss), "fft4_cols_inv(dh)");
         if (Lc != Lk) {
             c10::cuda::CUDAStreamGuard sg(side);
             d_ker.narrow(1, 0, Lc).copy_(dk);
@@ -477,7 +477,7 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
         check(ddsp_b200_fft4_rows_filter(fp(work_g), fpm(work_g), slots, fp(hspec), pair ? 0 : p.n, 1, fp(p.tw), fp(p.st2),
                                          p.n1, p.n2, st),
               "fft4_rows_filter(conj)");
-        check(ddsp_b200_fft4_cols_inv(fp(work_g), fpm(d_sig), R, n, pair, fp(p.st1), p.n1, p.n2, st),
+        check(ddsp_b200_fft4_cols_inv(fp(work_g), fpm(d_sig), R, n, pair, opt_fp(p.st1), p.n1, p.n2, st),
               "fft4_cols_inv(dx)");
     }
     if (fork) {

@@ -92,8 +92,17 @@ class SynthStep:
         # two backward branches overlap as well; under capture both become parallel graph branches.
         cur = torch.cuda.current_stream()
         side = self._side_stream
+        kernel = hspec = None
+        if self.reverb is not None:
+            # the reverb's impulse depends on the reverb parameters only.  Its autograd node stays on this stream; its
+            # spectrum (two launches, no autograd) is computed on the side stream, off the critical path
+            impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
+            taps = min(s.samples, s.reverb_length)
+            kernel = impulse.reshape(1, s.reverb_length)[:, :taps]
         side.wait_stream(cur)
         with torch.cuda.stream(side):
+            if kernel is not None:
+                hspec = F_._ops.fftconv_spectrum(kernel.detach(), s.samples)
             # FilteredNoise.get_controls + forward in one launch
             noise = F_.FilteredNoiseFused.apply(leaves[2], i["noise"], None, -5.0)
         _, _, weights = F_.HarmonicControlsWeights.apply(leaves[0], leaves[1], i["pitch"], float(s.sample_rate))
@@ -101,11 +110,9 @@ class SynthStep:
         cur.wait_stream(side)
         noise.record_stream(cur)
         if self.reverb is not None:
-            impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
-            taps = min(s.samples, s.reverb_length)
-            kernel = impulse.reshape(1, s.reverb_length)[:, :taps]
+            hspec.record_stream(cur)
             # decoder.py:121's `harmonic + noise` is formed by the reverb's first pass while it loads its input
-            signal = F_.FFTConvolve.apply(harmonic.squeeze(-1), kernel, None, noise.squeeze(-1)).unsqueeze(-1)
+            signal = F_.FFTConvolve.apply(harmonic.squeeze(-1), kernel, hspec, noise.squeeze(-1)).unsqueeze(-1)
         else:
             signal = harmonic + noise
         return signal

@@ -161,6 +161,7 @@ int ddsp_b200_fft4_rows_filter(const float *work, float *dst, int64_t slots, con
 /* out = rows of IFFT( FFT(g) * conj(FFT(x)) ), summed over slots into one slot when reduce != 0.
  * scratch: ddsp_b200_fft4_correlate_splits(slots, reduce) * n1*n2 complex (partial spectra).      */
 int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce);
+int64_t ddsp_b200_fft4_correlate_splits_plan(int64_t slots, int reduce, int n1, int n2);   /* the same, for a given plan */
 int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots, int reduce,
                                   float *scratch, float *out, const float *twiddle, const float *stage2,
                                   int n1, int n2, void *stream);

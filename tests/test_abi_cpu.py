@@ -55,7 +55,10 @@ def test_argument_errors_do_not_need_a_gpu(pkg):
     n1, n2 = ctypes.c_int(), ctypes.c_int()
     plan = lib.ddsp_b200_conv_plan
     plan.argtypes = [ctypes.c_int64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
-    assert plan(64000 + 16000 - 1, n1, n2) == 0 and n1.value * n2.value == 1 << 17
+    # config 2: the 5-smooth length 20 * 4096 = 81920 >= 79999 (0.625x the data of 2^17); config 4: 2^18
+    assert plan(64000 + 16000 - 1, n1, n2) == 0 and (n1.value, n2.value) == (20, 4096)
+    assert plan(90000, n1, n2) == 0 and (n1.value, n2.value) == (24, 4096)
+    assert plan(60000, n1, n2) == 0 and n1.value * n2.value == 1 << 16
     assert plan(192000 + 48000 - 1, n1, n2) == 0 and n1.value * n2.value == 1 << 18
     tiles = lib.ddsp_b200_mss_tiles
     tiles.restype = ctypes.c_int64
