@@ -29,6 +29,19 @@ def hann_window_like_reference(n_fft: int, device) -> torch.Tensor:
     return w
 
 
+_WINDOW_SETS = {}
+
+
+def hann_windows_like_reference(scales: Sequence[int], device) -> torch.Tensor:
+    """The scales' windows back to back (the layout ``mss_loss_fwd`` takes), built once per (scales, device)."""
+    key = (tuple(int(s) for s in scales), str(device))
+    w = _WINDOW_SETS.get(key)
+    if w is None:
+        w = torch.cat([hann_window_like_reference(s, device) for s in key[0]])
+        _WINDOW_SETS[key] = w
+    return w
+
+
 class ScaleFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -346,7 +359,7 @@ class MultiScaleSpectralLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, target, rec, scales, overlap):
         scales = [int(s) for s in scales]
-        windows = torch.cat([hann_window_like_reference(s, rec.device) for s in scales])
+        windows = hann_windows_like_reference(scales, rec.device)
         need = bool(ctx.needs_input_grad[1])
         loss, d_rec = _ops.mss_loss_fwd(target, rec, scales, float(overlap), windows, need)
         if need:

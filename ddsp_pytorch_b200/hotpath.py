@@ -127,7 +127,7 @@ class SynthStep:
         # reconstruction that the fused loss launch already produced goes straight into the synth chain's backward
         # (core.multiscale_spectral_loss would multiply it by that 1 in a separate elementwise launch)
         scales = [int(x) for x in s.scales]
-        windows = torch.cat([F_.hann_window_like_reference(x, signal.device) for x in scales])
+        windows = F_.hann_windows_like_reference(scales, signal.device)
         loss, d_rec = F_._ops.mss_loss_fwd(self.inputs["target"], signal.detach().squeeze(-1), scales, float(s.overlap),
                                            windows, True)
         grads = torch.autograd.grad(signal, leaves, grad_outputs=d_rec.view_as(signal))

@@ -1,7 +1,7 @@
 """GPU parity at the BENCHMARKED shapes and through whole chains (round-2 additions, VERDICT r01 "parity holes").
 
 * the long convolution / reverb, forward AND gradients (d x, d noise, d decay, d wet) for a fixed grad_output at
-  config 2 (B=64, N=64000, L=16000: n = 2^17, 8-way split partial spectra) and config 4 (N=192000, L=48000: n = 2^18)
+  config 2 (B=64, N=64000, L=16000: transform length 20 x 4096, split partial spectra) and config 4 (N=192000, L=48000: n = 2^18)
 * the gradient chain controls -> harmonic + noise -> reverb with a LINEAR loss on the signal (no L1 sign ties), 1e-3
 * the whole model's parameter gradients against a float64 run of the unmodified reference (golden fixture)
 * the ctypes example of INTEGRATION.md section 3, executed verbatim
@@ -40,9 +40,11 @@ def rel(got, ref):
 
 
 # ------------------------------------------------------------------------------- K3 at the bench shapes
-@pytest.mark.parametrize("B,N,L,sr", [(64, 64000, 16000, 16000), (4, 192000, 48000, 48000), (5, 64000, 16000, 16000)])
+@pytest.mark.parametrize("B,N,L,sr", [(64, 64000, 16000, 16000), (4, 192000, 48000, 48000), (5, 64000, 16000, 16000),
+                                       (3, 70000, 20000, 16000)])
 def test_reverb_forward_and_gradients_at_bench_shapes(ddsp, orc, B, N, L, sr):
-    """modules.py:21-35 + core.py:169-176 at the shapes bench.py runs (config 2, config 4) and an odd batch."""
+    """modules.py:21-35 + core.py:169-176 at the shapes bench.py runs (config 2: transform length 20 x 4096; config 4:
+    2^18), an odd batch, and a length that takes the 24 x 4096 transform."""
     from ddsp_pytorch_b200.models.modules import Reverb
     torch.manual_seed(B)
     rv = Reverb(L, sr, initial_wet=0.4, initial_decay=3.0)
