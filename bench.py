@@ -357,6 +357,8 @@ def init_dist(world, dev):
     # keep stdout to the single JSON line: NCCL writes its version banner (and, at INFO, its topology lines) to
     # stdout unless it is given a file; whoever asked for NCCL_DEBUG output still gets it, on stderr
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"            # level VERSION prints the banner to stdout whatever the file
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
     return dist
