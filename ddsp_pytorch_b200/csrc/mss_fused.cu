@@ -281,7 +281,8 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
 #pragma unroll
             for (int dq = 0; dq < 4; ++dq)
                 wgat[dq] = __ldg(reinterpret_cast<const float4 *>(window + ((4 * tid) & (HOP - 1)) + dq * HOP));
-            __syncthreads();
+            if (!(abl & 4)) __syncthreads();          // (bit 2 of the ablation knob: timing without the CTA barriers)
+            else gsync<T>(grp);
             // ---- ordered gather overlap-add over the batch's (NFB + 3) hops, four positions per thread
             float *Pb = ws + sc.p_off + (size_t)b * sc.rowlen;
             const float *cold = carry + cb * (3 * HOP);
@@ -311,7 +312,8 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
                 else *reinterpret_cast<float4 *>(cnew + (j - NFB) * HOP + n0) = acc;
             }
             cb ^= 1;
-            __syncthreads();
+            if (!(abl & 4)) __syncthreads();
+            else gsync<T>(grp);
         } else {
             gsync<T>(grp);                                        // exchange area is reused by the next batch
         }

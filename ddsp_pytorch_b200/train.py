@@ -125,28 +125,48 @@ class ShardedLoader:
         epoch, self.epoch = self.epoch, self.epoch + 1
         q: "queue.Queue" = queue.Queue(maxsize=self.depth)
 
+        stop = threading.Event()
+
         def produce():
             for step in range(len(self)):
+                if stop.is_set():
+                    return
                 host = self.dataset.batch(self.indices(epoch, step))
                 if self.copy_stream is not None:
                     host = {k: v.pin_memory() for k, v in host.items()}
-                q.put(host)
-            q.put(None)
+                while not stop.is_set():
+                    try:
+                        q.put(host, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+            if not stop.is_set():
+                q.put(None)
 
-        threading.Thread(target=produce, daemon=True).start()
-        while True:
-            host = q.get()
-            if host is None:
-                return
-            if self.copy_stream is None:
-                yield host
-                continue
-            with torch.cuda.stream(self.copy_stream):
-                dev = {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
-            torch.cuda.current_stream(self.device).wait_stream(self.copy_stream)
-            for v in dev.values():
-                v.record_stream(torch.cuda.current_stream(self.device))
-            yield dev
+        worker = threading.Thread(target=produce, daemon=True)
+        worker.start()
+        try:
+            while True:
+                host = q.get()
+                if host is None:
+                    return
+                if self.copy_stream is None:
+                    yield host
+                    continue
+                with torch.cuda.stream(self.copy_stream):
+                    dev = {k: v.to(self.device, non_blocking=True) for k, v in host.items()}
+                torch.cuda.current_stream(self.device).wait_stream(self.copy_stream)
+                for v in dev.values():
+                    v.record_stream(torch.cuda.current_stream(self.device))
+                yield dev
+        finally:                                     # the consumer left (break at the step limit): release the worker
+            stop.set()
+            while not q.empty():
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    break
+            worker.join(timeout=5)
 
 
 class Trainer:
@@ -236,9 +256,9 @@ def build_model(name: str, kwargs: dict) -> torch.nn.Module:
     """``train.py:34-42``."""
     from .models.decoder import DDSPDecoder
     from .models.encoder import DDSPAutoencoder
-    if name == "decoder":
+    if name in ("decoder", "single-inst-decoder"):           # config.yaml:14 / this CLI's short name
         return DDSPDecoder(**kwargs)
-    if name == "autoencoder":
+    if name in ("autoencoder", "mfcc-autoencoder"):          # autoencoder.yaml:14
         return DDSPAutoencoder(**kwargs)
     raise ValueError(f"invalid model name: {name}")
 
@@ -267,6 +287,11 @@ def run(args) -> dict:
     mean_l, std_l = loudness_stats(data, args.batch)
     trainer = Trainer(model, args.scales, args.overlap, args.lr, mean_l, std_l, device, use_graph=not (args.no_graph or args.cpu_noise))      # a CPU draw cannot be captured
     trainer.sync_parameters()
+    # parameters are identical on every rank (same seed + broadcast); the noise draws must NOT be: with one seed all
+    # ranks would excite voices i and i + B/world with the same noise, which a single-GPU run of the batch never does
+    torch.manual_seed(args.seed + 1000 * (rank + 1))
+    if device.type == "cuda":
+        torch.cuda.manual_seed(args.seed + 1000 * (rank + 1))
     loader = ShardedLoader(data, args.batch, rank, world, device, seed=args.seed)
     if len(loader) == 0:
         raise ValueError(f"dataset of {len(data)} examples is smaller than the global batch {args.batch}")
@@ -274,7 +299,8 @@ def run(args) -> dict:
     out_dir = Path(args.root) / args.name
     if rank == 0:
         out_dir.mkdir(parents=True, exist_ok=True)
-        config = {"model": {"name": args.model, "kwargs": kwargs},
+        ref_names = {"decoder": "single-inst-decoder", "autoencoder": "mfcc-autoencoder"}     # train.py:37-40, config.yaml:14
+        config = {"model": {"name": ref_names[args.model], "kwargs": kwargs},
                   "data": {"mean_loudness": mean_l, "std_loudness": std_l},
                   "train": {"scales": list(args.scales), "overlap": args.overlap, "lr": args.lr, "batch": args.batch,
                             "steps": args.steps, "world_size": world}}
@@ -301,9 +327,11 @@ def run(args) -> dict:
                 last = value
                 seen += 1
                 running += (value - running) / seen                 # train.py:136-139
-                if rank == 0 and running < best:                    # train.py:141-147
-                    best = running
-                    torch.save(model.state_dict(), out_dir / "state.pth")
+                if seen >= args.ckpt_window or done == args.steps:  # train.py:141-151: compare the window's mean,
+                    if rank == 0 and running < best:                # keep the best, start a new window
+                        best = running
+                        torch.save(model.state_dict(), out_dir / "state.pth")
+                    running, seen = 0.0, 0
             if done >= args.steps:
                 break
     end.record()
@@ -338,6 +366,8 @@ def parser() -> argparse.ArgumentParser:
     ap.add_argument("--warmup", type=int, default=5, help="steps excluded from the ms_per_step report")
     ap.add_argument("--batch", type=int, default=16, help="GLOBAL batch (config.yaml train.batch), split over the ranks")
     ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--ckpt-window", type=int, default=10, help="logged losses per checkpoint comparison (the reference "
+                    "compares the mean of one epoch, train.py:141-151, and resets it)")
     ap.add_argument("--scales", type=int, nargs="+", default=[4096, 2048, 1024, 512, 256, 128])
     ap.add_argument("--overlap", type=float, default=0.75)
     ap.add_argument("--hidden-size", type=int, default=512)

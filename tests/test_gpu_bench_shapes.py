@@ -156,3 +156,25 @@ def test_integration_md_ctypes_example(ddsp, orc):
     ref = orc.filtered_noise(mags.double().cpu(), noise.double().cpu(), ns["bs"])
     assert out.shape == ref.shape
     assert float((out.double().cpu() - ref).abs().max()) <= 1e-6
+
+
+# ------------------------------------------------------------------------------- device-side noise draw
+def test_device_noise_option_matches_oracle_on_the_same_draw(ddsp, orc):
+    """FilteredNoise.device_noise (the training harness's default: no CPU draw, no H2D copy of the noise): the module's
+    output equals the oracle's modules.py:116-128 on the very tensor the device generator produced for that seed, and the
+    draw is uniform(-1, 1) like the reference's."""
+    from ddsp_pytorch_b200.models.modules import FilteredNoise
+    B, T, bs, NB = 3, 40, 160, 65
+    fn = FilteredNoise(block_size=bs, window_size=NB)
+    fn.device_noise = True
+    mags = torch.rand(B, T, NB, generator=torch.Generator().manual_seed(2)) * 0.5
+    torch.cuda.manual_seed(77)
+    y = fn(mags.cuda())
+    torch.cuda.manual_seed(77)
+    noise = torch.rand(B, T, bs, device="cuda", dtype=torch.float32) * 2 - 1
+    ref = orc.filtered_noise(mags.double(), noise.double().cpu(), bs)
+    assert y.shape == ref.shape
+    assert float((y.double().cpu() - ref).abs().max()) <= 1e-6
+    big = torch.rand(64, 400, bs, device="cuda") * 2 - 1
+    assert abs(float(big.mean())) < 2e-3 and abs(float(big.var()) - 1.0 / 3.0) < 2e-3
+    assert float(big.min()) >= -1.0 and float(big.max()) < 1.0
