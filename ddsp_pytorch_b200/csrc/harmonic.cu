@@ -71,6 +71,7 @@ phase_scan_kernel(const float *__restrict__ f0, const double *__restrict__ phase
 // Forward.  CTA = FR consecutive frames of one voice; thread = SPT consecutive samples.
 // ------------------------------------------------------------------------------------------
 constexpr int kFwdThreads = 128;
+constexpr int kFwdMaxThreads = 640;   // packed forward: one sweep of a 16-frame, 160-sample tile (small batches)
 
 template <int SPT>
 __global__ void __launch_bounds__(kFwdThreads)
@@ -169,7 +170,7 @@ harmonic_frames_fwd_kernel(const float *__restrict__ weights, const uint64_t *__
 // accumulators live in 64-bit registers, weights sit in shared memory already duplicated (A, A) so one
 // LDS.128 feeds two harmonics.  Per harmonic and 4 samples: 6 packed math instructions instead of 12.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kFwdThreads)
+__global__ void __launch_bounds__(kFwdMaxThreads)
 harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t *__restrict__ phi,
                               const uint64_t *__restrict__ delta, float *__restrict__ audio, int T,
                               int H, int Hp, int bs, int FR) {
@@ -183,7 +184,8 @@ harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t 
     const int nfr = min(FR, T - t0);
     const int tid = threadIdx.x;
     const float *wg = weights + ((size_t)b * T + t0) * H;
-    for (int i = tid; i < nfr * Hp; i += kFwdThreads) {
+    const int nthr = blockDim.x;                          // kFwdThreads, or more when the grid alone cannot fill the GPU
+    for (int i = tid; i < nfr * Hp; i += nthr) {
         const int f = i / Hp, k = i - f * Hp;
         const float a = k < H ? __ldg(wg + (size_t)f * H + k) : 0.f;
         w2[i] = make_float2(a, a);
@@ -196,7 +198,7 @@ harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t 
 
     const int S = nfr * bs;
     float *out = audio + ((size_t)b * T + t0) * bs;
-    for (int i0 = tid * 4; i0 < S; i0 += kFwdThreads * 4) {
+    for (int i0 = tid * 4; i0 < S; i0 += nthr * 4) {
         const int f = i0 / bs;
         const int j0 = i0 - f * bs;
         const uint64_t ph = sphi[f], dl = sdel[f];
@@ -643,8 +645,16 @@ extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_
         if (smem2 > 48 * 1024)
             cudaFuncSetAttribute(harmonic_frames_fwd_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem2);
-        harmonic_frames_fwd_x2_kernel<<<grid, kFwdThreads, smem2, st>>>(weights, phi, delta, audio, T, H, Hp,
-                                                                       bs, fr);
+        // few voices (strong scaling leaves 8 per GPU, realtime 1): the grid alone leaves most warp slots empty, so
+        // the CTA takes more threads = fewer sweeps per thread, until about 16 warps per SM are in flight
+        int threads = kFwdThreads;
+        const long long ctas = (long long)grid.x * grid.y;
+        const int max_useful = (int)(((long long)fr * bs / 4 + 31) / 32 * 32);          // one sweep covers the tile
+        while (threads < kFwdMaxThreads && threads < max_useful && ctas * (threads / 32) < 16ll * DDSP_SM_COUNT)
+            threads += kFwdThreads;
+        if (threads > max_useful) threads = max_useful > kFwdThreads ? max_useful : kFwdThreads;
+        if (threads > kFwdMaxThreads) threads = kFwdMaxThreads;
+        harmonic_frames_fwd_x2_kernel<<<grid, threads, smem2, st>>>(weights, phi, delta, audio, T, H, Hp, bs, fr);
     } else if (spt == 4) LAUNCH(4); else if (spt == 2) LAUNCH(2); else LAUNCH(1);
 #undef LAUNCH
     return ddsp_launch_status();

@@ -147,19 +147,6 @@ __device__ __forceinline__ void load_frames(float (&r)[20], float (&g)[20], cons
     }
 }
 
-// The same lines, asked into L1 ahead of time (no registers held): issued before the gather, used after it.
-template <int N, int T>
-__device__ __forceinline__ void prefetch_frames(const float *__restrict__ xr, const float *__restrict__ xt, int start,
-                                                int t, int Ni) {
-    if (start >= 0 && start + N / 4 + N <= Ni) {
-#pragma unroll
-        for (int q = 0; q < 20; ++q) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(xr + start + t + q * T));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(xt + start + t + q * T));
-        }
-    }
-}
-
 template <int LG, bool GRAD>
 __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, int B, int Ni, int abl,
                                           const float *__restrict__ target, const float *__restrict__ rec,

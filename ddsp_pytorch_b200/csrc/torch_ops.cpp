@@ -509,8 +509,9 @@ std::tuple<Tensor, Tensor, Tensor> reverb_impulse_bwd(const Tensor &d_imp_, cons
     TORCH_CHECK(d_imp.numel() <= L, "reverb impulse backward: d_impulse longer than the impulse");
     c10::cuda::CUDAGuard guard(noise.device());
     Tensor dn = at::empty_like(noise), dd = at::empty_like(decay), dw = at::empty_like(wet);
+    Tensor scratch = at::empty({ddsp_b200_reverb_impulse_bwd_scratch() / 8}, noise.options().dtype(at::kDouble));
     check(ddsp_b200_reverb_impulse_bwd(fp(d_imp), (int)d_imp.numel(), fp(noise), fp(decay), fp(wet), fp(t),
-                                       fpm(dn), fpm(dd), fpm(dw), (int)L, cur_stream()),
+                                       fpm(dn), fpm(dd), fpm(dw), (int)L, scratch.data_ptr(), cur_stream()),
           "reverb_impulse_bwd");
     return {dn, dd, dw};
 }

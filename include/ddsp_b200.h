@@ -171,10 +171,12 @@ int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int6
  * decay, wet: device scalars; t: the module's (float32) time buffer.                            */
 int ddsp_b200_reverb_impulse_fwd(const float *noise, const float *decay, const float *wet,
                                  const float *t, float *impulse, int L, void *stream);
-/* d_noise[L], d_decay[1], d_wet[1] from d_impulse[0..Lvalid) (taps >= Lvalid were cropped). */
+/* d_noise[L], d_decay[1], d_wet[1] from d_impulse[0..Lvalid) (taps >= Lvalid were cropped).
+ * scratch: ddsp_b200_reverb_impulse_bwd_scratch() BYTES, 8-byte aligned (per-block partial sums in double).  */
+int64_t ddsp_b200_reverb_impulse_bwd_scratch(void);
 int ddsp_b200_reverb_impulse_bwd(const float *d_impulse, int Lvalid, const float *noise,
                                  const float *decay, const float *wet, const float *t,
-                                 float *d_noise, float *d_decay, float *d_wet, int L, void *stream);
+                                 float *d_noise, float *d_decay, float *d_wet, int L, void *scratch, void *stream);
 
 /* ---- a11  multiscale_fft, one scale                           (ddsp/core.py:27-41) --------- */
 /* signal[B,N] -> mag[B, n_fft/2+1, frames], frames = 1 + N/hop (centred, reflect padded, periodic

@@ -178,3 +178,69 @@ def test_device_noise_option_matches_oracle_on_the_same_draw(ddsp, orc):
     big = torch.rand(64, 400, bs, device="cuda") * 2 - 1
     assert abs(float(big.mean())) < 2e-3 and abs(float(big.var()) - 1.0 / 3.0) < 2e-3
     assert float(big.min()) >= -1.0 and float(big.max()) < 1.0
+
+
+# ------------------------------------------------------------------------------- paths outside the fast ranges
+def test_stft_sizes_outside_the_register_fft_range(ddsp, orc):
+    """n_fft = 32 and 16 (below the 64..4096 range of the register FFT) take the generic shared-memory transform:
+    magnitudes, their gradient, and the fused loss (per-scale launches, not the all-scales kernel) against the float64
+    oracle.  A size nothing supports fails loudly."""
+    g = torch.Generator().manual_seed(21)
+    B, N = 2, 5000
+    scales, ov = [32, 16], 0.75
+    with pytest.raises(RuntimeError):
+        ddsp.multiscale_fft(torch.zeros(1, 40000, device="cuda"), [16384], ov)
+    tgt = 0.1 * torch.randn(B, N, generator=g)
+    rec = 0.1 * torch.randn(B, N, generator=g)
+    r64 = rec.double().requires_grad_(True)
+    mags64 = orc.multiscale_fft(r64, scales, ov)
+    r = rec.cuda().requires_grad_(True)
+    mags = ddsp.multiscale_fft(r, scales, ov)
+    for a, b in zip(mags, mags64):
+        assert a.shape == b.shape
+        assert float((a.detach().double().cpu() - b.detach()).abs().max()) <= 1e-4
+    go = [torch.randn(m.shape, generator=g) for m in mags64]
+    sum((m * w.double()).sum() for m, w in zip(mags64, go)).backward()
+    sum((m * w.cuda()).sum() for m, w in zip(mags, go)).backward()
+    assert rel(r.grad, r64.grad) <= GRAD_REL
+    r64b = rec.double().requires_grad_(True)
+    ref = orc.mss_loss(tgt.double(), r64b, scales, ov)
+    ref.backward()
+    r32 = rec.clone().requires_grad_(True)
+    orc.mss_loss(tgt, r32, scales, ov).backward()
+    rb = rec.cuda().requires_grad_(True)
+    loss = ddsp.multiscale_spectral_loss(tgt.cuda(), rb, scales, ov)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 5e-6 * abs(float(ref))
+    ref32 = float((r32.grad.double() - r64b.grad).norm() / r64b.grad.norm())
+    assert rel(rb.grad, r64b.grad) <= max(GRAD_REL, 1.5 * ref32)
+
+
+def test_filtered_noise_without_design_table(ddsp, orc):
+    """design == NULL in the C ABI selects the first-generation kernels (cosine sums per frame): forward and backward
+    through ctypes against the oracle."""
+    import ctypes
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int
+    B, T, NB, bs = 2, 30, 65, 160
+    g = torch.Generator().manual_seed(5)
+    mags = torch.rand(B, T, NB, generator=g)
+    noise = torch.rand(B, T, bs, generator=g) * 2 - 1
+    go = torch.randn(B, T * bs, 1, generator=g)
+    m64 = mags.double().requires_grad_(True)
+    ref = orc.filtered_noise(m64, noise.double(), bs)
+    (ref * go.double()).sum().backward()
+    md, nd, god = mags.cuda(), noise.cuda(), go.cuda().contiguous()
+    out = torch.empty(B, T * bs, 1, device="cuda")
+    dm = torch.empty(B, T, NB, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    lib.ddsp_b200_filtered_noise_fwd.restype = i32
+    lib.ddsp_b200_filtered_noise_fwd.argtypes = [vp] * 5 + [i64, i32, i32, i32, ctypes.c_float, vp]
+    lib.ddsp_b200_filtered_noise_bwd.restype = i32
+    lib.ddsp_b200_filtered_noise_bwd.argtypes = [vp] * 5 + [i64, i32, i32, i32, ctypes.c_float, vp]
+    assert lib.ddsp_b200_filtered_noise_fwd(md.data_ptr(), nd.data_ptr(), None, None, out.data_ptr(), B * T, NB, bs, 0, 0.0, st) == 0
+    assert lib.ddsp_b200_filtered_noise_bwd(god.data_ptr(), nd.data_ptr(), None, None, dm.data_ptr(), B * T, NB, bs, 0, 0.0, st) == 0
+    torch.cuda.synchronize()
+    assert float((out.double().cpu() - ref.detach()).abs().max()) <= 1e-6
+    assert rel(dm, m64.grad) <= GRAD_REL
