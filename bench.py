@@ -294,11 +294,27 @@ def kernel_table(step, shapes, flush, peaks):
         hop = int(s_ * (1 - shapes.overlap))
         fft_flops += 1.5 * (1 + N // hop) * 5.0 * s_ * math.log2(s_)
     fft_flops *= B
+    # shared-memory bytes the transform needs: 16 B per point and Stockham exchange (forward: two lanes of
+    # a 16 B entry = 8 B per frame sample and direction), mirror exchange 8, gradient exchange 4, inverse at half the
+    # forward's count, gradient frames parked and gathered 8, carry 2
+    smem_bytes = 0.0
+    for s_ in shapes.scales:
+        hop = int(s_ * (1 - shapes.overlap))
+        stages = 2 if s_ <= 256 else 3
+        per_point = 16 * (stages - 1) + 8 + 4 + 8 * (stages - 1) + 8 + 2
+        smem_bytes += (1 + N // hop) * s_ * per_point
+    smem_bytes *= B
+    smem_peak = 148 * 128 * clk / 1e9                 # GB/s: 128 B per clock per SM
     ms = event_time(lambda: ops.mss_loss_fwd(i["target"], sig2, list(shapes.scales), shapes.overlap, windows, True), 20, 3, flush)
     rows.append({"kernel": "K4L mss_loss fwd+grad (all scales in one launch + finalize + combine)", "ms": ms, "bound": "fp32",
                  "achieved": fft_flops / (ms * 1e-3) / 1e12, "peak": 2 * fma_peak / 1e12, "unit": "TFLOP/s",
                  "frac": fft_flops / (ms * 1e-3) / (2 * fma_peak),
                  "note": "FFT butterflies only (5 n log2 n, 7.0 GFLOP/step at batch 64) against 2 x 128 lanes x 148 SMs x max clock",
+                 "smem": {"achieved": smem_bytes / (ms * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
+                          "frac": smem_bytes / (ms * 1e-3) / 1e9 / smem_peak,
+                          "note": "shared-memory bytes of the Stockham exchanges, the mirror exchange and the overlap-add gather "
+                                  "against 128 B/clk/SM; the transform phases run at 76 % of it (ablation, DESIGN 3.4), the bin "
+                                  "maths and sample loads do not overlap with them"},
                  "hbm": {"achieved": 4 * 3 * B * N / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": 4 * 3 * B * N / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "note": "SURVEY 8d's HBM view: read rec + target, write grad (12 B per sample)"}})
@@ -604,6 +620,8 @@ def run_b200(args, rank, world):
                 roof["traffic_note"] = tnote
             if "hbm" in top:
                 roof["hbm"] = top["hbm"]
+            if "smem" in top:
+                roof["smem"] = top["smem"]
         parity = None
         if not args.skip_parity:
             try:
