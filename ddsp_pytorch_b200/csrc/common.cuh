@@ -83,6 +83,18 @@ __device__ __forceinline__ float ddsp_scale_grad(float x) {             // ln10 
     return 2.302585092994046f * ddsp_scale_core(x) * (1.f / (1.f + expf(x)));
 }
 
+// both at once (the backward of the controls needs the value for the normalisation and the derivative for the chain):
+// one exp(-|x|), one log1p, one exp, one division instead of five exponentials, two log1p and a division
+__device__ __forceinline__ void ddsp_scale_fn_grad(float x, float *fn, float *grad) {
+    const float e = expf(-fabsf(x));                                    // exp(-|x|) in (0, 1]
+    const float sp = fmaxf(-x, 0.f) + log1pf(e);                        // softplus(-x)
+    const float core = 2.f * expf(-2.302585092994046f * sp);            // 2 sigmoid(x)^ln10
+    const float r = 1.f / (1.f + e);
+    const float sig_neg = x >= 0.f ? e * r : r;                         // sigmoid(-x) = 1 - sigmoid(x)
+    *fn = core + 1e-7f;
+    *grad = 2.302585092994046f * core * sig_neg;
+}
+
 #define DDSP_PI_F 3.14159265358979323846f
 #define DDSP_2PI_F 6.28318530717958647692f
 

@@ -52,18 +52,36 @@ controls_fwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__
     const float f = f0[row];
     const float *dr = dist_raw + row * H;
     float *dn = dist + row * H;
+    // unnormalised values stay in registers for rows up to kKeepF * 32 harmonics (longer rows park them in `dist`)
+    constexpr int kKeepF = 8;
+    float vk[kKeepF];
     float sum = 0.f;
-    for (int k = lane; k < H; k += 32) {
+#pragma unroll
+    for (int i = 0; i < kKeepF; ++i) {
+        const int k = lane + 32 * i;
+        vk[i] = k < H ? scale_fn(dr[k]) * nyquist_mask(f, k + 1, nyq) : 0.f;
+        sum += vk[i];
+    }
+    for (int k = lane + 32 * kKeepF; k < H; k += 32) {
         const float v = scale_fn(dr[k]) * nyquist_mask(f, k + 1, nyq);
         dn[k] = v;
         sum += v;
     }
     sum = ddsp_warp_sum(sum);
     const float amp = scale_fn(amp_raw[row]);
-    for (int k = lane; k < H; k += 32) {
+#pragma unroll
+    for (int i = 0; i < kKeepF; ++i) {
+        const int k = lane + 32 * i;
+        if (k < H) {
+            const float n = vk[i] / sum;
+            dn[k] = n;
+            if (weights) weights[row * H + k] = n * amp;            // modules.py:73: distribution *= amplitudes
+        }
+    }
+    for (int k = lane + 32 * kKeepF; k < H; k += 32) {
         const float n = dn[k] / sum;                            // same thread re-reads its own write
         dn[k] = n;
-        if (weights) weights[row * H + k] = n * amp;            // modules.py:73: distribution *= amplitudes
+        if (weights) weights[row * H + k] = n * amp;
     }
     if (lane == 0) amps[row] = amp;
 }
@@ -82,11 +100,34 @@ controls_bwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__
     const float *gd = d_dist ? d_dist + row * H : nullptr;
     const float *gw = d_weights ? d_weights + row * H : nullptr;
     float *out = d_dist_raw + row * H;
-    const float amp = scale_fn(amp_raw[row]);
+    float amp, amp_grad;
+    ddsp_scale_fn_grad(amp_raw[row], &amp, &amp_grad);
     // n_k = v_k / S;  total gradient on n_k:  g_k = d_dist_k + d_weights_k * amp
     //   dv_k = (g_k - sum_j g_j n_j) / S ;   d amp = d_amps + sum_k d_weights_k n_k
+    // value and derivative of scale_function are evaluated together, once per element, and kept in registers for
+    // the second pass (rows up to kKeep * 32 harmonics; longer rows re-evaluate)
+    constexpr int kKeep = 8;
+    float gk[kKeep], dk[kKeep];
     float sum = 0.f, dot = 0.f, wdot = 0.f;
-    for (int k = lane; k < H; k += 32) {
+#pragma unroll
+    for (int i = 0; i < kKeep; ++i) {
+        const int k = lane + 32 * i;
+        gk[i] = 0.f;
+        dk[i] = 0.f;
+        if (k < H) {
+            float fn, gr;
+            ddsp_scale_fn_grad(dr[k], &fn, &gr);
+            const float mask = nyquist_mask(f, k + 1, nyq);
+            const float v = fn * mask;
+            const float g = (gd ? gd[k] : 0.f) + (gw ? gw[k] * amp : 0.f);
+            sum += v;
+            dot = fmaf(g, v, dot);
+            if (gw) wdot = fmaf(gw[k], v, wdot);
+            gk[i] = g;
+            dk[i] = mask * gr;
+        }
+    }
+    for (int k = lane + 32 * kKeep; k < H; k += 32) {
         const float v = scale_fn(dr[k]) * nyquist_mask(f, k + 1, nyq);
         const float g = (gd ? gd[k] : 0.f) + (gw ? gw[k] * amp : 0.f);
         sum += v;
@@ -97,11 +138,16 @@ controls_bwd_kernel(const float *__restrict__ amp_raw, const float *__restrict__
     const float inv = 1.f / sum;
     dot = ddsp_warp_sum(dot) * inv;                   // sum_j g_j n_j
     wdot = ddsp_warp_sum(wdot) * inv;                 // sum_k d_weights_k n_k
-    for (int k = lane; k < H; k += 32) {
+#pragma unroll
+    for (int i = 0; i < kKeep; ++i) {
+        const int k = lane + 32 * i;
+        if (k < H) out[k] = (gk[i] - dot) * inv * dk[i];
+    }
+    for (int k = lane + 32 * kKeep; k < H; k += 32) {
         const float g = (gd ? gd[k] : 0.f) + (gw ? gw[k] * amp : 0.f);
         out[k] = (g - dot) * inv * nyquist_mask(f, k + 1, nyq) * scale_grad(dr[k]);
     }
-    if (lane == 0) d_amp_raw[row] = ((d_amps ? d_amps[row] : 0.f) + wdot) * scale_grad(amp_raw[row]);
+    if (lane == 0) d_amp_raw[row] = ((d_amps ? d_amps[row] : 0.f) + wdot) * amp_grad;
 }
 
 inline int ew_blocks(int64_t n) {
