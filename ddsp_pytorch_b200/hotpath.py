@@ -27,14 +27,13 @@ class SynthStep:
         s = self.shapes = shapes
         dev = torch.device(device)
         f32 = dict(device=dev, dtype=torch.float32)
-        self.inputs = {
-            "amp_raw": torch.zeros(s.batch, s.frames, 1, **f32),
-            "dist_raw": torch.zeros(s.batch, s.frames, s.n_harmonic, **f32),
-            "mag_raw": torch.zeros(s.batch, s.frames, s.n_bands, **f32),
-            "pitch": torch.full((s.batch, s.frames, 1), 220.0, **f32),
-            "noise": torch.zeros(s.batch, s.frames, s.block_size, **f32),
-            "target": torch.zeros(s.batch, s.samples, **f32),
-        }
+        # one contiguous block holds every input (each at a 16-byte-aligned offset), so that a host batch laid out the
+        # same way (``pack_host``) reaches the device with ONE copy
+        self._layout = [("amp_raw", (s.batch, s.frames, 1)), ("dist_raw", (s.batch, s.frames, s.n_harmonic)),
+                        ("mag_raw", (s.batch, s.frames, s.n_bands)), ("pitch", (s.batch, s.frames, 1)),
+                        ("noise", (s.batch, s.frames, s.block_size)), ("target", (s.batch, s.samples))]
+        self.inputs, self._flat_in = self._alloc_inputs(dev)
+        self.inputs["pitch"].fill_(220.0)
         self.reverb = None
         if s.reverb_length is not None:
             from .models.modules import Reverb
@@ -48,6 +47,29 @@ class SynthStep:
         self._graph = None
         self._graph_fwd = None
         self._dist = None                  # set by enable_grad_allreduce (data-parallel training config)
+
+    def _offsets(self):
+        off, out = 0, []
+        for name, shape in self._layout:
+            n = 1
+            for d in shape:
+                n *= d
+            out.append((name, shape, off, n))
+            off += (n + 3) & ~3
+        return out, off
+
+    def _alloc_inputs(self, dev):
+        offs, total = self._offsets()
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        return {name: flat[o:o + n].view(shape) for name, shape, o, n in offs}, flat
+
+    def pack_host(self, host: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """A pinned host block with the batch in the device layout (what a data loader's collate function would fill)."""
+        offs, total = self._offsets()
+        flat = torch.zeros(total, dtype=torch.float32).pin_memory()
+        for name, shape, o, n in offs:
+            flat[o:o + n].view(shape).copy_(host[name])
+        return flat
 
     # ---- data parallel: the shared parameters' gradients are averaged over the ranks (SURVEY 8e) -------
     def enable_grad_allreduce(self, dist, group=None):
@@ -222,13 +244,15 @@ class SynthStep:
         batch straight into the idle set on the copy stream while the other set's graph runs; ``step_fed`` replays the
         graph of the set that was fed.  No staging buffers and no device-to-device copy: per step the GPU sees one
         H2D transfer (copy engine) and one graph launch."""
-        first = self.inputs
-        second = {k: v.clone() for k, v in first.items()}
+        first, first_flat = self.inputs, self._flat_in
+        second, second_flat = self._alloc_inputs(first_flat.device)
+        second_flat.copy_(first_flat)
         self._pair = []
-        for inputs in (first, second):
+        for inputs, flat in ((first, first_flat), (second, second_flat)):
             self.inputs = inputs
             graph = self.capture(forward_only=False, warmup=warmup)
-            self._pair.append({"inputs": inputs, "graph": graph, "signal": self.signal, "loss": self.loss, "grads": self.grads})
+            self._pair.append({"inputs": inputs, "flat": flat, "graph": graph, "signal": self.signal, "loss": self.loss,
+                               "grads": self.grads})
         self.inputs = first
         self._graph = self._pair[0]["graph"]
         self._copy_stream2 = torch.cuda.Stream()
@@ -239,16 +263,21 @@ class SynthStep:
         self._loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
         return self._pair
 
-    def feed(self, host: Dict[str, torch.Tensor]) -> int:
-        """Host batch (pinned tensors) -> the idle input set, on the copy stream; returns the bytes queued."""
+    def feed(self, host) -> int:
+        """Host batch -> the idle input set, on the copy stream; returns the bytes queued.  ``host`` is a dict of pinned
+        tensors (one copy each) or one pinned block from ``pack_host`` (a single copy)."""
         k = self._fill
         self._copy_stream2.wait_event(self._used[k])             # the graph that last read this set has finished
         n = 0
         with torch.cuda.stream(self._copy_stream2), torch.no_grad():
-            for name in INPUT_NAMES:
-                if name in host:
-                    self._pair[k]["inputs"][name].copy_(host[name], non_blocking=True)
-                    n += host[name].numel() * host[name].element_size()
+            if isinstance(host, torch.Tensor):
+                self._pair[k]["flat"].copy_(host, non_blocking=True)
+                n = host.numel() * host.element_size()
+            else:
+                for name in INPUT_NAMES:
+                    if name in host:
+                        self._pair[k]["inputs"][name].copy_(host[name], non_blocking=True)
+                        n += host[name].numel() * host[name].element_size()
             self._fed[k].record(self._copy_stream2)
         return n
 
