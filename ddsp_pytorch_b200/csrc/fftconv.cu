@@ -526,7 +526,11 @@ extern "C" int ddsp_b200_conv_plan(int64_t min_len, int *n1, int *n2) {
     }
     int lg = ddsp_ilog2(min_len);
     if (lg < 12) lg = 12;
+    // 128 columns x long rows measured best at 2^17 and 2^18 (tools sweep with DDSP_B200_CONV_LG1: 2^18 bulk render
+    // 10.71 ms with 512 x 512, 10.24 ms with 128 x 2048); rows are capped at 4096 points
     int lg1 = lg / 2;
+    if (lg1 > 7) lg1 = 7;
+    if (lg - lg1 > 12) lg1 = lg - 12;
     if (lg1 > 9) lg1 = 9;
     if (const char *e = getenv("DDSP_B200_CONV_LG1")) {          // tuning knob: split of the four-step transform
         const int v = atoi(e);
