@@ -46,6 +46,7 @@ __device__ __forceinline__ float fmul(float a, float b) {
 
 constexpr int CH = 8;          // independent chains per thread
 
+// (the clock64 span is CTA 0's; with 8 CTAs per SM the CTAs run in waves, so compare the ms column)
 // MODE 0 ffma  1 ffma2  2 fadd  3 fadd2  4 fmul  5 fmul2  6 ffma2 + 1 iadd/lop per ffma2  7 ffma2 + 1 LDS.128 per 4
 //      8 ffma + 1 int op per ffma   9 ffma2 + 2 int ops per ffma2   10 ffma2 + 1 LDS.64 + 1 STS.64 per 4
 //      11 fadd2 + fmul2 + ffma2 round robin (butterfly-like mix)
@@ -55,8 +56,14 @@ __global__ void __launch_bounds__(256) pace(int iters, float seed, float *out, l
     float a[CH], b = seed, c = seed * 0.5f;
     uint64_t A[CH], B2 = pk2(seed, seed), C2 = pk2(c, c);
     int x[CH];
+    uint64_t Bv[CH], Cv[CH];
+    float bv[CH], cv[CH];
 #pragma unroll
-    for (int i = 0; i < CH; ++i) { a[i] = seed + i; A[i] = pk2(a[i], a[i] + 1.f); x[i] = threadIdx.x + i; }
+    for (int i = 0; i < CH; ++i) {
+        a[i] = seed + i; A[i] = pk2(a[i], a[i] + 1.f); x[i] = threadIdx.x + i;
+        bv[i] = seed * (1.f + 0.001f * i); cv[i] = seed * (0.5f - 0.001f * i);
+        Bv[i] = pk2(bv[i], bv[i] * 1.001f); Cv[i] = pk2(cv[i], cv[i] * 1.001f);
+    }
     sm[threadIdx.x * 4] = seed; sm[threadIdx.x * 4 + 1] = seed; sm[threadIdx.x * 4 + 2] = seed; sm[threadIdx.x * 4 + 3] = seed;
     __syncthreads();
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
@@ -94,6 +101,9 @@ __global__ void __launch_bounds__(256) pace(int iters, float seed, float *out, l
                         asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(sbase + (threadIdx.x << 4) + 8), "f"(v.x), "f"(v.y));
                     }
                 }
+                if (MODE == 12) A[i] = fma2(A[i], Bv[i], Cv[i]);          // three distinct register pairs per instruction
+                if (MODE == 13) a[i] = ffma(a[i], bv[i], cv[i]);          // three distinct registers per instruction
+                if (MODE == 14) { A[i] = fma2(Bv[i], Cv[i], A[i]); Cv[i] = add2(Cv[i], A[i]); }   // Reinsch-like pair
                 if (MODE == 11) {
                     if (i % 3 == 0) A[i] = add2(A[i], B2);
                     else if (i % 3 == 1) A[i] = mul2(A[i], B2);
@@ -108,7 +118,11 @@ __global__ void __launch_bounds__(256) pace(int iters, float seed, float *out, l
     for (int i = 0; i < CH; ++i) {
         float lo, hi;
         asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(A[i]));
-        s += a[i] + lo + hi + (float)x[i];
+        s += a[i] + lo + hi + (float)x[i] + bv[i] + cv[i];
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(Cv[i]));
+        s += lo + hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(Bv[i]));
+        s += lo + hi;
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
@@ -145,7 +159,7 @@ int main() {
     long long *clk;
     cudaMalloc(&out, 148 * 8 * 256 * sizeof(float));
     cudaMalloc(&clk, 148 * 8 * sizeof(long long));
-    for (int c : {2, 4, 8}) {
+    for (int c : {8}) {
         run<0>("ffma (scalar, 3 registers)", 1, c, out, clk);
         run<1>("ffma2 (fma.rn.f32x2)", 2, c, out, clk);
         run<2>("fadd (scalar)", 1, c, out, clk);
@@ -153,6 +167,9 @@ int main() {
         run<4>("fmul (scalar)", 1, c, out, clk);
         run<5>("fmul2", 2, c, out, clk);
         run<11>("fadd2 / fmul2 / ffma2 mix", 2, c, out, clk);
+        run<12>("ffma2, three distinct register pairs", 2, c, out, clk);
+        run<13>("ffma, three distinct registers", 1, c, out, clk);
+        run<14>("ffma2 + fadd2 (Reinsch step, distinct pairs)", 2, c, out, clk);
         run<8>("ffma + 2 int ops (xor, add) per ffma", 1, c, out, clk);
         run<6>("ffma2 + 2 int ops (xor, add) per ffma2", 2, c, out, clk);
         run<9>("ffma2 + 4 int ops per ffma2", 2, c, out, clk);
