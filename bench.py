@@ -59,6 +59,8 @@ def parse():
     p.add_argument("--global-batch", type=int, default=WORKLOAD["batch"],
                    help="experiments only: the benchmark config is batch 64 (BASELINE.json configs[1])")
     p.add_argument("--skip-kernels", action="store_true")
+    p.add_argument("--allreduce-outside", action="store_true",
+                   help="N>1: queue the gradient all-reduce after the graph instead of inside it (A/B of the overlap)")
     p.add_argument("--skip-configs", action="store_true", help="do not measure the other BASELINE.json configurations")
     p.add_argument("--skip-parity", action="store_true")
     p.add_argument("--bulk-voices", type=int, default=1024, help="voices per GPU of --workload bulk")
@@ -334,9 +336,10 @@ def parity_check(step, shapes, host, dev):
     out = orc.synth_chain(d["amp_raw"], d["dist_raw"], d["mag_raw"], d["pitch"], d["noise"], shapes.block_size,
                           shapes.sample_rate, rp)
     ref_sig = out["signal"]
-    step.run()
+    with step.local_only():                      # this check runs on rank 0 alone: no collective
+        step.run()
     torch.cuda.synchronize()
-    audio_bench = float((step.signal[:n].double().cpu() - ref_sig).abs().max())
+    audio_bench = float((step.signal[:n].detach().double().cpu() - ref_sig).abs().max())
     small = SynthShapes(**{**shapes.__dict__, "batch": n})
     s2 = SynthStep(small, dev, reverb_state=step.reverb.state_dict())
     s2.load_inputs({k: v[:n].contiguous() for k, v in host.items()}, non_blocking=False)
@@ -345,7 +348,7 @@ def parity_check(step, shapes, host, dev):
     ref_loss = float(orc.mss_loss(d["target"], ref_sig.squeeze(-1), list(shapes.scales), shapes.overlap))
     return {"against": "float64 oracle (oracle/ddsp_oracle.py), 2-voice slice of the benchmark inputs",
             "audio_max_abs_bench_shape": audio_bench,
-            "audio_max_abs_2_voices": float((s2.signal.double().cpu() - ref_sig).abs().max()),
+            "audio_max_abs_2_voices": float((s2.signal.detach().double().cpu() - ref_sig).abs().max()),
             "audio_peak": float(ref_sig.abs().max()),
             "loss_rel_2_voices": abs(float(s2.loss) - ref_loss) / abs(ref_loss),
             "tolerance": {"audio_max_abs": 1e-4, "loss_rel": 1e-5},
@@ -502,8 +505,12 @@ def run_b200(args, rank, world):
     use_graph = not args.no_graph
     graph_note = "CUDA graph replay"
     if dist is not None:
-        step.enable_grad_allreduce(dist)            # packed into one flat buffer inside the graph, reduced in place
-        graph_note += " + one NCCL all-reduce (AVG) launch on the packed parameter gradients"
+        # the reverb's backward comes first; its packed parameter gradients are averaged by one NCCL all-reduce on a
+        # communication stream, a node of the same graph, while the synthesisers' backward runs
+        step.enable_grad_allreduce(dist, in_step=not args.allreduce_outside)
+        graph_note += (" + one eager NCCL all-reduce (AVG) launch on the packed parameter gradients" if args.allreduce_outside
+                       else ", the NCCL all-reduce (AVG) of the packed parameter gradients is a node of the graph, "
+                            "overlapped with the synthesisers' backward")
     if use_graph:
         try:
             step.capture(forward_only=False)
@@ -663,6 +670,7 @@ def run_b200(args, rank, world):
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
+        step.release_graphs()                        # the graphs hold NCCL nodes: they go before the communicator
         dist.barrier()
         dist.destroy_process_group()
 

@@ -72,24 +72,43 @@ class SynthStep:
         return flat
 
     # ---- data parallel: the shared parameters' gradients are averaged over the ranks -------
-    def enable_grad_allreduce(self, dist, group=None):
+    def enable_grad_allreduce(self, dist, group=None, in_step: bool = True):
         """Voices are sharded over the ranks; the only shared parameters on this path are the reverb's
-        (noise, decay, wet).  run() packs their gradients into one flat buffer (a node of the step's CUDA
-        graph); allreduce_grads() averages that buffer with ONE NCCL all-reduce (op AVG) per step.  The collective
-        itself stays outside the graph: every rank must take the same decision about capturing it, and a capture
-        that fails on one rank only would leave the ranks waiting for each other."""
+        (noise, decay, wet).  Their gradients are packed into one flat buffer and averaged with ONE NCCL all-reduce
+        (op AVG) per step.
+
+        ``in_step=True`` (default): the collective is part of run() and therefore a node of the captured CUDA graph.
+        The backward is cut in two: the reverb's backward first (it ends with the parameter gradients), then the
+        all-reduce is queued on a communication stream while the harmonic / noise / controls backward runs on the
+        compute streams; the step joins both at its end.  Every rank must then call run() / replay() the same number
+        of times (a rank that steps alone waits for its peers forever): use ``local_only()`` around single-rank calls.
+        ``in_step=False``: run() only packs; the caller queues ``allreduce_grads()`` after each step."""
         assert self.reverb is not None
-        self._dist, self._group = dist, group
+        self._dist, self._group, self._in_step = dist, group, bool(in_step)
         self._sizes = [p.numel() for p in self.reverb.parameters()]
         self._flat = torch.zeros(sum(self._sizes), device=self.loss.device, dtype=torch.float32)
+        self._comm_stream = torch.cuda.Stream(device=self.loss.device)
 
-    def _pack(self):
-        torch.cat([g.reshape(-1) for g in self.grads[3:]], out=self._flat)
-        shapes = [g.shape for g in self.grads[3:]]
-        self.grads = tuple(self.grads[:3]) + tuple(c.view(sh) for c, sh in zip(self._flat.split(self._sizes), shapes))
+    def local_only(self):
+        """Context manager: run()/forward_backward() without the collective (parity checks on one rank)."""
+        step = self
+
+        class _Local:
+            def __enter__(self):
+                self.saved = step._dist
+                step._dist = None
+
+            def __exit__(self, *a):
+                step._dist = self.saved
+        return _Local()
+
+    def _pack(self, rev_grads):
+        torch.cat([g.reshape(-1) for g in rev_grads], out=self._flat)
+        return tuple(c.view(g.shape) for c, g in zip(self._flat.split(self._sizes), rev_grads))
 
     def allreduce_grads(self):
-        if self._dist is not None:
+        """The collective of the ``in_step=False`` mode (a no-op otherwise: run() already contains it)."""
+        if self._dist is not None and not self._in_step:
             self._dist.all_reduce(self._flat, op=self._dist.ReduceOp.AVG, group=self._group)
 
     # ---- the path -------------------------------------------------------------------------
@@ -102,8 +121,9 @@ class SynthStep:
                        (self.reverb.noise, self.reverb.decay, self.reverb.wet)]
         return leaves
 
-    def forward(self, leaves=None) -> torch.Tensor:
-        """decoder.py:110-125: controls -> harmonic + filtered noise (+ reverb).  (B,N,1)"""
+    def forward(self, leaves=None, parts: bool = False):
+        """decoder.py:110-125: controls -> harmonic + filtered noise (+ reverb).  (B,N,1)
+        ``parts=True`` also returns the two synthesiser outputs the mix was formed from."""
         i, s = self.inputs, self.shapes
         if leaves is None:
             leaves = [i["amp_raw"], i["dist_raw"], i["mag_raw"]]
@@ -134,17 +154,19 @@ class SynthStep:
         if self.reverb is not None:
             hspec.record_stream(cur)
             # decoder.py:121's `harmonic + noise` is formed by the reverb's first pass while it loads its input
-            signal = F_.FFTConvolve.apply(harmonic.squeeze(-1), kernel, hspec, noise.squeeze(-1)).unsqueeze(-1)
+            h2, n2 = harmonic.squeeze(-1), noise.squeeze(-1)
+            signal = F_.FFTConvolve.apply(h2, kernel, hspec, n2).unsqueeze(-1)
         else:
+            h2, n2 = harmonic, noise
             signal = harmonic + noise
-        return signal
+        return (signal, h2, n2) if parts else signal
 
     def forward_backward(self):
         """train.py:89-103,129 on the synth part: loss and gradients of every leaf
         (amp_raw, dist_raw, mag_raw, reverb.noise, reverb.decay, reverb.wet)."""
         s = self.shapes
         leaves = self._leaves()
-        signal = self.forward(leaves)
+        signal, h2, n2 = self.forward(leaves, parts=True)
         # train.py:129 is loss.backward(): the loss node's upstream gradient is exactly 1, so the gradient w.r.t. the
         # reconstruction that the fused loss launch already produced goes straight into the synth chain's backward
         # (core.multiscale_spectral_loss would multiply it by that 1 in a separate elementwise launch)
@@ -152,15 +174,28 @@ class SynthStep:
         windows = F_.hann_windows_like_reference(scales, signal.device)
         loss, d_rec = F_._ops.mss_loss_fwd(self.inputs["target"], signal.detach().squeeze(-1), scales, float(s.overlap),
                                            windows, True)
-        grads = torch.autograd.grad(signal, leaves, grad_outputs=d_rec.view_as(signal))
-        return signal, loss, grads
+        if self._dist is None or self.reverb is None:
+            grads = torch.autograd.grad(signal, leaves, grad_outputs=d_rec.view_as(signal))
+            return signal, loss, grads
+        # data parallel: the reverb's backward first, so that the collective on its parameter gradients is in flight
+        # while the two synthesisers' backward runs (the two autograd calls walk disjoint parts of the graph)
+        cut = torch.autograd.grad(signal, [h2, n2] + leaves[3:], grad_outputs=d_rec.view_as(signal))
+        rev = self._pack(cut[2:])
+        cur = torch.cuda.current_stream()
+        if self._in_step:
+            comm = self._comm_stream
+            comm.wait_stream(cur)
+            with torch.cuda.stream(comm):
+                self._dist.all_reduce(self._flat, op=self._dist.ReduceOp.AVG, group=self._group)
+        front = torch.autograd.grad([h2, n2], leaves[:3], grad_outputs=[cut[0], cut[1]])
+        if self._in_step:
+            cur.wait_stream(comm)
+        return signal, loss, tuple(front) + rev
 
     # ---- eager / graph execution ---------------------------------------------------------
     def run(self):
         self.signal, loss, self.grads = self.forward_backward()
         self.loss = loss
-        if self._dist is not None:
-            self._pack()
         return loss
 
     def run_forward(self):
@@ -187,6 +222,15 @@ class SynthStep:
         else:
             self._graph = graph
         return graph
+
+    def release_graphs(self):
+        """Drop every captured graph.  A graph that holds an NCCL node must be gone before its communicator is
+        destroyed (destroy_process_group() waits for it otherwise)."""
+        self._graph = self._graph_fwd = None
+        self._pair = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
 
     def replay(self, forward_only: bool = False):
         (self._graph_fwd if forward_only else self._graph).replay()

@@ -501,6 +501,48 @@ def test_hotpath_step_against_oracle(ddsp, orc):
             assert torch.equal(a, b)
 
 
+def test_data_parallel_step_matches_the_plain_step():
+    """with the gradient all-reduce enabled the backward is cut in two (reverb first, then the collective on
+    a communication stream, a node of the captured graph, beside the synthesisers' backward).  On a one-rank NCCL
+    group the average is the identity, so eager and replayed gradients must equal the plain step's bit for bit."""
+    import torch.distributed as dist
+    from ddsp_pytorch_b200.hotpath import SynthShapes, SynthStep, synthetic_inputs
+    shapes = SynthShapes(batch=2, frames=30, block_size=160, n_harmonic=100, n_bands=65, sample_rate=16000,
+                         reverb_length=2000, scales=(1024, 512, 256, 128), overlap=0.75)
+    torch.manual_seed(0)
+    step = SynthStep(shapes, "cuda")
+    step.load_inputs(synthetic_inputs(shapes, seed=9))
+    step.run()
+    plain = [g_.clone() for g_ in step.grads]
+    plain_loss = step.loss.clone()
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29741", rank=0, world_size=1,
+                                device_id=torch.device("cuda", torch.cuda.current_device()))
+    try:
+        step.enable_grad_allreduce(dist)
+        step.run()
+        torch.cuda.synchronize()
+        assert torch.equal(step.loss, plain_loss)
+        for a, b in zip(step.grads, plain):
+            assert torch.equal(a.reshape(b.shape), b)
+        step.capture()
+        for _ in range(2):
+            step.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(step.grads, plain):
+            assert torch.equal(a.reshape(b.shape), b)
+        with step.local_only():                      # no collective: what a single rank may call on its own
+            step.run()
+        torch.cuda.synchronize()
+        for a, b in zip(step.grads, plain):
+            assert torch.equal(a.reshape(b.shape), b)
+    finally:
+        step.release_graphs()
+        if created:
+            dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------- edge cases
 @pytest.mark.parametrize("B,T,bs,H,NB", [(1, 1, 128, 1, 65), (2, 3, 128, 7, 65), (1, 5, 256, 33, 33),
                                            (3, 2, 64, 13, 9), (1, 2, 160, 101, 65)])
