@@ -274,6 +274,17 @@ def harmonic_synth_frames(f0, weights, block_size: int, sample_rate, phase0: Opt
     return _F.HarmonicFrames.apply(f0, weights, int(block_size), float(sample_rate), phase0)
 
 
+def harmonic_raw_supported(n_harmonic: int, block_size: int) -> bool:
+    return bool(_F._ops.harmonic_raw_supported(int(n_harmonic), int(block_size)))
+
+
+def harmonic_synth_from_raw(first, dist_raw, f0, block_size: int, sample_rate, phase0: Optional[torch.Tensor] = None):
+    """Extension: ``HarmonicSynth.get_controls`` + ``HarmonicSynth.forward`` (modules.py:44-80) on the control net's raw
+    outputs in one launch.  ``first`` = the projection output (B,T,H+1) and ``dist_raw=None``, or amp_raw (B,T,1) and
+    dist_raw (B,T,H).  -> (audio, phase_end, amplitudes, weights = normalised distribution x amplitudes)."""
+    return _F.HarmonicFromRaw.apply(first, dist_raw, f0, int(block_size), float(sample_rate), phase0)
+
+
 def filtered_noise(magnitudes, noise):
     """Extension: FilteredNoise.forward with the uniform(-1,1) draw passed in (B,T,block)."""
     return _F.FilteredNoise.apply(magnitudes, noise)

@@ -95,6 +95,12 @@ __device__ __forceinline__ void ddsp_scale_fn_grad(float x, float *fn, float *gr
     *grad = 2.302585092994046f * core * sig_neg;
 }
 
+// (mask.float() + 1e-4) of remove_above_nyquist (ddsp/core.py:73): both branches are float32 sums; the product
+// f0 * k is rounded once, as the reference's float32 multiply is
+__device__ __forceinline__ float ddsp_nyquist_mask(float f0, int k1, float nyq) {
+    return (__fmul_rn(f0, (float)k1) < nyq) ? (1.0f + 1e-4f) : 1e-4f;
+}
+
 #define DDSP_PI_F 3.14159265358979323846f
 #define DDSP_2PI_F 6.28318530717958647692f
 

@@ -12,10 +12,7 @@ namespace {
 
 __device__ __forceinline__ float scale_fn(float x) { return ddsp_scale_fn(x); }
 __device__ __forceinline__ float scale_grad(float x) { return ddsp_scale_grad(x); }
-// (mask.float() + 1e-4) of core.py:73: both branches are float32 sums
-__device__ __forceinline__ float nyquist_mask(float f0, int k1, float nyq) {
-    return (__fmul_rn(f0, (float)k1) < nyq) ? (1.0f + 1e-4f) : 1e-4f;   // single rounded product
-}
+__device__ __forceinline__ float nyquist_mask(float f0, int k1, float nyq) { return ddsp_nyquist_mask(f0, k1, nyq); }
 
 __global__ void scale_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;

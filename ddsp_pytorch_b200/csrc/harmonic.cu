@@ -170,10 +170,22 @@ harmonic_frames_fwd_kernel(const float *__restrict__ weights, const uint64_t *__
 // accumulators live in 64-bit registers, weights sit in shared memory already duplicated (A, A) so one
 // LDS.128 feeds two harmonics.  Per harmonic and 4 samples: 6 packed math instructions instead of 12.
 // ------------------------------------------------------------------------------------------
+// RAW: the CTA's weights are not read but computed from the control net's raw outputs in the prologue --
+// HarmonicSynth.get_controls (modules.py:44-67: scale_function on both, Nyquist mask, normalise) and the in-place
+// `distribution *= amplitudes` of modules.py:73, with the arithmetic of controls_fwd_kernel (bit-identical results);
+// one warp per frame row.  Amplitudes and weights are also written out (the model returns them as harmonic_ctrls).
+struct RawControls {
+    const float *amp_raw, *dist_raw, *f0;    // rows of amp_stride / dist_stride floats (views into the projection)
+    long long amp_stride, dist_stride;
+    float nyq;
+    float *amps, *weights;                   // [B*T], [B*T][H]
+};
+
+template <bool RAW>
 __global__ void __launch_bounds__(kFwdMaxThreads)
 harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t *__restrict__ phi,
                               const uint64_t *__restrict__ delta, float *__restrict__ audio, int T,
-                              int H, int Hp, int bs, int FR) {
+                              int H, int Hp, int bs, int FR, const RawControls rc) {
     extern __shared__ __align__(16) float smem[];
     float2 *w2 = reinterpret_cast<float2 *>(smem);                         // [FR][Hp] of (A, A)
     uint64_t *sphi = reinterpret_cast<uint64_t *>(w2 + (size_t)FR * Hp);   // [FR]
@@ -183,12 +195,46 @@ harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t 
     const int t0 = blockIdx.x * FR;
     const int nfr = min(FR, T - t0);
     const int tid = threadIdx.x;
-    const float *wg = weights + ((size_t)b * T + t0) * H;
     const int nthr = blockDim.x;                          // kFwdThreads, or more when the grid alone cannot fill the GPU
-    for (int i = tid; i < nfr * Hp; i += nthr) {
-        const int f = i / Hp, k = i - f * Hp;
-        const float a = k < H ? __ldg(wg + (size_t)f * H + k) : 0.f;
-        w2[i] = make_float2(a, a);
+    if (RAW) {
+        const int lane = tid & 31;
+        constexpr int kKeepF = 8;                          // H <= 256 (the host falls back to the two-launch path above)
+        for (int f = tid >> 5; f < nfr; f += nthr >> 5) {
+            const size_t row = (size_t)b * T + t0 + f;
+            const float fq = rc.f0[row];
+            const float *dr = rc.dist_raw + row * rc.dist_stride;
+            float vk[kKeepF];
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < kKeepF; ++i) {
+                const int k = lane + 32 * i;
+                vk[i] = k < H ? ddsp_scale_fn(dr[k]) * ddsp_nyquist_mask(fq, k + 1, rc.nyq) : 0.f;
+                sum += vk[i];
+            }
+            sum = ddsp_warp_sum(sum);
+            const float amp = ddsp_scale_fn(rc.amp_raw[row * rc.amp_stride]);
+#pragma unroll
+            for (int i = 0; i < kKeepF; ++i) {
+                const int k = lane + 32 * i;
+                if (k < Hp) {
+                    float a = 0.f;
+                    if (k < H) {
+                        const float n = vk[i] / sum;
+                        a = n * amp;                       // modules.py:73: distribution *= amplitudes
+                        rc.weights[row * H + k] = a;
+                    }
+                    w2[f * Hp + k] = make_float2(a, a);
+                }
+            }
+            if (lane == 0) rc.amps[row] = amp;
+        }
+    } else {
+        const float *wg = weights + ((size_t)b * T + t0) * H;
+        for (int i = tid; i < nfr * Hp; i += nthr) {
+            const int f = i / Hp, k = i - f * Hp;
+            const float a = k < H ? __ldg(wg + (size_t)f * H + k) : 0.f;
+            w2[i] = make_float2(a, a);
+        }
     }
     if (tid < nfr) {
         sphi[tid] = phi[(size_t)b * T + t0 + tid];
@@ -330,10 +376,22 @@ harmonic_frames_bwd_w_kernel(const float *__restrict__ g_audio, const uint64_t *
 
 // Backward w.r.t. weights, packed-FP32 variant: one thread walks time for TWO harmonics (k, k+1) held in
 // a register pair; g is staged duplicated (g, g) so the packed FFMA2 needs no per-step packing.
+// RAW: the chunk partials are not written out as d_weights but taken through the backward of the controls
+// (controls_bwd_kernel's arithmetic with d_amps = d_dist = 0) in the epilogue, one warp per frame row: the gradient
+// arrives at the control net's raw outputs in the same launch.
+struct RawControlsGrad {
+    const float *amp_raw, *dist_raw, *f0;
+    long long amp_stride, dist_stride;
+    float nyq;
+    float *d_amp_raw, *d_dist_raw;           // rows of damp_stride / ddist_stride floats
+    long long damp_stride, ddist_stride;
+};
+
+template <bool RAW>
 __global__ void __launch_bounds__(kBwdThreads)
 harmonic_frames_bwd_w_x2_kernel(const float *__restrict__ g_audio, const uint64_t *__restrict__ phi,
                                 const uint64_t *__restrict__ delta, float *__restrict__ d_weights,
-                                int T, int H, int bs, int FR, int nchunk, int clen) {
+                                int T, int H, int bs, int FR, int nchunk, int clen, const RawControlsGrad rc) {
     extern __shared__ __align__(16) float smem[];
     float2 *g2 = reinterpret_cast<float2 *>(smem);                       // [FR*bs] of (g, g)
     float *part = smem + 2 * (((size_t)FR * bs + 1) & ~(size_t)1);       // [nchunk][FR][H]
@@ -393,6 +451,52 @@ harmonic_frames_bwd_w_x2_kernel(const float *__restrict__ g_audio, const uint64_
         if (2 * kp + 1 < H) dst[1] = rr[1] ? e0[1] - e1[1] : e0[1] + e1[1];
     }
     __syncthreads();
+    if (RAW) {
+        const int lane = tid & 31;
+        constexpr int kKeep = 8;                                         // H <= 256
+        for (int f = tid >> 5; f < nfr; f += kBwdThreads >> 5) {
+            const size_t row = (size_t)b * T + t0 + f;
+            const float fq = rc.f0[row];
+            const float *dr = rc.dist_raw + row * rc.dist_stride;
+            float amp, amp_grad;
+            ddsp_scale_fn_grad(rc.amp_raw[row * rc.amp_stride], &amp, &amp_grad);
+            // n_k = v_k / S;  g_k = d_weights_k * amp;  dv_k = (g_k - sum_j g_j n_j) / S;  d amp = sum_k d_weights_k n_k
+            float gk[kKeep], dk[kKeep];
+            float sum = 0.f, dot = 0.f, wdot = 0.f;
+#pragma unroll
+            for (int i = 0; i < kKeep; ++i) {
+                const int k = lane + 32 * i;
+                gk[i] = 0.f;
+                dk[i] = 0.f;
+                if (k < H) {
+                    float dwk = 0.f;
+                    for (int c = 0; c < nchunk; ++c) dwk += part[((size_t)c * nfr + f) * H + k];
+                    float fn, gr;
+                    ddsp_scale_fn_grad(dr[k], &fn, &gr);
+                    const float mask = ddsp_nyquist_mask(fq, k + 1, rc.nyq);
+                    const float v = fn * mask;
+                    const float g = dwk * amp;
+                    sum += v;
+                    dot = fmaf(g, v, dot);
+                    wdot = fmaf(dwk, v, wdot);
+                    gk[i] = g;
+                    dk[i] = mask * gr;
+                }
+            }
+            sum = ddsp_warp_sum(sum);
+            const float inv = 1.f / sum;
+            dot = ddsp_warp_sum(dot) * inv;
+            wdot = ddsp_warp_sum(wdot) * inv;
+            float *out = rc.d_dist_raw + row * rc.ddist_stride;
+#pragma unroll
+            for (int i = 0; i < kKeep; ++i) {
+                const int k = lane + 32 * i;
+                if (k < H) out[k] = (gk[i] - dot) * inv * dk[i];
+            }
+            if (lane == 0) rc.d_amp_raw[row * rc.damp_stride] = wdot * amp_grad;
+        }
+        return;
+    }
     float *dw = d_weights + ((size_t)b * T + t0) * H;
     for (int i = tid; i < nfr * H; i += kBwdThreads) {
         float acc = 0.f;
@@ -618,11 +722,9 @@ static int frames_per_cta(int bs, int T, int sweep, int cap) {
     return fr < 1 ? 1 : fr;
 }
 
-extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_t *phi,
-                                             const uint64_t *delta, float *audio, int B, int T,
-                                             int H, int block_size, void *stream) {
-    DDSP_REQUIRE(weights && phi && delta && audio && B > 0 && T > 0 && H > 0 && block_size > 0);
-    DDSP_REQUIRE(B <= 65535);
+// shared by the two forward entry points; rc = nullptr: weights are read, else computed in the prologue (x2 kernel only)
+static int launch_frames_fwd(const float *weights, const RawControls *rc, const uint64_t *phi, const uint64_t *delta,
+                             float *audio, int B, int T, int H, int block_size, cudaStream_t st) {
     const int bs = block_size;
     const int spt = (bs % 4 == 0) ? 4 : (bs % 2 == 0) ? 2 : 1;
     const int Hp = (H + 3) & ~3;
@@ -630,7 +732,6 @@ extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_
     const size_t smem = (size_t)fr * Hp * sizeof(float) + 2 * (size_t)fr * sizeof(uint64_t);
     if (smem > 200 * 1024) return DDSP_B200_EUNSUPPORTED;
     dim3 grid((T + fr - 1) / fr, B);
-    cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(SPT)                                                                              \
     do {                                                                                         \
         if (smem > 48 * 1024)                                                                    \
@@ -641,10 +742,9 @@ extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_
     } while (0)
     static const bool scalar_only = getenv("DDSP_B200_HARMONIC_SCALAR") != nullptr;   // A/B switch
     const size_t smem2 = 2 * (size_t)fr * Hp * sizeof(float) + 2 * (size_t)fr * sizeof(uint64_t);
-    if (spt == 4 && !scalar_only && smem2 <= 200 * 1024) {
-        if (smem2 > 48 * 1024)
-            cudaFuncSetAttribute(harmonic_frames_fwd_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem2);
+    const bool packed = spt == 4 && smem2 <= 200 * 1024 && (rc || !scalar_only);
+    if (rc && (!packed || H > 256)) return DDSP_B200_EUNSUPPORTED;
+    if (packed) {
         // few voices (strong scaling leaves 8 per GPU, realtime 1): the grid alone leaves most warp slots empty, so
         // the CTA takes more threads = fewer sweeps per thread, until about 16 warps per SM are in flight
         int threads = kFwdThreads;
@@ -654,22 +754,58 @@ extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_
             threads += kFwdThreads;
         if (threads > max_useful) threads = max_useful > kFwdThreads ? max_useful : kFwdThreads;
         if (threads > kFwdMaxThreads) threads = kFwdMaxThreads;
-        harmonic_frames_fwd_x2_kernel<<<grid, threads, smem2, st>>>(weights, phi, delta, audio, T, H, Hp, bs, fr);
+        if (rc) {
+            if (smem2 > 48 * 1024)
+                cudaFuncSetAttribute(harmonic_frames_fwd_x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem2);
+            harmonic_frames_fwd_x2_kernel<true><<<grid, threads, smem2, st>>>(nullptr, phi, delta, audio, T, H, Hp, bs,
+                                                                               fr, *rc);
+        } else {
+            if (smem2 > 48 * 1024)
+                cudaFuncSetAttribute(harmonic_frames_fwd_x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem2);
+            harmonic_frames_fwd_x2_kernel<false><<<grid, threads, smem2, st>>>(weights, phi, delta, audio, T, H, Hp, bs,
+                                                                                fr, RawControls{});
+        }
     } else if (spt == 4) LAUNCH(4); else if (spt == 2) LAUNCH(2); else LAUNCH(1);
 #undef LAUNCH
     return ddsp_launch_status();
 }
 
-extern "C" int ddsp_b200_harmonic_frames_bwd_weights(const float *g_audio, const uint64_t *phi,
-                                                     const uint64_t *delta, float *d_weights, int B,
-                                                     int T, int H, int block_size, void *stream) {
-    DDSP_REQUIRE(g_audio && phi && delta && d_weights && B > 0 && T > 0 && H > 0 && block_size > 0);
+extern "C" int ddsp_b200_harmonic_frames_fwd(const float *weights, const uint64_t *phi,
+                                             const uint64_t *delta, float *audio, int B, int T,
+                                             int H, int block_size, void *stream) {
+    DDSP_REQUIRE(weights && phi && delta && audio && B > 0 && T > 0 && H > 0 && block_size > 0);
     DDSP_REQUIRE(B <= 65535);
+    return launch_frames_fwd(weights, nullptr, phi, delta, audio, B, T, H, block_size, (cudaStream_t)stream);
+}
+
+extern "C" int ddsp_b200_harmonic_frames_raw_supported(int H, int block_size) {
+    const int Hp = (H + 3) & ~3;
+    const int fr = frames_per_cta(block_size, 1 << 30, kFwdThreads * 4, 32);
+    return H >= 1 && H <= 256 && block_size > 0 && block_size % 4 == 0 &&
+           2 * (size_t)fr * Hp * sizeof(float) + 2 * (size_t)fr * sizeof(uint64_t) <= 200 * 1024;
+}
+
+extern "C" int ddsp_b200_harmonic_frames_raw_fwd(const float *amp_raw, int64_t amp_stride, const float *dist_raw,
+                                                 int64_t dist_stride, const float *f0, const uint64_t *phi,
+                                                 const uint64_t *delta, float *amps, float *weights, float *audio,
+                                                 int B, int T, int H, int block_size, float sample_rate,
+                                                 void *stream) {
+    DDSP_REQUIRE(amp_raw && dist_raw && f0 && phi && delta && amps && weights && audio);
+    DDSP_REQUIRE(B > 0 && B <= 65535 && T > 0 && H > 0 && block_size > 0 && amp_stride >= 1 && dist_stride >= H);
+    if (!ddsp_b200_harmonic_frames_raw_supported(H, block_size)) return DDSP_B200_EUNSUPPORTED;
+    RawControls rc{amp_raw, dist_raw, f0, amp_stride, dist_stride, sample_rate * 0.5f, amps, weights};
+    return launch_frames_fwd(nullptr, &rc, phi, delta, audio, B, T, H, block_size, (cudaStream_t)stream);
+}
+
+static int launch_frames_bwd(const float *g_audio, const uint64_t *phi, const uint64_t *delta, float *d_weights,
+                             const RawControlsGrad *rc, int B, int T, int H, int block_size, cudaStream_t st) {
     const int bs = block_size;
     const int nchunk = (bs + kChunk - 1) / kChunk;
     const int clen = (((bs + nchunk - 1) / nchunk) + 1) & ~1;   // even, so chunk parity is uniform
     static const bool scalar_only = getenv("DDSP_B200_HARMONIC_SCALAR") != nullptr;   // A/B switch
-    const bool packed = !scalar_only;
+    const bool packed = rc || !scalar_only;
     const int per_frame = nchunk * (packed ? (H + 1) / 2 : H);          // work items per frame
     // enough (chunk, frame, harmonic) items for >= 4 sweeps of the CTA
     int fr = (4 * kBwdThreads + per_frame - 1) / per_frame;
@@ -683,20 +819,51 @@ extern "C" int ddsp_b200_harmonic_frames_bwd_weights(const float *g_audio, const
     const size_t smem = bytes(fr);
     if (smem > 200 * 1024) return DDSP_B200_EUNSUPPORTED;
     dim3 grid((T + fr - 1) / fr, B);
+    if (rc) {
+        if (H > 256) return DDSP_B200_EUNSUPPORTED;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(harmonic_frames_bwd_w_x2_kernel<true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        harmonic_frames_bwd_w_x2_kernel<true><<<grid, kBwdThreads, smem, st>>>(g_audio, phi, delta, nullptr, T, H, bs, fr,
+                                                                               nchunk, clen, *rc);
+        return ddsp_launch_status();
+    }
     if (packed) {
         if (smem > 48 * 1024)
-            cudaFuncSetAttribute(harmonic_frames_bwd_w_x2_kernel,
+            cudaFuncSetAttribute(harmonic_frames_bwd_w_x2_kernel<false>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        harmonic_frames_bwd_w_x2_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(
-            g_audio, phi, delta, d_weights, T, H, bs, fr, nchunk, clen);
+        harmonic_frames_bwd_w_x2_kernel<false><<<grid, kBwdThreads, smem, st>>>(g_audio, phi, delta, d_weights, T, H, bs,
+                                                                                fr, nchunk, clen, RawControlsGrad{});
         return ddsp_launch_status();
     }
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(harmonic_frames_bwd_w_kernel,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    harmonic_frames_bwd_w_kernel<<<grid, kBwdThreads, smem, (cudaStream_t)stream>>>(
-        g_audio, phi, delta, d_weights, T, H, bs, fr, nchunk, clen);
+    harmonic_frames_bwd_w_kernel<<<grid, kBwdThreads, smem, st>>>(g_audio, phi, delta, d_weights, T, H, bs, fr, nchunk,
+                                                                  clen);
     return ddsp_launch_status();
+}
+
+extern "C" int ddsp_b200_harmonic_frames_bwd_weights(const float *g_audio, const uint64_t *phi,
+                                                     const uint64_t *delta, float *d_weights, int B,
+                                                     int T, int H, int block_size, void *stream) {
+    DDSP_REQUIRE(g_audio && phi && delta && d_weights && B > 0 && T > 0 && H > 0 && block_size > 0);
+    DDSP_REQUIRE(B <= 65535);
+    return launch_frames_bwd(g_audio, phi, delta, d_weights, nullptr, B, T, H, block_size, (cudaStream_t)stream);
+}
+
+extern "C" int ddsp_b200_harmonic_frames_raw_bwd(const float *g_audio, const float *amp_raw, int64_t amp_stride,
+                                                 const float *dist_raw, int64_t dist_stride, const float *f0,
+                                                 const uint64_t *phi, const uint64_t *delta, float *d_amp_raw,
+                                                 int64_t d_amp_stride, float *d_dist_raw, int64_t d_dist_stride,
+                                                 int B, int T, int H, int block_size, float sample_rate,
+                                                 void *stream) {
+    DDSP_REQUIRE(g_audio && amp_raw && dist_raw && f0 && phi && delta && d_amp_raw && d_dist_raw);
+    DDSP_REQUIRE(B > 0 && B <= 65535 && T > 0 && H > 0 && block_size > 0);
+    DDSP_REQUIRE(amp_stride >= 1 && dist_stride >= H && d_amp_stride >= 1 && d_dist_stride >= H);
+    RawControlsGrad rc{amp_raw, dist_raw, f0, amp_stride, dist_stride, sample_rate * 0.5f,
+                       d_amp_raw, d_dist_raw, d_amp_stride, d_dist_stride};
+    return launch_frames_bwd(g_audio, phi, delta, nullptr, &rc, B, T, H, block_size, (cudaStream_t)stream);
 }
 
 extern "C" int ddsp_b200_harmonic_frames_bwd_f0(const float *g_audio, const float *weights,

@@ -148,19 +148,20 @@ __device__ __forceinline__ void load_frames(float (&r)[20], float (&g)[20], cons
 }
 
 template <int LG, bool GRAD>
-__device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, int B, int Ni, int abl,
+__device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, int B, int Ni,
                                           const float *__restrict__ target, const float *__restrict__ rec,
                                           float *__restrict__ ws, float *__restrict__ partial,
                                           unsigned char *smem) {
     using namespace pfft;
     using P = Plan<LG>;
-    constexpr int N = P::N, T = P::T, G = kThreads / T, NFB = 2 * G, HOP = N / 4, HS = N / 2;
-    constexpr int LH = LG - 2;                                    // log2(hop)
+    constexpr int N = P::N, T = P::T, G = kThreads / T, HOP = N / 4, HS = N / 2;
     constexpr int GBYTES = (N + N / 16) * 16;                     // bytes of one group's work buffer
-    constexpr int PLANE_OFF = (N + N / 16) * 8;                   // gradient frames parked here (after the inverse buffer)
     constexpr int EX2_OFF = 13 * N;                               // mirrored gradient bins
     static_assert(kThreads % T == 0 && G * GBYTES == kWorkBytes, "work buffer layout");
-    float *carry = reinterpret_cast<float *>(smem + kWorkBytes);  // [2][3*HOP]
+    // thread-private strips (float4 [3][kThreads], conflict free): the running overlap-add carry (12 slots = 3 hops)
+    // and the head of the run (its first 3 hops, which still miss the previous run's tail)
+    float4 *cpriv = reinterpret_cast<float4 *>(smem + kWorkBytes);
+    float4 *hpriv = cpriv + 3 * kThreads;
     __shared__ float red[2][kThreads / 32];
 
     const int tid = threadIdx.x;
@@ -169,33 +170,38 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
     E *gbuf = reinterpret_cast<E *>(gbase);
     float2 *ibuf = reinterpret_cast<float2 *>(gbase);
     float2 *ex2 = reinterpret_cast<float2 *>(gbase + EX2_OFF);
-    float *plane = reinterpret_cast<float *>(gbase + PLANE_OFF);
-    // Groups narrower than a warp park their frames at the same bank offsets; XOR-ing the sample index with a
-    // per-group multiple of T (below 32) spreads the groups of a warp over the banks.  Multiples of 4: float4 reads
-    // of the gather stay intact.
-    const int swz = T < 32 ? ((grp * T) & 31) : 0;
 
     const float *xr = rec + (size_t)b * Ni;
     const float *xt = target + (size_t)b * Ni;
     const float *__restrict__ window = sc.window;
     const float2 *__restrict__ tw = sc.tw;
-    const int FT = 1 << sc.ft_log;
+    // the tile's frames are split into G contiguous RUNS of RL frames, one per thread group: the overlap-add of a
+    // run's frames stays inside the thread (frame f+1's sample slot q is frame f's slot q+4)
+    const int rl_log = sc.ft_log - (12 - LG);                    // log2(FT / G) with G = 2^(12-LG); >= 2 (make_plan)
+    const int RL = 1 << rl_log;
     const int f0 = tile << sc.ft_log;
-    const int f1 = min(f0 + FT, sc.frames);
+    const int f1 = min(f0 + (1 << sc.ft_log), sc.frames);
+    const int run0 = f0 + (grp << rl_log);
+    // a run is taken whole or not at all; groups that share a warp take the same decision (frames past f1 are zeros)
+    const int grp_w = T < 32 ? (tid & ~31) / T : grp;
+    const bool active = f0 + (grp_w << rl_log) < f1;
     const float rs = rsqrtf((float)N);
     const float rs2 = 0.5f * rs;                                  // spectra are kept doubled (no 1/2 in the untangle)
     const float kc = sc.inv_cnt * rs;
+    float *Pb = ws + sc.p_off + (size_t)b * sc.rowlen;
 
-    if (GRAD)
-        for (int i = tid; i < 3 * HOP; i += kThreads) carry[i] = 0.f;
-    int cb = 0;
+    if (GRAD) {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { cpriv[k * kThreads + tid] = z4; hpriv[k * kThreads + tid] = z4; }
+    }
     V lin = bc(0.f), lgs = bc(0.f);
 
-    // samples of frames A = fb + 2 grp (slots 0..15) and B = A + 1 (slots 4..19) of rec and target
+    // samples of frames A (slots 0..15) and B = A + 1 (slots 4..19) of rec and target
     float r[20], g[20];
 
-    for (int fb = f0; fb < f1; fb += NFB) {
-        const int fA = fb + 2 * grp;
+    for (int p = 0; active && p < (RL >> 1); ++p) {
+        const int fA = run0 + 2 * p;
         const float mA = fA < f1 ? 1.f : 0.f, mB = fA + 1 < f1 ? 1.f : 0.f;
         load_frames<N, T>(r, g, xr, xt, fA * HOP - HS, t, Ni);
         C x[16];
@@ -237,12 +243,11 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
         bin_math<LG, GRAD, 6>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
         bin_math<LG, GRAD, 7>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
         if (t == 0) bin_math<LG, GRAD, 8>(x, zi, gbuf, ex2, t, own, rs2, kc, lin, lgs);
+        gsync<T>(grp);                                            // mirror bins read; gradient mirror bins written
         if (GRAD) {
-            gsync<T>(grp);
 #pragma unroll
             for (int q = 8; q < 16; ++q) zi[q] = zfft::from_f2(ex2[(q - 8) * T + t]);
             // ---- inverse transform of U_A + i U_B, (re, im) in the lanes: one transform per thread here
-            if (!(abl & 2)) {
             zfft::stage_compute_store<LG, 0, true>(zi, ibuf, t, tw);
             gsync<T>(grp);
             zfft::stage_load<LG, 1>(zi, ibuf, t);
@@ -251,66 +256,85 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
                 zfft::stage_compute_store<LG, 1, true>(zi, ibuf, t, tw);
                 gsync<T>(grp);
                 zfft::stage_load<LG, 2>(zi, ibuf, t);
+                gsync<T>(grp);                                    // the next pair's first stage reuses the buffer
                 zfft::stage_compute_regs<LG, 2, true>(zi, t, tw);
             } else {
+                gsync<T>(grp);
                 zfft::stage_compute_regs<LG, 1, true>(zi, t, tw);
             }
+            // ---- overlap-add in registers.  Slot s of this pair is padded position fA*HOP + t + s*T: the carry of
+            // the run's earlier frames (slots 0..11), then frame A (slots 0..15), then frame B (slots 4..19): every
+            // position sums its frames oldest first.  Slots 0..7 are finished, 8..19 are carried to the next pair.
+            float acc[20];
+            {
+                const float4 c0 = cpriv[tid], c1 = cpriv[kThreads + tid], c2 = cpriv[2 * kThreads + tid];
+                acc[0] = c0.x; acc[1] = c0.y; acc[2] = c0.z; acc[3] = c0.w;
+                acc[4] = c1.x; acc[5] = c1.y; acc[6] = c1.z; acc[7] = c1.w;
+                acc[8] = c2.x; acc[9] = c2.y; acc[10] = c2.z; acc[11] = c2.w;
+#pragma unroll
+                for (int s = 12; s < 20; ++s) acc[s] = 0.f;
             }
-            // ---- the next batch's samples start their trip from L2 now; they land during the gather
-            // ---- park the two real gradient frames (unwindowed) for the gather
+            float ub[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const float2 v = zfft::to_f2(zi[slot_of_q<LG>(q)]);
-                plane[(t + q * T) ^ swz] = v.x;
-                plane[N + ((t + q * T) ^ swz)] = v.y;
+                const float w = __ldg(window + t + q * T);
+                acc[q] = fmaf(w, v.x, acc[q]);
+                ub[q] = w * v.y;
             }
-            float4 wgat[4];                                       // window at the thread's four positions of every frame phase
 #pragma unroll
-            for (int dq = 0; dq < 4; ++dq)
-                wgat[dq] = __ldg(reinterpret_cast<const float4 *>(window + ((4 * tid) & (HOP - 1)) + dq * HOP));
-            if (!(abl & 4)) __syncthreads();          // (bit 2 of the ablation knob: timing without the CTA barriers)
-            else gsync<T>(grp);
-            // ---- ordered gather overlap-add over the batch's (NFB + 3) hops, four positions per thread
-            float *Pb = ws + sc.p_off + (size_t)b * sc.rowlen;
-            const float *cold = carry + cb * (3 * HOP);
-            float *cnew = carry + (cb ^ 1) * (3 * HOP);
-            for (int v = tid; v < ((abl & 1) ? 0 : (NFB + 3) * (HOP / 4)); v += kThreads) {
-                // rel = 4 tid + 1024 it and hop divides 1024: n0 (and so the window values) is the same every iteration
-                const int rel = v * 4, j = rel >> LH, n0 = rel & (HOP - 1);
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < 3) acc = *reinterpret_cast<const float4 *>(cold + j * HOP + n0);
+            for (int q = 0; q < 16; ++q) acc[q + 4] += ub[q];
+            float *Pp = Pb + (size_t)fA * HOP + t;
+            if (p == 0) {                                         // the run's first 8 slots wait for the previous run's tail
+                hpriv[tid] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                hpriv[kThreads + tid] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            } else {
+                if (p == 1) {
+                    hpriv[2 * kThreads + tid] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                } else {
 #pragma unroll
-                for (int dq = 3; dq >= 0; --dq) {                 // frames j-3 .. j, oldest first
-                    const int qf = j - dq;
-                    if (qf >= 0 && qf < NFB) {
-                        const int gq = qf >> 1;
-                        const int n = (n0 + dq * HOP) ^ (T < 32 ? ((gq * T) & 31) : 0);
-                        const float *pl = reinterpret_cast<const float *>(smem + (size_t)gq * GBYTES + PLANE_OFF) +
-                                          (qf & 1) * N;
-                        const float4 xv = *reinterpret_cast<const float4 *>(pl + n);
-                        const float4 wv = wgat[dq];
-                        acc.x = fmaf(wv.x, xv.x, acc.x);
-                        acc.y = fmaf(wv.y, xv.y, acc.y);
-                        acc.z = fmaf(wv.z, xv.z, acc.z);
-                        acc.w = fmaf(wv.w, xv.w, acc.w);
-                    }
+                    for (int s = 0; s < 4; ++s) Pp[s * T] = acc[s];
                 }
-                if (j < NFB) *reinterpret_cast<float4 *>(Pb + (size_t)fb * HOP + rel) = acc;
-                else *reinterpret_cast<float4 *>(cnew + (j - NFB) * HOP + n0) = acc;
+#pragma unroll
+                for (int s = 4; s < 8; ++s) Pp[s * T] = acc[s];
             }
-            cb ^= 1;
-            if (!(abl & 4)) __syncthreads();
-            else gsync<T>(grp);
-        } else {
-            gsync<T>(grp);                                        // exchange area is reused by the next batch
+            cpriv[tid] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+            cpriv[kThreads + tid] = make_float4(acc[12], acc[13], acc[14], acc[15]);
+            cpriv[2 * kThreads + tid] = make_float4(acc[16], acc[17], acc[18], acc[19]);
         }
     }
     if (GRAD) {
-        // tail of the tile: belongs to the head of the next tile (or to the end of the signal): halo buffer
-        float *Hb = ws + sc.h_off + ((size_t)b * sc.tiles + tile) * (3 * HOP);
-        const float *cold = carry + cb * (3 * HOP);
-        for (int i = tid; i < 3 * HOP / 4; i += kThreads)
-            reinterpret_cast<float4 *>(Hb)[i] = reinterpret_cast<const float4 *>(cold)[i];
+        // ---- run boundaries: the first 3 hops of a run = its own head + the final carry of the previous group's
+        // run; the last group's carry belongs to the head of the next tile (or to the end of the signal): halo buffer
+        __syncthreads();
+        float4 h[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            h[k] = hpriv[k * kThreads + tid];
+            if (grp > 0) {
+                const float4 c = cpriv[k * kThreads + tid - T];
+                h[k].x += c.x; h[k].y += c.y; h[k].z += c.z; h[k].w += c.w;
+            }
+        }
+        float *Pp = Pb + (size_t)run0 * HOP + t;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            Pp[(4 * k + 0) * T] = h[k].x;
+            Pp[(4 * k + 1) * T] = h[k].y;
+            Pp[(4 * k + 2) * T] = h[k].z;
+            Pp[(4 * k + 3) * T] = h[k].w;
+        }
+        if (grp == G - 1) {
+            float *Hb = ws + sc.h_off + ((size_t)b * sc.tiles + tile) * (3 * HOP) + t;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 c = cpriv[k * kThreads + tid];
+                Hb[(4 * k + 0) * T] = c.x;
+                Hb[(4 * k + 1) * T] = c.y;
+                Hb[(4 * k + 2) * T] = c.z;
+                Hb[(4 * k + 3) * T] = c.w;
+            }
+        }
     }
     float l0, l1, g0, g1;
     get(lin, l0, l1);
@@ -344,13 +368,13 @@ mss_fused_kernel(const float *__restrict__ target, const float *__restrict__ rec
     const int tile = local / a.B, b = local - tile * a.B;
     const int Ni = (int)a.N;
     switch (sc.lg) {
-        case 6: tile_body<6, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
-        case 7: tile_body<7, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
-        case 8: tile_body<8, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
-        case 9: tile_body<9, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
-        case 10: tile_body<10, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
-        case 11: tile_body<11, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
-        default: tile_body<12, GRAD>(sc, b, tile, a.B, Ni, a.pad_, target, rec, ws, partial, smem); break;
+        case 6: tile_body<6, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
+        case 7: tile_body<7, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
+        case 8: tile_body<8, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
+        case 9: tile_body<9, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
+        case 10: tile_body<10, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
+        case 11: tile_body<11, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
+        default: tile_body<12, GRAD>(sc, b, tile, a.B, Ni, target, rec, ws, partial, smem); break;
     }
 }
 
@@ -376,6 +400,7 @@ __device__ __forceinline__ Vec<W> padded_grad(const ScaleDesc &sc, const float *
     const int fi = i >> lh, n0 = i & (sc.hop - 1);
     const int tl = fi >> sc.ft_log, within = fi & ((1 << sc.ft_log) - 1);
     Vec<W> v = Vec<W>::zero();
+    if (fi >= sc.frames + 3) return v;               // past the last frame's tail: nothing was written there
     if (fi < sc.last_end) v = Vec<W>::load(ws + sc.p_off + (size_t)b * sc.rowlen + i);
     if (tl >= 1 && tl < sc.tiles && within < 3)
         v.add(Vec<W>::load(ws + sc.h_off + ((size_t)b * sc.tiles + (tl - 1)) * (3 * sc.hop) + within * sc.hop + n0));
@@ -494,16 +519,15 @@ int make_plan(int B, int64_t N, const int *scales, int n_scales, Plan2 *out) {
         while ((1 << d.lg) < s) ++d.lg;
         d.hop = s / 4;
         d.frames = 1 + (int)(N / d.hop);
-        const int nfb = 2 * (kThreads / (s / 16));
-        int ft_log = 2;                                              // halo logic needs >= 3 frames per tile
-        while ((1 << ft_log) < nfb) ++ft_log;
+        const int groups = kThreads / (s / 16);                      // thread groups per CTA = runs per tile
+        int ft_log = 2;                                              // a run is >= 4 frames (two pairs: head + carry logic)
+        while ((1 << ft_log) < 4 * groups) ++ft_log;
         while ((1 << (ft_log + 1)) <= d.frames && ddsp_ceil_div(d.frames, 1 << ft_log) > want_tiles) ++ft_log;
         d.ft_log = ft_log;
         d.tiles = (int)ddsp_ceil_div(d.frames, 1 << ft_log);
         d.item0 = item;
         item += d.tiles * B;
-        const int last_f0 = (d.tiles - 1) << ft_log;
-        d.last_end = last_f0 + (int)ddsp_ceil_div(d.frames - last_f0, nfb) * nfb;
+        d.last_end = d.tiles << ft_log;                              // every tile writes all of its FT hops
         long long rl = (long long)d.last_end * d.hop;
         if (rl < N + s) rl = N + s;
         d.rowlen = (int)((rl + 3) & ~3ll);
@@ -523,10 +547,10 @@ int make_plan(int B, int64_t N, const int *scales, int n_scales, Plan2 *out) {
         if (d.hop > max_hop) max_hop = d.hop;
     }
     a.n_items = item;
-    a.pad_ = getenv("DDSP_B200_MSS_ABLATE") ? atoi(getenv("DDSP_B200_MSS_ABLATE")) : 0;   // timing experiments only
+    a.pad_ = 0;
     out->ws_floats = off;
     out->partial_pairs = pairs;
-    out->smem = (size_t)kWorkBytes + 2 * 3 * (size_t)max_hop * sizeof(float);
+    out->smem = (size_t)kWorkBytes + 2 * 3 * kThreads * sizeof(float4);   // + the private carry / head strips
     return DDSP_B200_OK;
 }
 

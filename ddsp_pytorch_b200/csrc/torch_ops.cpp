@@ -241,6 +241,122 @@ std::tuple<Tensor, Tensor> harmonic_bwd(const Tensor &g_, const Tensor &weights_
     return {dw, df0};
 }
 
+// ---------------------------------------------------------------------------------------- a3 + a6 in one launch
+// decoder.py:106-110 -> modules.py:44-80: the projection's raw outputs go straight into the oscillator bank.
+// `first` is either the projection output param (B,T,H+1) with dist_raw absent (amplitude = column 0, distribution =
+// columns 1..H, read in place), or amp_raw (B,T,1) with dist_raw (B,T,H).
+int64_t harmonic_raw_supported(int64_t H, int64_t block_size) {
+    return ddsp_b200_harmonic_frames_raw_supported((int)H, (int)block_size);
+}
+
+struct RawViews {
+    Tensor first, dist;
+    const float *amp, *dst;
+    int64_t amp_stride, dist_stride, B, T, H;
+    bool joint;
+};
+
+RawViews raw_views(const Tensor &first_, const c10::optional<Tensor> &dist_raw_) {
+    RawViews v;
+    v.first = prep(first_, "amplitudes / projection");
+    v.joint = !(dist_raw_.has_value() && dist_raw_->defined());
+    TORCH_CHECK(v.first.dim() == 3, "harmonic_raw: expected (B,T,.) tensors");
+    v.B = v.first.size(0);
+    v.T = v.first.size(1);
+    if (v.joint) {
+        v.H = v.first.size(2) - 1;
+        TORCH_CHECK(v.H >= 1, "harmonic_raw: the projection must be (B,T,H+1)");
+        v.amp = fp(v.first);
+        v.dst = v.amp + 1;
+        v.amp_stride = v.dist_stride = v.H + 1;
+    } else {
+        v.dist = prep(*dist_raw_, "harmonic_distribution");
+        TORCH_CHECK(v.dist.dim() == 3 && v.dist.size(0) == v.B && v.dist.size(1) == v.T && v.first.size(2) == 1,
+                    "harmonic_raw: amplitudes (B,T,1) and harmonic_distribution (B,T,H) expected");
+        v.H = v.dist.size(2);
+        v.amp = fp(v.first);
+        v.dst = fp(v.dist);
+        v.amp_stride = 1;
+        v.dist_stride = v.H;
+    }
+    return v;
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> harmonic_raw_fwd(
+    const Tensor &first_, const c10::optional<Tensor> &dist_raw_, const Tensor &f0_, int64_t block_size,
+    double sample_rate, const c10::optional<Tensor> &phase0_) {
+    RawViews v = raw_views(first_, dist_raw_);
+    Tensor f0 = prep(f0_, "f0");
+    const int64_t B = v.B, T = v.T, H = v.H;
+    TORCH_CHECK(f0.numel() == B * T, "harmonic_raw_fwd: f0 must be (B,T,1)");
+    c10::cuda::CUDAGuard guard(f0.device());
+    auto opt = f0.options();
+    Tensor phi = at::empty({B, T}, opt.dtype(at::kLong)), delta = at::empty({B, T}, opt.dtype(at::kLong));
+    Tensor phase_end = at::empty({B}, opt.dtype(at::kDouble));
+    Tensor audio = at::empty({B, T * block_size, 1}, opt);
+    Tensor amps = at::empty({B, T, 1}, opt), weights = at::empty({B, T, H}, opt);
+    if (B == 0 || T == 0) return {audio, phase_end.zero_(), phi, delta, amps, weights};
+    const double *p0 = nullptr;
+    Tensor phase0;
+    if (phase0_.has_value() && phase0_->defined()) {
+        phase0 = phase0_->contiguous();
+        TORCH_CHECK(phase0.is_cuda() && phase0.scalar_type() == at::kDouble && phase0.numel() == B,
+                    "harmonic_raw_fwd: phase0 must be a CUDA float64 tensor of B turns");
+        p0 = phase0.data_ptr<double>();
+    }
+    check(ddsp_b200_phase_scan(fp(f0), p0, (uint64_t *)phi.data_ptr<int64_t>(),
+                               (uint64_t *)delta.data_ptr<int64_t>(), phase_end.data_ptr<double>(),
+                               (int)B, (int)T, (int)block_size, sample_rate, cur_stream()),
+          "phase_scan");
+    check(ddsp_b200_harmonic_frames_raw_fwd(v.amp, v.amp_stride, v.dst, v.dist_stride, fp(f0),
+                                            (const uint64_t *)phi.data_ptr<int64_t>(),
+                                            (const uint64_t *)delta.data_ptr<int64_t>(), fpm(amps), fpm(weights),
+                                            fpm(audio), (int)B, (int)T, (int)H, (int)block_size,
+                                            (float)sample_rate, cur_stream()),
+          "harmonic_frames_raw_fwd");
+    return {audio, phase_end, phi, delta, amps, weights};
+}
+
+// joint (projection) form: (d_param (B,T,H+1), empty); split form: (d_amp_raw (B,T,1), d_dist_raw (B,T,H))
+std::tuple<Tensor, Tensor> harmonic_raw_bwd(const Tensor &g_, const Tensor &first_,
+                                            const c10::optional<Tensor> &dist_raw_, const Tensor &f0_,
+                                            const Tensor &phi, const Tensor &delta, int64_t block_size,
+                                            double sample_rate) {
+    RawViews v = raw_views(first_, dist_raw_);
+    Tensor g = prep(g_, "grad_audio"), f0 = prep(f0_, "f0");
+    const int64_t B = v.B, T = v.T, H = v.H;
+    TORCH_CHECK(g.numel() == B * T * block_size && f0.numel() == B * T, "harmonic_raw_bwd: shape mismatch");
+    TORCH_CHECK(phi.is_cuda() && phi.scalar_type() == at::kLong && phi.is_contiguous() &&
+                    delta.is_cuda() && delta.scalar_type() == at::kLong && delta.is_contiguous() &&
+                    phi.numel() == B * T && delta.numel() == B * T,
+                "harmonic_raw_bwd: bad phase workspace");
+    c10::cuda::CUDAGuard guard(g.device());
+    Tensor d0, d1;
+    float *da, *dd;
+    int64_t das, dds;
+    if (v.joint) {
+        d0 = at::empty({B, T, H + 1}, g.options());
+        d1 = at::empty({0}, g.options());
+        da = fpm(d0);
+        dd = da + 1;
+        das = dds = H + 1;
+    } else {
+        d0 = at::empty({B, T, 1}, g.options());
+        d1 = at::empty({B, T, H}, g.options());
+        da = fpm(d0);
+        dd = fpm(d1);
+        das = 1;
+        dds = H;
+    }
+    if (B == 0 || T == 0) return {d0, d1};
+    check(ddsp_b200_harmonic_frames_raw_bwd(fp(g), v.amp, v.amp_stride, v.dst, v.dist_stride, fp(f0),
+                                            (const uint64_t *)phi.data_ptr<int64_t>(),
+                                            (const uint64_t *)delta.data_ptr<int64_t>(), da, das, dd, dds, (int)B,
+                                            (int)T, (int)H, (int)block_size, (float)sample_rate, cur_stream()),
+          "harmonic_frames_raw_bwd");
+    return {d0, d1};
+}
+
 // ---------------------------------------------------------------------------------------- a5 generic
 std::tuple<Tensor, Tensor> harmonic_ar_fwd(const Tensor &f0_, const Tensor &amps_, double sample_rate) {
     Tensor f0 = prep(f0_, "f0"), a = prep(amps_, "amplitudes");
@@ -818,6 +934,9 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("harmonic_controls_bwd(Tensor amplitudes, Tensor harmonic_distribution, Tensor f0, Tensor? d_amps, Tensor? d_dist, Tensor? d_weights, float sample_rate) -> (Tensor, Tensor)");
     m.def("harmonic_fwd(Tensor f0, Tensor weights, int block_size, float sample_rate, Tensor? phase0) -> (Tensor, Tensor, Tensor, Tensor)");
     m.def("harmonic_bwd(Tensor grad_audio, Tensor weights, Tensor phi, Tensor delta, int block_size, float sample_rate, bool need_f0) -> (Tensor, Tensor)");
+    m.def("harmonic_raw_supported(int n_harmonic, int block_size) -> int", harmonic_raw_supported);
+    m.def("harmonic_raw_fwd(Tensor first, Tensor? dist_raw, Tensor f0, int block_size, float sample_rate, Tensor? phase0) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)");
+    m.def("harmonic_raw_bwd(Tensor grad_audio, Tensor first, Tensor? dist_raw, Tensor f0, Tensor phi, Tensor delta, int block_size, float sample_rate) -> (Tensor, Tensor)");
     m.def("harmonic_ar_fwd(Tensor f0, Tensor amplitudes, float sample_rate) -> (Tensor, Tensor)");
     m.def("harmonic_ar_bwd(Tensor grad_audio, Tensor amplitudes, Tensor phase, float sample_rate, bool need_f0) -> (Tensor, Tensor)");
     m.def("amp_to_ir_fwd(Tensor amp, int target_size) -> Tensor");
@@ -850,6 +969,8 @@ TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
     m.impl("harmonic_controls_bwd", harmonic_controls_bwd);
     m.impl("harmonic_fwd", harmonic_fwd);
     m.impl("harmonic_bwd", harmonic_bwd);
+    m.impl("harmonic_raw_fwd", harmonic_raw_fwd);
+    m.impl("harmonic_raw_bwd", harmonic_raw_bwd);
     m.impl("harmonic_ar_fwd", harmonic_ar_fwd);
     m.impl("harmonic_ar_bwd", harmonic_ar_bwd);
     m.impl("amp_to_ir_fwd", amp_to_ir_fwd);

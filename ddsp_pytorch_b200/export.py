@@ -60,6 +60,8 @@ class ScriptDDSP(nn.Module):
         self.mean_loudness: float = float(mean_loudness)
         self.std_loudness: float = float(std_loudness)
         self.noise_bias: float = float(ddsp.noise_synth.initial_bias)
+        self.fused_controls: bool = bool(torch.ops.ddsp_b200.harmonic_raw_supported(
+            int(ddsp.harmonic_proj.out_features) - 1, self.block_size))
 
     def forward(self, pitch: torch.Tensor, loudness: torch.Tensor) -> torch.Tensor:
         """pitch, loudness: (B, N, 1) at audio rate, N a multiple of block_size -> audio (B, N, 1)."""
@@ -83,13 +85,17 @@ class ScriptDDSP(nn.Module):
         hidden = self.out_mlp(torch.cat([gru_out, f0, ld], -1))
 
         param = self.harmonic_proj(hidden)
-        amps, dist, weights = torch.ops.ddsp_b200.harmonic_controls_fwd(
-            param[..., :1], param[..., 1:], f0, self.sample_rate, True)
         phase0: Optional[torch.Tensor] = None
         if self.realtime:
             phase0 = self.phase.expand(f0.shape[0]).contiguous()
-        audio, phase_end, phi, delta = torch.ops.ddsp_b200.harmonic_fwd(
-            f0, weights, self.block_size, self.sample_rate, phase0)
+        if self.fused_controls:      # get_controls inside the oscillator bank's launch, param read in place
+            audio, phase_end, phi, delta, amps, weights = torch.ops.ddsp_b200.harmonic_raw_fwd(
+                param, None, f0, self.block_size, self.sample_rate, phase0)
+        else:
+            amps, dist, weights = torch.ops.ddsp_b200.harmonic_controls_fwd(
+                param[..., :1], param[..., 1:], f0, self.sample_rate, True)
+            audio, phase_end, phi, delta = torch.ops.ddsp_b200.harmonic_fwd(
+                f0, weights, self.block_size, self.sample_rate, phase0)
         if self.realtime:
             self.phase.copy_(phase_end[:1])
 

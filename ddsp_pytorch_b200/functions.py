@@ -128,6 +128,48 @@ class HarmonicFrames(torch.autograd.Function):
         return (df0.view(f0_shape) if need_f0 else None), dw, None, None, None
 
 
+class HarmonicFromRaw(torch.autograd.Function):
+    """decoder.py:106-110 + modules.py:44-80 in ONE launch per direction: the control net's raw outputs go straight
+    into the oscillator bank, whose prologue applies get_controls (scale_function, Nyquist mask, normalise) and the
+    in-place ``distribution *= amplitudes``; the backward's epilogue takes the weight gradients through the controls'
+    backward.  ``first`` = the projection output (B,T,H+1) with ``dist_raw=None`` (read and differentiated in place, no
+    slicing copies), or amp_raw (B,T,1) with dist_raw (B,T,H).
+    -> (audio (B,T*bs,1), phase_end (B), amplitudes (B,T,1), weights (B,T,H))."""
+
+    @staticmethod
+    def forward(ctx, first, dist_raw, f0, block_size, sample_rate, phase0):
+        audio, phase_end, phi, delta, amps, weights = _ops.harmonic_raw_fwd(
+            first, dist_raw, f0, int(block_size), float(sample_rate), phase0)
+        ctx.save_for_backward(first, dist_raw, f0, phi, delta)
+        ctx.cfg = (int(block_size), float(sample_rate))
+        ctx.mark_non_differentiable(phase_end)
+        ctx.set_materialize_grads(False)
+        return audio, phase_end, amps, weights
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_audio, _g_phase, g_amps, g_weights):
+        first, dist_raw, f0, phi, delta = ctx.saved_tensors
+        bs, sr = ctx.cfg
+        joint = dist_raw is None
+        if g_audio is None:
+            g_audio = torch.zeros(f0.shape[0], f0.shape[1] * bs, 1, device=f0.device, dtype=f0.dtype)
+        if g_amps is None and g_weights is None:
+            d0, d1 = _ops.harmonic_raw_bwd(g_audio, first, dist_raw, f0, phi, delta, bs, sr)
+            return d0, (None if joint else d1), None, None, None, None
+        # someone differentiates the returned controls as well (never the reference's training loop): two launches
+        a_raw = first[..., :1] if joint else first
+        d_raw = first[..., 1:] if joint else dist_raw
+        amps, _, weights = _ops.harmonic_controls_fwd(a_raw, d_raw, f0, sr, True)
+        dw, _ = _ops.harmonic_bwd(g_audio, weights, phi, delta, bs, sr, False)
+        if g_weights is not None:
+            dw = dw + g_weights
+        da, dd = _ops.harmonic_controls_bwd(a_raw, d_raw, f0, g_amps, None, dw, sr)
+        if joint:
+            return torch.cat([da.view_as(a_raw), dd.view_as(d_raw)], -1), None, None, None, None, None
+        return da.view_as(first), dd.view_as(dist_raw), None, None, None, None
+
+
 class HarmonicAudioRate(torch.autograd.Function):
     """core.py:136-141: f0 (B,N,1), amplitudes (B,N,H) at audio rate -> (B,N,1)."""
 

@@ -147,8 +147,12 @@ class SynthStep:
                 hspec = F_._ops.fftconv_spectrum(kernel.detach(), s.samples)
             # FilteredNoise.get_controls + forward in one launch
             noise = F_.FilteredNoiseFused.apply(leaves[2], i["noise"], None, -5.0)
-        _, _, weights = F_.HarmonicControlsWeights.apply(leaves[0], leaves[1], i["pitch"], float(s.sample_rate))
-        harmonic, _ = core.harmonic_synth_frames(i["pitch"], weights, s.block_size, s.sample_rate)
+        # HarmonicSynth.get_controls + forward in one launch (the controls are the oscillator bank's prologue)
+        if core.harmonic_raw_supported(s.n_harmonic, s.block_size):
+            harmonic = core.harmonic_synth_from_raw(leaves[0], leaves[1], i["pitch"], s.block_size, s.sample_rate)[0]
+        else:
+            _, _, weights = F_.HarmonicControlsWeights.apply(leaves[0], leaves[1], i["pitch"], float(s.sample_rate))
+            harmonic, _ = core.harmonic_synth_frames(i["pitch"], weights, s.block_size, s.sample_rate)
         cur.wait_stream(side)
         noise.record_stream(cur)
         if self.reverb is not None:

@@ -58,11 +58,9 @@ class _SynthWiring(nn.Module):
         self.register_buffer("phase", torch.zeros(1))
 
     def _synthesize(self, hidden, f0, loudness, noise=None) -> Dict[str, torch.Tensor]:
+        # decoder.py:106-110: projection -> get_controls -> forward; the controls ride in the oscillator bank's launch
         param = self.harmonic_proj(hidden)
-        amplitudes = param[..., :1]
-        harmonic_distribution = param[..., 1:]
-        harmonic_ctrls = self.harmonic_synth.get_controls(amplitudes, harmonic_distribution, f0)
-        harmonic = self.harmonic_synth(**harmonic_ctrls)
+        harmonic, harmonic_ctrls = self.harmonic_synth.synthesize(param, f0)
 
         magnitudes = self.noise_proj(hidden)
         noise_ctrls = self.noise_synth.get_controls(magnitudes)
@@ -102,10 +100,8 @@ class DDSPDecoder(_SynthWiring):
         decoder.py:99 but restarts the phase at 0 every call), reverb is left to the host."""
         hidden = self.decoder(f0, loudness, realtime=True)
         param = self.harmonic_proj(hidden)
-        ctrls = self.harmonic_synth.get_controls(param[..., :1], param[..., 1:], f0)
         phase0 = self.phase.double().expand(f0.shape[0]).contiguous()
-        harmonic = self.harmonic_synth(ctrls["amplitudes"], ctrls["harmonic_distribution"], f0,
-                                       phase0=phase0)
+        harmonic, _ = self.harmonic_synth.synthesize(param, f0, phase0=phase0)
         self.phase.copy_(self.harmonic_synth._phase_end[:1].to(self.phase.dtype))
         magnitudes = self.noise_synth.get_controls(self.noise_proj(hidden))["magnitudes"]
         return harmonic + self.noise_synth(magnitudes)

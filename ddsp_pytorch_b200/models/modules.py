@@ -67,6 +67,21 @@ class HarmonicSynth(nn.Module):
         return audio
 
 
+    def synthesize(self, param, f0, phase0: Optional[torch.Tensor] = None):
+        """Extension: ``get_controls`` + ``forward`` on the projection output ``param`` (B,T,H+1) of decoder.py:106
+        (amplitude = column 0, distribution = columns 1..H) in one launch: the controls are computed in the oscillator
+        bank's prologue.  Returns (audio, harmonic_ctrls) with the dict the reference holds AFTER forward
+        (``harmonic_distribution`` already scaled by the amplitudes, modules.py:73)."""
+        fusable = (param.is_cuda and param.dtype == torch.float32 and not f0.requires_grad
+                   and core.harmonic_raw_supported(param.shape[-1] - 1, self.block_size))
+        if not fusable:
+            ctrls = self.get_controls(param[..., :1], param[..., 1:], f0)
+            return self.forward(ctrls["amplitudes"], ctrls["harmonic_distribution"], f0, phase0), ctrls
+        audio, self._phase_end, amps, weights = core.harmonic_synth_from_raw(
+            param, None, f0, self.block_size, self.sample_rate, phase0)
+        return audio, {"f0": f0, "harmonic_distribution": weights, "amplitudes": amps}
+
+
 class FilteredNoise(nn.Module):
     """ddsp/models/modules.py:101-128."""
 

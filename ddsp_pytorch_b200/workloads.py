@@ -171,8 +171,7 @@ class BulkRenderer:
         ops, i = torch.ops.ddsp_b200, self.inp
         if draw:
             self.noise.uniform_(-1, 1)
-        _, _, w = ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], float(self.SR), True)
-        audio = ops.harmonic_fwd(i["pitch"], w, self.BS, float(self.SR), None)[0]
+        audio = ops.harmonic_raw_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], self.BS, float(self.SR), None)[0]
         sig = ops.noise_fwd(i["mag_raw"], self.noise, audio, True, -5.0)
         return ops.fftconv_fwd(sig.squeeze(-1), self.impulse, False, self.hspec)[0]
 

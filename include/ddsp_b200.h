@@ -82,6 +82,27 @@ int ddsp_b200_harmonic_frames_bwd_f0(const float *g_audio, const float *weights,
                                      float *d_f0, int B, int T, int H, int block_size,
                                      double sample_rate, void *stream);
 
+/* ---- a3+a6 in one launch: projection outputs -> controls -> audio   (ddsp/models/decoder.py:106-110,
+ *      ddsp/models/modules.py:44-67,73 get_controls + the in-place product, modules.py:69-80 forward) -------------
+ * The control net's raw outputs go straight into the oscillator bank: the bank's prologue applies scale_function,
+ * the Nyquist mask and the normalisation to the CTA's frame rows (bit-identical to ddsp_b200_harmonic_controls_fwd),
+ * and the backward's epilogue takes the weight gradients through the controls' backward.  amp_raw / dist_raw (and
+ * their gradients) are rows of amp_stride / dist_stride floats, so views into the (rows, H+1) output of
+ * decoder.py:106 `harmonic_proj` are read and written in place (amp_raw = param, stride H+1; dist_raw = param + 1).
+ * Outputs: amps[B*T], weights[B*T,H] (what the reference's harmonic_ctrls dict holds after forward), audio[B,T*bs].
+ * H <= 256 and block_size % 4 == 0 (ddsp_b200_harmonic_frames_raw_supported), else DDSP_B200_EUNSUPPORTED: use the
+ * two-launch path above.                                                                                          */
+int ddsp_b200_harmonic_frames_raw_supported(int H, int block_size);
+int ddsp_b200_harmonic_frames_raw_fwd(const float *amp_raw, int64_t amp_stride, const float *dist_raw,
+                                      int64_t dist_stride, const float *f0, const uint64_t *phi,
+                                      const uint64_t *delta, float *amps, float *weights, float *audio, int B,
+                                      int T, int H, int block_size, float sample_rate, void *stream);
+int ddsp_b200_harmonic_frames_raw_bwd(const float *g_audio, const float *amp_raw, int64_t amp_stride,
+                                      const float *dist_raw, int64_t dist_stride, const float *f0,
+                                      const uint64_t *phi, const uint64_t *delta, float *d_amp_raw,
+                                      int64_t d_amp_stride, float *d_dist_raw, int64_t d_dist_stride, int B, int T,
+                                      int H, int block_size, float sample_rate, void *stream);
+
 /* ---- a5  harmonic_synth at audio rate (generic signature)    (ddsp/core.py:136-141) -------- */
 /* f0[B,N], amps[B,N,H] -> audio[B,N];  phase[B*N] uint64 workspace (Q0.64 turns, inclusive). */
 int ddsp_b200_phase_scan_audio_rate(const float *f0, uint64_t *phase, int B, int64_t N,

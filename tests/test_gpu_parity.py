@@ -447,6 +447,70 @@ def test_fused_controls_and_noise_match_unfused(ddsp):
     assert torch.equal(harm2.grad, harm.grad)
 
 
+@pytest.mark.parametrize("B,T,bs,H", [(3, 37, 160, 100), (2, 5, 512, 64), (1, 2, 128, 7), (2, 19, 160, 256)])
+def test_controls_fused_into_the_oscillator_bank(ddsp, B, T, bs, H):
+    """decoder.py:106-110 + modules.py:44-80 in one launch per direction: the projection output
+    goes straight into the bank.  Same arithmetic as the two-launch path, so audio, controls and gradients are equal
+    bit for bit -- for the projection form (param (B,T,H+1) read and differentiated in place) and the split form."""
+    from ddsp_pytorch_b200 import functions as F_
+    assert ddsp.core.harmonic_raw_supported(H, bs)
+    gen = torch.Generator().manual_seed(B * 1000 + T)
+    sr = 16000.0
+    param0 = torch.randn(B, T, H + 1, generator=gen).cuda()
+    f0 = (80 + 700 * torch.rand(B, T, 1, generator=gen)).cuda()
+    go = torch.randn(B, T * bs, 1, generator=gen).cuda()
+    # reference: the two-launch path on slices of the projection
+    p1 = param0.clone().requires_grad_(True)
+    amps1, _, w1 = F_.HarmonicControlsWeights.apply(p1[..., :1], p1[..., 1:], f0, sr)
+    y1, pe1 = ddsp.core.harmonic_synth_frames(f0, w1, bs, sr)
+    (y1 * go).sum().backward()
+    # projection form
+    p2 = param0.clone().requires_grad_(True)
+    y2, pe2, amps2, w2 = ddsp.core.harmonic_synth_from_raw(p2, None, f0, bs, sr)
+    (y2 * go).sum().backward()
+    assert torch.equal(y2, y1) and torch.equal(pe2, pe1) and torch.equal(amps2, amps1) and torch.equal(w2, w1)
+    assert torch.equal(p2.grad, p1.grad)
+    # split form (the hot path's leaves)
+    a3 = param0[..., :1].clone().requires_grad_(True)
+    d3 = param0[..., 1:].clone().requires_grad_(True)
+    y3, _, amps3, w3 = ddsp.core.harmonic_synth_from_raw(a3, d3, f0, bs, sr)
+    (y3 * go).sum().backward()
+    assert torch.equal(y3, y1) and torch.equal(amps3, amps1) and torch.equal(w3, w1)
+    assert torch.equal(a3.grad, p1.grad[..., :1]) and torch.equal(d3.grad, p1.grad[..., 1:])
+    # gradients through the returned controls too (not the training loop's case): the two-launch backward
+    p4 = param0.clone().requires_grad_(True)
+    y4, _, amps4, w4 = ddsp.core.harmonic_synth_from_raw(p4, None, f0, bs, sr)
+    ga, gw = torch.randn_like(amps4), torch.randn_like(w4)
+    ((y4 * go).sum() + (amps4 * ga).sum() + (w4 * gw).sum()).backward()
+    p5 = param0.clone().requires_grad_(True)
+    amps5, _, w5 = F_.HarmonicControlsWeights.apply(p5[..., :1], p5[..., 1:], f0, sr)
+    y5, _ = ddsp.core.harmonic_synth_frames(f0, w5, bs, sr)
+    ((y5 * go).sum() + (amps5 * ga).sum() + (w5 * gw).sum()).backward()
+    assert_grad(p4.grad, p5.grad, 1e-5)
+    # streaming phase carry
+    ph = torch.rand(B, generator=gen).double().cuda()
+    ya, pea, _, _ = ddsp.core.harmonic_synth_from_raw(param0, None, f0, bs, sr, ph)
+    yb, peb = ddsp.core.harmonic_synth_frames(f0, w1.detach(), bs, sr, ph)
+    assert torch.equal(ya, yb) and torch.equal(pea, peb)
+
+
+def test_model_uses_the_fused_controls_and_matches_the_two_launch_path(ddsp):
+    """DDSPDecoder._synthesize goes through HarmonicSynth.synthesize; the returned harmonic_ctrls dict holds what the
+    reference's holds after forward (distribution already scaled by the amplitudes, modules.py:73)."""
+    from ddsp_pytorch_b200.models.modules import HarmonicSynth
+    hs = HarmonicSynth(160, 16000)
+    gen = torch.Generator().manual_seed(5)
+    param = torch.randn(2, 30, 101, generator=gen).cuda().requires_grad_(True)
+    f0 = (100 + 400 * torch.rand(2, 30, 1, generator=gen)).cuda()
+    audio, ctrls = hs.synthesize(param, f0)
+    ref_ctrls = hs.get_controls(param[..., :1], param[..., 1:], f0)
+    ref_audio = hs(**ref_ctrls)
+    assert torch.equal(audio, ref_audio)
+    assert torch.equal(ctrls["amplitudes"], ref_ctrls["amplitudes"])
+    assert torch.equal(ctrls["harmonic_distribution"], ref_ctrls["harmonic_distribution"])     # mutated in place by forward
+    assert ctrls["f0"] is f0
+
+
 def test_hotpath_step_against_oracle(ddsp, orc):
     """SynthStep (the benchmarked callable): audio, loss and every gradient against the float64 oracle,
     eager and CUDA-graph replay."""
