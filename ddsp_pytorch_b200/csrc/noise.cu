@@ -428,12 +428,26 @@ filtered_noise2_fwd_kernel(const float *__restrict__ mags, const float *__restri
             const float *mb = rowbase + rb_ * L.stride + L.m();
             const float4 *d4 = reinterpret_cast<const float4 *>(D) + c;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), e = a;
-            for (int k = 0; k < NB; ++k) {
-                const float4 u = d4[k * (F / 4)];
-                const float x = ma[k], y = mb[k];
-                a.x = fmaf(x, u.x, a.x); a.y = fmaf(x, u.y, a.y); a.z = fmaf(x, u.z, a.z); a.w = fmaf(x, u.w, a.w);
-                e.x = fmaf(y, u.x, e.x); e.y = fmaf(y, u.y, e.y); e.z = fmaf(y, u.z, e.z); e.w = fmaf(y, u.w, e.w);
+#define DDSP_N2_MAC(X, Y, U)                                                                                  \
+    a.x = fmaf(X, U.x, a.x); a.y = fmaf(X, U.y, a.y); a.z = fmaf(X, U.z, a.z); a.w = fmaf(X, U.w, a.w);      \
+    e.x = fmaf(Y, U.x, e.x); e.y = fmaf(Y, U.y, e.y); e.z = fmaf(Y, U.z, e.z); e.w = fmaf(Y, U.w, e.w);
+            // four magnitudes of both rows per LDS.128 (NB - 1 is a multiple of 4), same summation order as one by one
+            for (int k = 0; k < NB - 1; k += 4) {
+                const float4 xa = *reinterpret_cast<const float4 *>(ma + k);
+                const float4 xb = *reinterpret_cast<const float4 *>(mb + k);
+                const float4 u0 = d4[k * (F / 4)], u1 = d4[(k + 1) * (F / 4)];
+                const float4 u2 = d4[(k + 2) * (F / 4)], u3 = d4[(k + 3) * (F / 4)];
+                DDSP_N2_MAC(xa.x, xb.x, u0)
+                DDSP_N2_MAC(xa.y, xb.y, u1)
+                DDSP_N2_MAC(xa.z, xb.z, u2)
+                DDSP_N2_MAC(xa.w, xb.w, u3)
             }
+            {
+                const float4 u = d4[(NB - 1) * (F / 4)];
+                const float x = ma[NB - 1], y = mb[NB - 1];
+                DDSP_N2_MAC(x, y, u)
+            }
+#undef DDSP_N2_MAC
             reinterpret_cast<float4 *>(rowbase + ra * L.stride + L.taps())[c] = a;
             if (rb_ != ra) reinterpret_cast<float4 *>(rowbase + rb_ * L.stride + L.taps())[c] = e;
         }
@@ -525,25 +539,43 @@ filtered_noise2_bwd_kernel(const float *__restrict__ g_out, const float *__restr
             *reinterpret_cast<float4 *>(rb + L.taps() + (far ? half : 0) + 4 * tg) = a;
         }
         __syncthreads();
-        // ---- d m[r][4kg..] = sum_j dtaps[r][j] * Dt[j][...]
-        for (int it = tid; it < nr * (NBq / 4); it += kN2Threads) {
-            const int r = it / (NBq / 4), kg = it - r * (NBq / 4);
-            const float *dt = rowbase + r * L.stride + L.taps();
+        // ---- d m[r][4kg..] = sum_j dtaps[r][j] * Dt[j][...], two rows per thread and four taps per LDS.128
+        //      (F is a multiple of 4; same summation order as one by one)
+        for (int it = tid; it < ((nr + 1) >> 1) * (NBq / 4); it += kN2Threads) {
+            const int rp = it / (NBq / 4), kg = it - rp * (NBq / 4);
+            const int ra = 2 * rp, rb_ = min(2 * rp + 1, nr - 1);
+            const float *ta = rowbase + ra * L.stride + L.taps();
+            const float *tb = rowbase + rb_ * L.stride + L.taps();
             const float4 *d4 = reinterpret_cast<const float4 *>(Dt) + kg;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = 0; j < F; ++j) {
-                const float t = dt[j];
-                const float4 u = d4[j * (NBq / 4)];
-                a.x = fmaf(t, u.x, a.x); a.y = fmaf(t, u.y, a.y); a.z = fmaf(t, u.z, a.z); a.w = fmaf(t, u.w, a.w);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), e = a;
+#define DDSP_N2_MAC(X, Y, U)                                                                                  \
+    a.x = fmaf(X, U.x, a.x); a.y = fmaf(X, U.y, a.y); a.z = fmaf(X, U.z, a.z); a.w = fmaf(X, U.w, a.w);      \
+    e.x = fmaf(Y, U.x, e.x); e.y = fmaf(Y, U.y, e.y); e.z = fmaf(Y, U.z, e.z); e.w = fmaf(Y, U.w, e.w);
+            for (int j = 0; j < F; j += 4) {
+                const float4 xa = *reinterpret_cast<const float4 *>(ta + j);
+                const float4 xb = *reinterpret_cast<const float4 *>(tb + j);
+                const float4 u0 = d4[j * (NBq / 4)], u1 = d4[(j + 1) * (NBq / 4)];
+                const float4 u2 = d4[(j + 2) * (NBq / 4)], u3 = d4[(j + 3) * (NBq / 4)];
+                DDSP_N2_MAC(xa.x, xb.x, u0)
+                DDSP_N2_MAC(xa.y, xb.y, u1)
+                DDSP_N2_MAC(xa.z, xb.z, u2)
+                DDSP_N2_MAC(xa.w, xb.w, u3)
             }
-            const float av[4] = {a.x, a.y, a.z, a.w};
+#undef DDSP_N2_MAC
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = 4 * kg + e;
-                if (k < NB) {
-                    float d = av[e];
-                    if (apply_scale) d *= ddsp_scale_grad(__ldg(mags_raw + (r0 + r) * NB + k) + bias);
-                    d_mags[(r0 + r) * NB + k] = d;
+            for (int h2 = 0; h2 < 2; ++h2) {
+                if (h2 == 1 && rb_ == ra) break;
+                const int r = h2 ? rb_ : ra;
+                const float4 acc = h2 ? e : a;
+                const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int k = 4 * kg + q;
+                    if (k < NB) {
+                        float d = av[q];
+                        if (apply_scale) d *= ddsp_scale_grad(__ldg(mags_raw + (r0 + r) * NB + k) + bias);
+                        d_mags[(r0 + r) * NB + k] = d;
+                    }
                 }
             }
         }
