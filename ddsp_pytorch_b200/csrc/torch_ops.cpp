@@ -528,16 +528,22 @@ std::tuple<Tensor, Tensor, Tensor> fftconv_fwd(const Tensor &signal_, const Tens
     return {out, none, none};
 }
 
-std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, const Tensor &kernel_,
-                                       const c10::optional<Tensor> &work_x_, const c10::optional<Tensor> &hspec_,
-                                       bool need_signal, bool need_kernel) {
+// The two gradients can be taken in two calls (the data-parallel step wants the kernel gradient first, so that its
+// all-reduce is in flight while the signal gradient and everything upstream of it is computed): `work_g_` = the
+// transform of grad_out returned by an earlier call; the signal-gradient chain filters it in place, so it is valid for
+// further calls only as long as need_signal was false.
+std::tuple<Tensor, Tensor, Tensor> fftconv_bwd_parts(const Tensor &g_, const Tensor &signal_, const Tensor &kernel_,
+                                                     const c10::optional<Tensor> &work_x_,
+                                                     const c10::optional<Tensor> &hspec_,
+                                                     const c10::optional<Tensor> &work_g_, bool need_signal,
+                                                     bool need_kernel) {
     Tensor g = prep(g_, "grad_out"), sig = prep(signal_, "signal"), ker = prep(kernel_, "kernel");
     const int64_t R = sig.size(0), n = sig.size(1), Rk = ker.size(0), Lk = ker.size(1);
     TORCH_CHECK(g.dim() == 2 && g.size(0) == R && g.size(1) == n, "fftconv backward: grad shape mismatch");
     c10::cuda::CUDAGuard guard(sig.device());
     Tensor d_sig = need_signal ? at::empty_like(sig) : at::empty({0}, sig.options());
     Tensor d_ker = need_kernel ? at::zeros_like(ker) : at::empty({0}, sig.options());
-    if (R == 0 || n == 0 || (!need_signal && !need_kernel)) return {d_sig, d_ker};
+    if (R == 0 || n == 0 || (!need_signal && !need_kernel)) return {d_sig, d_ker, at::empty({0}, sig.options())};
     const int64_t Lc = std::min(Lk, n);
     Tensor kc = Lc == Lk ? ker : ker.narrow(1, 0, Lc).contiguous();
     ConvPlan p = conv_plan(sig.device(), n + Lc - 1);
@@ -545,8 +551,15 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
     const int64_t slots = pair ? (R + 1) / 2 : R;
     auto main_stream = at::cuda::getCurrentCUDAStream();
     void *st = (void *)main_stream.stream();
-    Tensor work_g = at::empty({slots, p.n, 2}, sig.options());
-    check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(g)");
+    Tensor work_g;
+    if (work_g_.has_value() && work_g_->defined() && work_g_->numel() == slots * p.n * 2) {
+        work_g = *work_g_;
+        TORCH_CHECK(work_g.is_cuda() && work_g.scalar_type() == at::kFloat && work_g.is_contiguous(),
+                    "fftconv backward: bad work_g");
+    } else {
+        work_g = at::empty({slots, p.n, 2}, sig.options());
+        check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(g)");
+    }
     // d_kernel and d_signal are independent after the transform of g: the kernel-gradient chain runs on a
     // pool stream (it only reads work_g), the signal-gradient chain (which filters work_g in place) waits
     // for the correlation to have consumed work_g.
@@ -601,7 +614,14 @@ std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g_, const Tensor &signal_, 
         join.record(side);
         join.block(main_stream);
     }
-    return {d_sig, d_ker};
+    return {d_sig, d_ker, work_g};
+}
+
+std::tuple<Tensor, Tensor> fftconv_bwd(const Tensor &g, const Tensor &signal, const Tensor &kernel,
+                                       const c10::optional<Tensor> &work_x, const c10::optional<Tensor> &hspec,
+                                       bool need_signal, bool need_kernel) {
+    auto r = fftconv_bwd_parts(g, signal, kernel, work_x, hspec, c10::nullopt, need_signal, need_kernel);
+    return {std::get<0>(r), std::get<1>(r)};
 }
 
 Tensor reverb_impulse_fwd(const Tensor &noise_, const Tensor &decay_, const Tensor &wet_, const Tensor &t_) {
@@ -946,6 +966,7 @@ TORCH_LIBRARY(ddsp_b200, m) {
     m.def("fftconv_spectrum(Tensor kernel, int n_signal) -> Tensor");
     m.def("fftconv_fwd(Tensor signal, Tensor kernel, bool keep_transforms, Tensor? hspec=None, Tensor? signal2=None) -> (Tensor, Tensor, Tensor)");
     m.def("fftconv_bwd(Tensor grad_out, Tensor signal, Tensor kernel, Tensor? work_x, Tensor? hspec, bool need_signal, bool need_kernel) -> (Tensor, Tensor)");
+    m.def("fftconv_bwd_parts(Tensor grad_out, Tensor signal, Tensor kernel, Tensor? work_x, Tensor? hspec, Tensor? work_g, bool need_signal, bool need_kernel) -> (Tensor, Tensor, Tensor)");
     m.def("reverb_impulse_fwd(Tensor noise, Tensor decay, Tensor wet, Tensor t) -> Tensor");
     m.def("reverb_impulse_bwd(Tensor d_impulse, Tensor noise, Tensor decay, Tensor wet, Tensor t) -> (Tensor, Tensor, Tensor)");
     m.def("stft_mag_fwd(Tensor signal, Tensor window, int n_fft, int hop) -> Tensor");
@@ -980,6 +1001,7 @@ TORCH_LIBRARY_IMPL(ddsp_b200, CUDA, m) {
     m.impl("fftconv_spectrum", fftconv_spectrum);
     m.impl("fftconv_fwd", fftconv_fwd);
     m.impl("fftconv_bwd", fftconv_bwd);
+    m.impl("fftconv_bwd_parts", fftconv_bwd_parts);
     m.impl("reverb_impulse_fwd", reverb_impulse_fwd);
     m.impl("reverb_impulse_bwd", reverb_impulse_bwd);
     m.impl("stft_mag_fwd", stft_mag_fwd);

@@ -258,10 +258,45 @@ class FFTConvolve(torch.autograd.Function):
         signal, kernel, work_x, hspec = ctx.saved_tensors
         n = len(ctx.needs_input_grad)
         need = list(ctx.needs_input_grad) + [False] * 4
-        ds, dk = _ops.fftconv_bwd(g, signal, kernel, work_x if work_x.numel() else None,
-                                  hspec if hspec.numel() else None, need[0] or need[3], need[1])
+        wx, hs = (work_x if work_x.numel() else None), (hspec if hspec.numel() else None)
+        part = _FFTCONV_PART[0]
+        if part is None:
+            ds, dk = _ops.fftconv_bwd(g, signal, kernel, wx, hs, need[0] or need[3], need[1])
+        elif part == "kernel":
+            # first of two calls over the same grad_output: the kernel gradient only; the transform of g is kept
+            _, dk, ctx._work_g = _ops.fftconv_bwd_parts(g, signal, kernel, wx, hs, None, False, need[1])
+            ctx._work_g_key = (g.data_ptr(), g._version)
+            ds = None
+        else:
+            kept = getattr(ctx, "_work_g", None)
+            if kept is not None and ctx._work_g_key != (g.data_ptr(), g._version):
+                kept = None
+            ds, _, _ = _ops.fftconv_bwd_parts(g, signal, kernel, wx, hs, kept, need[0] or need[3], False)
+            ctx._work_g = None                        # filtered in place by the call above
+            dk = None
         grads = ((ds if need[0] else None), (dk if need[1] else None), None, (ds if need[3] else None))
         return grads[:n]
+
+
+_FFTCONV_PART = [None]
+
+
+class fftconv_backward_part:
+    """Context manager for callers that take FFTConvolve's two gradients in two ``autograd.grad`` calls over the same
+    grad_output (``retain_graph=True`` on the first): ``"kernel"`` computes the kernel gradient only and keeps the
+    transform of grad_output, ``"signal"`` reuses it for the signal gradient.  The data-parallel step does this to have
+    the reverb parameters' all-reduce in flight during the rest of the backward (hotpath.SynthStep)."""
+
+    def __init__(self, part: str):
+        assert part in ("kernel", "signal")
+        self.part = part
+
+    def __enter__(self):
+        self.saved = _FFTCONV_PART[0]
+        _FFTCONV_PART[0] = self.part
+
+    def __exit__(self, *a):
+        _FFTCONV_PART[0] = self.saved
 
 
 class ReverbImpulse(torch.autograd.Function):

@@ -181,17 +181,20 @@ class SynthStep:
         if self._dist is None or self.reverb is None:
             grads = torch.autograd.grad(signal, leaves, grad_outputs=d_rec.view_as(signal))
             return signal, loss, grads
-        # data parallel: the reverb's backward first, so that the collective on its parameter gradients is in flight
-        # while the two synthesisers' backward runs (the two autograd calls walk disjoint parts of the graph)
-        cut = torch.autograd.grad(signal, [h2, n2] + leaves[3:], grad_outputs=d_rec.view_as(signal))
-        rev = self._pack(cut[2:])
+        # data parallel: the reverb PARAMETERS' backward first (long convolution's kernel gradient -> impulse backward),
+        # so that the collective on them is in flight while the convolution's signal gradient and the two
+        # synthesisers' backward run.  Two autograd calls over the same gradient; the transform of d_rec is shared.
+        g = d_rec.view_as(signal)
+        with F_.fftconv_backward_part("kernel"):
+            rev = self._pack(torch.autograd.grad(signal, leaves[3:], grad_outputs=g, retain_graph=True))
         cur = torch.cuda.current_stream()
         if self._in_step:
             comm = self._comm_stream
             comm.wait_stream(cur)
             with torch.cuda.stream(comm):
                 self._dist.all_reduce(self._flat, op=self._dist.ReduceOp.AVG, group=self._group)
-        front = torch.autograd.grad([h2, n2], leaves[:3], grad_outputs=[cut[0], cut[1]])
+        with F_.fftconv_backward_part("signal"):
+            front = torch.autograd.grad(signal, leaves[:3], grad_outputs=g)
         if self._in_step:
             cur.wait_stream(comm)
         return signal, loss, tuple(front) + rev
