@@ -239,6 +239,58 @@ def load_peaks():
     return peaks
 
 
+class near_gpu:
+    """Context manager: run the body with the process bound to the CPUs NVML lists as local to the GPU, so that pinned
+    host buffers allocated (first touched) inside land on the GPU's NUMA node.  Best effort: any failure leaves the
+    affinity alone."""
+
+    def __init__(self, dev):
+        self.dev, self.saved = dev, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(self.dev)
+            uuid = getattr(props, "uuid", None)
+            h = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{uuid}") if uuid is not None else \
+                pynvml.nvmlDeviceGetHandleByIndex(self.dev.index or 0)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed and (cpus & allowed) != allowed:
+                self.saved = allowed
+                os.sched_setaffinity(0, cpus & allowed)
+        except Exception:
+            self.saved = None
+        return self
+
+    def __exit__(self, *a):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+
+
+def h2d_rate(block, step, flush):
+    """The host link alone: the step's pinned input block copied into the idle input set, nothing else running."""
+    dst = step._pair[1]["flat"]
+    s = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    ts = []
+    with torch.cuda.stream(s):
+        for _ in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(s)
+            dst.copy_(block, non_blocking=True)
+            b.record(s)
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[len(ts) // 2]
+    nbytes = block.numel() * block.element_size()
+    return {"ms_per_batch": ms, "gb_per_s": nbytes / (ms * 1e-3) / 1e9,
+            "note": "host->device copy of one step's inputs on an otherwise idle GPU; when this exceeds ms_per_step of "
+                    "the device-timed value, e2e is bound by the host link, not by the kernels"}
+
+
 def ncu_traffic(key):
     """DRAM bytes per launch from the committed ncu --set full capture (profiles/r02_ncu_traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
@@ -280,9 +332,15 @@ def kernel_table(step, shapes, flush, peaks):
         r["note"] = note
         rows.append(r)
 
-    add("K1 harmonic_frames_fwd", lambda: ops.harmonic_fwd(i["pitch"], w, bs, sr, None), fma_ops=2 * hs,
+    # the step's own form of K1: get_controls rides in the bank's prologue, its backward in the backward's epilogue
+    # (phase scan included in the forward's time, as in the op)
+    add("K0+K1 harmonic_raw_fwd (controls + oscillator bank)",
+        lambda: ops.harmonic_raw_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], bs, sr, None), fma_ops=2 * hs,
         note="SURVEY 8d: 2 FMA per harmonic-sample (recurrence + weighted sum) vs 148 SM x 128 lanes x max clock")
-    add("K1 harmonic_frames_bwd", lambda: ops.harmonic_bwd(g, w, phi, delta, bs, sr, False), fma_ops=2 * hs)
+    add("K0+K1 harmonic_raw_bwd (oscillator bank + controls backward)",
+        lambda: ops.harmonic_raw_bwd(g, i["amp_raw"], i["dist_raw"], i["pitch"], phi, delta, bs, sr), fma_ops=2 * hs)
+    add("K1 harmonic_frames_fwd (bank alone, weights given)", lambda: ops.harmonic_fwd(i["pitch"], w, bs, sr, None), fma_ops=2 * hs)
+    add("K1 harmonic_frames_bwd (bank alone, d weights)", lambda: ops.harmonic_bwd(g, w, phi, delta, bs, sr, False), fma_ops=2 * hs)
     add("K2 filtered_noise_fwd", lambda: ops.noise_fwd(i["mag_raw"], i["noise"], audio, True, -5.0), alg_bytes=4 * B * T * (NB + 3 * bs))
     add("K2 filtered_noise_bwd", lambda: ops.noise_bwd(g, i["noise"], i["mag_raw"], NB, True, -5.0), alg_bytes=4 * B * T * (NB + 2 * bs))
     kept = ops.fftconv_fwd(sig2, imp, True)
@@ -298,12 +356,12 @@ def kernel_table(step, shapes, flush, peaks):
     fft_flops *= B
     # shared-memory bytes the transform needs: 16 B per point and Stockham exchange (forward: two lanes of
     # a 16 B entry = 8 B per frame sample and direction), mirror exchange 8, gradient exchange 4, inverse at half the
-    # forward's count, gradient frames parked and gathered 8, carry 2
+    # forward's count, overlap-add carry and run heads in thread-private strips 3
     smem_bytes = 0.0
     for s_ in shapes.scales:
         hop = int(s_ * (1 - shapes.overlap))
         stages = 2 if s_ <= 256 else 3
-        per_point = 16 * (stages - 1) + 8 + 4 + 8 * (stages - 1) + 8 + 2
+        per_point = 16 * (stages - 1) + 8 + 4 + 8 * (stages - 1) + 3
         smem_bytes += (1 + N // hop) * s_ * per_point
     smem_bytes *= B
     smem_peak = 148 * 128 * clk / 1e9                 # GB/s: 128 B per clock per SM
@@ -314,13 +372,13 @@ def kernel_table(step, shapes, flush, peaks):
                  "note": "FFT butterflies only (5 n log2 n, 7.0 GFLOP/step at batch 64) against 2 x 128 lanes x 148 SMs x max clock",
                  "smem": {"achieved": smem_bytes / (ms * 1e-3) / 1e9, "peak": smem_peak, "unit": "GB/s",
                           "frac": smem_bytes / (ms * 1e-3) / 1e9 / smem_peak,
-                          "note": "shared-memory bytes of the Stockham exchanges, the mirror exchange and the overlap-add gather "
-                                  "against 128 B/clk/SM; the transform phases run at 76 % of it (ablation, DESIGN 3.4), the bin "
-                                  "maths and sample loads do not overlap with them"},
+                          "note": "shared-memory bytes of the Stockham exchanges, the mirror exchanges and the overlap-add carry "
+                                  "against 128 B/clk/SM; the transform phases run at 76 % of it (DESIGN 3.4), the bin maths and "
+                                  "sample loads do not overlap with them"},
                  "hbm": {"achieved": 4 * 3 * B * N / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": 4 * 3 * B * N / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "note": "SURVEY 8d's HBM view: read rec + target, write grad (12 B per sample)"}})
-    add("K0 harmonic_controls_fwd", lambda: ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr, True),
+    add("K0 harmonic_controls_fwd (standalone op; inside K1's launch in the step)", lambda: ops.harmonic_controls_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], sr, True),
         alg_bytes=4 * B * T * (2 * H + 3))
     return rows
 
@@ -575,9 +633,12 @@ def run_b200(args, rank, world):
     e2e_steps = max(10, args.steps // 2)
     hosts = [host, {k: v.clone().pin_memory() for k, v in host.items()}]
     paired = use_graph
+    link = None
     if paired:
         step.capture_pair()
-        hosts = [step.pack_host(h) for h in hosts]          # one pinned block per batch: one H2D copy per step
+        with near_gpu(dev):                                 # first touch on the GPU's NUMA node
+            hosts = [step.pack_host(h) for h in hosts]      # one pinned block per batch: one H2D copy per step
+        link = h2d_rate(hosts[0], step, flush)
 
     fed_bytes = [h2d]
 
@@ -661,7 +722,7 @@ def run_b200(args, rank, world):
                        "launch": graph_note},
             "fwd": {"value": samples_per_step / (fwd_ms * 1e-3), "unit": UNIT, "ms_per_step": fwd_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": fed_bytes[0] * world, "d2h_bytes_per_step": 4 * world,
-                    "ms_per_step": 1e3 * float(te) / e2e_steps, "loss": loss_host,
+                    "ms_per_step": 1e3 * float(te) / e2e_steps, "loss": loss_host, "h2d_link": link,
                     "how": "pinned host -> H2D on the copy stream straight into the idle one of two static input sets (next "
                            "batch in flight during the step) -> one graph launch -> loss D2H read every step (waited for "
                            "one step later); wall clock between synchronisations"},

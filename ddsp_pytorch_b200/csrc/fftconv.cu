@@ -212,11 +212,16 @@ rows_kernel(const float2 *src_work, float2 *dst_work, const float2 *__restrict__
 // Correlation, phase 1: partial[split][k1][k2] = sum over the slots of this split of
 // FFT_row(G)[k2] * conj(FFT_row(X)[k2]).  The accumulator lives in registers (same positions as the
 // last stage's outputs).
-template <int LG2, bool TWIN>
+// FINISH (one row per CTA, TWIN): the last of a row's `nsplit` CTAs to arrive (a counter per row, which it resets)
+// also does phase 2 for that row -- sum of the partial spectra in split order (so the result does not depend on which
+// CTA came last), inverse row transform, inter-step twiddle -- instead of a second, 20-CTA launch on the critical path
+// of the reverb's backward.
+template <int LG2, bool TWIN, bool FINISH = false>
 __global__ void __launch_bounds__(kRowThreads)
 rows_corr_kernel(const float2 *__restrict__ work_g, const float2 *__restrict__ work_x, int64_t slots,
-                 int nsplit, float2 *__restrict__ partial, const float2 *__restrict__ twn,
-                 const float2 *__restrict__ stw, int n1) {
+                 int nsplit, float2 *partial, const float2 *__restrict__ twn,
+                 const float2 *__restrict__ stw, int n1, float2 *__restrict__ final_out = nullptr,
+                 int *__restrict__ counters = nullptr) {
     using P = Plan<LG2>;
     constexpr int n2 = P::N, T = P::T, PITCH = P::PITCH, ROWS = RowCfg<LG2>::ROWS;
     constexpr int R = Stage<LG2, P::STAGES - 1>::R, M = 16 / R;
@@ -275,6 +280,34 @@ rows_corr_kernel(const float2 *__restrict__ work_g, const float2 *__restrict__ w
     for (int m = 0; m < M; ++m)
 #pragma unroll
         for (int r = 0; r < R; ++r) out[stage_out_index<LG2, P::STAGES - 1>(t, m, r)] = acc[m * R + r];
+    if (FINISH) {
+        static_assert(!FINISH || (ROWS == 1 && TWIN), "fused finish: one row per CTA, twiddles in shared memory");
+        __shared__ int is_last;
+        __threadfence();                                   // this CTA's partial spectrum is visible device-wide
+        __syncthreads();
+        if (tid == 0) {
+            const int old = atomicAdd(&counters[k1], 1);
+            is_last = old == nsplit - 1;
+            if (is_last) counters[k1] = 0;                 // ready for the next launch on this workspace
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = make_float2(0.f, 0.f);
+        for (int sp = 0; sp < nsplit; ++sp) {
+            const float2 *src = partial + ((size_t)sp * n1 + k1) * n2;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = c_add(v[r], __ldcg(src + t + r * T));
+        }
+        stage_compute_store<LG2, 0, true>(v, buf, t, stw);
+        mid_stages<LG2, true>(v, buf, t, stw, true);
+        const StepTwiddle st{thi + g * (n2 / 16), tlo + g * 16};
+        float2 *row = final_out + (size_t)k1 * n2;
+        stage_compute_sink<LG2, P::STAGES - 1, true>(v, t, stw, [&](int i2, float2 val) {
+            row[i2] = c_mul(val, st.at(i2, true));
+        });
+    }
 }
 
 // Correlation, phase 2: out[o][k1] = IFFT_row(sum of `nsum` partial spectra) * W_n^(-i2 k1)
@@ -651,17 +684,23 @@ extern "C" int ddsp_b200_fft4_rows_filter(const float *work, float *dst, int64_t
 
 extern "C" int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce) {
     if (!reduce) return slots;
-    return slots < 8 ? slots : 8;
+    return (slots < 8 ? slots : 8) + 1;                // + the counter plane of the in-launch finish (5-smooth plans)
 }
 
 // splits for a given plan: the correlate kernel runs one CTA per SM, so (row blocks) x splits should not spill into a
 // second, nearly empty wave (20 rows x 8 splits = 160 CTAs on 148 SMs did)
-extern "C" int64_t ddsp_b200_fft4_correlate_splits_plan(int64_t slots, int reduce, int n1, int n2) {
+static int64_t corr_splits(int64_t slots, int reduce, int n1, int n2) {
     if (!reduce) return slots;
     int64_t s = slots < 8 ? slots : 8;
     if (direct_n1(n1) && n2 == 4096)
         while (s > 1 && (int64_t)n1 * s > DDSP_SM_COUNT) --s;
     return s;
+}
+// the reduce form on the 5-smooth plans finishes inside the correlate launch: one more scratch plane holds its row counters
+static bool corr_fused_finish(int reduce, int n1, int n2) { return reduce && direct_n1(n1) && n2 == 4096; }
+
+extern "C" int64_t ddsp_b200_fft4_correlate_splits_plan(int64_t slots, int reduce, int n1, int n2) {
+    return corr_splits(slots, reduce, n1, n2) + (corr_fused_finish(reduce, n1, n2) ? 1 : 0);
 }
 
 extern "C" int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots,
@@ -669,11 +708,22 @@ extern "C" int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *w
                                              const float *stage2, int n1, int n2, void *stream) {
     DDSP_REQUIRE(work_g && work_x && scratch && out && twiddle && stage2 && slots > 0 && slots <= 65535);
     DDSP_REQUIRE(plan_ok(n1, n2));
-    const int nsplit = (int)ddsp_b200_fft4_correlate_splits_plan(slots, reduce, n1, n2);
+    const int nsplit = (int)corr_splits(slots, reduce, n1, n2);
     const int nsum = reduce ? nsplit : 1;
     const int nout = reduce ? 1 : (int)slots;
     int s = DDSP_B200_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    if (corr_fused_finish(reduce, n1, n2)) {
+        if ((s = set_smem(rows_corr_kernel<12, true, true>, row_smem<12>()))) return s;
+        int *counters = reinterpret_cast<int *>(scratch + (size_t)nsplit * n1 * n2 * 2);     // the extra scratch plane
+        cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)n1 * sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+        rows_corr_kernel<12, true, true><<<dim3(n1, nsplit), kRowThreads, row_smem<12>(), st>>>(
+            reinterpret_cast<const float2 *>(work_g), reinterpret_cast<const float2 *>(work_x), slots, nsplit,
+            reinterpret_cast<float2 *>(scratch), reinterpret_cast<const float2 *>(twiddle),
+            reinterpret_cast<const float2 *>(stage2), n1, reinterpret_cast<float2 *>(out), counters);
+        return ddsp_launch_status();
+    }
     if (direct_n1(n1)) {
         if ((s = set_smem(rows_corr_kernel<12, true>, row_smem<12>())) ||
             (s = set_smem(rows_corr_finish_kernel<12>, row_smem<12>())))

@@ -197,18 +197,25 @@ harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t 
     const int tid = threadIdx.x;
     const int nthr = blockDim.x;                          // kFwdThreads, or more when the grid alone cannot fill the GPU
     if (RAW) {
+        // phase A, every thread busy: v = scale_function(raw) * mask per (frame, harmonic), parked in the weight table
+        for (int i = tid; i < nfr * H; i += nthr) {
+            const int f = i / H, k = i - f * H;
+            const size_t row = (size_t)b * T + t0 + f;
+            const float v = ddsp_scale_fn(rc.dist_raw[row * rc.dist_stride + k]) * ddsp_nyquist_mask(rc.f0[row], k + 1, rc.nyq);
+            w2[f * Hp + k].x = v;
+        }
+        __syncthreads();
+        // phase B, one warp per frame row: normalise (controls_fwd_kernel's summation order), scale by the amplitude
         const int lane = tid & 31;
         constexpr int kKeepF = 8;                          // H <= 256 (the host falls back to the two-launch path above)
         for (int f = tid >> 5; f < nfr; f += nthr >> 5) {
             const size_t row = (size_t)b * T + t0 + f;
-            const float fq = rc.f0[row];
-            const float *dr = rc.dist_raw + row * rc.dist_stride;
             float vk[kKeepF];
             float sum = 0.f;
 #pragma unroll
             for (int i = 0; i < kKeepF; ++i) {
                 const int k = lane + 32 * i;
-                vk[i] = k < H ? ddsp_scale_fn(dr[k]) * ddsp_nyquist_mask(fq, k + 1, rc.nyq) : 0.f;
+                vk[i] = k < H ? w2[f * Hp + k].x : 0.f;
                 sum += vk[i];
             }
             sum = ddsp_warp_sum(sum);
@@ -452,35 +459,45 @@ harmonic_frames_bwd_w_x2_kernel(const float *__restrict__ g_audio, const uint64_
     }
     __syncthreads();
     if (RAW) {
+        // phase A, every thread busy: per (frame, harmonic) the chunk sum, scale_function's value and derivative
+        // (the expensive part), parked as  part[0] = d weight,  sv = v = fn * mask,  sd = mask * fn'
+        float *sv = part + (size_t)nchunk * nfr * H;                     // [nfr][H]   (extra shared memory of the RAW launch)
+        float *sd = sv + (size_t)FR * H;
+        for (int i = tid; i < nfr * H; i += kBwdThreads) {
+            const int f = i / H, k = i - f * H;
+            const size_t row = (size_t)b * T + t0 + f;
+            float dwk = 0.f;
+            for (int c = 0; c < nchunk; ++c) dwk += part[(size_t)c * nfr * H + i];
+            float fn, gr;
+            ddsp_scale_fn_grad(rc.dist_raw[row * rc.dist_stride + k], &fn, &gr);
+            const float mask = ddsp_nyquist_mask(rc.f0[row], k + 1, rc.nyq);
+            part[i] = dwk;
+            sv[i] = fn * mask;
+            sd[i] = mask * gr;
+        }
+        __syncthreads();
+        // phase B, one warp per frame row: the normalisation's three sums and the outputs (controls_bwd_kernel's
+        // arithmetic and summation order)
         const int lane = tid & 31;
         constexpr int kKeep = 8;                                         // H <= 256
         for (int f = tid >> 5; f < nfr; f += kBwdThreads >> 5) {
             const size_t row = (size_t)b * T + t0 + f;
-            const float fq = rc.f0[row];
-            const float *dr = rc.dist_raw + row * rc.dist_stride;
             float amp, amp_grad;
             ddsp_scale_fn_grad(rc.amp_raw[row * rc.amp_stride], &amp, &amp_grad);
             // n_k = v_k / S;  g_k = d_weights_k * amp;  dv_k = (g_k - sum_j g_j n_j) / S;  d amp = sum_k d_weights_k n_k
-            float gk[kKeep], dk[kKeep];
+            float gk[kKeep];
             float sum = 0.f, dot = 0.f, wdot = 0.f;
 #pragma unroll
             for (int i = 0; i < kKeep; ++i) {
                 const int k = lane + 32 * i;
                 gk[i] = 0.f;
-                dk[i] = 0.f;
                 if (k < H) {
-                    float dwk = 0.f;
-                    for (int c = 0; c < nchunk; ++c) dwk += part[((size_t)c * nfr + f) * H + k];
-                    float fn, gr;
-                    ddsp_scale_fn_grad(dr[k], &fn, &gr);
-                    const float mask = ddsp_nyquist_mask(fq, k + 1, rc.nyq);
-                    const float v = fn * mask;
+                    const float dwk = part[f * H + k], v = sv[f * H + k];
                     const float g = dwk * amp;
                     sum += v;
                     dot = fmaf(g, v, dot);
                     wdot = fmaf(dwk, v, wdot);
                     gk[i] = g;
-                    dk[i] = mask * gr;
                 }
             }
             sum = ddsp_warp_sum(sum);
@@ -491,7 +508,7 @@ harmonic_frames_bwd_w_x2_kernel(const float *__restrict__ g_audio, const uint64_
 #pragma unroll
             for (int i = 0; i < kKeep; ++i) {
                 const int k = lane + 32 * i;
-                if (k < H) out[k] = (gk[i] - dot) * inv * dk[i];
+                if (k < H) out[k] = (gk[i] - dot) * inv * sd[f * H + k];
             }
             if (lane == 0) rc.d_amp_raw[row * rc.damp_stride] = wdot * amp_grad;
         }
@@ -813,7 +830,7 @@ static int launch_frames_bwd(const float *g_audio, const uint64_t *phi, const ui
     if (fr < 1) fr = 1;
     auto bytes = [&](int fr_) {
         const size_t gsz = packed ? 2 * (((size_t)fr_ * bs + 1) & ~(size_t)1) : (((size_t)fr_ * bs + 3) & ~(size_t)3);
-        return (gsz + (size_t)nchunk * fr_ * H) * sizeof(float);
+        return (gsz + (size_t)nchunk * fr_ * H + (rc ? 2 * (size_t)fr_ * H : 0)) * sizeof(float);
     };
     while (bytes(fr) > 200 * 1024 && fr > 1) fr = (fr + 1) / 2;
     const size_t smem = bytes(fr);

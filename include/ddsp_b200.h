@@ -180,7 +180,9 @@ int ddsp_b200_fft4_rows_filter(const float *work, float *dst, int64_t slots, con
                                int64_t h_slot_stride, int conj_h, const float *twiddle,
                                const float *stage2, int n1, int n2, void *stream);
 /* out = rows of IFFT( FFT(g) * conj(FFT(x)) ), summed over slots into one slot when reduce != 0.
- * scratch: ddsp_b200_fft4_correlate_splits(slots, reduce) * n1*n2 complex (partial spectra).      */
+ * scratch: ddsp_b200_fft4_correlate_splits_plan(slots, reduce, n1, n2) * n1*n2 complex: the partial spectra and, on
+ * the 5-smooth plans with reduce != 0, one more plane for the row counters of the in-launch finish (the call zeroes
+ * them).  ddsp_b200_fft4_correlate_splits is the plan-independent upper bound.                                      */
 int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce);
 int64_t ddsp_b200_fft4_correlate_splits_plan(int64_t slots, int reduce, int n1, int n2);   /* the same, for a given plan */
 int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots, int reduce,

@@ -21,6 +21,9 @@ for _ in range(iters):
     audio, _, phi, delta = ops.harmonic_fwd(i["pitch"], w, 160, 16000.0, None)
     g = torch.randn_like(audio)
     ops.harmonic_bwd(g, w, phi, delta, 160, 16000.0, False)
+    # the step's own form: controls computed in the bank's prologue / the controls' backward in the backward's epilogue
+    a2, _, phi2, delta2, _, _ = ops.harmonic_raw_fwd(i["amp_raw"], i["dist_raw"], i["pitch"], 160, 16000.0, None)
+    ops.harmonic_raw_bwd(g, i["amp_raw"], i["dist_raw"], i["pitch"], phi2, delta2, 160, 16000.0)
     ops.noise_fwd(i["mag_raw"], i["noise"], audio, True, -5.0)
     ops.noise_bwd(g, i["noise"], i["mag_raw"], 65, True, -5.0)
     sig2 = audio.squeeze(-1).contiguous()
