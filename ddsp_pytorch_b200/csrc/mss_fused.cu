@@ -18,10 +18,15 @@
 //     the loss terms and gradient spectra are computed in registers, the mirrored half of the gradient spectrum
 //     goes back the same way, and the inverse transform (one complex FFT carries the real gradients of BOTH
 //     frames: U_A + i U_B) starts from registers.
-//   * Overlap-add is a gather: the batch's gradient frames are parked in shared memory, every padded-signal position
-//     sums its <= 4 frames in frame order (+ the carry of the previous batch), finished positions go to the scale's
-//     gradient plane P, the last 3 hops are carried.  The carry of a tile's last batch goes to a small halo buffer
-//     that mss_combine2_kernel adds to the head of the next tile: no atomics, bit-reproducible.
+//   * Overlap-add stays in registers.  A tile's frames are split into contiguous RUNS, one per thread group; slot q of
+//     frame f+1 is slot q+4 of frame f IN THE SAME THREAD, so a thread adds the windowed gradient frames of its run into
+//     a 20-slot accumulator, stores the 8 finished slots of every pair to the scale's gradient plane P and carries 12
+//     (a thread-private strip of shared memory, no barrier).  At the end of the tile a run's first 3 hops receive the
+//     final carry of the previous group's run (read-modify-write of the thread's own stores); the last group's carry
+//     goes to a small halo buffer that mss_combine2_kernel adds to the head of the next tile.  No atomics, every
+//     position sums its frames oldest first: bit-reproducible.  80 KB of shared memory per CTA: two CTAs per SM leave
+//     64 KB of L1 for the sample re-reads (a pair re-reads 12 of its predecessor's 20 slots), the window and the stage
+//     twiddles.
 //   * mss_combine2_kernel sums the scales in order and folds the reflect padding back.
 #include <cstdlib>
 
@@ -119,20 +124,16 @@ __device__ __forceinline__ void bin_math(const pfft::C (&x)[16], pfft::V (&zi)[1
 
 // Samples t + qT, q = 0..19, of rec and target from `start` on (reflect padding at the signal's ends): frame A uses
 // slots 0..15, frame B = A + 1 hop uses slots 4..19.
-__device__ __forceinline__ float ld_stream(const float *p) {
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
+// (plain cached loads: slots 8..19 are read again by the same thread for the run's next pair and then hit in L1;
+// ld.global.nc.L1::no_allocate was 5 % slower here)
 template <int N, int T>
 __device__ __forceinline__ void load_frames(float (&r)[20], float (&g)[20], const float *__restrict__ xr,
                                             const float *__restrict__ xt, int start, int t, int Ni) {
     if (start >= 0 && start + N / 4 + N <= Ni) {
 #pragma unroll
         for (int q = 0; q < 20; ++q) {
-            r[q] = ld_stream(xr + start + t + q * T);
-            g[q] = ld_stream(xt + start + t + q * T);
+            r[q] = __ldg(xr + start + t + q * T);
+            g[q] = __ldg(xt + start + t + q * T);
         }
     } else {
 #pragma unroll
@@ -141,8 +142,8 @@ __device__ __forceinline__ void load_frames(float (&r)[20], float (&g)[20], cons
             m = m < 0 ? -m : m;
             m = m >= Ni ? 2 * (Ni - 1) - m : m;
             m = min(max(m, 0), Ni - 1);                      // only frames that do not exist reach this clamp
-            r[q] = ld_stream(xr + m);
-            g[q] = ld_stream(xt + m);
+            r[q] = __ldg(xr + m);
+            g[q] = __ldg(xt + m);
         }
     }
 }
@@ -158,10 +159,8 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
     constexpr int GBYTES = (N + N / 16) * 16;                     // bytes of one group's work buffer
     constexpr int EX2_OFF = 13 * N;                               // mirrored gradient bins
     static_assert(kThreads % T == 0 && G * GBYTES == kWorkBytes, "work buffer layout");
-    // thread-private strips (float4 [3][kThreads], conflict free): the running overlap-add carry (12 slots = 3 hops)
-    // and the head of the run (its first 3 hops, which still miss the previous run's tail)
+    // thread-private strip (float4 [3][kThreads], conflict free): the running overlap-add carry (12 slots = 3 hops)
     float4 *cpriv = reinterpret_cast<float4 *>(smem + kWorkBytes);
-    float4 *hpriv = cpriv + 3 * kThreads;
     __shared__ float red[2][kThreads / 32];
 
     const int tid = threadIdx.x;
@@ -193,7 +192,7 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
     if (GRAD) {
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { cpriv[k * kThreads + tid] = z4; hpriv[k * kThreads + tid] = z4; }
+        for (int k = 0; k < 3; ++k) cpriv[k * kThreads + tid] = z4;
     }
     V lin = bc(0.f), lgs = bc(0.f);
 
@@ -284,45 +283,35 @@ __device__ __forceinline__ void tile_body(const ScaleDesc &sc, int b, int tile, 
             }
 #pragma unroll
             for (int q = 0; q < 16; ++q) acc[q + 4] += ub[q];
+            // (the run's first 12 slots still miss the previous run's tail: fixed up at the end of the tile)
             float *Pp = Pb + (size_t)fA * HOP + t;
-            if (p == 0) {                                         // the run's first 8 slots wait for the previous run's tail
-                hpriv[tid] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                hpriv[kThreads + tid] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            } else {
-                if (p == 1) {
-                    hpriv[2 * kThreads + tid] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                } else {
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) Pp[s * T] = acc[s];
-                }
-#pragma unroll
-                for (int s = 4; s < 8; ++s) Pp[s * T] = acc[s];
-            }
+            for (int s = 0; s < 8; ++s) Pp[s * T] = acc[s];
             cpriv[tid] = make_float4(acc[8], acc[9], acc[10], acc[11]);
             cpriv[kThreads + tid] = make_float4(acc[12], acc[13], acc[14], acc[15]);
             cpriv[2 * kThreads + tid] = make_float4(acc[16], acc[17], acc[18], acc[19]);
         }
     }
     if (GRAD) {
-        // ---- run boundaries: the first 3 hops of a run = its own head + the final carry of the previous group's
-        // run; the last group's carry belongs to the head of the next tile (or to the end of the signal): halo buffer
+        // ---- run boundaries: the first 3 hops of a run also get the final carry of the previous group's run (a
+        // read-modify-write of this thread's own earlier stores; a run that was skipped has nothing there yet); the
+        // last group's carry belongs to the head of the next tile (or to the end of the signal): halo buffer
         __syncthreads();
-        float4 h[3];
+        if (grp > 0) {
+            float *Pp = Pb + (size_t)run0 * HOP + t;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            h[k] = hpriv[k * kThreads + tid];
-            if (grp > 0) {
+            for (int k = 0; k < 3; ++k) {
                 const float4 c = cpriv[k * kThreads + tid - T];
-                h[k].x += c.x; h[k].y += c.y; h[k].z += c.z; h[k].w += c.w;
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) {
+                    h.x = Pp[(4 * k + 0) * T]; h.y = Pp[(4 * k + 1) * T];
+                    h.z = Pp[(4 * k + 2) * T]; h.w = Pp[(4 * k + 3) * T];
+                }
+                Pp[(4 * k + 0) * T] = h.x + c.x;
+                Pp[(4 * k + 1) * T] = h.y + c.y;
+                Pp[(4 * k + 2) * T] = h.z + c.z;
+                Pp[(4 * k + 3) * T] = h.w + c.w;
             }
-        }
-        float *Pp = Pb + (size_t)run0 * HOP + t;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            Pp[(4 * k + 0) * T] = h[k].x;
-            Pp[(4 * k + 1) * T] = h[k].y;
-            Pp[(4 * k + 2) * T] = h[k].z;
-            Pp[(4 * k + 3) * T] = h[k].w;
         }
         if (grp == G - 1) {
             float *Hb = ws + sc.h_off + ((size_t)b * sc.tiles + tile) * (3 * HOP) + t;
@@ -550,7 +539,7 @@ int make_plan(int B, int64_t N, const int *scales, int n_scales, Plan2 *out) {
     a.pad_ = 0;
     out->ws_floats = off;
     out->partial_pairs = pairs;
-    out->smem = (size_t)kWorkBytes + 2 * 3 * kThreads * sizeof(float4);   // + the private carry / head strips
+    out->smem = (size_t)kWorkBytes + 3 * kThreads * sizeof(float4);       // + the private overlap-add carry strip
     return DDSP_B200_OK;
 }
 
@@ -596,10 +585,15 @@ extern "C" int ddsp_b200_mss_fused(const float *target, const float *rec, const 
     if (d_rec) {
         if ((e = cudaFuncSetAttribute(mss_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)) != cudaSuccess)
             return (int)e;
+        // two CTAs of 80 KB per SM: ask for the 164 KB shared-memory configuration, which leaves 64 KB of L1 for the
+        // sample re-reads, the window and the stage twiddles (48 KB of tables at n_fft 4096)
+        cudaFuncSetAttribute(mss_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             72);
         mss_fused_kernel<true><<<p.args.n_items, kThreads, p.smem, st>>>(target, rec, workspace, partial, p.args);
     } else {
         if ((e = cudaFuncSetAttribute(mss_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem)) != cudaSuccess)
             return (int)e;
+        cudaFuncSetAttribute(mss_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
         mss_fused_kernel<false><<<p.args.n_items, kThreads, p.smem, st>>>(target, rec, workspace, partial, p.args);
     }
     if ((s = ddsp_launch_status())) return s;

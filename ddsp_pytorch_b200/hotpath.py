@@ -135,15 +135,16 @@ class SynthStep:
         cur = torch.cuda.current_stream()
         side = self._side_stream
         kernel = hspec = None
-        if self.reverb is not None:
-            # the reverb's impulse depends on the reverb parameters only.  Its autograd node stays on this stream; its
-            # spectrum (two launches, no autograd) is computed on the side stream, off the critical path
-            impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
-            taps = min(s.samples, s.reverb_length)
-            kernel = impulse.reshape(1, s.reverb_length)[:, :taps]
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            if kernel is not None:
+            if self.reverb is not None:
+                # the reverb's impulse depends on the reverb parameters only: it is built, and its spectrum computed,
+                # on the side stream.  Autograd replays a node's backward on its forward stream, so the impulse's
+                # backward (two small launches at the very end of the step) also lands beside the oscillator bank's
+                # backward instead of after it
+                impulse = F_.ReverbImpulse.apply(leaves[3], leaves[4], leaves[5], self.reverb.t)
+                taps = min(s.samples, s.reverb_length)
+                kernel = impulse.reshape(1, s.reverb_length)[:, :taps]
                 hspec = F_._ops.fftconv_spectrum(kernel.detach(), s.samples)
             # FilteredNoise.get_controls + forward in one launch
             noise = F_.FilteredNoiseFused.apply(leaves[2], i["noise"], None, -5.0)
@@ -157,6 +158,7 @@ class SynthStep:
         noise.record_stream(cur)
         if self.reverb is not None:
             hspec.record_stream(cur)
+            kernel.record_stream(cur)
             # decoder.py:121's `harmonic + noise` is formed by the reverb's first pass while it loads its input
             h2, n2 = harmonic.squeeze(-1), noise.squeeze(-1)
             signal = F_.FFTConvolve.apply(h2, kernel, hspec, n2).unsqueeze(-1)
