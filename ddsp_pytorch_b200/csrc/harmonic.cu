@@ -179,6 +179,13 @@ struct RawControls {
     long long amp_stride, dist_stride;
     float nyq;
     float *amps, *weights;                   // [B*T], [B*T][H]
+    // scan != 0: the CTA also does the phase scan for its frames (phase_scan_kernel's integer arithmetic: exact and
+    // associative, so the same bits) and writes phi / delta for the backward; phase0 / phase_end as in the scan
+    int scan, block_size;
+    double inv_sr;
+    const double *phase0;
+    double *phase_end;
+    uint64_t *phi_out, *delta_out;
 };
 
 template <bool RAW>
@@ -243,11 +250,38 @@ harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t 
             w2[i] = make_float2(a, a);
         }
     }
-    if (tid < nfr) {
-        sphi[tid] = phi[(size_t)b * T + t0 + tid];
-        sdel[tid] = delta[(size_t)b * T + t0 + tid];
+    if (RAW && rc.scan) {
+        // phase before the CTA's first frame = phase0 + block * (sum of the increments of every earlier frame)
+        __shared__ uint64_t wsum[kFwdMaxThreads / 32];
+        const float *fv = rc.f0 + (size_t)b * T;
+        uint64_t part = 0;
+        for (int t = tid; t < t0; t += nthr) part += turns_to_q64((double)fv[t] * rc.inv_sr);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((tid & 31) == 0) wsum[tid >> 5] = part;
+        if (tid < nfr) sdel[tid] = turns_to_q64((double)fv[t0 + tid] * rc.inv_sr);
+        __syncthreads();
+        if (tid == 0) {
+            uint64_t run = rc.phase0 ? turns_to_q64(rc.phase0[b]) : 0ull;
+            for (int i = 0; i < (nthr >> 5); ++i) run += wsum[i] * (uint64_t)rc.block_size;
+            for (int f = 0; f < nfr; ++f) {
+                sphi[f] = run;
+                run += sdel[f] * (uint64_t)rc.block_size;
+            }
+            if (rc.phase_end && t0 + nfr == T) rc.phase_end[b] = (double)run * 5.421010862427522e-20;   // * 2^-64
+        }
+        __syncthreads();
+        if (tid < nfr) {
+            rc.phi_out[(size_t)b * T + t0 + tid] = sphi[tid];
+            rc.delta_out[(size_t)b * T + t0 + tid] = sdel[tid];
+        }
+    } else {
+        if (tid < nfr) {
+            sphi[tid] = phi[(size_t)b * T + t0 + tid];
+            sdel[tid] = delta[(size_t)b * T + t0 + tid];
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     const int S = nfr * bs;
     float *out = audio + ((size_t)b * T + t0) * bs;
@@ -812,7 +846,33 @@ extern "C" int ddsp_b200_harmonic_frames_raw_fwd(const float *amp_raw, int64_t a
     DDSP_REQUIRE(amp_raw && dist_raw && f0 && phi && delta && amps && weights && audio);
     DDSP_REQUIRE(B > 0 && B <= 65535 && T > 0 && H > 0 && block_size > 0 && amp_stride >= 1 && dist_stride >= H);
     if (!ddsp_b200_harmonic_frames_raw_supported(H, block_size)) return DDSP_B200_EUNSUPPORTED;
-    RawControls rc{amp_raw, dist_raw, f0, amp_stride, dist_stride, sample_rate * 0.5f, amps, weights};
+    RawControls rc{amp_raw, dist_raw, f0, amp_stride, dist_stride, sample_rate * 0.5f, amps, weights,
+                   0, block_size, 0.0, nullptr, nullptr, nullptr, nullptr};
+    return launch_frames_fwd(nullptr, &rc, phi, delta, audio, B, T, H, block_size, (cudaStream_t)stream);
+}
+
+extern "C" int ddsp_b200_harmonic_frames_raw_scan_fwd(const float *amp_raw, int64_t amp_stride, const float *dist_raw,
+                                                      int64_t dist_stride, const float *f0, const double *phase0,
+                                                      uint64_t *phi, uint64_t *delta, double *phase_end, float *amps,
+                                                      float *weights, float *audio, int B, int T, int H,
+                                                      int block_size, double sample_rate, void *stream) {
+    DDSP_REQUIRE(amp_raw && dist_raw && f0 && phi && delta && amps && weights && audio);
+    DDSP_REQUIRE(B > 0 && B <= 65535 && T > 0 && H > 0 && block_size > 0 && amp_stride >= 1 && dist_stride >= H);
+    DDSP_REQUIRE(sample_rate > 0);
+    if (!ddsp_b200_harmonic_frames_raw_supported(H, block_size)) return DDSP_B200_EUNSUPPORTED;
+    // every CTA of a voice redoes the scan over the voice's earlier frames: fine for 25 CTAs of 16 frames (config 2),
+    // not for 375 CTAs of one 512-sample frame (config 4), which take the scan as its own launch
+    const int fr = frames_per_cta(block_size, T, kFwdThreads * 4, 32);
+    if ((T + fr - 1) / fr > 64) {
+        phase_scan_kernel<<<B, kScanThreads, 0, (cudaStream_t)stream>>>(f0, phase0, phi, delta, phase_end, T, block_size,
+                                                                       1.0 / sample_rate);
+        int s = ddsp_launch_status();
+        if (s) return s;
+        return ddsp_b200_harmonic_frames_raw_fwd(amp_raw, amp_stride, dist_raw, dist_stride, f0, phi, delta, amps,
+                                                 weights, audio, B, T, H, block_size, (float)sample_rate, stream);
+    }
+    RawControls rc{amp_raw, dist_raw, f0, amp_stride, dist_stride, (float)sample_rate * 0.5f, amps, weights,
+                   1, block_size, 1.0 / sample_rate, phase0, phase_end, phi, delta};
     return launch_frames_fwd(nullptr, &rc, phi, delta, audio, B, T, H, block_size, (cudaStream_t)stream);
 }
 

@@ -304,16 +304,13 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> harmonic_raw_fwd(
                     "harmonic_raw_fwd: phase0 must be a CUDA float64 tensor of B turns");
         p0 = phase0.data_ptr<double>();
     }
-    check(ddsp_b200_phase_scan(fp(f0), p0, (uint64_t *)phi.data_ptr<int64_t>(),
-                               (uint64_t *)delta.data_ptr<int64_t>(), phase_end.data_ptr<double>(),
-                               (int)B, (int)T, (int)block_size, sample_rate, cur_stream()),
-          "phase_scan");
-    check(ddsp_b200_harmonic_frames_raw_fwd(v.amp, v.amp_stride, v.dst, v.dist_stride, fp(f0),
-                                            (const uint64_t *)phi.data_ptr<int64_t>(),
-                                            (const uint64_t *)delta.data_ptr<int64_t>(), fpm(amps), fpm(weights),
-                                            fpm(audio), (int)B, (int)T, (int)H, (int)block_size,
-                                            (float)sample_rate, cur_stream()),
-          "harmonic_frames_raw_fwd");
+    // phase scan, controls and oscillator bank in one launch
+    check(ddsp_b200_harmonic_frames_raw_scan_fwd(v.amp, v.amp_stride, v.dst, v.dist_stride, fp(f0), p0,
+                                                 (uint64_t *)phi.data_ptr<int64_t>(),
+                                                 (uint64_t *)delta.data_ptr<int64_t>(), phase_end.data_ptr<double>(),
+                                                 fpm(amps), fpm(weights), fpm(audio), (int)B, (int)T, (int)H,
+                                                 (int)block_size, sample_rate, cur_stream()),
+          "harmonic_frames_raw_scan_fwd");
     return {audio, phase_end, phi, delta, amps, weights};
 }
 

@@ -97,6 +97,13 @@ int ddsp_b200_harmonic_frames_raw_fwd(const float *amp_raw, int64_t amp_stride, 
                                       int64_t dist_stride, const float *f0, const uint64_t *phi,
                                       const uint64_t *delta, float *amps, float *weights, float *audio, int B,
                                       int T, int H, int block_size, float sample_rate, void *stream);
+/* The same with the phase scan inside the launch: phi / delta are OUTPUTS here (kept for the backward), phase0 (may be
+ * NULL) and phase_end (may be NULL) as in ddsp_b200_phase_scan; same bits as scan + ddsp_b200_harmonic_frames_raw_fwd. */
+int ddsp_b200_harmonic_frames_raw_scan_fwd(const float *amp_raw, int64_t amp_stride, const float *dist_raw,
+                                           int64_t dist_stride, const float *f0, const double *phase0, uint64_t *phi,
+                                           uint64_t *delta, double *phase_end, float *amps, float *weights,
+                                           float *audio, int B, int T, int H, int block_size, double sample_rate,
+                                           void *stream);
 int ddsp_b200_harmonic_frames_raw_bwd(const float *g_audio, const float *amp_raw, int64_t amp_stride,
                                       const float *dist_raw, int64_t dist_stride, const float *f0,
                                       const uint64_t *phi, const uint64_t *delta, float *d_amp_raw,
