@@ -78,9 +78,10 @@ class SynthStep:
         (op AVG) per step.
 
         ``in_step=True`` (default): the collective is part of run() and therefore a node of the captured CUDA graph.
-        The backward is cut in two: the reverb's backward first (it ends with the parameter gradients), then the
-        all-reduce is queued on a communication stream while the harmonic / noise / controls backward runs on the
-        compute streams; the step joins both at its end.  Every rank must then call run() / replay() the same number
+        The backward is cut in two: the reverb PARAMETERS' backward first (the long convolution's kernel gradient, then
+        the impulse's backward), then the all-reduce is queued on a communication stream while the convolution's signal
+        gradient and the harmonic / noise / controls backward run on the compute streams; the step joins both at its
+        end.  Every rank must then call run() / replay() the same number
         of times (a rank that steps alone waits for its peers forever): use ``local_only()`` around single-rank calls.
         ``in_step=False``: run() only packs; the caller queues ``allreduce_grads()`` after each step."""
         assert self.reverb is not None
@@ -121,9 +122,8 @@ class SynthStep:
                        (self.reverb.noise, self.reverb.decay, self.reverb.wet)]
         return leaves
 
-    def forward(self, leaves=None, parts: bool = False):
-        """decoder.py:110-125: controls -> harmonic + filtered noise (+ reverb).  (B,N,1)
-        ``parts=True`` also returns the two synthesiser outputs the mix was formed from."""
+    def forward(self, leaves=None):
+        """decoder.py:110-125: controls -> harmonic + filtered noise (+ reverb).  (B,N,1)"""
         i, s = self.inputs, self.shapes
         if leaves is None:
             leaves = [i["amp_raw"], i["dist_raw"], i["mag_raw"]]
@@ -160,19 +160,17 @@ class SynthStep:
             hspec.record_stream(cur)
             kernel.record_stream(cur)
             # decoder.py:121's `harmonic + noise` is formed by the reverb's first pass while it loads its input
-            h2, n2 = harmonic.squeeze(-1), noise.squeeze(-1)
-            signal = F_.FFTConvolve.apply(h2, kernel, hspec, n2).unsqueeze(-1)
+            signal = F_.FFTConvolve.apply(harmonic.squeeze(-1), kernel, hspec, noise.squeeze(-1)).unsqueeze(-1)
         else:
-            h2, n2 = harmonic, noise
             signal = harmonic + noise
-        return (signal, h2, n2) if parts else signal
+        return signal
 
     def forward_backward(self):
         """train.py:89-103,129 on the synth part: loss and gradients of every leaf
         (amp_raw, dist_raw, mag_raw, reverb.noise, reverb.decay, reverb.wet)."""
         s = self.shapes
         leaves = self._leaves()
-        signal, h2, n2 = self.forward(leaves, parts=True)
+        signal = self.forward(leaves)
         # train.py:129 is loss.backward(): the loss node's upstream gradient is exactly 1, so the gradient w.r.t. the
         # reconstruction that the fused loss launch already produced goes straight into the synth chain's backward
         # (core.multiscale_spectral_loss would multiply it by that 1 in a separate elementwise launch)
