@@ -59,6 +59,8 @@ def parse():
     p.add_argument("--global-batch", type=int, default=WORKLOAD["batch"],
                    help="experiments only: the benchmark config is batch 64 (BASELINE.json configs[1])")
     p.add_argument("--skip-kernels", action="store_true")
+    p.add_argument("--e2e-sets", type=int, default=3,
+                   help="static input sets (each with its own captured graph) of the end-to-end loop: sets - 1 batches in flight")
     p.add_argument("--allreduce-outside", action="store_true",
                    help="N>1: queue the gradient all-reduce after the graph instead of inside it (A/B of the overlap)")
     p.add_argument("--skip-configs", action="store_true", help="do not measure the other BASELINE.json configurations")
@@ -635,7 +637,7 @@ def run_b200(args, rank, world):
     paired = use_graph
     link = None
     if paired:
-        step.capture_pair()
+        step.capture_pair(sets=args.e2e_sets)
         with near_gpu(dev):                                 # first touch on the GPU's NUMA node
             hosts = [step.pack_host(h) for h in hosts]      # one pinned block per batch: one H2D copy per step
         link = h2d_rate(hosts[0], step, flush)
@@ -645,17 +647,27 @@ def run_b200(args, rank, world):
     def e2e_loop(n):
         last = 0.0
         if paired:
-            fed_bytes[0] = step.feed(hosts[0])
-            pending = None
+            # up to sets - 1 batches are in flight ahead of the running step; the loss of a step is read sets - 1 steps
+            # after it was queued (the host never stalls the device, the device never waits for the host's next call)
+            from collections import deque
+            ahead = args.e2e_sets - 1
+            pending, fed = deque(), 0
+            while fed < min(ahead, n):
+                fed_bytes[0] = step.feed(hosts[fed & 1])
+                fed += 1
             for k in range(n):
                 cur = step.step_fed()
                 step.allreduce_grads()
                 step.loss_to_host(cur)
-                step.feed(hosts[(k + 1) & 1])                    # H2D of the next batch, overlapped
-                if pending is not None:
-                    last = step.read_loss(pending)               # D2H of the previous step's result
-                pending = cur
-            return step.read_loss(pending)
+                if fed < n:
+                    step.feed(hosts[fed & 1])                    # H2D of a later batch, overlapped
+                    fed += 1
+                pending.append(cur)
+                if len(pending) > ahead:
+                    last = step.read_loss(pending.popleft())     # D2H of an earlier step's result
+            while pending:
+                last = step.read_loss(pending.popleft())
+            return last
         step.prefetch(hosts[0])
         for k in range(n):
             step.step_prefetched()
@@ -723,9 +735,9 @@ def run_b200(args, rank, world):
             "fwd": {"value": samples_per_step / (fwd_ms * 1e-3), "unit": UNIT, "ms_per_step": fwd_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": fed_bytes[0] * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": 1e3 * float(te) / e2e_steps, "loss": loss_host, "h2d_link": link,
-                    "how": "pinned host -> H2D on the copy stream straight into the idle one of two static input sets (next "
-                           "batch in flight during the step) -> one graph launch -> loss D2H read every step (waited for "
-                           "one step later); wall clock between synchronisations"},
+                    "how": f"pinned host -> H2D on the copy stream straight into an idle one of {args.e2e_sets} static input sets "
+                           f"({args.e2e_sets - 1} batches in flight ahead of the step) -> one graph launch per step -> loss D2H read "
+                           f"every step (waited for {args.e2e_sets - 1} steps later); wall clock between synchronisations"},
             "gpu_launches": launches, "roofline": roof, "parity": parity, "kernels": kernels, "cpu_baseline": cpu,
             "configs": configs, "clocks": clocks.summary(), "wall_s_timed_loop": t_wall,
         }

@@ -310,6 +310,10 @@ rows_corr_kernel(const float2 *__restrict__ work_g, const float2 *__restrict__ w
     }
 }
 
+__global__ void zero_ints_kernel(int *p, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = 0;
+}
+
 // Correlation, phase 2: out[o][k1] = IFFT_row(sum of `nsum` partial spectra) * W_n^(-i2 k1)
 template <int LG2>
 __global__ void __launch_bounds__(kRowThreads)
@@ -706,6 +710,18 @@ extern "C" int64_t ddsp_b200_fft4_correlate_splits_plan(int64_t slots, int reduc
 extern "C" int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots,
                                              int reduce, float *scratch, float *out, const float *twiddle,
                                              const float *stage2, int n1, int n2, void *stream) {
+    return ddsp_b200_fft4_rows_correlate_ex(work_g, work_x, slots, reduce, scratch, out, twiddle, stage2, n1, n2, 0,
+                                            stream);
+}
+
+extern "C" int64_t ddsp_b200_fft4_correlate_counter_offset(int64_t slots, int reduce, int n1, int n2) {
+    return corr_fused_finish(reduce, n1, n2) ? corr_splits(slots, reduce, n1, n2) * (int64_t)n1 * n2 * 2 : -1;
+}
+
+extern "C" int ddsp_b200_fft4_rows_correlate_ex(const float *work_g, const float *work_x, int64_t slots,
+                                                int reduce, float *scratch, float *out, const float *twiddle,
+                                                const float *stage2, int n1, int n2, int counters_zeroed,
+                                                void *stream) {
     DDSP_REQUIRE(work_g && work_x && scratch && out && twiddle && stage2 && slots > 0 && slots <= 65535);
     DDSP_REQUIRE(plan_ok(n1, n2));
     const int nsplit = (int)corr_splits(slots, reduce, n1, n2);
@@ -716,8 +732,13 @@ extern "C" int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *w
     if (corr_fused_finish(reduce, n1, n2)) {
         if ((s = set_smem(rows_corr_kernel<12, true, true>, row_smem<12>()))) return s;
         int *counters = reinterpret_cast<int *>(scratch + (size_t)nsplit * n1 * n2 * 2);     // the extra scratch plane
-        cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)n1 * sizeof(int), st);
-        if (e != cudaSuccess) return (int)e;
+        // the row counters must be zero on entry (the kernel leaves them zero).  A caller that cannot promise it gets
+        // them zeroed here, by a one-warp kernel rather than cudaMemsetAsync: a memset node may be scheduled on a copy
+        // engine, where it would queue behind the host->device transfer of the next batch
+        if (!counters_zeroed) {
+            zero_ints_kernel<<<1, 32, 0, st>>>(counters, n1);
+            if ((s = ddsp_launch_status())) return s;
+        }
         rows_corr_kernel<12, true, true><<<dim3(n1, nsplit), kRowThreads, row_smem<12>(), st>>>(
             reinterpret_cast<const float2 *>(work_g), reinterpret_cast<const float2 *>(work_x), slots, nsplit,
             reinterpret_cast<float2 *>(scratch), reinterpret_cast<const float2 *>(twiddle),

@@ -548,6 +548,28 @@ std::tuple<Tensor, Tensor, Tensor> fftconv_bwd_parts(const Tensor &g_, const Ten
     const int64_t slots = pair ? (R + 1) / 2 : R;
     auto main_stream = at::cuda::getCurrentCUDAStream();
     void *st = (void *)main_stream.stream();
+    // d_kernel and d_signal are independent after the transform of g: the kernel-gradient chain runs on a
+    // pool stream (it only reads work_g), the signal-gradient chain (which filters work_g in place) waits
+    // for the correlation to have consumed work_g.
+    const bool fork = need_kernel && need_signal;
+    at::cuda::CUDAStream side = fork ? at::cuda::getStreamFromPool(false, sig.device().index()) : main_stream;
+    void *ss = (void *)side.stream();
+    // the correlation's scratch (partial spectra + row counters) is allocated up front and its counters are zeroed on the
+    // side stream while the transform of g runs on the main stream: no zeroing launch on the backward's critical path
+    Tensor scratch;
+    int counters_zeroed = 0;
+    if (need_kernel) {
+        scratch = at::empty({ddsp_b200_fft4_correlate_splits_plan(slots, pair, p.n1, p.n2), p.n, 2}, sig.options());
+        const int64_t coff = ddsp_b200_fft4_correlate_counter_offset(slots, pair, p.n1, p.n2);
+        if (fork && coff >= 0) {
+            at::cuda::CUDAEvent begun;
+            begun.record(main_stream);
+            begun.block(side);
+            c10::cuda::CUDAStreamGuard sg(side);
+            scratch.view({-1}).narrow(0, coff, p.n1).zero_();
+            counters_zeroed = 1;
+        }
+    }
     Tensor work_g;
     if (work_g_.has_value() && work_g_->defined() && work_g_->numel() == slots * p.n * 2) {
         work_g = *work_g_;
@@ -557,12 +579,6 @@ std::tuple<Tensor, Tensor, Tensor> fftconv_bwd_parts(const Tensor &g_, const Ten
         work_g = at::empty({slots, p.n, 2}, sig.options());
         check(ddsp_b200_fft4_cols_fwd(fp(g), R, n, pair, fpm(work_g), fp(p.tw), opt_fp(p.st1), p.n1, p.n2, st), "fft4_cols_fwd(g)");
     }
-    // d_kernel and d_signal are independent after the transform of g: the kernel-gradient chain runs on a
-    // pool stream (it only reads work_g), the signal-gradient chain (which filters work_g in place) waits
-    // for the correlation to have consumed work_g.
-    const bool fork = need_kernel && need_signal;
-    at::cuda::CUDAStream side = fork ? at::cuda::getStreamFromPool(false, sig.device().index()) : main_stream;
-    void *ss = (void *)side.stream();
     // transforms kept by the forward pass (FFTConvolve saves them) are reused instead of recomputed
     Tensor hspec = (hspec_.has_value() && hspec_->defined() && hspec_->numel() == Rk * p.n * 2) ? *hspec_ : Tensor();
     Tensor saved_x = (work_x_.has_value() && work_x_->defined() && work_x_->numel() == slots * p.n * 2) ? *work_x_ : Tensor();
@@ -585,9 +601,8 @@ std::tuple<Tensor, Tensor, Tensor> fftconv_bwd_parts(const Tensor &g_, const Ten
                   "fft4_cols_fwd(x)");
         }
         Tensor corr = at::empty({Rk, p.n, 2}, sig.options());
-        Tensor scratch = at::empty({ddsp_b200_fft4_correlate_splits_plan(slots, pair, p.n1, p.n2), p.n, 2}, sig.options());
-        check(ddsp_b200_fft4_rows_correlate(fp(work_g), fp(work_x), slots, pair, fpm(scratch), fpm(corr),
-                                            fp(p.tw), fp(p.st2), p.n1, p.n2, ss),
+        check(ddsp_b200_fft4_rows_correlate_ex(fp(work_g), fp(work_x), slots, pair, fpm(scratch), fpm(corr),
+                                               fp(p.tw), fp(p.st2), p.n1, p.n2, counters_zeroed, ss),
               "fft4_rows_correlate");
         if (fork) corr_done.record(side);
         Tensor dk = Lc == Lk ? d_ker : at::empty({Rk, Lc}, sig.options());

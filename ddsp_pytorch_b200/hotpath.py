@@ -289,17 +289,23 @@ class SynthStep:
         else:
             self.run()
 
-    # ---- host-fed execution without device-side copies: two input sets, one captured graph each -------
-    def capture_pair(self, warmup: int = 3):
-        """Capture the forward+backward step TWICE, over two sets of static input buffers.  ``feed`` copies a host
-        batch straight into the idle set on the copy stream while the other set's graph runs; ``step_fed`` replays the
-        graph of the set that was fed.  No staging buffers and no device-to-device copy: per step the GPU sees one
-        H2D transfer (copy engine) and one graph launch."""
+    # ---- host-fed execution without device-side copies: several input sets, one captured graph each -------
+    def capture_pair(self, warmup: int = 3, sets: int = 2):
+        """Capture the forward+backward step once per set of static input buffers (``sets`` of them, two by default).
+        ``feed`` copies a host batch straight into the next idle set on the copy stream while the other sets' graphs
+        run; ``step_fed`` replays the graph of the oldest fed set.  No staging buffers and no device-to-device copy: per
+        step the GPU sees one H2D transfer (copy engine) and one graph launch.  With n sets the copy of a batch has n - 1
+        step times to arrive and the host may queue n - 1 steps ahead, which absorbs jitter of the host and of the
+        link; two sets already overlap copy and compute when neither stalls."""
+        assert sets >= 2
         first, first_flat = self.inputs, self._flat_in
-        second, second_flat = self._alloc_inputs(first_flat.device)
-        second_flat.copy_(first_flat)
+        entries = [(first, first_flat)]
+        for _ in range(sets - 1):
+            inputs, flat = self._alloc_inputs(first_flat.device)
+            flat.copy_(first_flat)
+            entries.append((inputs, flat))
         self._pair = []
-        for inputs, flat in ((first, first_flat), (second, second_flat)):
+        for inputs, flat in entries:
             self.inputs = inputs
             graph = self.capture(forward_only=False, warmup=warmup)
             self._pair.append({"inputs": inputs, "flat": flat, "graph": graph, "signal": self.signal, "loss": self.loss,
@@ -307,16 +313,18 @@ class SynthStep:
         self.inputs = first
         self._graph = self._pair[0]["graph"]
         self._copy_stream2 = torch.cuda.Stream()
-        self._fed = [torch.cuda.Event(), torch.cuda.Event()]
-        self._used = [torch.cuda.Event(), torch.cuda.Event()]
-        self._fill = 0
-        self._loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-        self._loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._fed = [torch.cuda.Event() for _ in range(sets)]
+        self._used = [torch.cuda.Event() for _ in range(sets)]
+        self._fill = 0                     # next set to feed
+        self._next = 0                     # next set to run
+        self._loss_host = torch.zeros(sets, dtype=torch.float32).pin_memory()
+        self._loss_ready = [torch.cuda.Event() for _ in range(sets)]
         return self._pair
 
     def feed(self, host) -> int:
-        """Host batch -> the idle input set, on the copy stream; returns the bytes queued.  ``host`` is a dict of pinned
-        tensors (one copy each) or one pinned block from ``pack_host`` (a single copy)."""
+        """Host batch -> the next idle input set, on the copy stream; returns the bytes queued.  ``host`` is a dict of
+        pinned tensors (one copy each) or one pinned block from ``pack_host`` (a single copy).  At most
+        ``sets - 1`` batches may be fed ahead of the step that is running."""
         k = self._fill
         self._copy_stream2.wait_event(self._used[k])             # the graph that last read this set has finished
         n = 0
@@ -330,18 +338,19 @@ class SynthStep:
                         self._pair[k]["inputs"][name].copy_(host[name], non_blocking=True)
                         n += host[name].numel() * host[name].element_size()
             self._fed[k].record(self._copy_stream2)
+        self._fill = (k + 1) % len(self._pair)
         return n
 
     def step_fed(self) -> int:
-        """Run the step on the set most recently fed; returns its index (for ``loss_to_host`` / ``read_loss``)."""
-        k = self._fill
+        """Run the step on the oldest fed set; returns its index (for ``loss_to_host`` / ``read_loss``)."""
+        k = self._next
         cur = torch.cuda.current_stream()
         cur.wait_event(self._fed[k])
         e = self._pair[k]
         e["graph"].replay()
         self._used[k].record(cur)
         self.inputs, self.signal, self.loss, self.grads = e["inputs"], e["signal"], e["loss"], e["grads"]
-        self._fill ^= 1
+        self._next = (k + 1) % len(self._pair)
         return k
 
     def loss_to_host(self, k: int):

@@ -188,13 +188,19 @@ int ddsp_b200_fft4_rows_filter(const float *work, float *dst, int64_t slots, con
                                const float *stage2, int n1, int n2, void *stream);
 /* out = rows of IFFT( FFT(g) * conj(FFT(x)) ), summed over slots into one slot when reduce != 0.
  * scratch: ddsp_b200_fft4_correlate_splits_plan(slots, reduce, n1, n2) * n1*n2 complex: the partial spectra and, on
- * the 5-smooth plans with reduce != 0, one more plane for the row counters of the in-launch finish (the call zeroes
- * them).  ddsp_b200_fft4_correlate_splits is the plan-independent upper bound.                                      */
+ * the 5-smooth plans with reduce != 0, one more plane for the row counters of the in-launch finish (zeroed by the
+ * call, or by the caller: ddsp_b200_fft4_rows_correlate_ex).  ddsp_b200_fft4_correlate_splits is the plan-independent upper bound.                                      */
 int64_t ddsp_b200_fft4_correlate_splits(int64_t slots, int reduce);
 int64_t ddsp_b200_fft4_correlate_splits_plan(int64_t slots, int reduce, int n1, int n2);   /* the same, for a given plan */
 int ddsp_b200_fft4_rows_correlate(const float *work_g, const float *work_x, int64_t slots, int reduce,
                                   float *scratch, float *out, const float *twiddle, const float *stage2,
                                   int n1, int n2, void *stream);
+/* The same for a caller that zeroed the row counters itself, off the critical path: n1 ints at float offset
+ * ddsp_b200_fft4_correlate_counter_offset(...) of scratch (-1: this plan has no counters).  The launch leaves them zero. */
+int64_t ddsp_b200_fft4_correlate_counter_offset(int64_t slots, int reduce, int n1, int n2);
+int ddsp_b200_fft4_rows_correlate_ex(const float *work_g, const float *work_x, int64_t slots, int reduce,
+                                     float *scratch, float *out, const float *twiddle, const float *stage2,
+                                     int n1, int n2, int counters_zeroed, void *stream);
 
 /* ---- a10  Reverb.build_impulse                       (ddsp/models/modules.py:21-26) -------- */
 /* impulse[l] = noise[l]*exp(-softplus(-decay)*t[l]*500)*sigmoid(wet), impulse[0] = 1; l < L.
