@@ -68,6 +68,55 @@ def test_argument_errors_do_not_need_a_gpu(pkg):
     assert tiles(64, 1000, 4096, 1024) == -1      # reflect padding needs n_fft/2 < N, like torch.stft
 
 
+def test_round2_host_logic_without_a_gpu(pkg):
+    """Host-side plans of the second-round entry points: no kernel is launched."""
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    i64, i32, vp = ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
+    # fused controls + oscillator bank: H <= 256, block_size a multiple of 4
+    sup = lib.ddsp_b200_harmonic_frames_raw_supported
+    sup.restype, sup.argtypes = i32, [i32, i32]
+    assert sup(100, 160) == 1 and sup(256, 512) == 1 and sup(64, 1024) == 1
+    assert sup(257, 160) == 0 and sup(100, 161) == 0 and sup(0, 160) == 0
+    raw = lib.ddsp_b200_harmonic_frames_raw_scan_fwd
+    raw.restype = i32
+    raw.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, ctypes.c_double, vp]
+    assert raw(None, 101, None, 101, None, None, None, None, None, None, None, None, 2, 4, 100, 160, 16000.0, None) == -1
+    bwd = lib.ddsp_b200_harmonic_frames_raw_bwd
+    bwd.restype = i32
+    bwd.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, ctypes.c_float, vp]
+    assert bwd(None, None, 1, None, 100, None, None, None, None, 1, None, 100, 2, 4, 100, 160, 16000.0, None) == -1
+    # correlation: the plan's scratch planes = splits that fill one wave of 148 SMs + one plane of row counters on
+    # the 5-smooth plans (the in-launch finish); the plan-independent count is an upper bound
+    plan = lib.ddsp_b200_fft4_correlate_splits_plan
+    plan.restype, plan.argtypes = i64, [i64, i32, i32, i32]
+    anyplan = lib.ddsp_b200_fft4_correlate_splits
+    anyplan.restype, anyplan.argtypes = i64, [i64, i32]
+    off = lib.ddsp_b200_fft4_correlate_counter_offset
+    off.restype, off.argtypes = i64, [i64, i32, i32, i32]
+    assert plan(32, 1, 20, 4096) == 8 and off(32, 1, 20, 4096) == 7 * 20 * 4096 * 2      # 20 rows x 7 splits = 140 CTAs
+    assert plan(32, 1, 24, 4096) == 7 and off(32, 1, 24, 4096) == 6 * 24 * 4096 * 2
+    assert plan(2, 1, 20, 4096) == 3 and off(2, 1, 20, 4096) == 2 * 20 * 4096 * 2
+    assert plan(32, 1, 512, 512) == 8 and off(32, 1, 512, 512) == -1                     # power-of-two plan: two launches
+    assert plan(5, 0, 20, 4096) == 5 and off(5, 0, 20, 4096) == -1                       # no reduction: one slot each
+    for slots in (1, 2, 7, 8, 32, 1000):
+        for n1, n2 in ((20, 4096), (24, 4096), (512, 512), (64, 4096)):
+            assert plan(slots, 1, n1, n2) <= anyplan(slots, 1)
+    # fused loss: workspace covers every tile's hops + halos; a run of frames per thread group is at least 4 frames
+    sizes = lib.ddsp_b200_mss_fused_sizes
+    sizes.restype = i32
+    sizes.argtypes = [i32, i64, ctypes.POINTER(i32), i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    scales = (i32 * 6)(4096, 2048, 1024, 512, 256, 128)
+    ws, part = i64(), i64()
+    assert sizes(64, 64000, scales, 6, ctypes.byref(ws), ctypes.byref(part)) == 0
+    assert ws.value >= 6 * 64 * (64000 + 128) and part.value > 0 and part.value % 2 == 0
+    small = (i32 * 1)(64)
+    assert sizes(1, 33, small, 1, ctypes.byref(ws), ctypes.byref(part)) == 0           # N just above n_fft / 2
+    assert sizes(1, 32, small, 1, ctypes.byref(ws), ctypes.byref(part)) == -2          # reflect padding needs pad < N
+    bad = (i32 * 1)(8192)
+    assert sizes(1, 64000, bad, 1, ctypes.byref(ws), ctypes.byref(part)) == -2
+
+
 def test_ops_registered_without_cpu_kernels(pkg):
     ops = torch.ops.ddsp_b200
     for name in ["harmonic_fwd", "harmonic_bwd", "noise_fwd", "noise_bwd", "fftconv_fwd", "fftconv_bwd",
