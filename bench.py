@@ -279,7 +279,7 @@ def h2d_rate(block, step, flush):
     torch.cuda.synchronize()
     ts = []
     with torch.cuda.stream(s):
-        for _ in range(6):
+        for _ in range(16):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(s)
             dst.copy_(block, non_blocking=True)
@@ -288,7 +288,7 @@ def h2d_rate(block, step, flush):
             ts.append(a.elapsed_time(b))
     ms = sorted(ts)[len(ts) // 2]
     nbytes = block.numel() * block.element_size()
-    return {"ms_per_batch": ms, "gb_per_s": nbytes / (ms * 1e-3) / 1e9,
+    return {"ms_per_batch": ms, "gb_per_s": nbytes / (ms * 1e-3) / 1e9, "ms_min": min(ts), "ms_max": max(ts), "copies": len(ts),
             "note": "host->device copy of one step's inputs on an otherwise idle GPU; when this exceeds ms_per_step of "
                     "the device-timed value, e2e is bound by the host link, not by the kernels"}
 
