@@ -563,6 +563,27 @@ extern "C" int ddsp_b200_mss_fused_sizes(int B, int64_t N, const int *scales, in
     return DDSP_B200_OK;
 }
 
+// The plan of one scale, for hosts that size buffers themselves and for the CPU test of the tile / run bookkeeping
+// (tests/test_abi_cpu.py): out = {frames, hop, frames per tile, tiles per voice, thread groups per CTA, frames per run,
+// first frame slot past the last tile, floats per voice of the gradient plane}.
+extern "C" int ddsp_b200_mss_fused_plan(int B, int64_t N, const int *scales, int n_scales, int which, int64_t *out8) {
+    DDSP_REQUIRE(scales && out8 && which >= 0 && which < n_scales);
+    Plan2 p;
+    int s = make_plan(B, N, scales, n_scales, &p);
+    if (s) return s;
+    const ScaleDesc &d = p.args.sc[which];
+    const int groups = kThreads / (scales[which] / 16);
+    out8[0] = d.frames;
+    out8[1] = d.hop;
+    out8[2] = 1ll << d.ft_log;
+    out8[3] = d.tiles;
+    out8[4] = groups;
+    out8[5] = (1ll << d.ft_log) / groups;
+    out8[6] = d.last_end;
+    out8[7] = d.rowlen;
+    return DDSP_B200_OK;
+}
+
 extern "C" int ddsp_b200_mss_fused(const float *target, const float *rec, const float *windows,
                                    const float *const *stage_twiddles, float *workspace, float *partial,
                                    float *d_rec, float *loss, int B, int64_t N, const int *scales, int n_scales,

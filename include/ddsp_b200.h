@@ -266,6 +266,9 @@ int ddsp_b200_mss_finish(const float *partial, const float *edge, const float *d
 int ddsp_b200_mss_fused_supported(const int *scales, const int *hops, int n_scales);
 int ddsp_b200_mss_fused_sizes(int B, int64_t N, const int *scales, int n_scales, int64_t *workspace_floats,
                               int64_t *partial_floats);
+/* plan of scale `which`: out8 = {frames, hop, frames per tile, tiles per voice, thread groups per CTA, frames per
+ * run, first frame slot past the last tile, floats per voice of the scale's gradient plane}                      */
+int ddsp_b200_mss_fused_plan(int B, int64_t N, const int *scales, int n_scales, int which, int64_t *out8);
 int ddsp_b200_mss_fused(const float *target, const float *rec, const float *windows,
                         const float *const *stage_twiddles, float *workspace, float *partial, float *d_rec,
                         float *loss, int B, int64_t N, const int *scales, int n_scales, void *stream);

@@ -117,6 +117,49 @@ def test_round2_host_logic_without_a_gpu(pkg):
     assert sizes(1, 64000, bad, 1, ctypes.byref(ws), ctypes.byref(part)) == -2
 
 
+@pytest.mark.parametrize("B", [1, 3, 8, 64])
+@pytest.mark.parametrize("N", [33, 1000, 2400, 9001, 64000, 192000])
+def test_fused_loss_tiles_and_runs_cover_every_hop_the_combine_reads(pkg, B, N):
+    """Bookkeeping of csrc/mss_fused.cu on the CPU.  A tile's frames are split into runs, one per thread group; a run is
+    taken whole or skipped, groups that share a warp decide together.  The gradient plane then holds: the hops of every
+    taken run, and the first three hops of every run but a tile's first (its head gets the previous run's carry even
+    when the run itself is skipped).  mss_combine2_kernel reads the plane for hop slots below min(last_end, frames + 3)
+    and the tiles' halos elsewhere: every one of those slots must have been written, and the plane must be large enough."""
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    plan = lib.ddsp_b200_mss_fused_plan
+    plan.restype = ctypes.c_int
+    plan.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int,
+                     ctypes.POINTER(ctypes.c_int64)]
+    all_scales = [s for s in (4096, 2048, 1024, 512, 256, 128, 64) if N > s // 2]
+    arr = (ctypes.c_int * len(all_scales))(*all_scales)
+    for which, n_fft in enumerate(all_scales):
+        out = (ctypes.c_int64 * 8)()
+        assert plan(B, N, arr, len(all_scales), which, out) == 0
+        frames, hop, ft, tiles, groups, rl, last_end, rowlen = list(out)
+        assert frames == 1 + N // hop and hop == n_fft // 4
+        assert ft == groups * rl and rl >= 4 and rl % 2 == 0 and ft & (ft - 1) == 0
+        assert tiles == -(-frames // ft) and last_end == tiles * ft
+        assert rowlen >= last_end * hop and rowlen >= N + n_fft and rowlen % 4 == 0
+        threads_per_group = n_fft // 16
+        written = set()
+        for tile in range(tiles):
+            f0, f1 = tile * ft, min((tile + 1) * ft, frames)
+            for g in range(groups):
+                run0 = f0 + g * rl
+                # groups narrower than a warp take the decision of the first group of their warp
+                gw = (g * threads_per_group // 32) * 32 // threads_per_group if threads_per_group < 32 else g
+                if f0 + gw * rl < f1:
+                    written.update(range(run0, run0 + rl))
+                if g > 0:
+                    written.update(range(run0, run0 + 3))
+        need = set(range(min(last_end, frames + 3)))
+        assert need <= written, (n_fft, sorted(need - written)[:5])
+        # the last real frame's tail (3 hops) is either in the plane or in the last tile's halo
+        assert frames + 2 < last_end + 3
+        assert max(written) < last_end
+
+
 def test_ops_registered_without_cpu_kernels(pkg):
     ops = torch.ops.ddsp_b200
     for name in ["harmonic_fwd", "harmonic_bwd", "noise_fwd", "noise_bwd", "fftconv_fwd", "fftconv_bwd",
