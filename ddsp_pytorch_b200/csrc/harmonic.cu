@@ -16,7 +16,9 @@
 //  * backward (d weights): one thread owns (frame, harmonic, chunk of samples) and walks TIME with
 //    the same recurrence (the frame's phase increment is constant), so the reduction over the
 //    frame's samples is a private accumulation; g is broadcast from shared memory.
+#include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -33,12 +35,57 @@ __device__ __forceinline__ uint64_t turns_to_q64(double turns) {
     return __double2ull_rz(turns * 18446744073709551616.0);
 }
 
+// Phase increment per sample of a float32 pitch, frac(f0 / sr) in Q0.64, in INTEGER arithmetic (no FP64 instructions in
+// the scans: every CTA of the oscillator bank converts the voice's earlier frames, the audio-rate scan converts every
+// sample).  f0 = m * 2^e with a 24-bit m; k = (1/sr as a double) * 2^104 as a 128-bit integer (53 significant bits:
+// exact); delta = (m * k) >> (40 - e) mod 2^64 = the EXACT product truncated -- the double form rounds the product to
+// 53 bits first, so this is the more accurate of the two; tests/test_abi_cpu.py checks the host build of this function
+// against exact rationals.  (Device time of the bank at config 2 is the same with either form.)
+struct PhaseK { uint64_t hi, lo; double inv_sr; };
+static PhaseK make_phase_k(double inv_sr) {
+    PhaseK k{0, 0, inv_sr};
+    int ex = 0;
+    const double fr = frexp(inv_sr, &ex);                       // inv_sr = fr * 2^ex, fr in [0.5, 1)
+    const uint64_t mant = (uint64_t)ldexp(fr, 53);              // exact 53-bit integer
+    const int sh = 104 + ex - 53;                               // k = mant << sh
+    if (inv_sr > 0 && sh >= 0 && sh < 64 && (sh == 0 || (mant >> (64 - sh)) < (1ull << 40))) {
+        k.lo = mant << sh;
+        k.hi = sh == 0 ? 0 : mant >> (64 - sh);
+    }                                                           // else hi = lo = 0: the kernels take the double form
+    return k;
+}
+__host__ __device__ __forceinline__ uint64_t pitch_to_q64(float f0, const PhaseK k) {
+#ifdef __CUDA_ARCH__
+    if (k.hi == 0 && k.lo == 0) return turns_to_q64((double)f0 * k.inv_sr);
+    const uint32_t bits = __float_as_uint(f0);
+#else
+    uint32_t bits;                                              // host build: the same integer arithmetic, for the CPU test
+    memcpy(&bits, &f0, sizeof bits);
+    if (k.hi == 0 && k.lo == 0) return 0;
+#endif
+    const int ex = (int)((bits >> 23) & 0xffu);
+    if (ex == 0) return 0;                                      // zero / denormal pitch
+    const uint64_t m = (uint64_t)((bits & 0x7fffffu) | 0x800000u);
+    const int sh = 40 - (ex - 150);                             // right shift of the 128-bit product
+    uint64_t d = 0;
+    if (sh >= 0 && sh < 128) {
+        const uint64_t p0 = m * k.lo;
+#ifdef __CUDA_ARCH__
+        const uint64_t p1 = __umul64hi(m, k.lo) + m * k.hi;     // m < 2^24, k.hi < 2^40: no overflow
+#else
+        const uint64_t p1 = (uint64_t)(((unsigned __int128)m * k.lo) >> 64) + m * k.hi;
+#endif
+        d = sh == 0 ? p0 : sh < 64 ? (p0 >> sh) | (p1 << (64 - sh)) : sh == 64 ? p1 : p1 >> (sh - 64);
+    }
+    return (bits >> 31) ? 0ull - d : d;                          // a negative pitch runs the phase backwards
+}
+
 constexpr int kScanThreads = 256;
 
 __global__ void __launch_bounds__(kScanThreads)
 phase_scan_kernel(const float *__restrict__ f0, const double *__restrict__ phase0,
                   uint64_t *__restrict__ phi, uint64_t *__restrict__ delta,
-                  double *__restrict__ phase_end, int T, int block_size, double inv_sr) {
+                  double *__restrict__ phase_end, int T, int block_size, const PhaseK pk) {
     __shared__ uint64_t tot[kScanThreads];
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
@@ -47,7 +94,7 @@ phase_scan_kernel(const float *__restrict__ f0, const double *__restrict__ phase
     const float *f = f0 + (size_t)b * T;
     uint64_t sum = 0;
     for (int t = lo; t < hi; ++t) {
-        uint64_t d = turns_to_q64((double)f[t] * inv_sr);
+        uint64_t d = pitch_to_q64(f[t], pk);
         delta[(size_t)b * T + t] = d;
         sum += d * (uint64_t)block_size;
     }
@@ -182,7 +229,7 @@ struct RawControls {
     // scan != 0: the CTA also does the phase scan for its frames (phase_scan_kernel's integer arithmetic: exact and
     // associative, so the same bits) and writes phi / delta for the backward; phase0 / phase_end as in the scan
     int scan, block_size;
-    double inv_sr;
+    PhaseK pk;
     const double *phase0;
     double *phase_end;
     uint64_t *phi_out, *delta_out;
@@ -255,11 +302,11 @@ harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t 
         __shared__ uint64_t wsum[kFwdMaxThreads / 32];
         const float *fv = rc.f0 + (size_t)b * T;
         uint64_t part = 0;
-        for (int t = tid; t < t0; t += nthr) part += turns_to_q64((double)fv[t] * rc.inv_sr);
+        for (int t = tid; t < t0; t += nthr) part += pitch_to_q64(fv[t], rc.pk);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if ((tid & 31) == 0) wsum[tid >> 5] = part;
-        if (tid < nfr) sdel[tid] = turns_to_q64((double)fv[t0 + tid] * rc.inv_sr);
+        if (tid < nfr) sdel[tid] = pitch_to_q64(fv[t0 + tid], rc.pk);
         __syncthreads();
         if (tid == 0) {
             uint64_t run = rc.phase0 ? turns_to_q64(rc.phase0[b]) : 0ull;
@@ -641,7 +688,7 @@ constexpr int kArThreads = 256;
 
 __global__ void __launch_bounds__(kArThreads)
 phase_scan_audio_rate_kernel(const float *__restrict__ f0, uint64_t *__restrict__ phase, int64_t N,
-                             double inv_sr) {
+                             const PhaseK pk) {
     __shared__ uint64_t tot[kArThreads];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int64_t per = (N + kArThreads - 1) / kArThreads;
@@ -650,7 +697,7 @@ phase_scan_audio_rate_kernel(const float *__restrict__ f0, uint64_t *__restrict_
     uint64_t *p = phase + (size_t)b * N;
     uint64_t sum = 0;
     for (int64_t n = lo; n < hi; ++n) {
-        sum += turns_to_q64((double)f[n] * inv_sr);
+        sum += pitch_to_q64(f[n], pk);
         p[n] = sum;                                   // inclusive within the chunk
     }
     tot[tid] = sum;
@@ -754,12 +801,17 @@ audio_rate_df0_kernel(const float *__restrict__ dphi, float *__restrict__ d_f0, 
 // ================================================================================================
 // C ABI
 // ================================================================================================
+// the integer phase increment evaluated on the HOST (same source as the kernels): frac(f0 / sample_rate) in Q0.64
+extern "C" uint64_t ddsp_b200_pitch_to_q64(float f0, double sample_rate) {
+    return pitch_to_q64(f0, make_phase_k(1.0 / sample_rate));
+}
+
 extern "C" int ddsp_b200_phase_scan(const float *f0, const double *phase0, uint64_t *phi,
                                     uint64_t *delta, double *phase_end, int B, int T,
                                     int block_size, double sample_rate, void *stream) {
     DDSP_REQUIRE(f0 && phi && delta && B > 0 && T > 0 && block_size > 0 && sample_rate > 0);
     phase_scan_kernel<<<B, kScanThreads, 0, (cudaStream_t)stream>>>(
-        f0, phase0, phi, delta, phase_end, T, block_size, 1.0 / sample_rate);
+        f0, phase0, phi, delta, phase_end, T, block_size, make_phase_k(1.0 / sample_rate));
     return ddsp_launch_status();
 }
 
@@ -847,7 +899,7 @@ extern "C" int ddsp_b200_harmonic_frames_raw_fwd(const float *amp_raw, int64_t a
     DDSP_REQUIRE(B > 0 && B <= 65535 && T > 0 && H > 0 && block_size > 0 && amp_stride >= 1 && dist_stride >= H);
     if (!ddsp_b200_harmonic_frames_raw_supported(H, block_size)) return DDSP_B200_EUNSUPPORTED;
     RawControls rc{amp_raw, dist_raw, f0, amp_stride, dist_stride, sample_rate * 0.5f, amps, weights,
-                   0, block_size, 0.0, nullptr, nullptr, nullptr, nullptr};
+                   0, block_size, PhaseK{0, 0, 0.0}, nullptr, nullptr, nullptr, nullptr};
     return launch_frames_fwd(nullptr, &rc, phi, delta, audio, B, T, H, block_size, (cudaStream_t)stream);
 }
 
@@ -865,14 +917,14 @@ extern "C" int ddsp_b200_harmonic_frames_raw_scan_fwd(const float *amp_raw, int6
     const int fr = frames_per_cta(block_size, T, kFwdThreads * 4, 32);
     if ((T + fr - 1) / fr > 64) {
         phase_scan_kernel<<<B, kScanThreads, 0, (cudaStream_t)stream>>>(f0, phase0, phi, delta, phase_end, T, block_size,
-                                                                       1.0 / sample_rate);
+                                                                       make_phase_k(1.0 / sample_rate));
         int s = ddsp_launch_status();
         if (s) return s;
         return ddsp_b200_harmonic_frames_raw_fwd(amp_raw, amp_stride, dist_raw, dist_stride, f0, phi, delta, amps,
                                                  weights, audio, B, T, H, block_size, (float)sample_rate, stream);
     }
     RawControls rc{amp_raw, dist_raw, f0, amp_stride, dist_stride, (float)sample_rate * 0.5f, amps, weights,
-                   1, block_size, 1.0 / sample_rate, phase0, phase_end, phi, delta};
+                   1, block_size, make_phase_k(1.0 / sample_rate), phase0, phase_end, phi, delta};
     return launch_frames_fwd(nullptr, &rc, phi, delta, audio, B, T, H, block_size, (cudaStream_t)stream);
 }
 
@@ -964,7 +1016,7 @@ extern "C" int ddsp_b200_phase_scan_audio_rate(const float *f0, uint64_t *phase,
                                                double sample_rate, void *stream) {
     DDSP_REQUIRE(f0 && phase && B > 0 && N > 0 && sample_rate > 0);
     phase_scan_audio_rate_kernel<<<B, kArThreads, 0, (cudaStream_t)stream>>>(f0, phase, N,
-                                                                              1.0 / sample_rate);
+                                                                              make_phase_k(1.0 / sample_rate));
     return ddsp_launch_status();
 }
 

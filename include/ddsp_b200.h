@@ -66,6 +66,9 @@ int ddsp_b200_harmonic_controls_bwd(const float *amp_raw, const float *dist_raw,
 /* Phase workspace: phi[B*T], delta[B*T] uint64 = phase at the start of each frame and phase
  * increment per sample, in turns as Q0.64 fixed point.  phase0[B] (may be NULL = 0) and
  * phase_end[B] (may be NULL) are turns in [0,1) as double: the streaming carry. */
+/* Host-side evaluation of the per-sample phase increment the scans use: frac(f0 / sample_rate) as Q0.64, the exact
+ * product of the float32 pitch and the double 1/sample_rate, truncated (integer arithmetic, no device needed). */
+uint64_t ddsp_b200_pitch_to_q64(float f0, double sample_rate);
 int ddsp_b200_phase_scan(const float *f0, const double *phase0, uint64_t *phi, uint64_t *delta,
                          double *phase_end, int B, int T, int block_size, double sample_rate,
                          void *stream);

@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -158,6 +159,34 @@ def test_fused_loss_tiles_and_runs_cover_every_hop_the_combine_reads(pkg, B, N):
         # the last real frame's tail (3 hops) is either in the plane or in the last tile's halo
         assert frames + 2 < last_end + 3
         assert max(written) < last_end
+
+
+def test_phase_increment_is_the_exact_product_truncated(pkg):
+    """csrc/harmonic.cu pitch_to_q64 (host build of the same source): frac(f0 / sr) in Q0.64 from integer arithmetic
+    must equal floor(frac(float32(f0) * double(1 / sr)) * 2^64) computed with exact rationals."""
+    from fractions import Fraction
+    import struct
+    from ddsp_pytorch_b200._lib import core_library
+    lib = core_library()
+    fn = lib.ddsp_b200_pitch_to_q64
+    fn.restype, fn.argtypes = ctypes.c_uint64, [ctypes.c_float, ctypes.c_double]
+    rng = np.random.default_rng(0)
+    pitches = np.concatenate([rng.uniform(20, 8000, 400), rng.uniform(0.001, 20, 50), rng.uniform(8000, 200000, 50),
+                              [0.0, 1.0, 440.0, 8000.0, 16000.0, 15999.999, 48000.0, 1e-30, 3e9, -440.0, -0.5]])
+    for sr in (16000.0, 48000.0, 44100.0, 22050.0, 8000.0):
+        inv = Fraction(1.0 / sr)                                   # the double the library multiplies by, exactly
+        for f in pitches.astype(np.float32):
+            exact = Fraction(float(f)) * inv
+            frac = exact - (exact.numerator // exact.denominator)
+            want = (frac.numerator << 64) // frac.denominator
+            if f < 0:                                              # the phase runs backwards: two's complement of |f0|'s
+                pos = Fraction(float(-f)) * inv
+                pf = pos - (pos.numerator // pos.denominator)
+                want = (-((pf.numerator << 64) // pf.denominator)) % (1 << 64)
+            if 0 < abs(float(f)) < 1.2e-38:
+                want = 0                                           # denormal pitch counts as silence
+            got = fn(ctypes.c_float(float(f)), sr)
+            assert got == want % (1 << 64), (float(f), sr, got, want)
 
 
 def test_ops_registered_without_cpu_kernels(pkg):
