@@ -235,8 +235,10 @@ struct RawControls {
     uint64_t *phi_out, *delta_out;
 };
 
+// (64 registers: eight 128-thread CTAs per SM.  The prologue's scan and controls would otherwise raise the count to 74
+// = six CTAs; __maxnreg__ and __launch_bounds__ exclude each other, 640 threads x 64 registers fit the register file)
 template <bool RAW>
-__global__ void __launch_bounds__(kFwdMaxThreads)
+__global__ void __maxnreg__(64)
 harmonic_frames_fwd_x2_kernel(const float *__restrict__ weights, const uint64_t *__restrict__ phi,
                               const uint64_t *__restrict__ delta, float *__restrict__ audio, int T,
                               int H, int Hp, int bs, int FR, const RawControls rc) {
